@@ -1,0 +1,54 @@
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+MODEL_CASES = ["default_bert", "script_pl_gru", "script_bpr_gru_k4", "direct_att_bert", "wide_intent_bert_full"]
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+def load_model_case(name, device="cpu"):
+    """-> (cfg, batch, state, golden dict) from tests/golden/model_<name>.npz"""
+    from intel_sigir2023_b200.config import IntelConfig
+    z = np.load(os.path.join(GOLDEN, f"model_{name}.npz"))
+    cfg = IntelConfig(**json.loads(bytes(z["cfg"]).decode()))
+    batch = {k[6:]: torch.from_numpy(z[k]).to(device) for k in z.files if k.startswith("batch.")}
+    batch["batch_size"] = int(batch["i_id_s"].shape[0])
+    batch["phase"] = "train"
+    state = {k[6:]: torch.from_numpy(z[k]).to(device) for k in z.files if k.startswith("state.")}
+    gold = {k: z[k] for k in z.files if not (k.startswith("batch.") or k.startswith("state.") or k == "cfg")}
+    return cfg, batch, state, gold
+
+
+def rel_err(a, b):
+    """max|a-b| / max|b|  (tolerance relative to the tensor's inf-norm)."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    den = max(np.abs(b).max(), 1e-30) if b.size else 1.0
+    return float(np.abs(a - b).max() / den) if b.size else 0.0
+
+
+LOSS_KW = dict(cal_diversity=1, diversity_alpha=0.05, intent_weight=0.1, ensemble_weight=1.0,
+               kl_weight=0.5, kl_temp=2.0)
+
+
+def assert_grad_close(g, ref, gmax, name, rtol=5e-4, afrac=2e-6):
+    """|g-ref| <= rtol*max|ref| + afrac*gmax, gmax = largest gradient entry of the whole model
+    (gradients that are analytically zero, e.g. softmax key biases, are pure rounding noise)."""
+    g = np.asarray(g, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    assert g.shape == ref.shape, (name, g.shape, ref.shape)
+    err = np.abs(g - ref).max() if ref.size else 0.0
+    bound = rtol * (np.abs(ref).max() if ref.size else 0.0) + afrac * gmax
+    assert err <= bound, (name, err, bound)
