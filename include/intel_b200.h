@@ -1,0 +1,198 @@
+/* libintel_b200 - C ABI of the B200-native IntEL hot path.
+ *
+ * The reference (JiayuLi-997/IntEL-SIGIR2023) is pure Python; it has no FFI.  Its plugin
+ * surface is three Python call signatures resolved by name (IntEL/src/main.py:127-130):
+ *
+ *   model(batch)            -> {"weights","ens_score","intents"}   models/IntEL/IntEL.py:117-124
+ *   criterion(out, batch)   -> (loss, ensemble_loss, intent_loss)  loss/Int{List,BPR,MSE}loss.py:14-19
+ *   BaseRunner.evaluate_method(...) / evaluate_intents(...)        helpers/BaseRunner.py:57-150
+ *
+ * The entry points below are what a ctypes binding of those three calls needs; each one
+ * names the reference code it replaces.  Conventions:
+ *   - plain pointers + sizes, no torch types; every pointer is DEVICE memory owned by the caller
+ *   - tensors arrive in the dtypes the reference's collate_batch delivers (int64 ids, float64
+ *     scores / intents); conversion happens inside the kernels' loads
+ *   - scratch comes from a caller workspace (query *_workspace_bytes first); the library never
+ *     allocates or frees device memory and never synchronises: all work is queued on `stream`
+ *   - forward calls leave their saved activations in the workspace; the matching backward call
+ *     must be given the same workspace, untouched
+ *   - backward entry points ACCUMULATE (+=) into the gradient buffers (dense, same shapes as the
+ *     parameters, zeroed by the caller) so torch.optim.Adam(weight_decay) stays drop-in
+ *   - return 0 on success, otherwise an INTEL_ERR_* code; intel_last_error() gives the message
+ *     (thread-local).  No exceptions cross the ABI.
+ */
+#ifndef INTEL_B200_H
+#define INTEL_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define INTEL_ABI_VERSION 1
+#define INTEL_MAX_BERT_LAYERS 4
+#define INTEL_MAX_TOPK 16
+#define INTEL_ENCODER_BERT4REC 0
+#define INTEL_ENCODER_GRU4REC 1
+
+typedef void* intel_stream_t; /* cudaStream_t */
+
+/* Shapes of one batch + model widths (flag names of IntEL.py:17-34). */
+typedef struct {
+    int64_t B, L, K, I;      /* sessions, padded list length, basic lists, intents */
+    int64_t H1, H2;          /* padded session-history / item-history lengths */
+    int64_t item_rows, class_rows, user_rows, ctx_rows;
+    int32_t d_iid, d_im, d_u, d_s, d_int, d_ctx;   /* i/im/u/s/intent/context_emb_size */
+    int32_t qsize;           /* cross_attn_qsize */
+    int32_t heads, layers;   /* num_heads, num_layers of the two self-attention stacks */
+    int32_t cross_attention; /* 1: CrossAtt pooling (default); 0: intent MLP gate */
+    int32_t encoder;         /* INTEL_ENCODER_* */
+    int32_t gru_hidden, bert_layers, bert_heads, history_max;
+} intel_dims_t;
+
+typedef struct {             /* layers.py TransformerLayer, one block of BERT4RecEncoder */
+    float *qw, *qb, *kw, *kb, *vw, *vb, *ln1w, *ln1b, *l1w, *l1b, *l2w, *l2b, *ln2w, *ln2b;
+} intel_bert_layer_t;
+
+typedef struct {             /* GeneralSeq.py:58-106 */
+    float* pos;                                          /* p_embeddings [history_max+1, d] */
+    intel_bert_layer_t layer[INTEL_MAX_BERT_LAYERS];
+    float *w_ih, *w_hh, *b_ih, *b_hh, *w_out;            /* nn.GRU l0 + out (bias-free) */
+} intel_encoder_t;
+
+typedef struct {             /* one self-attention stack of IntEL.py:182-197 */
+    float *wq, *wk, *wv, *w1, *b1, *w2, *b2, *lnw, *lnb;
+} intel_selfatt_t;
+
+/* Every parameter of the reference module (state_dict contract).  The same
+ * struct type carries the gradient buffers in the backward calls. */
+typedef struct {
+    float *iid_emb, *item_emb, *uid_emb, *ctx_emb;       /* embedding tables */
+    float *intent_w, *intent_b;                          /* intent_embeddings [d_int, I] */
+    float *score_w, *score_b;                            /* score_embeddings  [d_s, K]   */
+    intel_selfatt_t item, score;
+    float *xq_item, *xk_item, *xv_item;                  /* intent_item_attention.{query,key,value}_layer */
+    float *xq_score, *xk_score, *xv_score;               /* intent_score_attention.*                      */
+    float *gate_item_w0, *gate_item_b0, *gate_item_w2;   /* intent_item_embeddings.{0,2} (cross_attention=0) */
+    float *gate_score_w0, *gate_score_b0, *gate_score_w2;
+    float *head_w, *head_b;                              /* weight_embeddings [K, d_i+d_s+d_u+d_int] */
+    intel_encoder_t enc, item_enc;                       /* encoder / item_encoder */
+    float *pred_w, *pred_b;                              /* pred_layer [I, d_pred] */
+} intel_tensors_t;
+
+/* One collated batch (BaseModel.py:121-142 layout; ragged fields right-padded with 0). */
+typedef struct {
+    const int64_t *u_id;             /* [B]      u_id_c          */
+    const int64_t *i_id;             /* [B,L]    i_id_s          */
+    const int64_t *i_class;          /* [B,L]    i_class_c (NULL when class_rows == 0) */
+    const int64_t *session_len;      /* [B]                      */
+    const double  *scores;           /* [B,L,K]  float64         */
+    const int64_t *context_mh;       /* [B]                      */
+    const int64_t *his_context;      /* [B,H1]   his_context_mh  */
+    const double  *his_intents;      /* [B,H1,I] float64 dense   */
+    const int64_t *history_len;      /* [B]                      */
+    const int64_t *his_item_id;      /* [B,H2]                   */
+    const double  *his_item_int;     /* [B,H2,I] float64 one-hot */
+    const int64_t *history_item_len; /* [B]                      */
+} intel_batch_t;
+
+const char* intel_last_error(void);
+int intel_abi_version(void);
+
+/* ---- model forward / backward -------------------------------------------------------- */
+/* IntEL.predict_intent (IntEL.py:126-155): intents_out f32 [B,I] = softmax(pred_layer(...)). */
+size_t intel_intent_workspace_bytes(const intel_dims_t* d);
+int intel_intent_fwd(const intel_dims_t* d, const intel_tensors_t* params, const intel_batch_t* batch,
+                     float* intents_out, void* workspace, size_t workspace_bytes, intel_stream_t stream);
+/* autograd of the above: the incoming gradient is d_intents + d_intents_extra (f32 [B,I] each; the
+ * second, nullable, is the part that intel_ensemble_bwd produced); accumulates into `grads`. */
+int intel_intent_bwd(const intel_dims_t* d, const intel_tensors_t* params, const intel_batch_t* batch,
+                     const float* intents, const float* d_intents, const float* d_intents_extra,
+                     intel_tensors_t* grads,
+                     void* workspace, size_t workspace_bytes, intel_stream_t stream);
+
+/* IntEL.predict_ensemble (IntEL.py:158-217): weights_out f32 [B,L,K], ens_out f32 [B,L]. */
+size_t intel_ensemble_workspace_bytes(const intel_dims_t* d);
+int intel_ensemble_fwd(const intel_dims_t* d, const intel_tensors_t* params, const intel_batch_t* batch,
+                       const float* intents, float* weights_out, float* ens_out,
+                       void* workspace, size_t workspace_bytes, intel_stream_t stream);
+/* d_weights [B,L,K] / d_ens [B,L] may be NULL (treated as zero); d_intents_out f32 [B,I] is overwritten. */
+int intel_ensemble_bwd(const intel_dims_t* d, const intel_tensors_t* params, const intel_batch_t* batch,
+                       const float* intents, const float* d_weights, const float* d_ens,
+                       intel_tensors_t* grads, float* d_intents_out,
+                       void* workspace, size_t workspace_bytes, intel_stream_t stream);
+
+/* ---- losses with fused gradients ------------------------------------------------------ */
+/* Each writes the scalar loss (batch mean, diversity term folded in like the reference's in-place
+ * `loss +=`) to loss_out[0] (float64 accumulator) and the gradient of that scalar w.r.t. ens_score / weights to
+ * d_ens [B,L] / d_weights [B,L,K] (overwritten; d_weights may be NULL when cal_diversity == 0). */
+/* Listloss.forward (Listloss.py:12-43) */
+int intel_loss_pl_fwd_bwd(int64_t B, int64_t L, int64_t K, const float* ens, const float* weights,
+                          const double* scores, const int64_t* ranking, const int64_t* session_len,
+                          int cal_diversity, double alpha, double* loss_out, float* d_ens, float* d_weights,
+                          intel_stream_t stream);
+/* BPRloss.forward (BPRloss.py:12-56).  noise f32 [B,L,L] replays torch.rand_like (BPRloss.py:26);
+ * NULL -> counter-based in-kernel RNG keyed by `seed`. */
+int intel_loss_bpr_fwd_bwd(int64_t B, int64_t L, int64_t K, const float* ens, const float* weights,
+                           const double* scores, const int64_t* ranking, const int64_t* session_len,
+                           const float* noise, uint64_t seed, int cal_diversity, double alpha,
+                           double* loss_out, float* d_ens, float* d_weights, intel_stream_t stream);
+/* MSEloss.forward (MSEloss.py:12-30) */
+int intel_loss_mse_fwd_bwd(int64_t B, int64_t L, int64_t K, const float* ens, const float* weights,
+                           const double* scores, const int64_t* ranking, const int64_t* session_len,
+                           int cal_diversity, double alpha, double* loss_out, float* d_ens, float* d_weights,
+                           intel_stream_t stream);
+/* BaseIntloss.get_intloss (BaseIntloss.py:30-67): out[0]=intent_loss, out[1]=ce, out[2]=kl*T^2 (f64);
+ * d_pred f32 [B,I] = d intent_loss / d pred.  scratch: >= 16 bytes of device memory. */
+int intel_intent_loss_fwd_bwd(int64_t B, int64_t I, const float* pred, const double* true_intents,
+                              double kl_weight, double kl_temp, double* out, float* d_pred,
+                              void* scratch, intel_stream_t stream);
+/* y[i] = x[i] * (ca * *a + cb * *b) with device scalars a, b (either may be NULL): chains the upstream
+ * autograd scalar into the fused gradients without a host sync. */
+int intel_scale_by_device_scalar(int64_t n, const float* x, const double* a, double ca, const double* b,
+                                 double cb, float* y, intel_stream_t stream);
+
+/* ---- evaluation ------------------------------------------------------------------------ */
+/* BaseRunner.evaluate_method (BaseRunner.py:57-131), per-session terms then a deterministic reduction.
+ * pred f32 [N, ld], ranking i64 [N, ld] (rows padded as the batches were), session_len / pay / fav /
+ * click i64 [N]; max_len = max(max session_len over the whole eval set, max topk); topk[n_topk] host ints.
+ * sums f64 [n_topk * 7]: per k -> {ndcg_sum, pay_hr, pay_ndcg, fav_hr, fav_ndcg, click_hr, click_ndcg};
+ * counts f64 [4]: {N, #pay sessions, #fav sessions, #click sessions}.  Tie rule: see DESIGN.md. */
+size_t intel_ndcg_workspace_bytes(int64_t N, int n_topk);
+int intel_ndcg_topk(int64_t N, int64_t ld, const float* pred, const int64_t* ranking,
+                    const int64_t* session_len, const int64_t* pay, const int64_t* fav, const int64_t* click,
+                    int64_t max_len, const int32_t* topk, int n_topk, double* sums, double* counts,
+                    void* workspace, size_t workspace_bytes, intel_stream_t stream);
+/* BaseRunner.evaluate_intents (BaseRunner.py:133-150): sums f64 [n_topk*2] = {Int-NDCG, Int-HR} per k. */
+size_t intel_intent_topk_workspace_bytes(int64_t N, int n_topk);
+int intel_intent_topk(int64_t N, int64_t I, const double* true_intents, const float* pred_intents,
+                      const int32_t* topk, int n_topk, double* sums,
+                      void* workspace, size_t workspace_bytes, intel_stream_t stream);
+
+/* ---- fixed-weight list fusion (script/baselines.sh) ------------------------------------- */
+/* ens[b,l] = sum_k weights[b,l,k] * float(scores[b,l,k])   (GeneralSeq.py:23-32, IntEL.py:215) */
+int intel_fuse_fwd(int64_t B, int64_t L, int64_t K, const float* weights, const double* scores,
+                   float* ens_out, intel_stream_t stream);
+/* SingleSort.forward (SingleSort.py:23-32): ens = float(scores[:,:,column]) */
+int intel_select_list(int64_t B, int64_t L, int64_t K, const double* scores, int column, float* ens_out,
+                      intel_stream_t stream);
+/* Borda.forward (Borda.py:23-30): mean over lists of the ascending rank inside the padded list. */
+int intel_rank_lists(int64_t B, int64_t L, int64_t K, const double* scores, float* ens_out,
+                     intel_stream_t stream);
+
+/* ---- building blocks exposed for unit tests --------------------------------------------- */
+/* out[r, :] = table[idx[r], :]  (nn.Embedding forward) */
+int intel_gather_fwd(int64_t rows, int d, const float* table, const int64_t* idx, float* out, int ld_out,
+                     int relu, intel_stream_t stream);
+/* grad_table[idx[r], :] += d_out[r, :]  (embedding_dense_backward; dense grad) */
+int intel_scatter_add_bwd(int64_t rows, int d, const float* d_out, int ld, const int64_t* idx,
+                          float* grad_table, intel_stream_t stream);
+/* C[M,N] = A[M,K] * W[N,K]^T + bias  (nn.Linear) - fp32 FFMA tiles */
+int intel_linear_fwd(int64_t M, int64_t N, int64_t K, const float* A, const float* W, const float* bias,
+                     float* C, intel_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* INTEL_B200_H */

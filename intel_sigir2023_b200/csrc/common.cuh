@@ -1,0 +1,90 @@
+// Shared device/host helpers for the IntEL sm_100a kernels.
+#pragma once
+#include <stdint.h>
+
+#ifdef INTEL_EMU
+#include "cuda_emu.h"
+#define DYN_SMEM(T, name) T* name = reinterpret_cast<T*>(emu::S().dyn_smem)
+#define LAUNCH(kfn, grid, block, smem, stream, ...) \
+    emu::launch(grid, block, smem, [=]() { kfn(__VA_ARGS__); })
+#else
+#include <cuda_runtime.h>
+#define DYN_SMEM(T, name)                                          \
+    extern __shared__ __align__(16) unsigned char name##_raw_[];   \
+    T* name = reinterpret_cast<T*>(name##_raw_)
+#define LAUNCH(kfn, grid, block, smem, stream, ...) kfn<<<grid, block, smem, stream>>>(__VA_ARGS__)
+#endif
+
+#include <stdio.h>
+#include <string.h>
+
+namespace intel {
+
+// ---- error plumbing: no exceptions across the C ABI, int status + thread-local message ----
+enum { INTEL_OK = 0, INTEL_ERR_ARG = 1, INTEL_ERR_WORKSPACE = 2, INTEL_ERR_CUDA = 3, INTEL_ERR_UNSUPPORTED = 4 };
+void set_error(const char* fmt, ...);
+int check_launch(const char* what);
+
+#define INTEL_REQUIRE(cond, code, ...)        \
+    do {                                      \
+        if (!(cond)) {                        \
+            intel::set_error(__VA_ARGS__);    \
+            return code;                      \
+        }                                     \
+    } while (0)
+#define INTEL_TRY(expr)              \
+    do {                             \
+        int _st = (expr);            \
+        if (_st != 0) return _st;    \
+    } while (0)
+
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// B200: 148 SMs.  Streaming grids are sized in multiples of it (capped by the work).
+static const int kNumSMs = 148;
+static inline unsigned stream_grid(int64_t work_items, int per_sm) {
+    int64_t cap = (int64_t)kNumSMs * per_sm;
+    int64_t g = work_items < cap ? work_items : cap;
+    return (unsigned)(g < 1 ? 1 : g);
+}
+
+// ---- bump allocator over the caller-provided workspace ----
+struct Arena {
+    unsigned char* base;
+    size_t cap, off;
+    bool dry;  // size query: only count
+    Arena(void* p, size_t bytes) : base((unsigned char*)p), cap(bytes), off(0), dry(p == nullptr) {}
+    template <class T> T* take(size_t n) {
+        size_t start = align_up(off, 256);
+        off = start + n * sizeof(T);
+        if (dry) return nullptr;
+        return reinterpret_cast<T*>(base + start);
+    }
+    bool ok() const { return dry || off <= cap; }
+};
+
+// ---- warp helpers ----
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ int warp_sum_i(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+}  // namespace intel

@@ -1,0 +1,312 @@
+// Embedding gathers / dense-gradient scatter-adds, the dense-row intent embedding, and small
+// layout kernels.  All HBM-bound: coalesced / 16-byte vector accesses, grids sized to the SM count.
+#include "kernels.h"
+
+namespace intel {
+
+// ------------------------------------------------------------------------------------------------
+// gather: out[r, 0:d] = table[idx[r], 0:d]   (nn.Embedding forward; IntEL.py:135,141,147,148,170,172,178)
+// One thread per 16-byte chunk of an output row; rows of 16/32 floats are 64/128-byte segments.
+template <int VEC>
+__global__ void __launch_bounds__(256) gather_kernel(int64_t rows, int d, const float* __restrict__ table,
+                                                     const int64_t* __restrict__ idx, float* __restrict__ out,
+                                                     int64_t ld_out, int relu) {
+    const int per_row = d / VEC;
+    const int64_t total = rows * per_row;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = e / per_row;
+        const int c = (int)(e % per_row) * VEC;
+        const int64_t id = idx[r];
+        if (VEC == 4) {
+            float4 v = *reinterpret_cast<const float4*>(table + id * d + c);
+            if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+            *reinterpret_cast<float4*>(out + r * ld_out + c) = v;
+        } else {
+            float v = table[id * d + c];
+            out[r * ld_out + c] = relu ? fmaxf(v, 0.f) : v;
+        }
+    }
+}
+
+int gather_rows(int64_t rows, int d, const float* table, const int64_t* idx, float* out, int64_t ld_out, int relu,
+                cudaStream_t s) {
+    if (rows <= 0 || d <= 0) return INTEL_OK;
+    INTEL_REQUIRE(table && idx && out, INTEL_ERR_ARG, "gather: null pointer");
+    const bool vec = (d % 4 == 0) && (ld_out % 4 == 0) && (((uintptr_t)table | (uintptr_t)out) % 16 == 0);
+    const int64_t total = rows * (vec ? d / 4 : d);
+    unsigned grid = stream_grid(ceil_div(total, 256), 8);
+    if (vec) { auto k = gather_kernel<4>; LAUNCH(k, dim3(grid), dim3(256), 0, s, rows, d, table, idx, out, ld_out, relu); }
+    else { auto k = gather_kernel<1>; LAUNCH(k, dim3(grid), dim3(256), 0, s, rows, d, table, idx, out, ld_out, relu); }
+    return check_launch("gather");
+}
+
+// scatter-add: grad_table[idx[r], :] += d_out[r, :]   (embedding_dense_backward; the gradient stays
+// DENSE so torch.optim.Adam(weight_decay) is a drop-in).  fp32 atomics.
+__global__ void __launch_bounds__(256) scatter_add_kernel(int64_t rows, int d, const float* __restrict__ d_out,
+                                                          int64_t ld, const int64_t* __restrict__ idx,
+                                                          float* grad_table, const float* __restrict__ relu_table) {
+    const int64_t total = rows * d;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = e / d;
+        const int c = (int)(e % d);
+        const int64_t id = idx[r];
+        float g = d_out[r * ld + c];
+        if (relu_table && !(relu_table[id * d + c] > 0.f)) g = 0.f;
+        if (g != 0.f) atomicAdd(grad_table + id * d + c, g);
+    }
+}
+
+int scatter_add_rows(int64_t rows, int d, const float* d_out, int64_t ld, const int64_t* idx, float* grad_table,
+                     const float* relu_table, cudaStream_t s) {
+    if (rows <= 0 || d <= 0) return INTEL_OK;
+    INTEL_REQUIRE(d_out && idx && grad_table, INTEL_ERR_ARG, "scatter_add: null pointer");
+    unsigned grid = stream_grid(ceil_div(rows * d, 256), 8);
+    LAUNCH(scatter_add_kernel, dim3(grid), dim3(256), 0, s, rows, d, d_out, ld, idx, grad_table, relu_table);
+    return check_launch("scatter_add");
+}
+
+// ------------------------------------------------------------------------------------------------
+// Dense float64 rows -> intent embedding (IntEL.py:136,142: nn.Linear(I, d_int) applied to the dense
+// [B,H,I] his_intents / one-hot his_item_int).  These two tensors are ~93% of the batch bytes
+// (SURVEY.md 8a-1), so the kernel is a pure HBM stream: one warp per row, 8-byte coalesced loads with
+// 4 loads in flight per lane, and arithmetic only for the (few) non-zero entries met on the way.
+static const int DR_UNROLL = 4;
+
+__device__ __forceinline__ void dense_row_accumulate(const double* __restrict__ x, int64_t I, int d, int lane,
+                                                     const float* __restrict__ Wt, float& acc0, float& acc1,
+                                                     int32_t* nz_idx, float* nz_val, int cap, int& cnt) {
+    for (int64_t base = 0; base < I; base += 32 * DR_UNROLL) {
+        double v[DR_UNROLL];
+#pragma unroll
+        for (int u = 0; u < DR_UNROLL; ++u) {
+            int64_t i = base + u * 32 + lane;
+            v[u] = (i < I) ? x[i] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < DR_UNROLL; ++u) {
+            unsigned m = __ballot_sync(0xffffffffu, v[u] != 0.0);
+            while (m) {
+                const int src = __ffs((int)m) - 1;
+                m &= m - 1;
+                const float fv = (float)__shfl_sync(0xffffffffu, v[u], src);
+                const int64_t i = base + u * 32 + src;
+                if (Wt) {
+                    if (lane < d) acc0 = fmaf(fv, Wt[i * d + lane], acc0);
+                    if (lane + 32 < d) acc1 = fmaf(fv, Wt[i * d + lane + 32], acc1);
+                }
+                if (nz_idx && lane == 0 && cnt < cap) { nz_idx[cnt] = (int32_t)i; nz_val[cnt] = fv; }
+                cnt++;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) dense_rows_fwd_kernel(int64_t R, int64_t I, int d, const double* __restrict__ X,
+                                                             const float* __restrict__ Wt, const float* __restrict__ bias,
+                                                             float* __restrict__ Y, int64_t ldy, int32_t* nz_idx,
+                                                             float* nz_val, int32_t* nz_cnt, int cap) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp; r < R; r += nwarps) {
+        float acc0 = (bias && lane < d) ? bias[lane] : 0.f;
+        float acc1 = (bias && lane + 32 < d) ? bias[lane + 32] : 0.f;
+        int cnt = 0;
+        dense_row_accumulate(X + r * I, I, d, lane, Wt, acc0, acc1, nz_idx ? nz_idx + r * cap : nullptr,
+                             nz_val ? nz_val + r * cap : nullptr, cap, cnt);
+        if (lane < d) Y[r * ldy + lane] = acc0;
+        if (lane + 32 < d) Y[r * ldy + lane + 32] = acc1;
+        if (nz_cnt && lane == 0) nz_cnt[r] = cnt;
+    }
+}
+
+int dense_rows_linear_fwd(int64_t R, int64_t I, int d, const double* X, const float* Wt, const float* bias, float* Y,
+                          int64_t ldy, int32_t* nz_idx, float* nz_val, int32_t* nz_cnt, int cap, cudaStream_t s) {
+    if (R <= 0) return INTEL_OK;
+    INTEL_REQUIRE(d <= 64, INTEL_ERR_UNSUPPORTED, "intent_emb_size %d > 64 not supported", d);
+    INTEL_REQUIRE(X && Wt && Y, INTEL_ERR_ARG, "dense_rows_linear_fwd: null pointer");
+    unsigned grid = stream_grid(ceil_div(R, 8), 8);
+    LAUNCH(dense_rows_fwd_kernel, dim3(grid), dim3(256), 0, s, R, I, d, X, Wt, bias, Y, ldy, nz_idx, nz_val, nz_cnt, cap);
+    return check_launch("dense_rows_fwd");
+}
+
+// backward w.r.t. the weight: dWt[i, :] += x[r,i] * dY[r, :]; uses the compacted non-zeros of the
+// forward pass, re-streaming only rows that overflowed the compaction capacity.
+__global__ void __launch_bounds__(256) dense_rows_bwd_kernel(int64_t R, int64_t I, int d, const double* __restrict__ X,
+                                                             const float* __restrict__ dY, int64_t lddy,
+                                                             const int32_t* __restrict__ nz_idx,
+                                                             const float* __restrict__ nz_val,
+                                                             const int32_t* __restrict__ nz_cnt, int cap, float* dWt) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp; r < R; r += nwarps) {
+        const float g0 = (lane < d) ? dY[r * lddy + lane] : 0.f;
+        const float g1 = (lane + 32 < d) ? dY[r * lddy + lane + 32] : 0.f;
+        const int cnt = nz_cnt ? nz_cnt[r] : cap + 1;
+        if (cnt <= cap) {
+            for (int e = 0; e < cnt; ++e) {
+                const int64_t i = nz_idx[r * cap + e];
+                const float fv = nz_val[r * cap + e];
+                if (lane < d) atomicAdd(dWt + i * d + lane, fv * g0);
+                if (lane + 32 < d) atomicAdd(dWt + i * d + lane + 32, fv * g1);
+            }
+        } else {
+            const double* x = X + r * I;
+            for (int64_t base = 0; base < I; base += 32) {
+                const int64_t ii = base + lane;
+                const double v = (ii < I) ? x[ii] : 0.0;
+                unsigned m = __ballot_sync(0xffffffffu, v != 0.0);
+                while (m) {
+                    const int src = __ffs((int)m) - 1;
+                    m &= m - 1;
+                    const float fv = (float)__shfl_sync(0xffffffffu, v, src);
+                    const int64_t i = base + src;
+                    if (lane < d) atomicAdd(dWt + i * d + lane, fv * g0);
+                    if (lane + 32 < d) atomicAdd(dWt + i * d + lane + 32, fv * g1);
+                }
+            }
+        }
+    }
+}
+
+int dense_rows_linear_bwd(int64_t R, int64_t I, int d, const double* X, const float* dY, int64_t lddy,
+                          const int32_t* nz_idx, const float* nz_val, const int32_t* nz_cnt, int cap, float* dWt,
+                          cudaStream_t s) {
+    if (R <= 0) return INTEL_OK;
+    INTEL_REQUIRE(d <= 64, INTEL_ERR_UNSUPPORTED, "intent_emb_size %d > 64 not supported", d);
+    unsigned grid = stream_grid(ceil_div(R, 8), 8);
+    LAUNCH(dense_rows_bwd_kernel, dim3(grid), dim3(256), 0, s, R, I, d, X, dY, lddy, nz_idx, nz_val, nz_cnt, cap, dWt);
+    return check_launch("dense_rows_bwd");
+}
+
+// ------------------------------------------------------------------------------------------------
+// out[c, r] (=|+=) in[r, c]  - 32x32 shared-memory tile transpose
+__global__ void __launch_bounds__(256) transpose_kernel(int64_t rows, int64_t cols, const float* __restrict__ in,
+                                                        float* out, int accumulate) {
+    __shared__ float tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int64_t c0 = (int64_t)blockIdx.x * 32, r0 = (int64_t)blockIdx.y * 32;
+    for (int i = ty; i < 32; i += 8) {
+        int64_t r = r0 + i, c = c0 + tx;
+        tile[i][tx] = (r < rows && c < cols) ? in[r * cols + c] : 0.f;
+    }
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+        int64_t c = c0 + i, r = r0 + tx;
+        if (c < cols && r < rows) {
+            float v = tile[tx][i];
+            if (accumulate) out[c * rows + r] += v; else out[c * rows + r] = v;
+        }
+    }
+}
+
+int transpose(int64_t rows, int64_t cols, const float* in, float* out, int accumulate, cudaStream_t s) {
+    if (rows <= 0 || cols <= 0) return INTEL_OK;
+    dim3 grid((unsigned)ceil_div(cols, 32), (unsigned)ceil_div(rows, 32));
+    LAUNCH(transpose_kernel, grid, dim3(256), 0, s, rows, cols, in, out, accumulate);
+    return check_launch("transpose");
+}
+
+// ------------------------------------------------------------------------------------------------
+// score_embeddings (IntEL.py:190): Y[r, c] = b[c] + sum_k W[c,k] float(scores[r,k]); xs = float(scores)
+__global__ void __launch_bounds__(256) score_embed_kernel(int64_t R, int K, int d, const double* __restrict__ scores,
+                                                          const float* __restrict__ W, const float* __restrict__ b,
+                                                          float* __restrict__ Y, float* __restrict__ xs) {
+    const int64_t total = R * d;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = e / d;
+        const int c = (int)(e % d);
+        float acc = b[c];
+        for (int k = 0; k < K; ++k) acc = fmaf(W[c * K + k], (float)scores[r * K + k], acc);
+        Y[e] = acc;
+        if (xs && c < K) xs[r * K + c] = (float)scores[r * K + c];
+    }
+}
+
+int score_embed_fwd(int64_t R, int K, int d, const double* scores, const float* W, const float* b, float* Y, float* xs,
+                    cudaStream_t s) {
+    if (R <= 0) return INTEL_OK;
+    INTEL_REQUIRE(!xs || K <= d, INTEL_ERR_UNSUPPORTED, "score_embed: model_num %d > s_emb_size %d", K, d);
+    unsigned grid = stream_grid(ceil_div(R * d, 256), 8);
+    LAUNCH(score_embed_kernel, dim3(grid), dim3(256), 0, s, R, K, d, scores, W, b, Y, xs);
+    return check_launch("score_embed");
+}
+
+// ------------------------------------------------------------------------------------------------
+// BERT4RecEncoder learned positions (GeneralSeq.py:93-96): position index is t for live slots, 0 for pads
+__global__ void __launch_bounds__(256) add_pos_kernel(int64_t B, int64_t T, int d, const int64_t* __restrict__ lens,
+                                                      const float* __restrict__ pos, float* seq) {
+    const int64_t total = B * T * d;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(e % d);
+        const int64_t bt = e / d;
+        const int64_t t = bt % T, bb = bt / T;
+        const int64_t p = (t < lens[bb]) ? t : 0;
+        seq[e] += pos[p * d + c];
+    }
+}
+int add_positions(int64_t B, int64_t T, int d, const int64_t* lens, const float* pos, float* seq, cudaStream_t s) {
+    if (B * T <= 0) return INTEL_OK;
+    unsigned grid = stream_grid(ceil_div(B * T * d, 256), 8);
+    LAUNCH(add_pos_kernel, dim3(grid), dim3(256), 0, s, B, T, d, lens, pos, seq);
+    return check_launch("add_positions");
+}
+
+__global__ void __launch_bounds__(256) add_pos_bwd_kernel(int64_t B, int64_t T, int d, const int64_t* __restrict__ lens,
+                                                          const float* __restrict__ d_seq, float* d_pos) {
+    const int64_t total = B * T * d;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(e % d);
+        const int64_t bt = e / d;
+        const int64_t t = bt % T, bb = bt / T;
+        const int64_t p = (t < lens[bb]) ? t : 0;
+        const float g = d_seq[e];
+        if (g != 0.f) atomicAdd(d_pos + p * d + c, g);
+    }
+}
+int add_positions_bwd(int64_t B, int64_t T, int d, const int64_t* lens, const float* d_seq, float* d_pos,
+                      cudaStream_t s) {
+    if (B * T <= 0) return INTEL_OK;
+    unsigned grid = stream_grid(ceil_div(B * T * d, 256), 8);
+    LAUNCH(add_pos_bwd_kernel, dim3(grid), dim3(256), 0, s, B, T, d, lens, d_seq, d_pos);
+    return check_launch("add_positions_bwd");
+}
+
+// his_vector = seq[b, len-1]  (GeneralSeq.py:105)
+__global__ void __launch_bounds__(256) take_last_kernel(int64_t B, int64_t T, int d, const int64_t* __restrict__ lens,
+                                                        const float* __restrict__ X, float* out, int64_t ld_out, int bwd) {
+    const int64_t total = B * d;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(e % d);
+        const int64_t bb = e / d;
+        int64_t t = lens[bb] - 1;
+        if (t < 0) t = 0;
+        if (t >= T) t = T - 1;
+        if (!bwd) out[bb * ld_out + c] = X[(bb * T + t) * d + c];
+        else const_cast<float*>(X)[(bb * T + t) * d + c] = out[bb * ld_out + c];
+    }
+}
+int take_last(int64_t B, int64_t T, int d, const int64_t* lens, const float* X, float* out, int64_t ld_out,
+              cudaStream_t s) {
+    if (B <= 0) return INTEL_OK;
+    unsigned grid = stream_grid(ceil_div(B * d, 256), 8);
+    LAUNCH(take_last_kernel, dim3(grid), dim3(256), 0, s, B, T, d, lens, X, out, ld_out, 0);
+    return check_launch("take_last");
+}
+int take_last_bwd(int64_t B, int64_t T, int d, const int64_t* lens, const float* d_out, int64_t ld, float* dX,
+                  cudaStream_t s) {
+    if (B <= 0) return INTEL_OK;
+    unsigned grid = stream_grid(ceil_div(B * d, 256), 8);
+    LAUNCH(take_last_kernel, dim3(grid), dim3(256), 0, s, B, T, d, lens, (const float*)dX, const_cast<float*>(d_out), ld, 1);
+    return check_launch("take_last_bwd");
+}
+
+int fill_zero(void* p, size_t bytes, cudaStream_t s) {
+    if (!bytes) return INTEL_OK;
+    cudaError_t e = cudaMemsetAsync(p, 0, bytes, s);
+    if (e != cudaSuccess) { set_error("cudaMemsetAsync: %s", cudaGetErrorString(e)); return INTEL_ERR_CUDA; }
+    return INTEL_OK;
+}
+
+}  // namespace intel

@@ -1,0 +1,245 @@
+// Weight head + weighted fusion of the K basic lists (IntEL.py:212-215) and the small element-wise
+// kernels around it.  HBM-bound streaming: the float64 score tensor is read once per pass.
+#include "kernels.h"
+
+namespace intel {
+
+static const int FUSE_MAX_K = 16;
+
+// One warp per session: the K-vector of weights is per session for valid rows (all valid rows share the
+// pooled cross-attention vector) and a second vector for pad rows.
+__global__ void __launch_bounds__(256) head_fuse_fwd_kernel(int64_t B, int64_t L, int K,
+                                                            const float* __restrict__ w_valid,
+                                                            const float* __restrict__ w_pad,
+                                                            const double* __restrict__ scores,
+                                                            const int64_t* __restrict__ lens,
+                                                            float* __restrict__ weights, float* __restrict__ ens) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t b = warp; b < B; b += nwarps) {
+        const int64_t n = lens[b];
+        float wv[FUSE_MAX_K], wp[FUSE_MAX_K];
+#pragma unroll
+        for (int k = 0; k < FUSE_MAX_K; ++k) {
+            wv[k] = (k < K) ? w_valid[b * K + k] : 0.f;
+            wp[k] = (k < K) ? w_pad[b * K + k] : 0.f;
+        }
+        for (int64_t l = lane; l < L; l += 32) {
+            const bool valid = l < n;
+            const double* x = scores + (b * L + l) * K;
+            float* wo = weights + (b * L + l) * K;
+            float acc = 0.f;
+#pragma unroll
+            for (int k = 0; k < FUSE_MAX_K; ++k) {
+                if (k < K) {
+                    const float wk = valid ? wv[k] : wp[k];
+                    wo[k] = wk;
+                    acc = fmaf(wk, (float)x[k], acc);
+                }
+            }
+            ens[b * L + l] = acc;
+        }
+    }
+}
+
+int head_fuse_fwd(int64_t B, int64_t L, int K, const float* w_valid, const float* w_pad, const double* scores,
+                  const int64_t* lens, float* weights, float* ens, cudaStream_t s) {
+    if (B <= 0) return INTEL_OK;
+    INTEL_REQUIRE(K <= FUSE_MAX_K, INTEL_ERR_UNSUPPORTED, "model_num %d > %d", K, FUSE_MAX_K);
+    unsigned grid = stream_grid(ceil_div(B, 8), 8);
+    LAUNCH(head_fuse_fwd_kernel, dim3(grid), dim3(256), 0, s, B, L, K, w_valid, w_pad, scores, lens, weights, ens);
+    return check_launch("head_fuse_fwd");
+}
+
+__global__ void __launch_bounds__(256) head_fuse_bwd_kernel(int64_t B, int64_t L, int K,
+                                                            const float* __restrict__ d_weights,
+                                                            const float* __restrict__ d_ens,
+                                                            const double* __restrict__ scores,
+                                                            const int64_t* __restrict__ lens,
+                                                            float* __restrict__ dw_valid, float* __restrict__ dw_pad) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t b = warp; b < B; b += nwarps) {
+        const int64_t n = lens[b];
+        float av[FUSE_MAX_K], ap[FUSE_MAX_K];
+#pragma unroll
+        for (int k = 0; k < FUSE_MAX_K; ++k) { av[k] = 0.f; ap[k] = 0.f; }
+        for (int64_t l = lane; l < L; l += 32) {
+            const bool valid = l < n;
+            const float ge = d_ens ? d_ens[b * L + l] : 0.f;
+#pragma unroll
+            for (int k = 0; k < FUSE_MAX_K; ++k) {
+                if (k < K) {
+                    float g = ge * (float)scores[(b * L + l) * K + k];
+                    if (d_weights) g += d_weights[(b * L + l) * K + k];
+                    if (valid) av[k] += g; else ap[k] += g;
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < FUSE_MAX_K; ++k) {
+            if (k < K) {
+                const float sv = warp_sum(av[k]), sp = warp_sum(ap[k]);
+                if (lane == 0) { dw_valid[b * K + k] = sv; dw_pad[b * K + k] = sp; }
+            }
+        }
+    }
+}
+
+int head_fuse_bwd(int64_t B, int64_t L, int K, const float* d_weights, const float* d_ens, const double* scores,
+                  const int64_t* lens, float* dw_valid, float* dw_pad, cudaStream_t s) {
+    if (B <= 0) return INTEL_OK;
+    INTEL_REQUIRE(K <= FUSE_MAX_K, INTEL_ERR_UNSUPPORTED, "model_num %d > %d", K, FUSE_MAX_K);
+    unsigned grid = stream_grid(ceil_div(B, 8), 8);
+    LAUNCH(head_fuse_bwd_kernel, dim3(grid), dim3(256), 0, s, B, L, K, d_weights, d_ens, scores, lens, dw_valid, dw_pad);
+    return check_launch("head_fuse_bwd");
+}
+
+// ---- per-item fusion: ens[r] = sum_k weights[r,k] * float(scores[r,k]) (fixed-weight baselines and
+//      the cross_attention=0 branch) ----
+__global__ void __launch_bounds__(256) item_fuse_fwd_kernel(int64_t R, int K, const float* __restrict__ weights,
+                                                            const double* __restrict__ scores, float* __restrict__ ens) {
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < R; r += (int64_t)gridDim.x * blockDim.x) {
+        float acc = 0.f;
+        for (int k = 0; k < K; ++k) acc = fmaf(weights[r * K + k], (float)scores[r * K + k], acc);
+        ens[r] = acc;
+    }
+}
+int item_fuse_fwd(int64_t R, int K, const float* weights, const double* scores, float* ens, cudaStream_t s) {
+    if (R <= 0) return INTEL_OK;
+    unsigned grid = stream_grid(ceil_div(R, 256), 8);
+    LAUNCH(item_fuse_fwd_kernel, dim3(grid), dim3(256), 0, s, R, K, weights, scores, ens);
+    return check_launch("item_fuse_fwd");
+}
+
+__global__ void __launch_bounds__(256) item_fuse_bwd_kernel(int64_t R, int K, const float* __restrict__ d_weights,
+                                                            const float* __restrict__ d_ens,
+                                                            const double* __restrict__ scores, float* __restrict__ g) {
+    const int64_t total = R * K;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        float v = d_ens ? d_ens[e / K] * (float)scores[e] : 0.f;
+        if (d_weights) v += d_weights[e];
+        g[e] = v;
+    }
+}
+int item_fuse_bwd(int64_t R, int K, const float* d_weights, const float* d_ens, const double* scores, float* g,
+                  cudaStream_t s) {
+    if (R <= 0) return INTEL_OK;
+    unsigned grid = stream_grid(ceil_div(R * K, 256), 8);
+    LAUNCH(item_fuse_bwd_kernel, dim3(grid), dim3(256), 0, s, R, K, d_weights, d_ens, scores, g);
+    return check_launch("item_fuse_bwd");
+}
+
+// ---- gate (cross_attention = 0, IntEL.py:205-209): Y[b,l,:] = X[b,l,:] * m[b,:] ----
+__global__ void __launch_bounds__(256) gate_fwd_kernel(int64_t B, int64_t L, int d, const float* __restrict__ X,
+                                                       const float* __restrict__ m, float* __restrict__ Y, int64_t ldy) {
+    const int64_t total = B * L * d;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(e % d);
+        const int64_t row = e / d;
+        Y[row * ldy + c] = X[e] * m[(row / L) * d + c];
+    }
+}
+int gate_fwd(int64_t B, int64_t L, int d, const float* X, const float* m, float* Y, int64_t ldy, cudaStream_t s) {
+    if (B * L <= 0) return INTEL_OK;
+    unsigned grid = stream_grid(ceil_div(B * L * d, 256), 8);
+    LAUNCH(gate_fwd_kernel, dim3(grid), dim3(256), 0, s, B, L, d, X, m, Y, ldy);
+    return check_launch("gate_fwd");
+}
+
+// dX[b,l,:] = dY * m[b];  dm[b,:] = sum_l dY[b,l,:] * X[b,l,:]   (one warp per session)
+__global__ void __launch_bounds__(256) gate_bwd_kernel(int64_t B, int64_t L, int d, const float* __restrict__ X,
+                                                       const float* __restrict__ m, const float* __restrict__ dY,
+                                                       int64_t lddy, float* __restrict__ dX, float* __restrict__ dm) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t b = warp; b < B; b += nwarps) {
+        for (int c = lane; c < d; c += 32) {
+            const float mc = m[b * d + c];
+            float acc = 0.f;
+            for (int64_t l = 0; l < L; ++l) {
+                const float g = dY[(b * L + l) * lddy + c];
+                acc = fmaf(g, X[(b * L + l) * d + c], acc);
+                dX[(b * L + l) * d + c] = g * mc;
+            }
+            dm[b * d + c] = acc;
+        }
+    }
+}
+int gate_bwd(int64_t B, int64_t L, int d, const float* X, const float* m, const float* dY, int64_t lddy, float* dX,
+             float* dm, cudaStream_t s) {
+    if (B <= 0) return INTEL_OK;
+    unsigned grid = stream_grid(ceil_div(B, 8), 8);
+    LAUNCH(gate_bwd_kernel, dim3(grid), dim3(256), 0, s, B, L, d, X, m, dY, lddy, dX, dm);
+    return check_launch("gate_bwd");
+}
+
+// ---- broadcast a per-session vector over the list slots (h_u / h_intent repeat, IntEL.py:178,212) ----
+__global__ void __launch_bounds__(256) bcast_rows_kernel(int64_t B, int64_t L, int d, const float* __restrict__ v,
+                                                         int64_t ldv, float* __restrict__ out, int64_t ldo) {
+    const int64_t total = B * L * d;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(e % d);
+        const int64_t row = e / d;
+        out[row * ldo + c] = v[(row / L) * ldv + c];
+    }
+}
+int bcast_rows(int64_t B, int64_t L, int d, const float* v, int64_t ldv, float* out, int64_t ldo, cudaStream_t s) {
+    if (B * L <= 0) return INTEL_OK;
+    unsigned grid = stream_grid(ceil_div(B * L * d, 256), 8);
+    LAUNCH(bcast_rows_kernel, dim3(grid), dim3(256), 0, s, B, L, d, v, ldv, out, ldo);
+    return check_launch("bcast_rows");
+}
+
+__global__ void __launch_bounds__(256) bcast_rows_bwd_kernel(int64_t B, int64_t L, int d, const float* __restrict__ dout,
+                                                             int64_t ldo, float* dv, int64_t ldv, int accumulate) {
+    const int64_t total = B * d;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(e % d);
+        const int64_t b = e / d;
+        float acc = 0.f;
+        for (int64_t l = 0; l < L; ++l) acc += dout[(b * L + l) * ldo + c];
+        if (accumulate) dv[b * ldv + c] += acc; else dv[b * ldv + c] = acc;
+    }
+}
+int bcast_rows_bwd(int64_t B, int64_t L, int d, const float* dout, int64_t ldo, float* dv, int64_t ldv, int accumulate,
+                   cudaStream_t s) {
+    if (B <= 0) return INTEL_OK;
+    unsigned grid = stream_grid(ceil_div(B * d, 256), 8);
+    LAUNCH(bcast_rows_bwd_kernel, dim3(grid), dim3(256), 0, s, B, L, d, dout, ldo, dv, ldv, accumulate);
+    return check_launch("bcast_rows_bwd");
+}
+
+// dx[r, c] = dy[r, c] * (v[r, c] > 0) on strided [rows, cols] views (dx may alias dy)
+__global__ void __launch_bounds__(256) relu_bwd_kernel(int64_t rows, int cols, const float* dy, int64_t lddy,
+                                                       const float* __restrict__ v, int64_t ldv, float* dx, int64_t lddx) {
+    const int64_t n = rows * cols;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = e / cols;
+        const int c = (int)(e % cols);
+        dx[r * lddx + c] = (v[r * ldv + c] > 0.f) ? dy[r * lddy + c] : 0.f;
+    }
+}
+int relu_bwd(int64_t rows, int cols, const float* dy, int64_t lddy, const float* v, int64_t ldv, float* dx, int64_t lddx,
+             cudaStream_t s) {
+    if (rows * cols <= 0) return INTEL_OK;
+    unsigned grid = stream_grid(ceil_div(rows * cols, 256), 8);
+    LAUNCH(relu_bwd_kernel, dim3(grid), dim3(256), 0, s, rows, cols, dy, lddy, v, ldv, dx, lddx);
+    return check_launch("relu_bwd");
+}
+
+__global__ void __launch_bounds__(256) add_inplace_kernel(int64_t n, float* y, const float* __restrict__ x) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x)
+        y[e] += x[e];
+}
+int add_inplace(int64_t n, float* y, const float* x, cudaStream_t s) {
+    if (n <= 0) return INTEL_OK;
+    unsigned grid = stream_grid(ceil_div(n, 256), 8);
+    LAUNCH(add_inplace_kernel, dim3(grid), dim3(256), 0, s, n, y, x);
+    return check_launch("add_inplace");
+}
+
+}  // namespace intel

@@ -1,0 +1,130 @@
+// Internal (C++) launch interface between the orchestration code (api_*.cu) and the kernels.
+// Everything is asynchronous on `s`; int return = INTEL_* status.
+#pragma once
+#include "common.cuh"
+
+namespace intel {
+
+// ---- gemm.cu: fp32 FFMA tiled GEMM, C = epilogue(op(A) * op(B)) -------------------------------
+struct Gemm {
+    int64_t M = 0, N = 0, K = 0;
+    const float* A = nullptr; int64_t lda = 0; bool a_t = false;  // a_t: A stored [K][M]
+    const float* B = nullptr; int64_t ldb = 0; bool b_t = false;  // b_t: B stored [K][N]; else [N][K] (nn.Linear)
+    float* C = nullptr; int64_t ldc = 0;
+    const float* bias = nullptr;                        // + bias[n]
+    const float* add = nullptr; int64_t ldadd = 0;      // + add[m,n]
+    const float* mask = nullptr; int64_t ldmask = 0;    // *= (mask[m,n] > 0)   (relu backward)
+    bool relu_a = false, relu_b = false, relu_out = false;
+    int accumulate = 0;   // 0: C = r   1: C += r   2: atomicAdd(C, r) (required when splits > 1)
+    int splits = 1;       // split of the inner dimension (0 = pick automatically for accumulate == 2)
+};
+int gemm(const Gemm& g, cudaStream_t s);
+// C[M,N] = A[M,K] W[N,K]^T (+bias)
+int linear(int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* W, int64_t ldw,
+           const float* bias, float* C, int64_t ldc, cudaStream_t s, bool relu_a = false, bool relu_out = false,
+           const float* add = nullptr, int64_t ldadd = 0);
+// dX[M,K] (=|+=) dY[M,N] W[N,K]  (optionally masked by relu input)
+int linear_dx(int64_t M, int64_t N, int64_t K, const float* dY, int64_t lddy, const float* W, int64_t ldw,
+              float* dX, int64_t lddx, cudaStream_t s, int accumulate = 0, const float* mask = nullptr,
+              int64_t ldmask = 0);
+// dW[N,K] += dY[M,N]^T X[M,K];  db[N] += colsum(dY)   (db may be null)
+int linear_dw(int64_t M, int64_t N, int64_t K, const float* dY, int64_t lddy, const float* X, int64_t ldx,
+              float* dW, int64_t lddw, float* db, cudaStream_t s, bool relu_x = false);
+int colsum(int64_t M, int64_t N, const float* X, int64_t ld, float* out, cudaStream_t s);
+
+// ---- embed.cu ---------------------------------------------------------------------------------
+int gather_rows(int64_t rows, int d, const float* table, const int64_t* idx, float* out, int64_t ld_out,
+                int relu, cudaStream_t s);
+// grad_table[idx[r]] += d_out[r] (* (table[idx[r]] > 0) when relu_table != null)
+int scatter_add_rows(int64_t rows, int d, const float* d_out, int64_t ld, const int64_t* idx, float* grad_table,
+                     const float* relu_table, cudaStream_t s);
+// out[b, l, :] += table[idx[b]]-style broadcast helpers are not needed: per-session rows are gathered once.
+
+// Dense float64 rows X[R, I] times the intent_embeddings weight, exploiting that the rows are (nearly)
+// one-hot / few-hot: Y[r, :] = sum_i float(X[r,i]) * Wt[i, :] + bias.  Wt is the [I, d] transpose.
+// The non-zeros met on the way are compacted (cap entries per row) so the backward pass does not have
+// to stream the dense rows again; rows with more than `cap` non-zeros are re-streamed.
+int dense_rows_linear_fwd(int64_t R, int64_t I, int d, const double* X, const float* Wt, const float* bias,
+                          float* Y, int64_t ldy, int32_t* nz_idx, float* nz_val, int32_t* nz_cnt, int cap,
+                          cudaStream_t s);
+// dWt[i, :] += float(X[r,i]) * dY[r, :]
+int dense_rows_linear_bwd(int64_t R, int64_t I, int d, const double* X, const float* dY, int64_t lddy,
+                          const int32_t* nz_idx, const float* nz_val, const int32_t* nz_cnt, int cap,
+                          float* dWt, cudaStream_t s);
+// out[c, r] (=|+=) in[r, c]
+int transpose(int64_t rows, int64_t cols, const float* in, float* out, int accumulate, cudaStream_t s);
+// scores f64 [R,K] -> Y[R, d] = W[d,K] x + b  (score_embeddings) and the f32 copy xs[R,K]
+int score_embed_fwd(int64_t R, int K, int d, const double* scores, const float* W, const float* b, float* Y,
+                    float* xs, cudaStream_t s);
+// seq[b, t, :] += pos[(t < len[b]) ? t : 0, :]   (BERT4RecEncoder positions)
+int add_positions(int64_t B, int64_t T, int d, const int64_t* lens, const float* pos, float* seq, cudaStream_t s);
+// d_pos[(t < len[b]) ? t : 0, :] += d_seq[b, t, :]
+int add_positions_bwd(int64_t B, int64_t T, int d, const int64_t* lens, const float* d_seq, float* d_pos,
+                      cudaStream_t s);
+// out[b, :] = X[b, len[b]-1, :]   and its backward (dX zero elsewhere; dX must be pre-zeroed)
+int take_last(int64_t B, int64_t T, int d, const int64_t* lens, const float* X, float* out, int64_t ld_out,
+              cudaStream_t s);
+int take_last_bwd(int64_t B, int64_t T, int d, const int64_t* lens, const float* d_out, int64_t ld, float* dX,
+                  cudaStream_t s);
+int fill_zero(void* p, size_t bytes, cudaStream_t s);
+
+// ---- attn.cu ------------------------------------------------------------------------------------
+// LayerNorm over the last dim (eps 1e-5); stats[r] = {mean, rstd}
+int layernorm_fwd(int64_t R, int d, const float* Z, const float* gamma, const float* beta, float* Y,
+                  float* stats, cudaStream_t s);
+int layernorm_bwd(int64_t R, int d, const float* dY, const float* Z, const float* stats, const float* gamma,
+                  float* dZ, float* dgamma, float* dbeta, cudaStream_t s);
+// Multi-head attention without output projection (layers.py:31-60).  QKV [B,T,3d] (q|k|v), O [B,T,d].
+// lens == null: every slot is a live key (IntEL stacks); else keys j >= lens[b] are masked (BERT4Rec).
+int mha_fwd(int64_t B, int64_t T, int d, int heads, const float* QKV, const int64_t* lens, float* O,
+            cudaStream_t s);
+int mha_bwd(int64_t B, int64_t T, int d, int heads, const float* QKV, const int64_t* lens, const float* dO,
+            float* dQKV, cudaStream_t s);
+// Pooled cross attention (attention.py:54-63 collapsed): att_j = scale * X[b,j].qk[b],
+// shift by the max over all L slots, softmax over j < n_b, xbar = sum_j p_j X[b,j].
+int cross_pool_fwd(int64_t B, int64_t L, int d, const float* X, const float* qk, const int64_t* lens,
+                   float scale, float* p, float* xbar, cudaStream_t s);
+// dX[b,j] (=) p_j dxbar + scale datt_j qk ; dqk[b] = scale sum_j datt_j X[b,j]
+int cross_pool_bwd(int64_t B, int64_t L, int d, const float* X, const float* qk, const int64_t* lens,
+                   float scale, const float* p, const float* dxbar, float* dX, float* dqk, cudaStream_t s);
+// softmax over rows and its backward: dZ = p * (dP - sum(p dP))
+int softmax_rows(int64_t R, int64_t N, const float* Z, float* P, cudaStream_t s);
+int softmax_rows_bwd(int64_t R, int64_t N, const float* P, const float* dP, const float* dP2, float* dZ,
+                     cudaStream_t s);   // incoming gradient dP + dP2 (dP2 nullable)
+
+// ---- gru.cu -------------------------------------------------------------------------------------
+// One masked GRU step for all sessions (gate order r,z,n; torch.nn.GRU equations).
+// gi [B, T, 3h] (input projections incl. b_ih), gh [B, 3h] (= W_hh h_{t-1} + b_hh),
+// h_all [B, T+1, h] with h_all[:,0] = 0;  saves gates [B, T, 4h] = (r, z, n, gh_n).
+int gru_step_fwd(int64_t B, int64_t T, int h, int t, const int64_t* lens, const float* gi, const float* gh,
+                 float* h_all, float* gates, cudaStream_t s);
+// dh [B,h] is updated in place to d h_{t-1} (without the W_hh term, which the caller adds by GEMM);
+// dgi[:, t] and dgh_t [B, 3h] are written.
+int gru_step_bwd(int64_t B, int64_t T, int h, int t, const int64_t* lens, const float* h_all,
+                 const float* gates, float* dh, float* dgi, float* dgh_all, cudaStream_t s);
+
+// ---- fuse.cu ------------------------------------------------------------------------------------
+// weights[b,l,:] = l < n_b ? w_valid[b] : w_pad[b];  ens[b,l] = sum_k weights * float(scores)
+int head_fuse_fwd(int64_t B, int64_t L, int K, const float* w_valid, const float* w_pad, const double* scores,
+                  const int64_t* lens, float* weights, float* ens, cudaStream_t s);
+// dw_valid[b,k] = sum_{l<n} g, dw_pad[b,k] = sum_{l>=n} g with g = d_weights[b,l,k] + d_ens[b,l] x[b,l,k]
+int head_fuse_bwd(int64_t B, int64_t L, int K, const float* d_weights, const float* d_ens, const double* scores,
+                  const int64_t* lens, float* dw_valid, float* dw_pad, cudaStream_t s);
+// per-item variant (cross_attention = 0): ens[b,l] = sum_k weights[b,l,k] x ; g[b,l,k] as above
+int item_fuse_fwd(int64_t R, int K, const float* weights, const double* scores, float* ens, cudaStream_t s);
+int item_fuse_bwd(int64_t R, int K, const float* d_weights, const float* d_ens, const double* scores, float* g,
+                  cudaStream_t s);
+// gate (cross_attention = 0): Y[b,l,:] = X[b,l,:] * m[b,:]  and backward
+int gate_fwd(int64_t B, int64_t L, int d, const float* X, const float* m, float* Y, int64_t ldy, cudaStream_t s);
+int gate_bwd(int64_t B, int64_t L, int d, const float* X, const float* m, const float* dY, int64_t lddy,
+             float* dX, float* dm, cudaStream_t s);
+// out[b,l,:] = v[b,:] broadcast into a strided slice; and the reduction sum_l back
+int bcast_rows(int64_t B, int64_t L, int d, const float* v, int64_t ldv, float* out, int64_t ldo, cudaStream_t s);
+int bcast_rows_bwd(int64_t B, int64_t L, int d, const float* dout, int64_t ldo, float* dv, int64_t ldv,
+                   int accumulate, cudaStream_t s);
+// y = x * (v > 0)
+int relu_bwd(int64_t rows, int cols, const float* dy, int64_t lddy, const float* v, int64_t ldv, float* dx,
+             int64_t lddx, cudaStream_t s);
+int add_inplace(int64_t n, float* y, const float* x, cudaStream_t s);
+
+}  // namespace intel

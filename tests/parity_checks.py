@@ -1,0 +1,200 @@
+"""Parity checks shared by the emulator tests (CPU, kernel logic) and the GPU tests (the real thing).
+Every check drives the product's Python host layer -> C ABI -> kernels and compares with the golden
+vectors of the unmodified reference and with the CPU oracle."""
+import argparse
+
+import numpy as np
+import torch
+
+from conftest import GOLDEN, LOSS_KW, assert_grad_close, load_model_case, rel_err
+from oracle import intel_oracle as O
+
+TOL = 1e-5   # north_star: scores / losses within 1e-5 relative (to the tensor's inf-norm), fp32
+
+
+def loss_args(**kw):
+    a = argparse.Namespace(**LOSS_KW)
+    for k, v in kw.items():
+        setattr(a, k, v)
+    return a
+
+
+def make_model(cfg, state, device):
+    from intel_sigir2023_b200.IntEL import IntEL
+    args = argparse.Namespace(device=torch.device(device), model_path="", buffer=1)
+    m = IntEL(args, cfg=cfg).to(device)
+    missing = m.load_state_dict(state, strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    return m
+
+
+def check_linear(device):
+    from intel_sigir2023_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(0)
+    for (M, N, K) in [(7, 5, 3), (130, 33, 17), (64, 64, 64), (300, 8, 40), (20, 100, 70)]:
+        A = torch.randn(M, K, generator=g).to(device)
+        W = torch.randn(N, K, generator=g).to(device)
+        b = torch.randn(N, generator=g).to(device)
+        Cout = torch.empty(M, N, device=device)
+        _lib.check(lib.intel_linear_fwd(M, N, K, _lib.ptr(A), _lib.ptr(W), _lib.ptr(b), _lib.ptr(Cout), _lib.stream_ptr(A.device)))
+        ref = A.cpu() @ W.cpu().t() + b.cpu()
+        assert rel_err(Cout.cpu().numpy(), ref.numpy()) < 2e-6, (M, N, K)
+
+
+def check_gather_scatter(device):
+    from intel_sigir2023_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(1)
+    for d in (16, 32, 6):
+        table = torch.randn(11, d, generator=g).to(device)
+        idx = torch.randint(0, 11, (37,), generator=g).to(device)
+        out = torch.empty(37, d, device=device)
+        _lib.check(lib.intel_gather_fwd(37, d, _lib.ptr(table), _lib.ptr(idx), _lib.ptr(out), d, 0, _lib.stream_ptr(out.device)))
+        assert torch.equal(out.cpu(), table.cpu()[idx.cpu()])          # index work: bit exact
+        gout = torch.randn(37, d, generator=g).to(device)
+        gt = torch.zeros(11, d, device=device)
+        _lib.check(lib.intel_scatter_add_bwd(37, d, _lib.ptr(gout), d, _lib.ptr(idx), _lib.ptr(gt), _lib.stream_ptr(out.device)))
+        ref = torch.zeros(11, d).index_add_(0, idx.cpu(), gout.cpu())
+        assert rel_err(gt.cpu().numpy(), ref.numpy()) < 1e-6
+
+
+def check_forward(name, device):
+    cfg, batch, state, gold = load_model_case(name, device)
+    model = make_model(cfg, state, device).eval()
+    with torch.no_grad():
+        out = model(batch)
+    cpu_batch = {k: (v.cpu() if torch.is_tensor(v) else v) for k, v in batch.items()}
+    ora = O.forward({k: v.cpu() for k, v in state.items()}, cfg, cpu_batch)
+    for k in ("intents", "weights", "ens_score"):
+        got = out[k].cpu().numpy()
+        assert got.shape == gold["out." + k].shape, k
+        assert rel_err(got, gold["out." + k]) < TOL, (name, k, "vs reference golden", rel_err(got, gold["out." + k]))
+        assert rel_err(got, ora[k].numpy()) < TOL, (name, k, "vs oracle")
+    # per-session rankings identical to the reference's (no exact ties in these fixtures)
+    n = cpu_batch["session_len"].numpy()
+    for b in range(len(n)):
+        a = np.argsort(-out["ens_score"][b, :n[b]].cpu().numpy(), kind="stable")
+        r = np.argsort(-gold["out.ens_score"][b, :n[b]], kind="stable")
+        gaps = np.abs(np.diff(np.sort(gold["out.ens_score"][b, :n[b]])))
+        if gaps.size == 0 or gaps.min() > 1e-4:
+            assert np.array_equal(a, r), (name, b)
+
+
+def check_backward(name, kind, device):
+    from intel_sigir2023_b200 import losses
+    cfg, batch, state, gold = load_model_case(name, device)
+    model = make_model(cfg, state, device).train()
+    crit = {"list": losses.IntListloss, "bpr": losses.IntBPRloss, "mse": losses.IntMSEloss}[kind](loss_args())
+    if kind == "bpr":
+        crit.bpr_noise = torch.from_numpy(gold["bpr_noise"]).to(device)
+    out = model(batch)
+    loss, ens_l, int_l = crit(out, batch)
+    got = np.array([loss.item(), ens_l.item(), int_l.item()])
+    ref = gold[f"loss.{kind}"]
+    assert np.allclose(got, ref, rtol=TOL, atol=1e-7), (name, kind, got, ref)
+    loss.backward()
+    names = [n for n, _ in model.named_parameters()]
+    gmax = max(np.abs(gold[f"grad.{kind}.{k}"]).max() for k in names)
+    for k, p in model.named_parameters():
+        assert p.grad is not None, k
+        assert_grad_close(p.grad.cpu().numpy(), gold[f"grad.{kind}.{k}"], gmax, f"{name}/{kind}/{k}")
+
+
+def check_loss_edge_cases(device):
+    """no-diversity variants, a session without positives (NaN like the reference), in-kernel BPR RNG."""
+    from intel_sigir2023_b200 import losses
+    cfg, batch, state, gold = load_model_case("default_bert", device)
+    cpu_batch = {k: (v.cpu() if torch.is_tensor(v) else v) for k, v in batch.items()}
+    out = {"ens_score": torch.from_numpy(gold["out.ens_score"]).to(device).requires_grad_(True),
+           "weights": torch.from_numpy(gold["out.weights"]).to(device).requires_grad_(True),
+           "intents": torch.from_numpy(gold["out.intents"]).to(device).requires_grad_(True)}
+    for kind, cls in (("list", losses.Listloss), ("mse", losses.MSEloss), ("bpr", losses.BPRloss)):
+        crit = cls(loss_args(cal_diversity=0))
+        noise = torch.from_numpy(gold["bpr_noise"])
+        crit.bpr_noise = noise.to(device)
+        l, _, _ = crit(out, batch)
+        o = {k: v.detach().cpu().requires_grad_(True) for k, v in out.items()}
+        if kind == "list":
+            ref = O.list_loss(o, cpu_batch, 0, 0.0)
+        elif kind == "mse":
+            ref = O.mse_loss(o, cpu_batch, 0, 0.0)
+        else:
+            ref = O.bpr_loss(o, cpu_batch, 0, 0.0, noise)
+        assert abs(l.item() - ref.item()) <= TOL * abs(ref.item()) + 1e-7, (kind, l.item(), ref.item())
+        out["ens_score"].grad = None
+        l.backward()
+        ref.backward()
+        assert rel_err(out["ens_score"].grad.cpu().numpy(), o["ens_score"].grad.numpy()) < 1e-4, kind
+    # in-kernel RNG: finite, and differs from seed to seed only through the negative choice
+    crit = losses.BPRloss(loss_args(cal_diversity=1))
+    l1, _, _ = crit(out, batch)
+    assert np.isfinite(l1.item())
+    # a session with no positive item: 0/0 -> NaN, as in the reference (Listloss.py:14)
+    nb = dict(batch)
+    nb["ranking"] = batch["ranking"].clone()
+    nb["ranking"][1] = 0
+    l, _, _ = losses.Listloss(loss_args(cal_diversity=0))(out, nb)
+    assert np.isnan(l.item())
+    # intent loss soft branch (prediction with an exact zero, BaseIntloss.py:32-35)
+    p = out["intents"].detach().clone()
+    p[0, 0] = 0.0
+    il = losses._IntentLossFn.apply(p.requires_grad_(True), batch["intents"], 0.5, 2.0)
+    ref, ce, kl = O.intent_loss(p.detach().cpu().requires_grad_(True), cpu_batch["intents"], 0.5, 2.0)
+    assert np.allclose(il.detach().cpu().numpy(), [ref.item(), ce.item(), kl.item()], rtol=TOL), (il, ref, ce, kl)
+
+
+def check_evaluate(tag, device):
+    from intel_sigir2023_b200 import evaluate
+    z = np.load(f"{GOLDEN}/eval.npz")
+    pos = {k: z[f"{tag}.pos.{k}"] for k in ("c_paynum_i", "c_favnum_i", "c_clicknum_i")}
+    topk, metrics = [3, 1, 5, 10], ["NDCG", "HR"]
+    res = evaluate.evaluate_method(list(z[f"{tag}.pred"]), list(z[f"{tag}.ranking"]), pos, topk, metrics,
+                                   z[f"{tag}.session_len"], device=device)
+    ora = O.evaluate_method(list(z[f"{tag}.pred"]), list(z[f"{tag}.ranking"]), pos, topk, metrics, z[f"{tag}.session_len"])
+    assert set(res.keys()) == set(ora.keys())
+    for k, v in ora.items():       # same tie rule as the oracle: every key, including fav_*
+        assert (np.isnan(v) and np.isnan(res[k])) or abs(res[k] - v) < 1e-9, (tag, k, res[k], v)
+    for k in res:                  # and the reference itself wherever it is well defined
+        if k.startswith("fav_") and tag != "B":
+            continue
+        ref = float(z[f"{tag}.metric.{k}"])
+        assert (np.isnan(ref) and np.isnan(res[k])) or abs(res[k] - ref) < 1e-6, (tag, k, res[k], ref)
+
+
+def check_evaluate_ties(device):
+    """exact ties (zero scores vs pad slots, duplicated scores): the documented stable tie rule == oracle."""
+    from intel_sigir2023_b200 import evaluate
+    z = np.load(f"{GOLDEN}/eval.npz")
+    pred = z["A.pred"].copy()
+    pred = np.round(pred * 4) / 4          # many duplicates, including exact zeros
+    pos = {k: z[f"A.pos.{k}"] for k in ("c_paynum_i", "c_favnum_i", "c_clicknum_i")}
+    topk, metrics = [3, 1, 5, 10], ["NDCG", "HR"]
+    res = evaluate.evaluate_method(list(pred), list(z["A.ranking"]), pos, topk, metrics, z["A.session_len"], device=device)
+    ora = O.evaluate_method(list(pred), list(z["A.ranking"]), pos, topk, metrics, z["A.session_len"])
+    for k, v in ora.items():
+        assert (np.isnan(v) and np.isnan(res[k])) or abs(res[k] - v) < 1e-9, (k, res[k], v)
+
+
+def check_evaluate_intents(device):
+    from intel_sigir2023_b200 import evaluate
+    z = np.load(f"{GOLDEN}/eval.npz")
+    res = evaluate.evaluate_intents(z["I.true"], z["I.pred"], topk=[1, 3, 5, 10, 30], device=device)
+    for k, v in res.items():
+        assert abs(v - float(z[f"I.metric.{k}"])) < 1e-6, (k, v)
+
+
+def check_baselines(device):
+    from intel_sigir2023_b200 import baselines
+    z = np.load(f"{GOLDEN}/eval.npz")
+    batch = {"scores": torch.from_numpy(z["F.scores"]).to(device)}
+    s = baselines.SingleSort(choose_list="pCVR")(batch)["ens_score"].cpu().numpy()
+    assert np.array_equal(s, z["F.single_pCVR"])
+    b = baselines.Borda()(batch)["ens_score"].cpu().numpy()
+    assert np.array_equal(b, O.borda({"scores": torch.from_numpy(z["F.scores"])})["ens_score"].numpy())
+    untied = (z["F.scores"] > 0).all(axis=2)
+    assert np.allclose(b[untied], z["F.borda"][untied])
+    raw = torch.rand(z["F.scores"].shape, generator=torch.Generator().manual_seed(3))
+    r = baselines.RandomFusion()(batch, raw.to(device))["ens_score"].cpu().numpy()
+    ref = O.random_fusion({"scores": torch.from_numpy(z["F.scores"])}, raw)["ens_score"].numpy()
+    assert rel_err(r, ref) < 1e-6

@@ -1,0 +1,67 @@
+"""Kernel logic + host orchestration on the CUDA emulator (tests/emu/cuda_emu.h): the same .cu sources
+compiled for CPU fibers.  This is a debugger for the build container (no GPU here); the parity gate
+proper is tests/test_gpu_parity.py."""
+import os
+import sys
+
+import pytest
+
+import parity_checks as P
+from conftest import MODEL_CASES
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "emu"))
+
+
+@pytest.fixture(scope="module", autouse=True)
+def emu_lib():
+    from build_emu import build_emu
+    from intel_sigir2023_b200 import _lib
+    path = build_emu()
+    old = (_lib._lib, _lib._allow_host_tensors)
+    _lib._lib = None
+    _lib.load(path)
+    _lib._allow_host_tensors = True
+    yield
+    _lib._lib, _lib._allow_host_tensors = old
+
+
+def test_linear():
+    P.check_linear("cpu")
+
+
+def test_gather_scatter():
+    P.check_gather_scatter("cpu")
+
+
+@pytest.mark.parametrize("name", MODEL_CASES)
+def test_forward(name):
+    P.check_forward(name, "cpu")
+
+
+@pytest.mark.parametrize("name", MODEL_CASES)
+@pytest.mark.parametrize("kind", ["list", "bpr", "mse"])
+def test_backward(name, kind):
+    if name == "wide_intent_bert_full" and kind != "list":
+        pytest.skip("emulator time: covered on the GPU")
+    P.check_backward(name, kind, "cpu")
+
+
+def test_loss_edge_cases():
+    P.check_loss_edge_cases("cpu")
+
+
+@pytest.mark.parametrize("tag", ["A", "B", "C"])
+def test_evaluate(tag):
+    P.check_evaluate(tag, "cpu")
+
+
+def test_evaluate_ties():
+    P.check_evaluate_ties("cpu")
+
+
+def test_evaluate_intents():
+    P.check_evaluate_intents("cpu")
+
+
+def test_baselines():
+    P.check_baselines("cpu")
