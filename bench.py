@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""IntEL hot-path benchmark (BASELINE.json metric: sessions/sec, train fwd+bwd; eval reported beside it).
+
+    python bench.py --gpus N --steps K --warmup W            # B200 path (one rank per GPU under torchrun)
+    python bench.py --impl reference --steps K --warmup W     # the reference's CPU PyTorch path (oracle port)
+
+A "step" is one pass of the hot path over one batch of synthetic Tmall-schema sessions:
+model forward (intent predictor + ensemble) + criterion + backward; the optimizer is excluded, as in
+SURVEY.md 8(d).  Workload = BASELINE.json configs[1] ("IntEL synthetic Tmall-schema, 1M sessions x 50
+candidates x K=4 basic lists, 1 B200"), streamed as batches of 4096 sessions per GPU with the IntEL-PL
+flags of the reference's own script (IntEL/script/IntEL.sh:21).  `value` has its inputs resident in HBM;
+`e2e` goes through the same public API with HOST (pinned) buffers, H2D copies and the loss read-back inside
+the timed region.  One JSON line on stdout (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from intel_sigir2023_b200 import synthetic                     # noqa: E402
+from intel_sigir2023_b200.config import IntelConfig             # noqa: E402
+
+VARIANTS = {
+    # the three runs of IntEL/script/IntEL.sh (lines 9, 15, 21) + the bare flag defaults
+    "pl": dict(loss="list", encoder="GRU4Rec", context_emb_size=32, intent_emb_size=32, cross_attn_qsize=64,
+               num_heads=2, num_layers=2, intent_weight=0.1, diversity_alpha=1e-4),
+    "bpr": dict(loss="bpr", encoder="GRU4Rec", context_emb_size=64, intent_emb_size=32, cross_attn_qsize=32,
+                num_heads=2, num_layers=2, intent_weight=0.01, diversity_alpha=1e-5),
+    "mse": dict(loss="mse", encoder="BERT4Rec", intent_weight=0.003, diversity_alpha=1e-5),
+    "default": dict(loss="list", encoder="BERT4Rec", intent_weight=0.1, diversity_alpha=1e-4),
+}
+MODEL_KEYS = ("encoder", "context_emb_size", "intent_emb_size", "cross_attn_qsize", "num_heads", "num_layers")
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--variant", default="pl", choices=sorted(VARIANTS))
+    ap.add_argument("--batch", type=int, default=4096, help="sessions per step per GPU")
+    ap.add_argument("--list_len", type=int, default=50)
+    ap.add_argument("--model_num", type=int, default=4)
+    ap.add_argument("--intent_num", type=int, default=1071)
+    ap.add_argument("--n_item", type=int, default=1_000_000)
+    ap.add_argument("--n_user", type=int, default=100_000)
+    ap.add_argument("--resident_batches", type=int, default=3, help="distinct batches kept in HBM and cycled")
+    ap.add_argument("--cpu_batch", type=int, default=512, help="sessions per CPU-baseline step")
+    ap.add_argument("--no_cpu_baseline", action="store_true")
+    ap.add_argument("--no_e2e", action="store_true")
+    ap.add_argument("--eval_steps", type=int, default=10)
+    ap.add_argument("--profile_mode", action="store_true", help="under ncu: only warm-up + timed steps, nothing else")
+    return ap.parse_args()
+
+
+def make_cfg(a) -> tuple:
+    v = VARIANTS[a.variant]
+    corpus = synthetic.CorpusSpec(n_item=a.n_item, n_class=357, n_user=a.n_user, n_ctx=931, model_num=a.model_num,
+                                  intent_num=a.intent_num, history_max=20)
+    cfg = IntelConfig(item_rows=corpus.item_rows, class_rows=corpus.n_class, user_rows=corpus.user_rows,
+                      ctx_rows=corpus.n_ctx, intent_num=corpus.intent_num, model_num=corpus.model_num,
+                      history_max=20, **{k: v[k] for k in MODEL_KEYS if k in v})
+    loss_args = argparse.Namespace(cal_diversity=1, diversity_alpha=v["diversity_alpha"], intent_weight=v["intent_weight"],
+                                   ensemble_weight=1.0, kl_temp=2.0, kl_weight=0.5)
+    return corpus, cfg, v["loss"], loss_args
+
+
+def batch_bytes(batch) -> int:
+    return sum(t.numel() * t.element_size() for t in batch.values() if torch.is_tensor(t))
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_rate(a, corpus, cfg, loss_kind, loss_args, steps: int, warmup: int):
+    """The reference's CPU PyTorch path, restated by oracle/intel_oracle.py (the unmodified reference
+    cannot travel to the GPU box), timed on this host's cores on a bounded sample."""
+    from oracle import intel_oracle as O
+    ncores = os.cpu_count() or 1
+    torch.set_num_threads(ncores)
+    B = a.cpu_batch
+    batch = synthetic.make_batch(corpus, synthetic.BatchSpec(batch_size=B, max_len=a.list_len, min_len=a.list_len), seed=11)
+    sd = {k: v.requires_grad_(True) for k, v in O.init_state(cfg, seed=0).items()}
+    noise = torch.rand(B, a.list_len, a.list_len) if loss_kind == "bpr" else None
+    kw = dict(cal_diversity=1, diversity_alpha=loss_args.diversity_alpha, intent_weight=loss_args.intent_weight,
+              ensemble_weight=1.0, kl_weight=0.5, kl_temp=2.0, noise=noise)
+
+    def step():
+        for p in sd.values():
+            p.grad = None
+        out = O.forward(sd, cfg, batch)
+        loss, _, _ = O.total_loss(loss_kind, out, batch, **kw)
+        loss.backward()
+        return float(loss)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return B * steps / dt, dt / steps * 1e3, ncores, f"{steps} steps x {B} sessions (L={a.list_len}, K={a.model_num}, I={a.intent_num}), fwd+loss+bwd"
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    corpus, cfg, loss_kind, loss_args = make_cfg(a)
+    steps, warmup = max(1, min(a.steps, 8)), max(1, min(a.warmup, 2))
+    rate, ms, ncores, sample = cpu_reference_rate(a, corpus, cfg, loss_kind, loss_args, steps, warmup)
+    line = {
+        "impl": "reference", "metric": "sessions/sec (train fwd+bwd)", "value": rate, "unit": "sessions/s",
+        "n_gpus": a.gpus, "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(a, cfg, loss_kind, a.cpu_batch),
+        "cpu_baseline": {"value": rate, "unit": "sessions/s", "cores": ncores, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": "sessions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(a, cfg, loss_kind, batch):
+    return {"workload": f"BASELINE.json configs[1]: IntEL synthetic Tmall-schema, {a.list_len} candidates x K={a.model_num}, "
+                        f"I={a.intent_num}, streamed in batches (1M sessions = {1_000_000 // max(batch, 1)} such steps)",
+            "variant": f"IntEL-{a.variant} (IntEL/script/IntEL.sh flags)", "loss": loss_kind, "cal_diversity": 1,
+            "encoder": cfg.encoder, "num_heads": cfg.num_heads, "num_layers": cfg.num_layers,
+            "batch_per_gpu": batch, "history_max": 20, "n_item": cfg.item_rows - 1,
+            "input_layout": "dense reference API (float64 [B,H,I] history intents)",
+            "l2_policy": "inputs larger than L2 (each resident batch > 1 GB), batches cycled"}
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(", ") for r in open(self.f.name) if r.strip()]
+        os.unlink(self.f.name)
+        sm = sorted(float(r[1]) for r in rows if len(r) >= 9 and r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            if len(r) >= 9:
+                for n, v in zip(names, r[5:9]):
+                    if v.strip().lower().startswith("active"):
+                        reasons.add(n)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(rows)}
+
+
+def run_b200(a):
+    import torch.distributed as dist
+    from intel_sigir2023_b200 import _lib, losses, evaluate, dp
+    from intel_sigir2023_b200.IntEL import IntEL
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU path)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+    corpus, cfg, loss_kind, loss_args = make_cfg(a)
+    torch.manual_seed(0)
+    model = IntEL(argparse.Namespace(device=dev, model_path="", buffer=1), cfg=cfg).to(dev)
+    crit = {"list": losses.IntListloss, "bpr": losses.IntBPRloss, "mse": losses.IntMSEloss}[loss_kind](loss_args)
+    reducer = dp.GradReducer(model, world) if world > 1 else None
+    B, L = a.batch, a.list_len
+    spec = synthetic.BatchSpec(batch_size=B, max_len=L, min_len=L)
+    # weak scaling: every rank owns its own shard of the session stream (different seeds)
+    resident = [synthetic.make_batch(corpus, spec, seed=1000 * rank + i, device=dev) for i in range(a.resident_batches)]
+    launches = {"n": 0}
+
+    def train_step(batch):
+        for p in model.parameters():
+            p.grad = None
+        out = model(batch)
+        loss, ens_l, int_l = crit(out, batch)
+        loss.backward()
+        if reducer is not None:
+            reducer.allreduce()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # ---- warm-up, then the timed region (inputs resident in HBM) ----
+    for i in range(a.warmup if a.profile_mode else max(a.warmup, 3)):
+        train_step(resident[i % len(resident)])
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms_total = timed(lambda i: train_step(resident[i % len(resident)]), a.steps)
+    clocks = sampler.stop() if sampler else None
+    ms_step = ms_total / a.steps
+    value = world * B / (ms_step * 1e-3)
+    if a.profile_mode:
+        if rank == 0:
+            print(json.dumps({"profile_mode": True, "ms_per_step_under_profiler": ms_step}))
+        return
+
+    # ---- launch count + live per-kernel timing (CUDA events around every launch; separate pass) ----
+    _lib.profile(True)
+    prof_steps = 3
+    for i in range(prof_steps):
+        train_step(resident[i % len(resident)])
+    prof = _lib.profile_report()
+    _lib.profile(False)
+    gpu_launches = int(sum(v["launches"] for v in prof.values()) / prof_steps * a.steps)
+    total_ms = sum(v["ms"] for v in prof.values())
+    top = max(prof.items(), key=lambda kv: kv[1]["ms"])
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    name, rec = top
+    achieved = rec["bytes"] / (rec["ms"] * 1e-3) / 1e9 if rec["ms"] > 0 else 0.0
+    roofline = {"kernel": name, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "share_of_step": rec["ms"] / total_ms if total_ms else None,
+                "avg_launch_us": rec["ms"] * 1e3 / rec["launches"],
+                "gflops": rec["flops"] / (rec["ms"] * 1e-3) / 1e9 if rec["ms"] > 0 else 0.0,
+                "per_kernel": {k: {"share": v["ms"] / total_ms, "gbs": (v["bytes"] / (v["ms"] * 1e-3) / 1e9) if v["ms"] > 0 else 0.0,
+                                   "launches_per_step": v["launches"] / prof_steps}
+                               for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}}
+
+    # ---- end to end: host (pinned) batch -> H2D -> step -> loss D2H, every step ----
+    e2e = None
+    if not a.no_e2e:
+        host = [{k: (v.cpu().pin_memory() if torch.is_tensor(v) else v) for k, v in resident[i].items()}
+                for i in range(min(2, len(resident)))]
+        h2d = batch_bytes(host[0])
+        loss_host = torch.zeros(1, dtype=torch.float64).pin_memory()
+
+        def e2e_step(i):
+            b = synthetic.batch_to(host[i % len(host)], dev, non_blocking=True)
+            loss = train_step(b)
+            loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+        for i in range(2):
+            e2e_step(i)
+        n_e2e = max(3, min(a.steps, 6))
+        ms_e2e = timed(e2e_step, n_e2e) / n_e2e
+        e2e = {"value": world * B / (ms_e2e * 1e-3), "unit": "sessions/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": 8, "ms_per_step": ms_e2e}
+
+    # ---- eval throughput: forward (no_grad) + evaluate_method on device ----
+    topk, metrics = [3, 1, 5, 10], ["NDCG", "HR"]
+
+    def eval_step(i):
+        b = resident[i % len(resident)]
+        with torch.no_grad():
+            out = model(b)
+        evaluate.ndcg_sums(out["ens_score"], b["ranking"], b["session_len"], b["c_paynum_i"], b["c_favnum_i"],
+                           b["c_clicknum_i"], max(L, max(topk)), topk)
+    model.eval()
+    for i in range(2):
+        eval_step(i)
+    ms_eval = timed(eval_step, a.eval_steps) / a.eval_steps
+    model.train()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    line = {
+        "metric": "sessions/sec (train fwd+bwd)", "value": value, "unit": "sessions/s", "n_gpus": world,
+        "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(a, cfg, loss_kind, B), "clocks": clocks, "gpu_launches": gpu_launches,
+        "roofline": roofline, "eval_sessions_per_s": world * B / (ms_eval * 1e-3),
+    }
+    if e2e is not None:
+        line["e2e"] = e2e
+    if not a.no_cpu_baseline and world == 1:
+        rate, ms, ncores, sample = cpu_reference_rate(a, corpus, cfg, loss_kind, loss_args, 4, 1)
+        line["cpu_baseline"] = {"value": rate, "unit": "sessions/s", "cores": ncores, "kind": "port", "sample": sample}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)

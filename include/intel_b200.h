@@ -181,6 +181,13 @@ int intel_select_list(int64_t B, int64_t L, int64_t K, const double* scores, int
 int intel_rank_lists(int64_t B, int64_t L, int64_t K, const double* scores, float* ens_out,
                      intel_stream_t stream);
 
+/* ---- optional per-kernel device timing (used by bench.py for the live roofline numbers) ------ */
+/* While enabled every kernel launch is bracketed by CUDA events on its stream. */
+int intel_profile_enable(int on);
+/* Synchronises the device, then writes one text line per kernel name: "name launches total_ms
+ * algorithmic_bytes flops" and clears the records. */
+int intel_profile_report(char* buf, size_t cap);
+
 /* ---- building blocks exposed for unit tests --------------------------------------------- */
 /* out[r, :] = table[idx[r], :]  (nn.Embedding forward) */
 int intel_gather_fwd(int64_t rows, int d, const float* table, const int64_t* idx, float* out, int ld_out,

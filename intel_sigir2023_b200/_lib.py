@@ -88,6 +88,8 @@ def _declare(lib: C.CDLL) -> None:
         "intel_gather_fwd": (i32, [i64, i32, _p, _p, _p, i32, i32, _p]),
         "intel_scatter_add_bwd": (i32, [i64, i32, _p, i32, _p, _p, _p]),
         "intel_linear_fwd": (i32, [i64, i64, i64, _p, _p, _p, _p, _p]),
+        "intel_profile_enable": (i32, [i32]),
+        "intel_profile_report": (i32, [C.c_char_p, sz]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)       # AttributeError if the header and the library disagree
@@ -100,7 +102,8 @@ EXPORTED = ["intel_last_error", "intel_abi_version", "intel_intent_workspace_byt
             "intel_loss_pl_fwd_bwd", "intel_loss_bpr_fwd_bwd", "intel_loss_mse_fwd_bwd", "intel_intent_loss_fwd_bwd",
             "intel_scale_by_device_scalar", "intel_ndcg_workspace_bytes", "intel_ndcg_topk",
             "intel_intent_topk_workspace_bytes", "intel_intent_topk", "intel_fuse_fwd", "intel_select_list",
-            "intel_rank_lists", "intel_gather_fwd", "intel_scatter_add_bwd", "intel_linear_fwd"]
+            "intel_rank_lists", "intel_gather_fwd", "intel_scatter_add_bwd", "intel_linear_fwd",
+            "intel_profile_enable", "intel_profile_report"]
 
 
 def load(path: Optional[str] = None) -> C.CDLL:
@@ -219,3 +222,18 @@ def make_batch(batch: Dict[str, object], cfg: IntelConfig) -> Batch:
     b.his_item_int = ptr(batch["his_item_int"], f64)
     b.history_item_len = ptr(batch["history_item_len"], i64)
     return b
+
+
+def profile(on: bool) -> None:
+    check(load().intel_profile_enable(1 if on else 0))
+
+
+def profile_report() -> Dict[str, Dict[str, float]]:
+    """{kernel name: {launches, ms, bytes, flops}} of the launches recorded since profile(True)."""
+    buf = C.create_string_buffer(1 << 16)
+    check(load().intel_profile_report(buf, len(buf)))
+    out: Dict[str, Dict[str, float]] = {}
+    for line in buf.value.decode().splitlines():
+        name, n, ms, by, fl = line.split()
+        out[name] = {"launches": float(n), "ms": float(ms), "bytes": float(by), "flops": float(fl)}
+    return out

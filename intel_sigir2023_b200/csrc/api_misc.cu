@@ -1,6 +1,10 @@
 // Error plumbing of the C ABI and the small building-block entry points exposed for unit tests.
 #include <stdarg.h>
 
+#include <map>
+#include <string>
+#include <vector>
+
 #include "kernels.h"
 #include "../../include/intel_b200.h"
 
@@ -15,12 +19,40 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
-int check_launch(const char* what) {
+#ifndef INTEL_EMU
+struct ProfRec { cudaEvent_t a, b; const char* what; double bytes, flops; };
+static bool g_prof_on = false, g_prof_pending = false;
+static cudaEvent_t g_pa, g_pb;
+static std::vector<ProfRec> g_recs;
+
+void prof_before(cudaStream_t s) {
+    if (!g_prof_on) return;
+    cudaEventCreate(&g_pa);
+    cudaEventCreate(&g_pb);
+    cudaEventRecord(g_pa, s);
+    g_prof_pending = true;
+}
+void prof_mark(cudaStream_t s) {
+    if (g_prof_on && g_prof_pending) cudaEventRecord(g_pb, s);
+}
+static void prof_commit(const char* what, double bytes, double flops) {
+    if (!g_prof_on || !g_prof_pending) return;
+    g_recs.push_back({g_pa, g_pb, what, bytes, flops});
+    g_prof_pending = false;
+}
+#else
+void prof_before(cudaStream_t) {}
+void prof_mark(cudaStream_t) {}
+static void prof_commit(const char*, double, double) {}
+#endif
+
+int check_launch(const char* what, double bytes, double flops) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         set_error("%s: launch failed: %s", what, cudaGetErrorString(e));
         return INTEL_ERR_CUDA;
     }
+    prof_commit(what, bytes, flops);
     return INTEL_OK;
 }
 
@@ -32,6 +64,45 @@ extern "C" {
 
 const char* intel_last_error(void) { return g_err; }
 int intel_abi_version(void) { return INTEL_ABI_VERSION; }
+
+int intel_profile_enable(int on) {
+#ifndef INTEL_EMU
+    g_prof_on = on != 0;
+    g_prof_pending = false;
+#endif
+    (void)on;
+    return INTEL_OK;
+}
+
+// Synchronises the device (the only call of the library that does), aggregates the recorded launches by
+// kernel name and writes one line per name: "name launches total_ms bytes flops".
+int intel_profile_report(char* buf, size_t cap) {
+    if (!buf || cap == 0) return INTEL_ERR_ARG;
+    buf[0] = 0;
+#ifndef INTEL_EMU
+    cudaError_t e = cudaDeviceSynchronize();
+    INTEL_REQUIRE(e == cudaSuccess, INTEL_ERR_CUDA, "profile_report: %s", cudaGetErrorString(e));
+    struct Agg { double n = 0, ms = 0, bytes = 0, flops = 0; };
+    std::map<std::string, Agg> agg;
+    for (auto& r : g_recs) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, r.a, r.b);
+        Agg& a = agg[r.what];
+        a.n += 1; a.ms += ms; a.bytes += r.bytes; a.flops += r.flops;
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    g_recs.clear();
+    size_t off = 0;
+    for (auto& kv : agg) {
+        int w = snprintf(buf + off, cap - off, "%s %.0f %.6f %.0f %.0f\n", kv.first.c_str(), kv.second.n, kv.second.ms,
+                         kv.second.bytes, kv.second.flops);
+        if (w < 0 || (size_t)w >= cap - off) break;
+        off += (size_t)w;
+    }
+#endif
+    return INTEL_OK;
+}
 
 int intel_gather_fwd(int64_t rows, int d, const float* table, const int64_t* idx, float* out, int ld_out, int relu,
                      intel_stream_t stream) {

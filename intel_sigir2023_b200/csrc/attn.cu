@@ -49,7 +49,7 @@ int layernorm_fwd(int64_t R, int d, const float* Z, const float* gamma, const fl
     INTEL_REQUIRE(d <= 32 * LN_MAX_PER_LANE, INTEL_ERR_UNSUPPORTED, "layernorm width %d > 256", d);
     unsigned grid = stream_grid(ceil_div(R, 8), 8);
     LAUNCH(layernorm_fwd_kernel, dim3(grid), dim3(256), 0, s, R, d, Z, gamma, beta, Y, stats);
-    return check_launch("layernorm_fwd");
+    return check_launch("layernorm_fwd", 8.0 * R * d, 8.0 * R * d);
 }
 
 __global__ void __launch_bounds__(256) layernorm_bwd_kernel(int64_t R, int d, const float* __restrict__ dY,
@@ -107,7 +107,7 @@ int layernorm_bwd(int64_t R, int d, const float* dY, const float* Z, const float
     INTEL_REQUIRE(d <= 32 * LN_MAX_PER_LANE, INTEL_ERR_UNSUPPORTED, "layernorm width %d > 256", d);
     unsigned grid = stream_grid(ceil_div(R, 8), 4);
     LAUNCH(layernorm_bwd_kernel, dim3(grid), dim3(256), 0, s, R, d, dY, Z, stats, gamma, dZ, dgamma, dbeta);
-    return check_launch("layernorm_bwd");
+    return check_launch("layernorm_bwd", 12.0 * R * d, 12.0 * R * d);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -182,7 +182,7 @@ int mha_fwd(int64_t B, int64_t T, int d, int heads, const float* QKV, const int6
     INTEL_REQUIRE(smem <= kMaxSmem, INTEL_ERR_UNSUPPORTED, "mha_fwd: list length %lld too long for one SM", (long long)T);
     if (smem > 48 * 1024) cudaFuncSetAttribute(mha_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     LAUNCH(mha_fwd_kernel, dim3((unsigned)(B * heads)), dim3(MHA_WARPS * 32), smem, s, T, d, heads, QKV, lens, O);
-    return check_launch("mha_fwd");
+    return check_launch("mha_fwd", 16.0 * B * T * d, 4.0 * B * T * T * d);
 }
 
 // Backward by recomputation.  Phase A (warp per query): softmax statistics (m, l), delta = sum_j p dP,
@@ -295,7 +295,7 @@ int mha_bwd(int64_t B, int64_t T, int d, int heads, const float* QKV, const int6
     INTEL_REQUIRE(smem <= kMaxSmem, INTEL_ERR_UNSUPPORTED, "mha_bwd: list length %lld too long for one SM", (long long)T);
     if (smem > 48 * 1024) cudaFuncSetAttribute(mha_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     LAUNCH(mha_bwd_kernel, dim3((unsigned)(B * heads)), dim3(MHA_WARPS * 32), smem, s, T, d, heads, QKV, lens, dO, dQKV);
-    return check_launch("mha_bwd");
+    return check_launch("mha_bwd", 28.0 * B * T * d, 16.0 * B * T * T * d);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -352,7 +352,7 @@ int cross_pool_fwd(int64_t B, int64_t L, int d, const float* X, const float* qk,
     INTEL_REQUIRE(smem <= 48 * 1024, INTEL_ERR_UNSUPPORTED, "cross_pool: list length %lld too long", (long long)L);
     LAUNCH(cross_pool_fwd_kernel, dim3((unsigned)ceil_div(B, XP_WARPS)), dim3(XP_WARPS * 32), smem, s, B, L, d, X, qk,
            lens, scale, p, xbar);
-    return check_launch("cross_pool_fwd");
+    return check_launch("cross_pool_fwd", 4.0 * B * L * (d + 1), 4.0 * B * L * d);
 }
 
 __global__ void __launch_bounds__(XP_WARPS * 32) cross_pool_bwd_kernel(int64_t B, int64_t L, int d,
@@ -403,7 +403,7 @@ int cross_pool_bwd(int64_t B, int64_t L, int d, const float* X, const float* qk,
     INTEL_REQUIRE(smem <= 48 * 1024, INTEL_ERR_UNSUPPORTED, "cross_pool: list length %lld too long", (long long)L);
     LAUNCH(cross_pool_bwd_kernel, dim3((unsigned)ceil_div(B, XP_WARPS)), dim3(XP_WARPS * 32), smem, s, B, L, d, X, qk,
            lens, scale, p, dxbar, dX, dqk);
-    return check_launch("cross_pool_bwd");
+    return check_launch("cross_pool_bwd", 4.0 * B * L * (2 * d + 1), 8.0 * B * L * d);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -429,7 +429,7 @@ int softmax_rows(int64_t R, int64_t N, const float* Z, float* P, cudaStream_t s)
     if (R <= 0) return INTEL_OK;
     unsigned grid = stream_grid(ceil_div(R, 8), 8);
     LAUNCH(softmax_rows_kernel, dim3(grid), dim3(256), 0, s, R, N, Z, P);
-    return check_launch("softmax_rows");
+    return check_launch("softmax_rows", 8.0 * R * N, 4.0 * R * N);
 }
 
 __global__ void __launch_bounds__(256) softmax_rows_bwd_kernel(int64_t R, int64_t N, const float* __restrict__ P,
@@ -456,7 +456,7 @@ int softmax_rows_bwd(int64_t R, int64_t N, const float* P, const float* dP, cons
     if (R <= 0) return INTEL_OK;
     unsigned grid = stream_grid(ceil_div(R, 8), 8);
     LAUNCH(softmax_rows_bwd_kernel, dim3(grid), dim3(256), 0, s, R, N, P, dP, dP2, dZ);
-    return check_launch("softmax_rows_bwd");
+    return check_launch("softmax_rows_bwd", 12.0 * R * N, 4.0 * R * N);
 }
 
 }  // namespace intel

@@ -12,7 +12,12 @@
 #define DYN_SMEM(T, name)                                          \
     extern __shared__ __align__(16) unsigned char name##_raw_[];   \
     T* name = reinterpret_cast<T*>(name##_raw_)
-#define LAUNCH(kfn, grid, block, smem, stream, ...) kfn<<<grid, block, smem, stream>>>(__VA_ARGS__)
+#define LAUNCH(kfn, grid, block, smem, stream, ...)            \
+    do {                                                       \
+        intel::prof_before(stream);                            \
+        kfn<<<grid, block, smem, stream>>>(__VA_ARGS__);       \
+        intel::prof_mark(stream);                              \
+    } while (0)
 #endif
 
 #include <stdio.h>
@@ -20,10 +25,15 @@
 
 namespace intel {
 
+// optional per-launch device timing (bench.py's live roofline): CUDA events around every kernel,
+// attributed by check_launch(name, algorithmic bytes, flops).  Off by default; no-ops in the emulator.
+void prof_before(cudaStream_t s);
+void prof_mark(cudaStream_t s);
+
 // ---- error plumbing: no exceptions across the C ABI, int status + thread-local message ----
 enum { INTEL_OK = 0, INTEL_ERR_ARG = 1, INTEL_ERR_WORKSPACE = 2, INTEL_ERR_CUDA = 3, INTEL_ERR_UNSUPPORTED = 4 };
 void set_error(const char* fmt, ...);
-int check_launch(const char* what);
+int check_launch(const char* what, double bytes = 0.0, double flops = 0.0);
 
 #define INTEL_REQUIRE(cond, code, ...)        \
     do {                                      \

@@ -37,7 +37,7 @@ int gather_rows(int64_t rows, int d, const float* table, const int64_t* idx, flo
     unsigned grid = stream_grid(ceil_div(total, 256), 8);
     if (vec) { auto k = gather_kernel<4>; LAUNCH(k, dim3(grid), dim3(256), 0, s, rows, d, table, idx, out, ld_out, relu); }
     else { auto k = gather_kernel<1>; LAUNCH(k, dim3(grid), dim3(256), 0, s, rows, d, table, idx, out, ld_out, relu); }
-    return check_launch("gather");
+    return check_launch("gather", (double)rows * (8.0 * d + 8.0), 0.0);
 }
 
 // scatter-add: grad_table[idx[r], :] += d_out[r, :]   (embedding_dense_backward; the gradient stays
@@ -62,7 +62,7 @@ int scatter_add_rows(int64_t rows, int d, const float* d_out, int64_t ld, const 
     INTEL_REQUIRE(d_out && idx && grad_table, INTEL_ERR_ARG, "scatter_add: null pointer");
     unsigned grid = stream_grid(ceil_div(rows * d, 256), 8);
     LAUNCH(scatter_add_kernel, dim3(grid), dim3(256), 0, s, rows, d, d_out, ld, idx, grad_table, relu_table);
-    return check_launch("scatter_add");
+    return check_launch("scatter_add", (double)rows * (12.0 * d + 8.0), (double)rows * d);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -127,7 +127,7 @@ int dense_rows_linear_fwd(int64_t R, int64_t I, int d, const double* X, const fl
     INTEL_REQUIRE(X && Wt && Y, INTEL_ERR_ARG, "dense_rows_linear_fwd: null pointer");
     unsigned grid = stream_grid(ceil_div(R, 8), 8);
     LAUNCH(dense_rows_fwd_kernel, dim3(grid), dim3(256), 0, s, R, I, d, X, Wt, bias, Y, ldy, nz_idx, nz_val, nz_cnt, cap);
-    return check_launch("dense_rows_fwd");
+    return check_launch("dense_rows_fwd", (double)R * (8.0 * I + 4.0 * d), 0.0);
 }
 
 // backward w.r.t. the weight: dWt[i, :] += x[r,i] * dY[r, :]; uses the compacted non-zeros of the
@@ -177,7 +177,7 @@ int dense_rows_linear_bwd(int64_t R, int64_t I, int d, const double* X, const fl
     INTEL_REQUIRE(d <= 64, INTEL_ERR_UNSUPPORTED, "intent_emb_size %d > 64 not supported", d);
     unsigned grid = stream_grid(ceil_div(R, 8), 8);
     LAUNCH(dense_rows_bwd_kernel, dim3(grid), dim3(256), 0, s, R, I, d, X, dY, lddy, nz_idx, nz_val, nz_cnt, cap, dWt);
-    return check_launch("dense_rows_bwd");
+    return check_launch("dense_rows_bwd", (double)R * (4.0 * d + 4.0), 0.0);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -230,7 +230,7 @@ int score_embed_fwd(int64_t R, int K, int d, const double* scores, const float* 
     INTEL_REQUIRE(!xs || K <= d, INTEL_ERR_UNSUPPORTED, "score_embed: model_num %d > s_emb_size %d", K, d);
     unsigned grid = stream_grid(ceil_div(R * d, 256), 8);
     LAUNCH(score_embed_kernel, dim3(grid), dim3(256), 0, s, R, K, d, scores, W, b, Y, xs);
-    return check_launch("score_embed");
+    return check_launch("score_embed", (double)R * (8.0 * K + 4.0 * d + 4.0 * K), 2.0 * R * K * d);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(EV_WARPS * 32) rank_lists_kernel(int64_t B, in
                 const float u = x[j * K + k];
                 rank += (u < v) || (u == v && j < l);
             }
-            acc += wk * (float)rank;
+            acc = __fadd_rn(acc, __fmul_rn(wk, (float)rank));   // torch: (w * rank).sum(2), no fma contraction
         }
         ens[b * L + l] = acc;
     }
@@ -332,7 +332,7 @@ int intel_ndcg_topk(int64_t N, int64_t ld, const float* pred, const int64_t* ran
     double* partial = reinterpret_cast<double*>(workspace);
     LAUNCH(ndcg_kernel, dim3(grid), dim3(EV_WARPS * 32), smem, s, N, ld, pred, ranking, session_len, pay, fav, click,
            max_len, tk, partial);
-    INTEL_TRY(check_launch("ndcg"));
+    INTEL_TRY(check_launch("ndcg", (double)N * ld * 12.0, 0.0));
     // fixed-order (deterministic) reduction of the per-block partial rows
     LAUNCH(reduce_partials_kernel, dim3(1), dim3(256), 0, s, (int64_t)grid, ncols, n_topk * EV_OUT, partial, sums);
     INTEL_TRY(check_launch("ndcg_reduce"));

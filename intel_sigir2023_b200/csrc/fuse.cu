@@ -49,7 +49,7 @@ int head_fuse_fwd(int64_t B, int64_t L, int K, const float* w_valid, const float
     INTEL_REQUIRE(K <= FUSE_MAX_K, INTEL_ERR_UNSUPPORTED, "model_num %d > %d", K, FUSE_MAX_K);
     unsigned grid = stream_grid(ceil_div(B, 8), 8);
     LAUNCH(head_fuse_fwd_kernel, dim3(grid), dim3(256), 0, s, B, L, K, w_valid, w_pad, scores, lens, weights, ens);
-    return check_launch("head_fuse_fwd");
+    return check_launch("head_fuse_fwd", (double)B * L * (8.0 * K + 4.0 * K + 4.0), 2.0 * B * L * K);
 }
 
 __global__ void __launch_bounds__(256) head_fuse_bwd_kernel(int64_t B, int64_t L, int K,
@@ -94,7 +94,7 @@ int head_fuse_bwd(int64_t B, int64_t L, int K, const float* d_weights, const flo
     INTEL_REQUIRE(K <= FUSE_MAX_K, INTEL_ERR_UNSUPPORTED, "model_num %d > %d", K, FUSE_MAX_K);
     unsigned grid = stream_grid(ceil_div(B, 8), 8);
     LAUNCH(head_fuse_bwd_kernel, dim3(grid), dim3(256), 0, s, B, L, K, d_weights, d_ens, scores, lens, dw_valid, dw_pad);
-    return check_launch("head_fuse_bwd");
+    return check_launch("head_fuse_bwd", (double)B * L * (8.0 * K + 4.0 * K + 4.0), 2.0 * B * L * K);
 }
 
 // ---- per-item fusion: ens[r] = sum_k weights[r,k] * float(scores[r,k]) (fixed-weight baselines and

@@ -113,7 +113,8 @@ static int launch_tile(const GemmDev& d, bool at, bool bt, cudaStream_t s) {
     else if (!at && bt) { auto k = gemm_kernel<BM, BN, false, true>; LAUNCH(k, grid, block, 0, s, d); }
     else if (at && bt) { auto k = gemm_kernel<BM, BN, true, true>; LAUNCH(k, grid, block, 0, s, d); }
     else { auto k = gemm_kernel<BM, BN, true, false>; LAUNCH(k, grid, block, 0, s, d); }
-    return check_launch("gemm");
+    const double bytes = 4.0 * ((double)d.M * d.K + (double)d.N * d.K + (double)d.M * d.N * (1 + (d.add != nullptr) + (d.mask != nullptr)));
+    return check_launch(at ? "gemm_wgrad" : (bt ? "gemm_dgrad" : "gemm_fwd"), bytes, 2.0 * d.M * d.N * d.K);
 }
 
 int gemm(const Gemm& g, cudaStream_t s) {
@@ -210,7 +211,7 @@ int colsum(int64_t M, int64_t N, const float* X, int64_t ld, float* out, cudaStr
     row_blocks = ceil_div(M, rpb);
     dim3 grid((unsigned)col_blocks, (unsigned)row_blocks);
     LAUNCH(colsum_kernel, grid, dim3(256), 0, s, M, N, X, ld, out, rpb);
-    return check_launch("colsum");
+    return check_launch("colsum", 4.0 * M * N, (double)M * N);
 }
 
 }  // namespace intel

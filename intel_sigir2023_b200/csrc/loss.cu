@@ -292,7 +292,8 @@ static int launch_loss(int which, LossArgs a, cudaStream_t s) {
     } else {
         LAUNCH(loss_mse_kernel, grid, block, 0, s, a);
     }
-    return check_launch("loss");
+    return check_launch(which == 0 ? "loss_pl" : (which == 1 ? "loss_bpr" : "loss_mse"),
+                        (double)a.B * a.L * (4.0 + 8.0 + 4.0 + (a.cal_div ? 16.0 * a.K : 0.0)), 0.0);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -419,7 +420,7 @@ int intel_intent_loss_fwd_bwd(int64_t B, int64_t I, const float* pred, const dou
     unsigned g2 = stream_grid(ceil_div(B, 8), 8);
     LAUNCH(intent_loss_kernel, dim3(g2), dim3(256), 0, s, B, I, pred, true_intents, (float)kl_weight,
            (float)(kl_temp * kl_temp), (const int*)scratch, out, d_pred);
-    return check_launch("intent_loss");
+    return check_launch("intent_loss", (double)B * I * 16.0, 0.0);
 }
 
 int intel_scale_by_device_scalar(int64_t n, const float* x, const double* a, double ca, const double* b, double cb,

@@ -304,6 +304,8 @@ static inline float __fdividef(float a, float b) { return a / b; }
 static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 static inline float __frcp_rn(float x) { return 1.0f / x; }
 static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
+static inline float __fmul_rn(float a, float b) { return a * b; }
+static inline float __fadd_rn(float a, float b) { return a + b; }
 static inline float __saturatef(float x) { return x < 0 ? 0 : (x > 1 ? 1 : x); }
 static inline int __float_as_int(float f) { return emu::from_bits<int>(emu::to_bits(f)); }
 static inline unsigned __float_as_uint(float f) { return emu::from_bits<unsigned>(emu::to_bits(f)); }

@@ -1,0 +1,82 @@
+"""World-size-2 data-parallel path on CPU (gloo): session sharding + gradient all-reduce + sharded
+evaluation must reproduce the single-process result.  The compute runs through the product's host layer on
+the CUDA emulator build of the kernels (tests/emu), so the N>1 host logic is what is covered here."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.join(HERE, "emu"))
+
+
+def _setup_emu():
+    from build_emu import build_emu
+    from intel_sigir2023_b200 import _lib
+    _lib._lib = None
+    _lib.load(build_emu())
+    _lib._allow_host_tensors = True
+
+
+def _grads_and_metrics(rank, world, case):
+    import parity_checks as P
+    from conftest import load_model_case
+    from intel_sigir2023_b200 import dp, losses, synthetic
+    cfg, batch, state, gold = load_model_case(case)
+    B = batch["batch_size"]
+    keep = B - (B % 2)                      # equal shards
+    batch = {k: (v[:keep] if torch.is_tensor(v) else v) for k, v in batch.items()}
+    batch["batch_size"] = keep
+    shard = synthetic.shard_batch(batch, rank, world)
+    model = P.make_model(cfg, state, "cpu").train()
+    crit = losses.IntListloss(P.loss_args())
+    out = model(shard)
+    loss, _, _ = crit(out, shard)
+    loss.backward()
+    dp.GradReducer(model, world).allreduce()
+    pos = {k: shard[k] for k in ("c_paynum_i", "c_favnum_i", "c_clicknum_i")}
+    res = dp.evaluate_sharded(out["ens_score"].detach(), shard["ranking"], pos, shard["session_len"], [3, 1, 5], ["NDCG", "HR"])
+    return {n: p.grad.clone() for n, p in model.named_parameters()}, res
+
+
+def _worker(rank, world, port, case, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.set_num_threads(1)
+    _setup_emu()
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    grads, res = _grads_and_metrics(rank, world, case)
+    if rank == 0:
+        q.put(({k: v.numpy() for k, v in grads.items()}, res))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("case", ["script_bpr_gru_k4", "default_bert"])
+def test_two_rank_grads_match_single_process(case):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, case, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    grads2, res2 = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    _setup_emu()
+    try:
+        grads1, res1 = _grads_and_metrics(0, 1, case)
+    finally:
+        from intel_sigir2023_b200 import _lib
+        _lib._lib, _lib._allow_host_tensors = None, False
+    gmax = max(float(v.abs().max()) for v in grads1.values())
+    for k, g in grads1.items():
+        err = np.abs(g.numpy() - grads2[k]).max()
+        assert err <= 1e-4 * float(g.abs().max()) + 2e-6 * gmax, (k, err)
+    for k, v in res1.items():
+        assert (np.isnan(v) and np.isnan(res2[k])) or abs(v - res2[k]) < 1e-9, (k, v, res2[k])
