@@ -199,6 +199,17 @@ int intel_scatter_add_bwd(int64_t rows, int d, const float* d_out, int ld, const
 int intel_linear_fwd(int64_t M, int64_t N, int64_t K, const float* A, const float* W, const float* bias,
                      float* C, intel_stream_t stream);
 
+/* dX[M,K] = dY[M,N] * W[N,K] (optionally * (relu_mask[M,K] > 0));  dW[N,K] += dY^T X, db[N] += colsum(dY) */
+int intel_linear_dx(int64_t M, int64_t N, int64_t K, const float* dY, const float* W, float* dX, const float* relu_mask,
+                    intel_stream_t stream);
+int intel_linear_dw(int64_t M, int64_t N, int64_t K, const float* dY, const float* X, float* dW, float* db,
+                    intel_stream_t stream);
+/* layers.py MultiHeadAttention core on packed qkv [B,T,3d] -> out [B,T,d]; lens nullable (key mask) */
+int intel_mha_fwd(int64_t B, int64_t T, int d, int heads, const float* qkv, const int64_t* lens, float* out,
+                  intel_stream_t stream);
+int intel_mha_bwd(int64_t B, int64_t T, int d, int heads, const float* qkv, const int64_t* lens, const float* d_out,
+                  float* d_qkv, intel_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

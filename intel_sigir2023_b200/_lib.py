@@ -88,6 +88,10 @@ def _declare(lib: C.CDLL) -> None:
         "intel_gather_fwd": (i32, [i64, i32, _p, _p, _p, i32, i32, _p]),
         "intel_scatter_add_bwd": (i32, [i64, i32, _p, i32, _p, _p, _p]),
         "intel_linear_fwd": (i32, [i64, i64, i64, _p, _p, _p, _p, _p]),
+        "intel_linear_dx": (i32, [i64, i64, i64, _p, _p, _p, _p, _p]),
+        "intel_linear_dw": (i32, [i64, i64, i64, _p, _p, _p, _p, _p]),
+        "intel_mha_fwd": (i32, [i64, i64, i32, i32, _p, _p, _p, _p]),
+        "intel_mha_bwd": (i32, [i64, i64, i32, i32, _p, _p, _p, _p, _p]),
         "intel_profile_enable": (i32, [i32]),
         "intel_profile_report": (i32, [C.c_char_p, sz]),
     }
@@ -103,7 +107,8 @@ EXPORTED = ["intel_last_error", "intel_abi_version", "intel_intent_workspace_byt
             "intel_scale_by_device_scalar", "intel_ndcg_workspace_bytes", "intel_ndcg_topk",
             "intel_intent_topk_workspace_bytes", "intel_intent_topk", "intel_fuse_fwd", "intel_select_list",
             "intel_rank_lists", "intel_gather_fwd", "intel_scatter_add_bwd", "intel_linear_fwd",
-            "intel_profile_enable", "intel_profile_report"]
+            "intel_profile_enable", "intel_profile_report", "intel_linear_dx", "intel_linear_dw", "intel_mha_fwd",
+            "intel_mha_bwd"]
 
 
 def load(path: Optional[str] = None) -> C.CDLL:

@@ -119,4 +119,24 @@ int intel_linear_fwd(int64_t M, int64_t N, int64_t K, const float* A, const floa
     return linear(M, N, K, A, K, W, K, bias, C, N, (cudaStream_t)stream);
 }
 
+int intel_linear_dx(int64_t M, int64_t N, int64_t K, const float* dY, const float* W, float* dX, const float* relu_mask,
+                    intel_stream_t stream) {
+    return linear_dx(M, N, K, dY, N, W, K, dX, K, (cudaStream_t)stream, 0, relu_mask, K);
+}
+
+int intel_linear_dw(int64_t M, int64_t N, int64_t K, const float* dY, const float* X, float* dW, float* db,
+                    intel_stream_t stream) {
+    return linear_dw(M, N, K, dY, N, X, K, dW, K, db, (cudaStream_t)stream, false);
+}
+
+int intel_mha_fwd(int64_t B, int64_t T, int d, int heads, const float* qkv, const int64_t* lens, float* out,
+                  intel_stream_t stream) {
+    return mha_fwd(B, T, d, heads, qkv, lens, out, (cudaStream_t)stream);
+}
+
+int intel_mha_bwd(int64_t B, int64_t T, int d, int heads, const float* qkv, const int64_t* lens, const float* d_out,
+                  float* d_qkv, intel_stream_t stream) {
+    return mha_bwd(B, T, d, heads, qkv, lens, d_out, d_qkv, (cudaStream_t)stream);
+}
+
 }  // extern "C"

@@ -280,9 +280,13 @@ int gru_fwd(const intel_dims_t* d, const intel_encoder_t& p, EncWs& e, const int
     GruWs& w = e.gru;
     INTEL_TRY(linear(R, 3 * h, dd, e.seq, dd, p.w_ih, dd, p.b_ih, w.gi, 3 * h, s));
     INTEL_TRY(fill_zero(w.h_all, (size_t)B * (T + 1) * h * 4, s));
-    for (int64_t t = 0; t < T; ++t) {
-        INTEL_TRY(linear(B, 3 * h, h, w.h_all + t * h, (T + 1) * h, p.w_hh, h, p.b_hh, w.gh, 3 * h, s));
-        INTEL_TRY(gru_step_fwd(B, T, h, (int)t, lens, w.gi, w.gh, w.h_all, w.gates, s));
+    if (h == 128) {
+        INTEL_TRY(gru_seq_fwd(B, T, h, lens, w.gi, p.w_hh, p.b_hh, w.h_all, w.gates, s));
+    } else {
+        for (int64_t t = 0; t < T; ++t) {
+            INTEL_TRY(linear(B, 3 * h, h, w.h_all + t * h, (T + 1) * h, p.w_hh, h, p.b_hh, w.gh, 3 * h, s));
+            INTEL_TRY(gru_step_fwd(B, T, h, (int)t, lens, w.gi, w.gh, w.h_all, w.gates, s));
+        }
     }
     return linear(B, dd, h, w.h_all + T * h, (T + 1) * h, p.w_out, h, nullptr, out, ld_out, s);
 }
@@ -295,9 +299,13 @@ int gru_bwd(const intel_dims_t* d, const intel_encoder_t& p, intel_encoder_t& g,
     INTEL_TRY(linear_dw(B, dd, h, dout, ld, w.h_all + T * h, (T + 1) * h, g.w_out, h, nullptr, s));
     INTEL_TRY(linear_dx(B, dd, h, dout, ld, p.w_out, h, w.dh, h, s));
     INTEL_TRY(fill_zero(w.dgh_all, (size_t)B * (T + 1) * 3 * h * 4, s));
-    for (int64_t t = T - 1; t >= 0; --t) {
-        INTEL_TRY(gru_step_bwd(B, T, h, (int)t, lens, w.h_all, w.gates, w.dh, w.dgi, w.dgh_all, s));
-        INTEL_TRY(linear_dx(B, 3 * h, h, w.dgh_all + t * 3 * h, (T + 1) * 3 * h, p.w_hh, h, w.dh, h, s, 1));
+    if (h == 128) {
+        INTEL_TRY(gru_seq_bwd(B, T, h, lens, p.w_hh, w.h_all, w.gates, w.dh, w.dgi, w.dgh_all, s));
+    } else {
+        for (int64_t t = T - 1; t >= 0; --t) {
+            INTEL_TRY(gru_step_bwd(B, T, h, (int)t, lens, w.h_all, w.gates, w.dh, w.dgi, w.dgh_all, s));
+            INTEL_TRY(linear_dx(B, 3 * h, h, w.dgh_all + t * 3 * h, (T + 1) * 3 * h, p.w_hh, h, w.dh, h, s, 1));
+        }
     }
     INTEL_TRY(linear_dw(B * (T + 1), 3 * h, h, w.dgh_all, 3 * h, w.h_all, h, g.w_hh, h, g.b_hh, s));
     INTEL_TRY(linear_dw(R, 3 * h, dd, w.dgi, 3 * h, e.seq, dd, g.w_ih, dd, g.b_ih, s));

@@ -111,194 +111,6 @@ int layernorm_bwd(int64_t R, int d, const float* dY, const float* Z, const float
 }
 
 // ------------------------------------------------------------------------------------------------
-// Multi-head attention, one CTA per (session, head).  K and V tiles of the head live in shared memory
-// (row stride dk+1: conflict-free both for lane-per-key and lane-per-channel access); each warp owns a
-// query at a time.  The reference's shift by the *global* max of the score tensor (layers.py:57) is a
-// pure numerics choice; the row max is used instead (softmax is shift invariant).
-static const int MHA_WARPS = 4;
-
-__global__ void __launch_bounds__(MHA_WARPS * 32) mha_fwd_kernel(int64_t T, int d, int heads,
-                                                                 const float* __restrict__ QKV,
-                                                                 const int64_t* __restrict__ lens,
-                                                                 float* __restrict__ O) {
-    DYN_SMEM(float, sm);
-    const int dk = d / heads, st = dk + 1;
-    const int64_t b = blockIdx.x / heads;
-    const int h = blockIdx.x % heads;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    int64_t nk = lens ? lens[b] : T;
-    if (nk > T) nk = T;
-    float* Ks = sm;
-    float* Vs = Ks + T * st;
-    float* qb = Vs + T * st + w * dk;              // [MHA_WARPS][dk]
-    float* pb = Vs + T * st + MHA_WARPS * dk + w * T;   // [MHA_WARPS][T]
-    const float* base = QKV + b * T * 3 * d + h * dk;
-    for (int64_t e = threadIdx.x; e < nk * dk; e += blockDim.x) {
-        const int64_t j = e / dk;
-        const int c = (int)(e % dk);
-        Ks[j * st + c] = base[j * 3 * d + d + c];
-        Vs[j * st + c] = base[j * 3 * d + 2 * d + c];
-    }
-    __syncthreads();
-    const float scale = 1.0f / sqrtf((float)dk);
-    for (int64_t i = w; i < T; i += MHA_WARPS) {
-        for (int c = lane; c < dk; c += 32) qb[c] = base[i * 3 * d + c];
-        __syncwarp();
-        float mx = -INFINITY;
-        for (int64_t j = lane; j < nk; j += 32) {
-            float sdot = 0.f;
-            for (int c = 0; c < dk; ++c) sdot = fmaf(qb[c], Ks[j * st + c], sdot);
-            sdot *= scale;
-            pb[j] = sdot;
-            mx = fmaxf(mx, sdot);
-        }
-        mx = warp_max(mx);
-        float sum = 0.f;
-        for (int64_t j = lane; j < nk; j += 32) {
-            const float e = expf(pb[j] - mx);
-            pb[j] = e;
-            sum += e;
-        }
-        sum = warp_sum(sum);
-        const float inv = (nk > 0) ? 1.0f / sum : 0.f;
-        __syncwarp();
-        for (int c = lane; c < dk; c += 32) {
-            float acc = 0.f;
-            for (int64_t j = 0; j < nk; ++j) acc = fmaf(pb[j], Vs[j * st + c], acc);
-            O[(b * T + i) * d + h * dk + c] = acc * inv;
-        }
-        __syncwarp();
-    }
-}
-
-static size_t mha_fwd_smem(int64_t T, int dk) { return (size_t)(2 * T * (dk + 1) + MHA_WARPS * dk + MHA_WARPS * T) * 4; }
-static size_t mha_bwd_smem(int64_t T, int dk) { return (size_t)(4 * T * (dk + 1) + 3 * T + 2 * MHA_WARPS * T) * 4; }
-static const size_t kMaxSmem = 200 * 1024;
-
-int mha_fwd(int64_t B, int64_t T, int d, int heads, const float* QKV, const int64_t* lens, float* O, cudaStream_t s) {
-    if (B <= 0 || T <= 0) return INTEL_OK;
-    INTEL_REQUIRE(heads > 0 && d % heads == 0, INTEL_ERR_ARG, "mha: d=%d not divisible by heads=%d", d, heads);
-    const size_t smem = mha_fwd_smem(T, d / heads);
-    INTEL_REQUIRE(smem <= kMaxSmem, INTEL_ERR_UNSUPPORTED, "mha_fwd: list length %lld too long for one SM", (long long)T);
-    if (smem > 48 * 1024) cudaFuncSetAttribute(mha_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    LAUNCH(mha_fwd_kernel, dim3((unsigned)(B * heads)), dim3(MHA_WARPS * 32), smem, s, T, d, heads, QKV, lens, O);
-    return check_launch("mha_fwd", 16.0 * B * T * d, 4.0 * B * T * T * d);
-}
-
-// Backward by recomputation.  Phase A (warp per query): softmax statistics (m, l), delta = sum_j p dP,
-// and dQ.  Phase B (warp per key): p and dS are recomputed from the statistics -> dK, dV.  No atomics.
-__global__ void __launch_bounds__(MHA_WARPS * 32) mha_bwd_kernel(int64_t T, int d, int heads,
-                                                                 const float* __restrict__ QKV,
-                                                                 const int64_t* __restrict__ lens,
-                                                                 const float* __restrict__ dO,
-                                                                 float* __restrict__ dQKV) {
-    DYN_SMEM(float, sm);
-    const int dk = d / heads, st = dk + 1;
-    const int64_t b = blockIdx.x / heads;
-    const int h = blockIdx.x % heads;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    int64_t nk = lens ? lens[b] : T;
-    if (nk > T) nk = T;
-    float* Qs = sm;
-    float* Ks = Qs + T * st;
-    float* Vs = Ks + T * st;
-    float* Gs = Vs + T * st;               // dO tile
-    float* sm_m = Gs + T * st;             // [T] row max
-    float* sm_l = sm_m + T;                // [T] row sum
-    float* sm_d = sm_l + T;                // [T] delta
-    float* pb = sm_d + T + w * T;          // [MHA_WARPS][T]
-    float* db = sm_d + T + MHA_WARPS * T + w * T;   // [MHA_WARPS][T]
-    const float* base = QKV + b * T * 3 * d + h * dk;
-    float* dbase = dQKV + b * T * 3 * d + h * dk;
-    for (int64_t e = threadIdx.x; e < T * dk; e += blockDim.x) {
-        const int64_t j = e / dk;
-        const int c = (int)(e % dk);
-        Qs[j * st + c] = base[j * 3 * d + c];
-        Ks[j * st + c] = base[j * 3 * d + d + c];
-        Vs[j * st + c] = base[j * 3 * d + 2 * d + c];
-        Gs[j * st + c] = dO[(b * T + j) * d + h * dk + c];
-    }
-    __syncthreads();
-    const float scale = 1.0f / sqrtf((float)dk);
-    // ---- phase A: per query ----
-    for (int64_t i = w; i < T; i += MHA_WARPS) {
-        float mx = -INFINITY;
-        for (int64_t j = lane; j < nk; j += 32) {
-            float sdot = 0.f, gdot = 0.f;
-            for (int c = 0; c < dk; ++c) {
-                sdot = fmaf(Qs[i * st + c], Ks[j * st + c], sdot);
-                gdot = fmaf(Gs[i * st + c], Vs[j * st + c], gdot);
-            }
-            sdot *= scale;
-            pb[j] = sdot;
-            db[j] = gdot;
-            mx = fmaxf(mx, sdot);
-        }
-        mx = warp_max(mx);
-        float sum = 0.f;
-        for (int64_t j = lane; j < nk; j += 32) {
-            const float e = expf(pb[j] - mx);
-            pb[j] = e;
-            sum += e;
-        }
-        sum = warp_sum(sum);
-        const float inv = (nk > 0) ? 1.0f / sum : 0.f;
-        float delta = 0.f;
-        for (int64_t j = lane; j < nk; j += 32) delta = fmaf(pb[j] * inv, db[j], delta);
-        delta = warp_sum(delta);
-        for (int64_t j = lane; j < nk; j += 32) db[j] = pb[j] * inv * (db[j] - delta) * scale;   // dS
-        if (lane == 0) { sm_m[i] = mx; sm_l[i] = inv; sm_d[i] = delta; }
-        __syncwarp();
-        for (int c = lane; c < dk; c += 32) {
-            float acc = 0.f;
-            for (int64_t j = 0; j < nk; ++j) acc = fmaf(db[j], Ks[j * st + c], acc);
-            dbase[i * 3 * d + c] = acc;
-        }
-        __syncwarp();
-    }
-    __syncthreads();
-    // ---- phase B: per key ----
-    for (int64_t j = w; j < T; j += MHA_WARPS) {
-        if (j >= nk) {   // masked key: no gradient
-            for (int c = lane; c < dk; c += 32) { dbase[j * 3 * d + d + c] = 0.f; dbase[j * 3 * d + 2 * d + c] = 0.f; }
-            continue;
-        }
-        for (int64_t i = lane; i < T; i += 32) {
-            float sdot = 0.f, gdot = 0.f;
-            for (int c = 0; c < dk; ++c) {
-                sdot = fmaf(Qs[i * st + c], Ks[j * st + c], sdot);
-                gdot = fmaf(Gs[i * st + c], Vs[j * st + c], gdot);
-            }
-            const float p = expf(sdot * scale - sm_m[i]) * sm_l[i];
-            pb[i] = p;
-            db[i] = p * (gdot - sm_d[i]) * scale;
-        }
-        __syncwarp();
-        for (int c = lane; c < dk; c += 32) {
-            float ak = 0.f, av = 0.f;
-            for (int64_t i = 0; i < T; ++i) {
-                ak = fmaf(db[i], Qs[i * st + c], ak);
-                av = fmaf(pb[i], Gs[i * st + c], av);
-            }
-            dbase[j * 3 * d + d + c] = ak;
-            dbase[j * 3 * d + 2 * d + c] = av;
-        }
-        __syncwarp();
-    }
-}
-
-int mha_bwd(int64_t B, int64_t T, int d, int heads, const float* QKV, const int64_t* lens, const float* dO, float* dQKV,
-            cudaStream_t s) {
-    if (B <= 0 || T <= 0) return INTEL_OK;
-    INTEL_REQUIRE(heads > 0 && d % heads == 0, INTEL_ERR_ARG, "mha: d=%d not divisible by heads=%d", d, heads);
-    const size_t smem = mha_bwd_smem(T, d / heads);
-    INTEL_REQUIRE(smem <= kMaxSmem, INTEL_ERR_UNSUPPORTED, "mha_bwd: list length %lld too long for one SM", (long long)T);
-    if (smem > 48 * 1024) cudaFuncSetAttribute(mha_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    LAUNCH(mha_bwd_kernel, dim3((unsigned)(B * heads)), dim3(MHA_WARPS * 32), smem, s, T, d, heads, QKV, lens, dO, dQKV);
-    return check_launch("mha_bwd", 28.0 * B * T * d, 16.0 * B * T * T * d);
-}
-
-// ------------------------------------------------------------------------------------------------
 // Pooled cross attention: one warp per session.  The reference broadcasts one [1,L] attention row
 // against the [L,L] pair mask (attention.py:57-60 via IntEL.py:201-204), so all valid rows of a
 // session share one pooled vector; pad rows get 0.  qk = W_k^T q and the value projection are applied

@@ -1,9 +1,14 @@
-// fp32 FFMA tiled GEMM for the dense contractions of the IntEL path (nn.Linear forward,
-// input gradients and weight gradients).  fp32 parity (1e-5) rules out plain TF32/BF16
-// tensor-core math, and every contraction here has a tiny inner
-// dimension (32..384) or a tiny output, so the kernel is a register-tiled FFMA GEMM:
-// 256 threads, BK = 16, each thread owns a (BM/16) x (BN/16) accumulator tile.
+// Tensor-core GEMM for the dense contractions of the IntEL path (nn.Linear forward, input gradients,
+// weight gradients).  fp32 parity (1e-5) rules out plain TF32/BF16 math, so every
+// product is formed as three m16n8k8 TF32 MMAs on hi/lo splits of the fp32 operands (mma.cuh); the first
+// FFMA version of this kernel was instruction-issue bound at 32 % FMA-pipe utilisation
+// (profiles/r01_summary.md) - the MMA form issues ~5x fewer instructions per MAC.
+//
+// All shapes here have a tiny inner dimension (32..384, 1071 at most) or a tiny output, so tiles are
+// 128 x {32,64} x 32 with register-staged prefetch of the next k-tile; operands may be stored k-major or
+// row-major (the three nn.Linear passes), selected at compile time.
 #include "kernels.h"
+#include "mma.cuh"
 
 namespace intel {
 
@@ -15,107 +20,415 @@ struct GemmDev {
     const float* bias;
     const float* add; int64_t ldadd;
     const float* mask; int64_t ldmask;
-    int relu_a, relu_b, relu_out, accumulate, splits;
+    int relu_a, relu_b, relu_out, accumulate, splits, vec_a, vec_b;
     int64_t kchunk;
 };
 
-static const int BK = 16;
+static const int BK = 32;
 
-template <int BM, int BN, bool AT, bool BT>
-__global__ void __launch_bounds__(256) gemm_kernel(GemmDev g) {
-    constexpr int TM = BM / 16, TN = BN / 16;
-    constexpr int SA = BM + 4, SB = BN + 4;
-    __shared__ float As[BK * SA];
-    __shared__ float Bs[BK * SB];
-    const int tid = threadIdx.x;
-    const int ty = tid >> 4, tx = tid & 15;
-    const int64_t m0 = (int64_t)blockIdx.x * BM;
-    const int64_t n0 = (int64_t)blockIdx.y * BN;
+// Global -> register staging of one operand tile.  TR = operand stored [K][rows] (rows contiguous),
+// otherwise [rows][K] (k contiguous).  Each thread owns NV float4 chunks.
+template <int ROWS, int NT, bool TR>
+struct TileLoader {
+    static constexpr int CH = ROWS * BK / 4;                 // float4 chunks per tile
+    static constexpr int NV = (CH + NT - 1) / NT;
+    static constexpr int LD = TR ? ROWS + 8 : BK + 4;       // shared-memory leading dimension
+    float4 v[NV];
+
+    __device__ __forceinline__ void load(const float* __restrict__ P, int64_t ld, int64_t r0, int64_t rmax, int64_t k0,
+                                         int64_t kend, int vec, int relu, int tid) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int e = tid + i * NT;
+            float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (e < CH) {
+                if (TR) {
+                    const int kk = e / (ROWS / 4), r4 = (e % (ROWS / 4)) * 4;
+                    const int64_t gk = k0 + kk, gr = r0 + r4;
+                    if (gk < kend) {
+                        const float* p = P + gk * ld + gr;
+                        if (vec && gr + 3 < rmax) x = *reinterpret_cast<const float4*>(p);
+                        else {
+                            if (gr < rmax) x.x = p[0];
+                            if (gr + 1 < rmax) x.y = p[1];
+                            if (gr + 2 < rmax) x.z = p[2];
+                            if (gr + 3 < rmax) x.w = p[3];
+                        }
+                    }
+                } else {
+                    const int rr = e / (BK / 4), k4 = (e % (BK / 4)) * 4;
+                    const int64_t gr = r0 + rr, gk = k0 + k4;
+                    if (gr < rmax) {
+                        const float* p = P + gr * ld + gk;
+                        if (vec && gk + 3 < kend) x = *reinterpret_cast<const float4*>(p);
+                        else {
+                            if (gk < kend) x.x = p[0];
+                            if (gk + 1 < kend) x.y = p[1];
+                            if (gk + 2 < kend) x.z = p[2];
+                            if (gk + 3 < kend) x.w = p[3];
+                        }
+                    }
+                }
+                if (relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+            }
+            v[i] = x;
+        }
+    }
+    __device__ __forceinline__ void store(float* s, int tid) const {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int e = tid + i * NT;
+            if (e < CH) {
+                if (TR) {
+                    const int kk = e / (ROWS / 4), r4 = (e % (ROWS / 4)) * 4;
+                    *reinterpret_cast<float4*>(s + kk * LD + r4) = v[i];
+                } else {
+                    const int rr = e / (BK / 4), k4 = (e % (BK / 4)) * 4;
+                    *reinterpret_cast<float4*>(s + rr * LD + k4) = v[i];
+                }
+            }
+        }
+    }
+};
+
+// element (row r, k) of a staged tile
+template <bool TR, int LD>
+__device__ __forceinline__ float tile_at(const float* s, int r, int k) { return TR ? s[k * LD + r] : s[r * LD + k]; }
+
+__device__ __forceinline__ void gemm_store(const GemmDev& g, int64_t gm, int64_t gn, float v, bool first) {
+    if (gm >= g.M || gn >= g.N) return;
+    if (first) {
+        if (g.bias) v += g.bias[gn];
+        if (g.add) v += g.add[gm * g.ldadd + gn];
+    }
+    if (g.relu_out) v = fmaxf(v, 0.f);
+    if (g.mask) v = (g.mask[gm * g.ldmask + gn] > 0.f) ? v : 0.f;
+    float* c = g.C + gm * g.ldc + gn;
+    if (g.accumulate == 0) *c = v;
+    else if (g.accumulate == 1) *c += v;
+    else atomicAdd(c, v);
+}
+
+template <int BM, int BN, int WM, int WN, bool AT, bool BT>
+__global__ void __launch_bounds__(WM * WN * 32) gemm_tc_kernel(GemmDev g) {
+    constexpr int NT = WM * WN * 32;
+    constexpr int TM = BM / WM / 16, TN = BN / WN / 8;
+    using LA = TileLoader<BM, NT, AT>;
+    using LB = TileLoader<BN, NT, BT>;
+    constexpr int SA = LA::LD, SB = LB::LD;
+    __shared__ __align__(16) float sA[AT ? BK * SA : BM * SA];
+    __shared__ __align__(16) float sB[BT ? BK * SB : BN * SB];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp / WN, wn = warp % WN;
+    const int gq = lane >> 2, tq = lane & 3;
+    const int64_t m0 = (int64_t)blockIdx.x * BM, n0 = (int64_t)blockIdx.y * BN;
     const int64_t kbeg = (int64_t)blockIdx.z * g.kchunk;
     const int64_t kend = (kbeg + g.kchunk < g.K) ? kbeg + g.kchunk : g.K;
 
-    float acc[TM][TN];
+    float acc[TM][TN][4];
 #pragma unroll
     for (int i = 0; i < TM; ++i)
 #pragma unroll
-        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+        for (int j = 0; j < TN; ++j)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[i][j][c] = 0.f;
 
+    LA la;
+    LB lb;
+    if (kbeg < kend) {
+        la.load(g.A, g.lda, m0, g.M, kbeg, kend, g.vec_a, g.relu_a, tid);
+        lb.load(g.B, g.ldb, n0, g.N, kbeg, kend, g.vec_b, g.relu_b, tid);
+    }
     for (int64_t k0 = kbeg; k0 < kend; k0 += BK) {
-        // ---- stage the A tile: As[kk][mm] ----
-#pragma unroll
-        for (int p = 0; p < (BM * BK) / 256; ++p) {
-            int e = tid + p * 256;
-            int kk, mm;
-            if (AT) { mm = e % BM; kk = e / BM; } else { kk = e % BK; mm = e / BK; }
-            int64_t gm = m0 + mm, gk = k0 + kk;
-            float v = 0.f;
-            if (gm < g.M && gk < kend) v = AT ? g.A[gk * g.lda + gm] : g.A[gm * g.lda + gk];
-            if (g.relu_a) v = fmaxf(v, 0.f);
-            As[kk * SA + mm] = v;
-        }
-        // ---- stage the B tile: Bs[kk][nn] ----
-#pragma unroll
-        for (int p = 0; p < (BN * BK) / 256; ++p) {
-            int e = tid + p * 256;
-            int kk, nn;
-            if (BT) { nn = e % BN; kk = e / BN; } else { kk = e % BK; nn = e / BK; }
-            int64_t gn = n0 + nn, gk = k0 + kk;
-            float v = 0.f;
-            if (gn < g.N && gk < kend) v = BT ? g.B[gk * g.ldb + gn] : g.B[gn * g.ldb + gk];
-            if (g.relu_b) v = fmaxf(v, 0.f);
-            Bs[kk * SB + nn] = v;
-        }
+        la.store(sA, tid);
+        lb.store(sB, tid);
         __syncthreads();
+        if (k0 + BK < kend) {     // prefetch the next k-tile into registers while this one is consumed
+            la.load(g.A, g.lda, m0, g.M, k0 + BK, kend, g.vec_a, g.relu_a, tid);
+            lb.load(g.B, g.ldb, n0, g.N, k0 + BK, kend, g.vec_b, g.relu_b, tid);
+        }
 #pragma unroll
-        for (int kk = 0; kk < BK; ++kk) {
-            float a[TM], b[TN];
+        for (int ks = 0; ks < BK / 8; ++ks) {
+            const int kb = ks * 8;
+            float af[TM][4], bf[TN][2];
 #pragma unroll
-            for (int i = 0; i < TM; ++i) a[i] = As[kk * SA + ty * TM + i];
+            for (int i = 0; i < TM; ++i) {
+                const int r = wm * (BM / WM) + i * 16 + gq;
+                af[i][0] = tile_at<AT, SA>(sA, r, kb + tq);
+                af[i][1] = tile_at<AT, SA>(sA, r + 8, kb + tq);
+                af[i][2] = tile_at<AT, SA>(sA, r, kb + tq + 4);
+                af[i][3] = tile_at<AT, SA>(sA, r + 8, kb + tq + 4);
+            }
 #pragma unroll
-            for (int j = 0; j < TN; ++j) b[j] = Bs[kk * SB + tx * TN + j];
+            for (int j = 0; j < TN; ++j) {
+                const int c = wn * (BN / WN) + j * 8 + gq;
+                bf[j][0] = tile_at<BT, SB>(sB, c, kb + tq);
+                bf[j][1] = tile_at<BT, SB>(sB, c, kb + tq + 4);
+            }
+            uint32_t ah[TM][4], al[TM][4], bh[TN][2], bl[TN][2];
 #pragma unroll
             for (int i = 0; i < TM; ++i)
 #pragma unroll
-                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+                for (int c = 0; c < 4; ++c) {
+                    ah[i][c] = to_tf32(af[i][c]);
+                    al[i][c] = to_tf32(af[i][c] - __uint_as_float(ah[i][c]));
+                }
+#pragma unroll
+            for (int j = 0; j < TN; ++j)
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    bh[j][c] = to_tf32(bf[j][c]);
+                    bl[j][c] = to_tf32(bf[j][c] - __uint_as_float(bh[j][c]));
+                }
+            // three passes over independent accumulators: no back-to-back dependent MMAs
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) mma_tf32(acc[i][j], al[i], bh[j]);
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) mma_tf32(acc[i][j], ah[i], bl[j]);
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) mma_tf32(acc[i][j], ah[i], bh[j]);
         }
         __syncthreads();
     }
 
     const bool first = (blockIdx.z == 0);
 #pragma unroll
-    for (int i = 0; i < TM; ++i) {
-        int64_t gm = m0 + ty * TM + i;
-        if (gm >= g.M) continue;
+    for (int i = 0; i < TM; ++i)
 #pragma unroll
         for (int j = 0; j < TN; ++j) {
-            int64_t gn = n0 + tx * TN + j;
-            if (gn >= g.N) continue;
-            float v = acc[i][j];
-            if (first) {
-                if (g.bias) v += g.bias[gn];
-                if (g.add) v += g.add[gm * g.ldadd + gn];
-            }
-            if (g.relu_out) v = fmaxf(v, 0.f);
-            if (g.mask) v = (g.mask[gm * g.ldmask + gn] > 0.f) ? v : 0.f;
-            float* c = g.C + gm * g.ldc + gn;
-            if (g.accumulate == 0) *c = v;
-            else if (g.accumulate == 1) *c += v;
-            else atomicAdd(c, v);
+            const int64_t gm = m0 + wm * (BM / WM) + i * 16 + gq;
+            const int64_t gn = n0 + wn * (BN / WN) + j * 8 + 2 * tq;
+            gemm_store(g, gm, gn, acc[i][j][0], first);
+            gemm_store(g, gm, gn + 1, acc[i][j][1], first);
+            gemm_store(g, gm + 8, gn, acc[i][j][2], first);
+            gemm_store(g, gm + 8, gn + 1, acc[i][j][3], first);
         }
+}
+
+// Weight-gradient shape: small output tile (32x32 per CTA), very long inner dimension.  The eight warps
+// of a CTA take different k-slices of each staged tile (split-K inside the CTA), partial tiles are summed
+// through shared memory, one atomicAdd per output element and CTA.  A stored [K][M], B stored [K][N].
+static const int WG_WARPS = 8, WG_BK = 16 * WG_WARPS;
+__global__ void __launch_bounds__(WG_WARPS * 32) gemm_wgrad_kernel(GemmDev g) {
+    constexpr int LD = 32 + 8;
+    __shared__ __align__(16) float sA[WG_BK * LD];
+    __shared__ __align__(16) float sB[WG_BK * LD];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int gq = lane >> 2, tq = lane & 3;
+    const int64_t m0 = (int64_t)blockIdx.x * 32, n0 = (int64_t)blockIdx.y * 32;
+    const int64_t kbeg = (int64_t)blockIdx.z * g.kchunk;
+    const int64_t kend = (kbeg + g.kchunk < g.K) ? kbeg + g.kchunk : g.K;
+    float acc[2][4][4];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[i][j][c] = 0.f;
+
+    float4 px[4], py[4];
+    auto fetch = [&](int64_t k0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int e = tid + i * (WG_WARPS * 32);
+            const int kk = e >> 3, r4 = (e & 7) * 4;
+            const int64_t gk = k0 + kk;
+            float4 x = make_float4(0.f, 0.f, 0.f, 0.f), y = x;
+            if (gk < kend) {
+                const float* pa = g.A + gk * g.lda + m0 + r4;
+                const float* pb = g.B + gk * g.ldb + n0 + r4;
+                if (g.vec_a && m0 + r4 + 3 < g.M) x = *reinterpret_cast<const float4*>(pa);
+                else {
+                    if (m0 + r4 < g.M) x.x = pa[0];
+                    if (m0 + r4 + 1 < g.M) x.y = pa[1];
+                    if (m0 + r4 + 2 < g.M) x.z = pa[2];
+                    if (m0 + r4 + 3 < g.M) x.w = pa[3];
+                }
+                if (g.vec_b && n0 + r4 + 3 < g.N) y = *reinterpret_cast<const float4*>(pb);
+                else {
+                    if (n0 + r4 < g.N) y.x = pb[0];
+                    if (n0 + r4 + 1 < g.N) y.y = pb[1];
+                    if (n0 + r4 + 2 < g.N) y.z = pb[2];
+                    if (n0 + r4 + 3 < g.N) y.w = pb[3];
+                }
+                if (g.relu_a) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+                if (g.relu_b) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
+            }
+            px[i] = x;
+            py[i] = y;
+        }
+    };
+    if (kbeg < kend) fetch(kbeg);
+    for (int64_t k0 = kbeg; k0 < kend; k0 += WG_BK) {
+        // stage [WG_BK][32] of both operands: 8 float4 per k-row, 4 chunks per thread and operand
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int e = tid + i * (WG_WARPS * 32);
+            const int kk = e >> 3, r4 = (e & 7) * 4;
+            *reinterpret_cast<float4*>(sA + kk * LD + r4) = px[i];
+            *reinterpret_cast<float4*>(sB + kk * LD + r4) = py[i];
+        }
+        __syncthreads();
+        if (k0 + WG_BK < kend) fetch(k0 + WG_BK);     // next tile in flight while this one is consumed
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+            const int kb = warp * 16 + ks * 8;
+            float af[2][4], bf[4][2];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int r = i * 16 + gq;
+                af[i][0] = sA[(kb + tq) * LD + r];
+                af[i][1] = sA[(kb + tq) * LD + r + 8];
+                af[i][2] = sA[(kb + tq + 4) * LD + r];
+                af[i][3] = sA[(kb + tq + 4) * LD + r + 8];
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int c = j * 8 + gq;
+                bf[j][0] = sB[(kb + tq) * LD + c];
+                bf[j][1] = sB[(kb + tq + 4) * LD + c];
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) mma_3xtf32(acc[i][j], af[i], bf[j]);
+        }
+        __syncthreads();
+    }
+    // cross-warp reduction through shared memory (8 partial 32x32 tiles fit in the staging buffers)
+    float* red = (warp < 4) ? sA + warp * 1024 : sB + (warp - 4) * 1024;
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int r = i * 16 + gq, c = j * 8 + 2 * tq;
+            red[r * 32 + c] = acc[i][j][0];
+            red[r * 32 + c + 1] = acc[i][j][1];
+            red[(r + 8) * 32 + c] = acc[i][j][2];
+            red[(r + 8) * 32 + c + 1] = acc[i][j][3];
+        }
+    __syncthreads();
+    const bool first = (blockIdx.z == 0);
+    for (int e = tid; e < 1024; e += WG_WARPS * 32) {
+        float v = 0.f;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) v += sA[w * 1024 + e] + sB[w * 1024 + e];
+        gemm_store(g, m0 + (e >> 5), n0 + (e & 31), v, first);
     }
 }
 
-template <int BM, int BN>
-static int launch_tile(const GemmDev& d, bool at, bool bt, cudaStream_t s) {
-    dim3 grid((unsigned)ceil_div(d.M, BM), (unsigned)ceil_div(d.N, BN), (unsigned)d.splits);
-    dim3 block(256);
-    if (!at && !bt) { auto k = gemm_kernel<BM, BN, false, false>; LAUNCH(k, grid, block, 0, s, d); }
-    else if (!at && bt) { auto k = gemm_kernel<BM, BN, false, true>; LAUNCH(k, grid, block, 0, s, d); }
-    else if (at && bt) { auto k = gemm_kernel<BM, BN, true, true>; LAUNCH(k, grid, block, 0, s, d); }
-    else { auto k = gemm_kernel<BM, BN, true, false>; LAUNCH(k, grid, block, 0, s, d); }
-    const double bytes = 4.0 * ((double)d.M * d.K + (double)d.N * d.K + (double)d.M * d.N * (1 + (d.add != nullptr) + (d.mask != nullptr)));
-    return check_launch(at ? "gemm_wgrad" : (bt ? "gemm_dgrad" : "gemm_fwd"), bytes, 2.0 * d.M * d.N * d.K);
+// Streaming form for the dominant shape of the two self-attention stacks: a very tall A[M,32] against a
+// 32 x N (N <= 32) weight.  No shared memory and no barriers: every warp keeps the whole weight as pre-split
+// hi/lo B fragments in registers and walks over 16-row m-tiles, reading its A fragments straight from global
+// memory.  The MMA k index is a free permutation as long as A and B agree, so k-step s / slot t is mapped to
+// memory column 8t + 2s (+1 for the t+4 slot): a lane's eight fragment values of a row are then one
+// contiguous 32-byte run (two 16-byte loads), and the four lanes of a row cover its 128 bytes exactly.
+template <bool BT>
+__global__ void __launch_bounds__(256) gemm_stream32_kernel(GemmDev g) {
+    const int lane = threadIdx.x & 31;
+    const int gq = lane >> 2, tq = lane & 3;
+    const int ntiles = (int)((g.N + 7) / 8);
+    uint32_t bh[4][4][2], bl[4][4][2];      // [n-tile][k-step][slot]
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const int64_t n = j * 8 + gq;
+                const int k = 8 * tq + 2 * s + c;
+                float w = 0.f;
+                if (j < ntiles && n < g.N) w = BT ? g.B[k * g.ldb + n] : g.B[n * g.ldb + k];
+                if (g.relu_b) w = fmaxf(w, 0.f);
+                bh[j][s][c] = to_tf32(w);
+                bl[j][s][c] = to_tf32(w - __uint_as_float(bh[j][s][c]));
+            }
+        }
+    }
+    const int64_t n_mt = (g.M + 15) / 16;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    float4 cur[4], nxt[4];
+    auto fetch = [&](int64_t mt, float4 (&v)[4]) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int64_t r = mt * 16 + gq + 8 * h;
+            if (r < g.M) {
+                const float4* p = reinterpret_cast<const float4*>(g.A + r * g.lda + 8 * tq);
+                v[2 * h] = p[0];
+                v[2 * h + 1] = p[1];
+            } else {
+                v[2 * h] = make_float4(0.f, 0.f, 0.f, 0.f);
+                v[2 * h + 1] = v[2 * h];
+            }
+        }
+    };
+    if (warp0 < n_mt) fetch(warp0, cur);
+    for (int64_t mt = warp0; mt < n_mt; mt += nwarps) {
+        if (mt + nwarps < n_mt) fetch(mt + nwarps, nxt);
+        // this lane's values: row gq -> lo[0..7], row gq+8 -> hi[0..7] (memory columns 8 tq .. 8 tq + 7)
+        float lo[8] = {cur[0].x, cur[0].y, cur[0].z, cur[0].w, cur[1].x, cur[1].y, cur[1].z, cur[1].w};
+        float hi[8] = {cur[2].x, cur[2].y, cur[2].z, cur[2].w, cur[3].x, cur[3].y, cur[3].z, cur[3].w};
+        if (g.relu_a) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { lo[i] = fmaxf(lo[i], 0.f); hi[i] = fmaxf(hi[i], 0.f); }
+        }
+        float acc[4][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[j][c] = 0.f;
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            const float af[4] = {lo[2 * s], hi[2 * s], lo[2 * s + 1], hi[2 * s + 1]};
+            uint32_t ah[4], al[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                ah[c] = to_tf32(af[c]);
+                al[c] = to_tf32(af[c] - __uint_as_float(ah[c]));
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (j < ntiles) {
+                    mma_tf32(acc[j], al, bh[j][s]);
+                    mma_tf32(acc[j], ah, bl[j][s]);
+                    mma_tf32(acc[j], ah, bh[j][s]);
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (j < ntiles) {
+                const int64_t gn = j * 8 + 2 * tq;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int64_t gm = mt * 16 + gq + 8 * h;
+                    gemm_store(g, gm, gn, acc[j][2 * h], true);
+                    gemm_store(g, gm, gn + 1, acc[j][2 * h + 1], true);
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) cur[i] = nxt[i];
+    }
 }
+
+template <int BM, int BN, int WM, int WN>
+static void launch_tc(const GemmDev& d, bool at, bool bt, cudaStream_t s) {
+    dim3 grid((unsigned)ceil_div(d.M, BM), (unsigned)ceil_div(d.N, BN), (unsigned)d.splits);
+    dim3 block(WM * WN * 32);
+    if (!at && !bt) { auto k = gemm_tc_kernel<BM, BN, WM, WN, false, false>; LAUNCH(k, grid, block, 0, s, d); }
+    else if (!at && bt) { auto k = gemm_tc_kernel<BM, BN, WM, WN, false, true>; LAUNCH(k, grid, block, 0, s, d); }
+    else { auto k = gemm_tc_kernel<BM, BN, WM, WN, true, true>; LAUNCH(k, grid, block, 0, s, d); }
+}
+
+static inline bool vec_ok(const float* p, int64_t ld) { return (((uintptr_t)p) % 16 == 0) && (ld % 4 == 0); }
 
 int gemm(const Gemm& g, cudaStream_t s) {
     if (g.M <= 0 || g.N <= 0) return INTEL_OK;
@@ -126,28 +439,58 @@ int gemm(const Gemm& g, cudaStream_t s) {
     d.A = g.A; d.lda = g.lda; d.B = g.B; d.ldb = g.ldb; d.C = g.C; d.ldc = g.ldc;
     d.bias = g.bias; d.add = g.add; d.ldadd = g.ldadd; d.mask = g.mask; d.ldmask = g.ldmask;
     d.relu_a = g.relu_a; d.relu_b = g.relu_b; d.relu_out = g.relu_out; d.accumulate = g.accumulate;
-    const bool small_m = g.M <= 32, small_n = g.N <= 32;
-    const int bm = small_m ? 32 : (small_n ? 128 : 64);
-    const int bn = small_n ? 32 : 64;
+    d.vec_a = vec_ok(g.A, g.lda);
+    d.vec_b = vec_ok(g.B, g.ldb);
+    INTEL_REQUIRE(g.a_t == false || g.b_t == true, INTEL_ERR_UNSUPPORTED, "gemm: A^T B layout is not used by this path");
+    const bool wgrad = g.a_t && g.b_t;
+    // tile choice: the largest tile that still yields ~2 waves of CTAs on the 148 SMs; weight gradients with a
+    // small output use the warp-split-K kernel, everything else the tiled kernel (with split-K when allowed)
+    const bool can_split = (g.accumulate == 2 && !g.relu_out && !g.mask && g.splits <= 0);
+    auto ctas = [&](int bm, int bn) { return ceil_div(g.M, bm) * ceil_div(g.N, bn); };
+    int cfg;   // 0: 128x64  1: 128x32  2: 64x64  3: 64x32  4: warp-split-K 32x32
+    if (wgrad && (g.M < 64 || g.N < 64)) cfg = 4;
+    else if (g.N <= 32) cfg = (ctas(128, 32) >= 2 * kNumSMs || can_split) ? 1 : 3;
+    else if (ctas(128, 64) >= 2 * kNumSMs || can_split) cfg = 0;
+    else if (ctas(64, 64) >= 2 * kNumSMs) cfg = 2;
+    else cfg = 3;
+    const int bm = cfg == 4 ? 32 : (cfg <= 1 ? 128 : 64), bn = (cfg == 0 || cfg == 2) ? 64 : 32;
+    const int bk = cfg == 4 ? WG_BK : BK;
     int splits = g.splits;
     if (splits <= 0) {
-        // weight-gradient shape: few output tiles, very long inner dimension -> fill ~2 waves
-        int64_t tiles = ceil_div(g.M, bm) * ceil_div(g.N, bn);
-        int64_t want = ceil_div(2 * kNumSMs, tiles);
-        int64_t maxs = ceil_div(g.K, 8 * BK);
-        splits = (int)(want < 1 ? 1 : (want > maxs ? maxs : want));
-        if (splits < 1) splits = 1;
+        splits = 1;
+        if (can_split) {
+            // few output tiles and a very long inner dimension: split it to fill ~2 waves of the 148 SMs
+            const int64_t want = ceil_div(2 * kNumSMs, ctas(bm, bn));
+            const int64_t maxs = ceil_div(g.K, 4 * bk);
+            splits = (int)(want < 1 ? 1 : (want > maxs ? maxs : want));
+            if (splits < 1) splits = 1;
+        }
     }
     INTEL_REQUIRE(splits == 1 || (g.accumulate == 2 && !g.relu_out && !g.mask), INTEL_ERR_ARG,
                   "gemm: split-K needs atomic accumulation and a linear epilogue");
     INTEL_REQUIRE(splits <= 65535, INTEL_ERR_ARG, "gemm: too many splits");
     d.splits = splits;
-    d.kchunk = ceil_div(ceil_div(g.K, splits), BK) * BK;
-    if (d.kchunk <= 0) d.kchunk = BK;
-    if (bm == 32 && bn == 32) return launch_tile<32, 32>(d, g.a_t, g.b_t, s);
-    if (bm == 32 && bn == 64) return launch_tile<32, 64>(d, g.a_t, g.b_t, s);
-    if (bm == 128) return launch_tile<128, 32>(d, g.a_t, g.b_t, s);
-    return launch_tile<64, 64>(d, g.a_t, g.b_t, s);
+    d.kchunk = ceil_div(ceil_div(g.K, splits), bk) * bk;
+    if (d.kchunk <= 0) d.kchunk = bk;
+    if (!g.a_t && g.K == 32 && g.N <= 32 && d.vec_a && g.accumulate != 2 && splits == 1 && g.M >= 2048) {
+        const unsigned grid = stream_grid(ceil_div(g.M, 16 * 8), 3);
+        if (g.b_t) { auto k = gemm_stream32_kernel<true>; LAUNCH(k, dim3(grid), dim3(256), 0, s, d); }
+        else { auto k = gemm_stream32_kernel<false>; LAUNCH(k, dim3(grid), dim3(256), 0, s, d); }
+    } else if (cfg == 4) {
+        dim3 grid((unsigned)ceil_div(d.M, 32), (unsigned)ceil_div(d.N, 32), (unsigned)d.splits);
+        LAUNCH(gemm_wgrad_kernel, grid, dim3(WG_WARPS * 32), 0, s, d);
+    } else if (cfg == 0) {
+        launch_tc<128, 64, 4, 2>(d, g.a_t, g.b_t, s);
+    } else if (cfg == 1) {
+        launch_tc<128, 32, 4, 1>(d, g.a_t, g.b_t, s);
+    } else if (cfg == 2) {
+        launch_tc<64, 64, 2, 2>(d, g.a_t, g.b_t, s);
+    } else {
+        launch_tc<64, 32, 2, 1>(d, g.a_t, g.b_t, s);
+    }
+    const double bytes = 4.0 * ((double)d.M * d.K + (double)d.N * d.K +
+                                (double)d.M * d.N * (1 + (d.add != nullptr) + (d.mask != nullptr)));
+    return check_launch(wgrad ? "gemm_wgrad" : (g.b_t ? "gemm_dgrad" : "gemm_fwd"), bytes, 2.0 * d.M * d.N * d.K);
 }
 
 int linear(int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* W, int64_t ldw,

@@ -76,3 +76,297 @@ int gru_step_bwd(int64_t B, int64_t T, int h, int t, const int64_t* lens, const 
 }
 
 }  // namespace intel
+
+// =================================================================================================
+// Fused recurrence for hidden size 128 (the reference hard-codes GRU4RecEncoder(hidden_size=128),
+// IntEL.py:105-106).  The per-step formulation above needs 2 launches per time step and runs its
+// [B,128]x[128,384] products on a few hundred CTAs; here ONE persistent CTA owns a tile of sessions for all
+// T steps: W_hh (384x128 fp32 = 192 KB) stays in shared memory for the whole kernel, the hidden state of the
+// tile lives in shared memory / registers, gh = W_hh h is formed by 3xTF32 tensor-core MMAs and the gate
+// math runs in the MMA epilogue on the accumulator fragments (each warp owns 16 hidden units: its r, z and n
+// columns of a unit land in the same lane).  HBM traffic is just gi in, h_all / gates out.
+// =================================================================================================
+#include "mma.cuh"
+
+namespace intel {
+
+static const int GH = 128;              // hidden size
+static const int GW = GH + 4;           // smem row stride of W_hh / h tiles (conflict-free fragment reads)
+static const int GF_SB = 32;            // sessions per CTA, forward
+static const int GB_SB = 16;            // sessions per CTA, backward
+static const int GD = 3 * GH + 4;       // smem row stride of the dgh tile
+
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+    hi = to_tf32(x);
+    lo = to_tf32(x - __uint_as_float(hi));
+}
+
+__device__ __forceinline__ void stage_whh(float* Ws, const float* __restrict__ w_hh) {
+    for (int e = threadIdx.x; e < 3 * GH * (GH / 4); e += blockDim.x) {
+        const int n = e / (GH / 4), k4 = (e % (GH / 4)) * 4;
+        *reinterpret_cast<float4*>(Ws + n * GW + k4) = *reinterpret_cast<const float4*>(w_hh + n * GH + k4);
+    }
+}
+
+__global__ void __launch_bounds__(256, 1) gru_seq_fwd_kernel(int64_t B, int64_t T, const int64_t* __restrict__ lens,
+                                                             const float* __restrict__ gi,
+                                                             const float* __restrict__ w_hh,
+                                                             const float* __restrict__ b_hh, float* __restrict__ h_all,
+                                                             float* __restrict__ gates) {
+    DYN_SMEM(float, sm);
+    float* Ws = sm;                          // [384][GW]
+    float* hs = Ws + 3 * GH * GW;            // [GF_SB][GW]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gq = lane >> 2, tq = lane & 3;
+    const int64_t b0 = (int64_t)blockIdx.x * GF_SB;
+    stage_whh(Ws, w_hh);
+    for (int e = threadIdx.x; e < GF_SB * GW; e += blockDim.x) hs[e] = 0.f;
+    // rows of this lane: r = i*16 + hh*8 + gq (i: m-tile, hh: half); columns: c = 16*warp + 8*ct + 2*tq + e
+    int64_t len_r[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int64_t b = b0 + (q >> 1) * 16 + (q & 1) * 8 + gq;
+        len_r[q] = (b < B) ? lens[b] : 0;
+    }
+    float bias[3][2][2];
+#pragma unroll
+    for (int gte = 0; gte < 3; ++gte)
+#pragma unroll
+        for (int ct = 0; ct < 2; ++ct)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) bias[gte][ct][e] = b_hh[gte * GH + 16 * warp + 8 * ct + 2 * tq + e];
+    __syncthreads();
+
+    for (int64_t t = 0; t < T; ++t) {
+        float acc[2][6][4];                 // [m-tile][gate*2 + ct][frag]
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 6; ++j)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[i][j][c] = 0.f;
+#pragma unroll 2
+        for (int ks = 0; ks < GH / 8; ++ks) {
+            const int k0 = ks * 8 + tq;
+            uint32_t ah[2][4], al[2][4];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                split_tf32(hs[(i * 16 + gq) * GW + k0], ah[i][0], al[i][0]);
+                split_tf32(hs[(i * 16 + gq + 8) * GW + k0], ah[i][1], al[i][1]);
+                split_tf32(hs[(i * 16 + gq) * GW + k0 + 4], ah[i][2], al[i][2]);
+                split_tf32(hs[(i * 16 + gq + 8) * GW + k0 + 4], ah[i][3], al[i][3]);
+            }
+            uint32_t bh[6][2], bl[6][2];
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+                const int n = (j >> 1) * GH + 16 * warp + 8 * (j & 1) + gq;
+                split_tf32(Ws[n * GW + k0], bh[j][0], bl[j][0]);
+                split_tf32(Ws[n * GW + k0 + 4], bh[j][1], bl[j][1]);
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 6; ++j) mma_tf32(acc[i][j], al[i], bh[j]);
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 6; ++j) mma_tf32(acc[i][j], ah[i], bl[j]);
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 6; ++j) mma_tf32(acc[i][j], ah[i], bh[j]);
+        }
+        // ---- gates on the accumulator fragments ----
+        float hn[2][2][2][2];               // [m-tile][half][ct][e]
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                const int row = i * 16 + hh * 8 + gq;
+                const int64_t b = b0 + row;
+                const bool live = (b < B) && (t < len_r[i * 2 + hh]);
+#pragma unroll
+                for (int ct = 0; ct < 2; ++ct) {
+                    const int c = 16 * warp + 8 * ct + 2 * tq;
+                    const float hp0 = hs[row * GW + c], hp1 = hs[row * GW + c + 1];
+                    float o0 = hp0, o1 = hp1;
+                    if (live) {
+                        const float* gib = gi + (b * T + t) * 3 * GH;
+                        const float2 ir = *reinterpret_cast<const float2*>(gib + c);
+                        const float2 iz = *reinterpret_cast<const float2*>(gib + GH + c);
+                        const float2 in = *reinterpret_cast<const float2*>(gib + 2 * GH + c);
+                        const float r0 = sigmoidf_(ir.x + acc[i][0 + ct][2 * hh] + bias[0][ct][0]);
+                        const float r1 = sigmoidf_(ir.y + acc[i][0 + ct][2 * hh + 1] + bias[0][ct][1]);
+                        const float z0 = sigmoidf_(iz.x + acc[i][2 + ct][2 * hh] + bias[1][ct][0]);
+                        const float z1 = sigmoidf_(iz.y + acc[i][2 + ct][2 * hh + 1] + bias[1][ct][1]);
+                        const float g0 = acc[i][4 + ct][2 * hh] + bias[2][ct][0];
+                        const float g1 = acc[i][4 + ct][2 * hh + 1] + bias[2][ct][1];
+                        const float n0 = tanhf(in.x + r0 * g0), n1 = tanhf(in.y + r1 * g1);
+                        o0 = (1.f - z0) * n0 + z0 * hp0;
+                        o1 = (1.f - z1) * n1 + z1 * hp1;
+                        float* gt = gates + (b * T + t) * 4 * GH;
+                        *reinterpret_cast<float2*>(gt + c) = make_float2(r0, r1);
+                        *reinterpret_cast<float2*>(gt + GH + c) = make_float2(z0, z1);
+                        *reinterpret_cast<float2*>(gt + 2 * GH + c) = make_float2(n0, n1);
+                        *reinterpret_cast<float2*>(gt + 3 * GH + c) = make_float2(g0, g1);
+                    }
+                    hn[i][hh][ct][0] = o0;
+                    hn[i][hh][ct][1] = o1;
+                    if (b < B) *reinterpret_cast<float2*>(h_all + (b * (T + 1) + t + 1) * GH + c) = make_float2(o0, o1);
+                }
+            }
+        __syncthreads();                    // every warp has finished reading the old state
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+                for (int ct = 0; ct < 2; ++ct) {
+                    const int row = i * 16 + hh * 8 + gq, c = 16 * warp + 8 * ct + 2 * tq;
+                    hs[row * GW + c] = hn[i][hh][ct][0];
+                    hs[row * GW + c + 1] = hn[i][hh][ct][1];
+                }
+        __syncthreads();
+    }
+}
+
+// h_all[:, 0] must be zero (the caller clears it); h_all [B, T+1, 128], gates [B, T, 512]
+int gru_seq_fwd(int64_t B, int64_t T, int h, const int64_t* lens, const float* gi, const float* w_hh,
+                const float* b_hh, float* h_all, float* gates, cudaStream_t s) {
+    if (B <= 0 || T <= 0) return INTEL_OK;
+    INTEL_REQUIRE(h == GH, INTEL_ERR_UNSUPPORTED, "fused GRU needs hidden size 128");
+    const size_t smem = (size_t)(3 * GH * GW + GF_SB * GW) * 4;
+    cudaFuncSetAttribute(gru_seq_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    LAUNCH(gru_seq_fwd_kernel, dim3((unsigned)ceil_div(B, GF_SB)), dim3(256), smem, s, B, T, lens, gi, w_hh, b_hh, h_all,
+           gates);
+    return check_launch("gru_seq_fwd", (double)B * T * (3 + 4 + 1) * GH * 4.0, 2.0 * B * T * 3 * GH * GH);
+}
+
+// Backward recurrence.  dh [B,128] holds d(loss)/d h_T on entry.  Writes dgi [B,T,384] and
+// dgh_all [B,T+1,384] (slot T untouched: the caller clears the buffer) for the weight-gradient GEMMs.
+__global__ void __launch_bounds__(256, 1) gru_seq_bwd_kernel(int64_t B, int64_t T, const int64_t* __restrict__ lens,
+                                                             const float* __restrict__ w_hh,
+                                                             const float* __restrict__ h_all,
+                                                             const float* __restrict__ gates,
+                                                             const float* __restrict__ dh_in, float* __restrict__ dgi,
+                                                             float* __restrict__ dgh_all) {
+    DYN_SMEM(float, sm);
+    float* Ws = sm;                          // [384][GW]   W_hh[k = gate column][n = hidden]
+    float* ds = Ws + 3 * GH * GW;            // [GB_SB][GD] dgh of the current step
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gq = lane >> 2, tq = lane & 3;
+    const int64_t b0 = (int64_t)blockIdx.x * GB_SB;
+    stage_whh(Ws, w_hh);
+    int64_t len_r[2];
+    float dh[2][2][2];                       // [half][ct][e]: rows gq / gq+8, cols 16*warp + 8*ct + 2*tq + e
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+        const int64_t b = b0 + hh * 8 + gq;
+        len_r[hh] = (b < B) ? lens[b] : 0;
+#pragma unroll
+        for (int ct = 0; ct < 2; ++ct) {
+            const int c = 16 * warp + 8 * ct + 2 * tq;
+            float2 v = make_float2(0.f, 0.f);
+            if (b < B) v = *reinterpret_cast<const float2*>(dh_in + b * GH + c);
+            dh[hh][ct][0] = v.x;
+            dh[hh][ct][1] = v.y;
+        }
+    }
+    __syncthreads();
+    for (int64_t t = T - 1; t >= 0; --t) {
+        // ---- gate derivatives for the elements this lane owns ----
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+            const int row = hh * 8 + gq;
+            const int64_t b = b0 + row;
+            const bool live = (b < B) && (t < len_r[hh]);
+#pragma unroll
+            for (int ct = 0; ct < 2; ++ct) {
+                const int c = 16 * warp + 8 * ct + 2 * tq;
+                float2 dr = make_float2(0.f, 0.f), dz = dr, dn = dr, dnr = dr;
+                if (live) {
+                    const float* gt = gates + (b * T + t) * 4 * GH;
+                    const float2 r = *reinterpret_cast<const float2*>(gt + c);
+                    const float2 z = *reinterpret_cast<const float2*>(gt + GH + c);
+                    const float2 n = *reinterpret_cast<const float2*>(gt + 2 * GH + c);
+                    const float2 gn = *reinterpret_cast<const float2*>(gt + 3 * GH + c);
+                    const float2 hp = *reinterpret_cast<const float2*>(h_all + (b * (T + 1) + t) * GH + c);
+                    const float g0 = dh[hh][ct][0], g1 = dh[hh][ct][1];
+                    dn.x = g0 * (1.f - z.x) * (1.f - n.x * n.x);
+                    dn.y = g1 * (1.f - z.y) * (1.f - n.y * n.y);
+                    dz.x = g0 * (hp.x - n.x) * z.x * (1.f - z.x);
+                    dz.y = g1 * (hp.y - n.y) * z.y * (1.f - z.y);
+                    dr.x = dn.x * gn.x * r.x * (1.f - r.x);
+                    dr.y = dn.y * gn.y * r.y * (1.f - r.y);
+                    dnr.x = dn.x * r.x;
+                    dnr.y = dn.y * r.y;
+                    dh[hh][ct][0] = g0 * z.x;
+                    dh[hh][ct][1] = g1 * z.y;
+                }
+                if (b < B) {
+                    float* di = dgi + (b * T + t) * 3 * GH;
+                    float* dg = dgh_all + (b * (T + 1) + t) * 3 * GH;
+                    *reinterpret_cast<float2*>(di + c) = dr;
+                    *reinterpret_cast<float2*>(di + GH + c) = dz;
+                    *reinterpret_cast<float2*>(di + 2 * GH + c) = dn;
+                    *reinterpret_cast<float2*>(dg + c) = dr;
+                    *reinterpret_cast<float2*>(dg + GH + c) = dz;
+                    *reinterpret_cast<float2*>(dg + 2 * GH + c) = dnr;
+                }
+                ds[row * GD + c] = dr.x;            ds[row * GD + c + 1] = dr.y;
+                ds[row * GD + GH + c] = dz.x;       ds[row * GD + GH + c + 1] = dz.y;
+                ds[row * GD + 2 * GH + c] = dnr.x;  ds[row * GD + 2 * GH + c + 1] = dnr.y;
+            }
+        }
+        __syncthreads();
+        // ---- dh_prev = dh * z + dgh W_hh : [16 x 384] x [384 x 128], this warp owns 16 output columns ----
+        float acc[2][4];
+#pragma unroll
+        for (int ct = 0; ct < 2; ++ct)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[ct][c] = 0.f;
+#pragma unroll 4
+        for (int ks = 0; ks < 3 * GH / 8; ++ks) {
+            const int k0 = ks * 8 + tq;
+            uint32_t ah[4], al[4];
+            split_tf32(ds[gq * GD + k0], ah[0], al[0]);
+            split_tf32(ds[(gq + 8) * GD + k0], ah[1], al[1]);
+            split_tf32(ds[gq * GD + k0 + 4], ah[2], al[2]);
+            split_tf32(ds[(gq + 8) * GD + k0 + 4], ah[3], al[3]);
+            uint32_t bh[2][2], bl[2][2];
+#pragma unroll
+            for (int ct = 0; ct < 2; ++ct) {
+                const int n = 16 * warp + 8 * ct + gq;
+                split_tf32(Ws[k0 * GW + n], bh[ct][0], bl[ct][0]);
+                split_tf32(Ws[(k0 + 4) * GW + n], bh[ct][1], bl[ct][1]);
+            }
+#pragma unroll
+            for (int ct = 0; ct < 2; ++ct) mma_tf32(acc[ct], al, bh[ct]);
+#pragma unroll
+            for (int ct = 0; ct < 2; ++ct) mma_tf32(acc[ct], ah, bl[ct]);
+#pragma unroll
+            for (int ct = 0; ct < 2; ++ct) mma_tf32(acc[ct], ah, bh[ct]);
+        }
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+            for (int ct = 0; ct < 2; ++ct) {
+                dh[hh][ct][0] += acc[ct][2 * hh];
+                dh[hh][ct][1] += acc[ct][2 * hh + 1];
+            }
+        __syncthreads();                    // the dgh tile is rewritten by the next step
+    }
+}
+
+int gru_seq_bwd(int64_t B, int64_t T, int h, const int64_t* lens, const float* w_hh, const float* h_all,
+                const float* gates, const float* dh_in, float* dgi, float* dgh_all, cudaStream_t s) {
+    if (B <= 0 || T <= 0) return INTEL_OK;
+    INTEL_REQUIRE(h == GH, INTEL_ERR_UNSUPPORTED, "fused GRU needs hidden size 128");
+    const size_t smem = (size_t)(3 * GH * GW + GB_SB * GD) * 4;
+    cudaFuncSetAttribute(gru_seq_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    LAUNCH(gru_seq_bwd_kernel, dim3((unsigned)ceil_div(B, GB_SB)), dim3(256), smem, s, B, T, lens, w_hh, h_all, gates,
+           dh_in, dgi, dgh_all);
+    return check_launch("gru_seq_bwd", (double)B * T * (4 + 1 + 3 + 3) * GH * 4.0, 2.0 * B * T * 3 * GH * GH);
+}
+
+}  // namespace intel

@@ -103,6 +103,14 @@ int gru_step_fwd(int64_t B, int64_t T, int h, int t, const int64_t* lens, const 
 int gru_step_bwd(int64_t B, int64_t T, int h, int t, const int64_t* lens, const float* h_all,
                  const float* gates, float* dh, float* dgi, float* dgh_all, cudaStream_t s);
 
+// Fused recurrence for hidden size 128: one persistent CTA per tile of sessions walks all T steps with W_hh
+// resident in shared memory (see gru.cu).  h_all [B,T+1,h] (slot 0 pre-zeroed), gates [B,T,4h],
+// dgi [B,T,3h], dgh_all [B,T+1,3h] (pre-zeroed), dh_in [B,h] = d loss / d h_T.
+int gru_seq_fwd(int64_t B, int64_t T, int h, const int64_t* lens, const float* gi, const float* w_hh,
+                const float* b_hh, float* h_all, float* gates, cudaStream_t s);
+int gru_seq_bwd(int64_t B, int64_t T, int h, const int64_t* lens, const float* w_hh, const float* h_all,
+                const float* gates, const float* dh_in, float* dgi, float* dgh_all, cudaStream_t s);
+
 // ---- fuse.cu ------------------------------------------------------------------------------------
 // weights[b,l,:] = l < n_b ? w_valid[b] : w_pad[b];  ens[b,l] = sum_k weights * float(scores)
 int head_fuse_fwd(int64_t B, int64_t L, int K, const float* w_valid, const float* w_pad, const double* scores,

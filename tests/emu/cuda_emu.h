@@ -29,7 +29,7 @@
 #define __shared__ static
 #define __constant__ static
 #define __launch_bounds__(...)
-#define __align__(n) alignas(n)
+#define __align__(n) __attribute__((aligned(n)))
 #define warpSize 32
 
 struct uint3 { unsigned x, y, z; };

@@ -32,7 +32,7 @@ def check_linear(device):
     from intel_sigir2023_b200 import _lib
     lib = _lib.load()
     g = torch.Generator().manual_seed(0)
-    for (M, N, K) in [(7, 5, 3), (130, 33, 17), (64, 64, 64), (300, 8, 40), (20, 100, 70)]:
+    for (M, N, K) in [(7, 5, 3), (130, 33, 17), (64, 64, 64), (300, 8, 40), (20, 100, 70), (3001, 32, 32), (2500, 24, 32)]:
         A = torch.randn(M, K, generator=g).to(device)
         W = torch.randn(N, K, generator=g).to(device)
         b = torch.randn(N, generator=g).to(device)
@@ -40,6 +40,58 @@ def check_linear(device):
         _lib.check(lib.intel_linear_fwd(M, N, K, _lib.ptr(A), _lib.ptr(W), _lib.ptr(b), _lib.ptr(Cout), _lib.stream_ptr(A.device)))
         ref = A.cpu() @ W.cpu().t() + b.cpu()
         assert rel_err(Cout.cpu().numpy(), ref.numpy()) < 2e-6, (M, N, K)
+
+
+def check_linear_grads(device):
+    """input / weight gradient GEMM variants on awkward shapes (tails in every dimension, split-K)."""
+    from intel_sigir2023_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(2)
+    for (M, N, K) in [(9, 5, 3), (1000, 33, 17), (4100, 32, 32), (257, 96, 40), (70, 130, 50)]:
+        dY = torch.randn(M, N, generator=g).to(device)
+        X = torch.randn(M, K, generator=g).to(device)
+        W = torch.randn(N, K, generator=g).to(device)
+        U = torch.randn(M, K, generator=g).to(device)
+        st = _lib.stream_ptr(dY.device)
+        dX = torch.empty(M, K, device=device)
+        _lib.check(lib.intel_linear_dx(M, N, K, _lib.ptr(dY), _lib.ptr(W), _lib.ptr(dX), _lib.ptr(U), st))
+        ref = (dY.cpu() @ W.cpu()) * (U.cpu() > 0)
+        assert rel_err(dX.cpu().numpy(), ref.numpy()) < 2e-6, ("dx", M, N, K)
+        dW = torch.zeros(N, K, device=device)
+        db = torch.zeros(N, device=device)
+        _lib.check(lib.intel_linear_dw(M, N, K, _lib.ptr(dY), _lib.ptr(X), _lib.ptr(dW), _lib.ptr(db), st))
+        assert rel_err(dW.cpu().numpy(), (dY.cpu().t() @ X.cpu()).numpy()) < 3e-6, ("dw", M, N, K)
+        assert rel_err(db.cpu().numpy(), dY.cpu().sum(0).numpy()) < 3e-6, ("db", M, N, K)
+
+
+def check_mha(device, shapes=((3, 12, 32, 2), (2, 50, 32, 2), (2, 100, 32, 1), (1, 130, 48, 2))):
+    """attention core vs torch on list lengths that span several 64-row query blocks, with and without key masks."""
+    from intel_sigir2023_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(4)
+    for (B, T, d, h) in shapes:
+        for masked in (False, True):
+            qkv = torch.randn(B, T, 3 * d, generator=g)
+            lens = torch.randint(1, T + 1, (B,), generator=g) if masked else None
+            dO = torch.randn(B, T, d, generator=g)
+            q = qkv.clone().requires_grad_(True)
+            dk = d // h
+            Q, K, V = (q[:, :, i * d:(i + 1) * d].view(B, T, h, dk).transpose(1, 2) for i in range(3))
+            s = Q @ K.transpose(-1, -2) / dk ** 0.5
+            if masked:
+                keym = torch.arange(T)[None, :] < lens[:, None]
+                s = s.masked_fill(~keym[:, None, None, :], float("-inf"))
+            ref = (s.softmax(-1) @ V).transpose(1, 2).reshape(B, T, d)
+            ref.backward(dO)
+            qd, dOd = qkv.to(device), dO.to(device)
+            ld = lens.to(device) if masked else None
+            out = torch.empty(B, T, d, device=device)
+            dq = torch.empty(B, T, 3 * d, device=device)
+            st = _lib.stream_ptr(qd.device)
+            _lib.check(lib.intel_mha_fwd(B, T, d, h, _lib.ptr(qd), _lib.ptr(ld), _lib.ptr(out), st))
+            _lib.check(lib.intel_mha_bwd(B, T, d, h, _lib.ptr(qd), _lib.ptr(ld), _lib.ptr(dOd), _lib.ptr(dq), st))
+            assert rel_err(out.cpu().numpy(), ref.detach().numpy()) < 3e-6, ("fwd", B, T, d, h, masked)
+            assert rel_err(dq.cpu().numpy(), q.grad.numpy()) < 1e-5, ("bwd", B, T, d, h, masked)
 
 
 def check_gather_scatter(device):
@@ -198,3 +250,37 @@ def check_baselines(device):
     r = baselines.RandomFusion()(batch, raw.to(device))["ens_score"].cpu().numpy()
     ref = O.random_fusion({"scores": torch.from_numpy(z["F.scores"])}, raw)["ens_score"].numpy()
     assert rel_err(r, ref) < 1e-6
+
+
+def check_against_oracle(device, seed=0, B=70, L=21, min_len=3, kind="list", corpus_kw=None, **cfg_kw):
+    """Seeded synthetic batch + random weights: product (forward, loss, parameter gradients) vs the CPU oracle.
+    Used for shapes the golden fixtures do not cover (B beyond one CTA tile, long lists, other widths)."""
+    from intel_sigir2023_b200 import losses, synthetic
+    from intel_sigir2023_b200.config import IntelConfig
+    ck = dict(n_item=300, n_class=11, n_user=40, n_ctx=23, model_num=3, intent_num=48, history_max=9)
+    ck.update(corpus_kw or {})
+    corpus = synthetic.CorpusSpec(**ck)
+    cfg = IntelConfig(item_rows=corpus.item_rows, class_rows=corpus.n_class, user_rows=corpus.user_rows,
+                      ctx_rows=corpus.n_ctx, intent_num=corpus.intent_num, model_num=corpus.model_num,
+                      history_max=corpus.history_max, **cfg_kw)
+    batch_cpu = synthetic.make_batch(corpus, synthetic.BatchSpec(batch_size=B, max_len=L, min_len=min_len), seed=seed)
+    state = O.init_state(cfg, seed=seed + 1)
+    model = make_model(cfg, {k: v.to(device) for k, v in state.items()}, device).train()
+    batch = {k: (v.to(device) if torch.is_tensor(v) else v) for k, v in batch_cpu.items()}
+    crit = {"list": losses.IntListloss, "bpr": losses.IntBPRloss, "mse": losses.IntMSEloss}[kind](loss_args())
+    noise = torch.rand(B, L, L, generator=torch.Generator().manual_seed(seed))
+    crit.bpr_noise = noise.to(device)
+    out = model(batch)
+    loss, _, _ = crit(out, batch)
+    loss.backward()
+    sd = {k: v.clone().requires_grad_(True) for k, v in state.items()}
+    ref = O.forward(sd, cfg, batch_cpu)
+    rl, _, _ = O.total_loss(kind, ref, batch_cpu, noise=noise, **LOSS_KW)
+    rl.backward()
+    for k in ("intents", "weights", "ens_score"):
+        assert rel_err(out[k].detach().cpu().numpy(), ref[k].detach().numpy()) < TOL, (k, cfg_kw)
+    assert abs(loss.item() - rl.item()) <= TOL * abs(rl.item()) + 1e-7, (loss.item(), rl.item())
+    gmax = max(float(p.grad.abs().max()) for p in sd.values() if p.grad is not None)
+    for k, p in model.named_parameters():
+        ref_g = sd[k].grad.numpy() if sd[k].grad is not None else np.zeros(tuple(p.shape), np.float32)
+        assert_grad_close(p.grad.cpu().numpy(), ref_g, gmax, f"{k} {cfg_kw}", rtol=1e-3, afrac=5e-6)

@@ -29,6 +29,14 @@ def test_linear():
     P.check_linear("cpu")
 
 
+def test_linear_grads():
+    P.check_linear_grads("cpu")
+
+
+def test_mha_blocks():
+    P.check_mha("cpu", shapes=((3, 12, 32, 2), (1, 70, 32, 2), (1, 130, 48, 2)))
+
+
 def test_gather_scatter():
     P.check_gather_scatter("cpu")
 
@@ -65,3 +73,8 @@ def test_evaluate_intents():
 
 def test_baselines():
     P.check_baselines("cpu")
+
+
+def test_against_oracle_multi_tile():
+    P.check_against_oracle("cpu", B=35, L=9, encoder="GRU4Rec", num_heads=2, num_layers=1,
+                           corpus_kw=dict(history_max=4, intent_num=24))

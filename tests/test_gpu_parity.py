@@ -30,6 +30,14 @@ def test_linear():
     P.check_linear(DEV)
 
 
+def test_linear_grads():
+    P.check_linear_grads(DEV)
+
+
+def test_mha_blocks():
+    P.check_mha(DEV)
+
+
 def test_gather_scatter():
     P.check_gather_scatter(DEV)
 
@@ -64,3 +72,14 @@ def test_evaluate_intents():
 
 def test_baselines():
     P.check_baselines(DEV)
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(B=70, L=21, encoder="GRU4Rec", num_heads=2, num_layers=2, context_emb_size=32, intent_emb_size=32),
+    dict(B=37, L=100, min_len=40, encoder="BERT4Rec", num_heads=1, num_layers=1),
+    dict(B=9, L=130, min_len=90, kind="bpr", encoder="GRU4Rec", num_heads=2, num_layers=1, cross_attn_qsize=64),
+    dict(B=33, L=50, min_len=50, kind="mse", encoder="BERT4Rec", cross_attention=0, num_heads=2,
+         corpus_kw=dict(model_num=4, intent_num=120, history_max=20)),
+])
+def test_against_oracle(cfg):
+    P.check_against_oracle(DEV, **cfg)
