@@ -61,6 +61,20 @@ def _cross_container(I: int, d: int) -> nn.Module:
     return m
 
 
+def _take_ws(model, nbytes: int, dev) -> torch.Tensor:
+    """Workspaces are multi-GB at B=4096: keep them in a per-model pool instead of round-tripping the
+    allocator every step.  Reuse is stream-ordered (same stream), so handing a buffer back right after the
+    kernels that use it were queued is safe."""
+    pool = model._ws_pool.setdefault((int(nbytes), str(dev)), [])
+    return pool.pop() if pool else torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
+
+
+def _give_ws(model, t: torch.Tensor) -> None:
+    pool = model._ws_pool.setdefault((t.numel(), str(t.device)), [])
+    if len(pool) < 2:
+        pool.append(t)
+
+
 class _IntelFn(torch.autograd.Function):
     """(parameters...) -> (weights, ens_score, intents); backward = ensemble_bwd then intent_bwd."""
 
@@ -77,18 +91,21 @@ class _IntelFn(torch.autograd.Function):
         P = _lib.make_tensors(cfg, tensors)
         bt = _lib.make_batch(batch, cfg)
         stream = _lib.stream_ptr(dev)
-        ws_int = torch.empty(lib.intel_intent_workspace_bytes(dims), dtype=torch.uint8, device=dev)
-        ws_ens = torch.empty(lib.intel_ensemble_workspace_bytes(dims), dtype=torch.uint8, device=dev)
+        ws_int = _take_ws(model, lib.intel_intent_workspace_bytes(dims), dev)
+        ws_ens = _take_ws(model, lib.intel_ensemble_workspace_bytes(dims), dev)
         intents = torch.empty(B, cfg.intent_num, dtype=torch.float32, device=dev)
         weights = torch.empty(B, L, cfg.model_num, dtype=torch.float32, device=dev)
         ens = torch.empty(B, L, dtype=torch.float32, device=dev)
         _lib.check(lib.intel_intent_fwd(dims, P, bt, _lib.ptr(intents), _lib.ptr(ws_int), ws_int.numel(), stream))
         _lib.check(lib.intel_ensemble_fwd(dims, P, bt, _lib.ptr(intents), _lib.ptr(weights), _lib.ptr(ens),
                                           _lib.ptr(ws_ens), ws_ens.numel(), stream))
-        ctx.model, ctx.batch, ctx.dims = model, batch, dims
-        ctx.ws_int, ctx.ws_ens, ctx.intents = ws_int, ws_ens, intents
-        ctx.params = params
-        ctx.mark_non_differentiable()
+        if any(ctx.needs_input_grad):
+            ctx.model, ctx.batch, ctx.dims = model, batch, dims
+            ctx.ws_int, ctx.ws_ens, ctx.intents = ws_int, ws_ens, intents
+            ctx.params = params
+        else:                       # inference: nothing is kept for a backward pass
+            _give_ws(model, ws_int)
+            _give_ws(model, ws_ens)
         return weights, ens, intents
 
     @staticmethod
@@ -115,6 +132,9 @@ class _IntelFn(torch.autograd.Function):
         if first is not None:
             _lib.check(lib.intel_intent_bwd(dims, P, bt, _lib.ptr(ctx.intents), _lib.ptr(first), _lib.ptr(extra), G,
                                             _lib.ptr(ctx.ws_int), ctx.ws_int.numel(), stream))
+        _give_ws(model, ctx.ws_int)
+        _give_ws(model, ctx.ws_ens)
+        ctx.ws_int = ctx.ws_ens = None
         return (None, None) + tuple(grads)
 
 
@@ -153,6 +173,7 @@ class IntEL(nn.Module):
         self.buffer = getattr(args, "buffer", 1)
         self.optimizer, self.scheduler = None, None
         self.check_list = list()
+        self._ws_pool = {}
         self.intent_num, self.model_num = c.intent_num, c.model_num
         self.user_num, self.item_num = c.user_rows, c.item_rows
         self.max_his = c.history_max

@@ -2,6 +2,7 @@
 #include <stdarg.h>
 
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -20,6 +21,17 @@ void set_error(const char* fmt, ...) {
 }
 
 #ifndef INTEL_EMU
+void ensure_smem_impl(const void* kernel, size_t smem) {
+    static std::mutex mu;
+    static std::map<const void*, size_t> done;
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = done.find(kernel);
+    if (it != done.end() && it->second >= smem) return;
+    const size_t want = 227 * 1024;      // opt in to the B200 maximum once
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > want ? smem : want));
+    done[kernel] = smem > want ? smem : want;
+}
+
 struct ProfRec { cudaEvent_t a, b; const char* what; double bytes, flops; };
 static bool g_prof_on = false, g_prof_pending = false;
 static cudaEvent_t g_pa, g_pb;

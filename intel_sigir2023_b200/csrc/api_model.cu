@@ -51,6 +51,10 @@ void stack_layout(Arena& a, int64_t R, int d, int layers, StackWs& w) {
 
 int stack_fwd(int64_t B, int64_t L, int d, int heads, int layers, const intel_selfatt_t& p, StackWs& w, cudaStream_t s) {
     const int64_t R = B * L;
+    if (trunk_supported(L, d, heads, layers)) {     // whole stack of a session on chip (trunk.cu)
+        const StackParams sp{p.wq, p.wk, p.wv, p.w1, p.b1, p.w2, p.b2, p.lnw, p.lnb};
+        return trunk_fwd(B, L, heads, layers, sp, w.X, s);
+    }
     for (int l = 0; l < layers; ++l) {
         INTEL_TRY(linear(R, d, d, w.X[l], d, p.wq, d, nullptr, w.QKV[l], 3 * d, s));
         INTEL_TRY(linear(R, d, d, w.X[l], d, p.wk, d, nullptr, w.QKV[l] + d, 3 * d, s));
@@ -67,6 +71,11 @@ int stack_fwd(int64_t B, int64_t L, int d, int heads, int layers, const intel_se
 int stack_bwd(int64_t B, int64_t L, int d, int heads, int layers, const intel_selfatt_t& p, intel_selfatt_t& g,
               StackWs& w, float* dX, float* t1, float* t2, float* dqkv, cudaStream_t s) {
     const int64_t R = B * L;
+    if (trunk_supported(L, d, heads, layers)) {
+        const StackParams sp{p.wq, p.wk, p.wv, p.w1, p.b1, p.w2, p.b2, p.lnw, p.lnb};
+        const StackGrads sg{g.wq, g.wk, g.wv, g.w1, g.b1, g.w2, g.b2, g.lnw, g.lnb};
+        return trunk_bwd(B, L, heads, layers, sp, sg, w.X, dX, s);
+    }
     for (int l = layers - 1; l >= 0; --l) {
         float* dZ = t1;
         INTEL_TRY(layernorm_bwd(R, d, dX, w.Z[l], w.st[l], p.lnw, dZ, g.lnw, g.lnb, s));

@@ -74,6 +74,17 @@ struct Arena {
     bool ok() const { return dry || off <= cap; }
 };
 
+// Opt a kernel in to > 48 KB of dynamic shared memory ONCE (the attribute call is a context-wide operation
+// that costs milliseconds; doing it per launch made the forward pass host-bound).
+#ifndef INTEL_EMU
+void ensure_smem_impl(const void* kernel, size_t smem);
+template <class K> inline void ensure_smem(K kernel, size_t smem) {
+    if (smem > 48 * 1024) ensure_smem_impl(reinterpret_cast<const void*>(kernel), smem);
+}
+#else
+template <class K> inline void ensure_smem(K, size_t) {}
+#endif
+
 // ---- warp helpers ----
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -326,7 +326,7 @@ int intel_ndcg_topk(int64_t N, int64_t ld, const float* pred, const int64_t* ran
     const size_t smem = (size_t)EV_WARPS * 2 * ld * 4;
     INTEL_REQUIRE(smem <= 200 * 1024, INTEL_ERR_UNSUPPORTED, "ndcg: row length %lld too long", (long long)ld);
     cudaStream_t s = (cudaStream_t)stream;
-    if (smem > 48 * 1024) cudaFuncSetAttribute(ndcg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    ensure_smem(ndcg_kernel, smem);
     const unsigned grid = ndcg_grid(N);
     const int ncols = n_topk * EV_OUT + 4;
     double* partial = reinterpret_cast<double*>(workspace);
@@ -355,7 +355,7 @@ int intel_intent_topk(int64_t N, int64_t I, const double* true_intents, const fl
     const size_t smem = (size_t)EV_WARPS * 2 * I * 8;
     INTEL_REQUIRE(smem <= 200 * 1024, INTEL_ERR_UNSUPPORTED, "intent_topk: intent_num %lld too large", (long long)I);
     cudaStream_t s = (cudaStream_t)stream;
-    if (smem > 48 * 1024) cudaFuncSetAttribute(intent_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    ensure_smem(intent_topk_kernel, smem);
     const unsigned grid = ndcg_grid(N);
     double* partial = reinterpret_cast<double*>(workspace);
     LAUNCH(intent_topk_kernel, dim3(grid), dim3(EV_WARPS * 32), smem, s, N, I, true_intents, pred_intents, tk, partial);
@@ -384,7 +384,7 @@ int intel_rank_lists(int64_t B, int64_t L, int64_t K, const double* scores, floa
     INTEL_REQUIRE(scores && ens_out, INTEL_ERR_ARG, "rank_lists: null pointer");
     const size_t smem = (size_t)EV_WARPS * L * K * 4;
     INTEL_REQUIRE(smem <= 200 * 1024, INTEL_ERR_UNSUPPORTED, "rank_lists: list too long");
-    if (smem > 48 * 1024) cudaFuncSetAttribute(rank_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    ensure_smem(rank_lists_kernel, smem);
     LAUNCH(rank_lists_kernel, dim3((unsigned)ceil_div(B, EV_WARPS)), dim3(EV_WARPS * 32), smem, (cudaStream_t)stream, B, L,
            (int)K, scores, ens_out);
     return check_launch("rank_lists");

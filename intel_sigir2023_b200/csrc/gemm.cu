@@ -20,7 +20,7 @@ struct GemmDev {
     const float* bias;
     const float* add; int64_t ldadd;
     const float* mask; int64_t ldmask;
-    int relu_a, relu_b, relu_out, accumulate, splits, vec_a, vec_b;
+    int relu_a, relu_b, relu_out, accumulate, splits, vec_a, vec_b, vec_c;
     int64_t kchunk;
 };
 
@@ -107,6 +107,30 @@ __device__ __forceinline__ void gemm_store(const GemmDev& g, int64_t gm, int64_t
     if (g.accumulate == 0) *c = v;
     else if (g.accumulate == 1) *c += v;
     else atomicAdd(c, v);
+}
+
+// two adjacent columns (gn even): one 8-byte access per operand when the layout allows it (g.vec_c)
+__device__ __forceinline__ void gemm_store2(const GemmDev& g, int64_t gm, int64_t gn, float v0, float v1, bool first) {
+    if (gm >= g.M) return;
+    if (!g.vec_c || gn + 1 >= g.N) {
+        gemm_store(g, gm, gn, v0, first);
+        gemm_store(g, gm, gn + 1, v1, first);
+        return;
+    }
+    if (first) {
+        if (g.bias) { const float2 b = *reinterpret_cast<const float2*>(g.bias + gn); v0 += b.x; v1 += b.y; }
+        if (g.add) { const float2 a = *reinterpret_cast<const float2*>(g.add + gm * g.ldadd + gn); v0 += a.x; v1 += a.y; }
+    }
+    if (g.relu_out) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+    if (g.mask) {
+        const float2 m = *reinterpret_cast<const float2*>(g.mask + gm * g.ldmask + gn);
+        v0 = m.x > 0.f ? v0 : 0.f;
+        v1 = m.y > 0.f ? v1 : 0.f;
+    }
+    float* c = g.C + gm * g.ldc + gn;
+    if (g.accumulate == 0) *reinterpret_cast<float2*>(c) = make_float2(v0, v1);
+    else if (g.accumulate == 1) { float2 o = *reinterpret_cast<float2*>(c); *reinterpret_cast<float2*>(c) = make_float2(o.x + v0, o.y + v1); }
+    else { atomicAdd(c, v0); atomicAdd(c + 1, v1); }
 }
 
 template <int BM, int BN, int WM, int WN, bool AT, bool BT>
@@ -204,10 +228,8 @@ __global__ void __launch_bounds__(WM * WN * 32) gemm_tc_kernel(GemmDev g) {
         for (int j = 0; j < TN; ++j) {
             const int64_t gm = m0 + wm * (BM / WM) + i * 16 + gq;
             const int64_t gn = n0 + wn * (BN / WN) + j * 8 + 2 * tq;
-            gemm_store(g, gm, gn, acc[i][j][0], first);
-            gemm_store(g, gm, gn + 1, acc[i][j][1], first);
-            gemm_store(g, gm + 8, gn, acc[i][j][2], first);
-            gemm_store(g, gm + 8, gn + 1, acc[i][j][3], first);
+            gemm_store2(g, gm, gn, acc[i][j][0], acc[i][j][1], first);
+            gemm_store2(g, gm + 8, gn, acc[i][j][2], acc[i][j][3], first);
         }
 }
 
@@ -409,8 +431,7 @@ __global__ void __launch_bounds__(256) gemm_stream32_kernel(GemmDev g) {
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const int64_t gm = mt * 16 + gq + 8 * h;
-                    gemm_store(g, gm, gn, acc[j][2 * h], true);
-                    gemm_store(g, gm, gn + 1, acc[j][2 * h + 1], true);
+                    gemm_store2(g, gm, gn, acc[j][2 * h], acc[j][2 * h + 1], true);
                 }
             }
         }
@@ -441,6 +462,8 @@ int gemm(const Gemm& g, cudaStream_t s) {
     d.relu_a = g.relu_a; d.relu_b = g.relu_b; d.relu_out = g.relu_out; d.accumulate = g.accumulate;
     d.vec_a = vec_ok(g.A, g.lda);
     d.vec_b = vec_ok(g.B, g.ldb);
+    auto even = [](const float* p, int64_t ld) { return p == nullptr || ((((uintptr_t)p) % 8 == 0) && (ld % 2 == 0)); };
+    d.vec_c = even(g.C, g.ldc) && even(g.add, g.ldadd) && even(g.mask, g.ldmask) && even(g.bias, 2);
     INTEL_REQUIRE(g.a_t == false || g.b_t == true, INTEL_ERR_UNSUPPORTED, "gemm: A^T B layout is not used by this path");
     const bool wgrad = g.a_t && g.b_t;
     // tile choice: the largest tile that still yields ~2 waves of CTAs on the 148 SMs; weight gradients with a

@@ -236,7 +236,7 @@ int gru_seq_fwd(int64_t B, int64_t T, int h, const int64_t* lens, const float* g
     if (B <= 0 || T <= 0) return INTEL_OK;
     INTEL_REQUIRE(h == GH, INTEL_ERR_UNSUPPORTED, "fused GRU needs hidden size 128");
     const size_t smem = (size_t)(3 * GH * GW + GF_SB * GW) * 4;
-    cudaFuncSetAttribute(gru_seq_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    ensure_smem(gru_seq_fwd_kernel, smem);
     LAUNCH(gru_seq_fwd_kernel, dim3((unsigned)ceil_div(B, GF_SB)), dim3(256), smem, s, B, T, lens, gi, w_hh, b_hh, h_all,
            gates);
     return check_launch("gru_seq_fwd", (double)B * T * (3 + 4 + 1) * GH * 4.0, 2.0 * B * T * 3 * GH * GH);
@@ -363,7 +363,7 @@ int gru_seq_bwd(int64_t B, int64_t T, int h, const int64_t* lens, const float* w
     if (B <= 0 || T <= 0) return INTEL_OK;
     INTEL_REQUIRE(h == GH, INTEL_ERR_UNSUPPORTED, "fused GRU needs hidden size 128");
     const size_t smem = (size_t)(3 * GH * GW + GB_SB * GD) * 4;
-    cudaFuncSetAttribute(gru_seq_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    ensure_smem(gru_seq_bwd_kernel, smem);
     LAUNCH(gru_seq_bwd_kernel, dim3((unsigned)ceil_div(B, GB_SB)), dim3(256), smem, s, B, T, lens, w_hh, h_all, gates,
            dh_in, dgi, dgh_all);
     return check_launch("gru_seq_bwd", (double)B * T * (4 + 1 + 3 + 3) * GH * 4.0, 2.0 * B * T * 3 * GH * GH);

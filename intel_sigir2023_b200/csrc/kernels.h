@@ -111,6 +111,16 @@ int gru_seq_fwd(int64_t B, int64_t T, int h, const int64_t* lens, const float* g
 int gru_seq_bwd(int64_t B, int64_t T, int h, const int64_t* lens, const float* w_hh, const float* h_all,
                 const float* gates, const float* dh_in, float* dgi, float* dgh_all, cudaStream_t s);
 
+// ---- trunk.cu: fused self-attention stack (d = 32, L <= 64): all layers of a session on chip -----
+struct StackParams { const float *wq, *wk, *wv, *w1, *b1, *w2, *b2, *lnw, *lnb; };
+struct StackGrads { float *wq, *wk, *wv, *w1, *b1, *w2, *b2, *lnw, *lnb; };
+bool trunk_supported(int64_t L, int d, int heads, int layers);
+// X[0] = stack input [B*L,32]; X[l+1] receives the output of layer l
+int trunk_fwd(int64_t B, int64_t L, int heads, int layers, const StackParams& p, float* const* X, cudaStream_t s);
+// dX: d loss / d X[layers] on entry, d loss / d X[0] on return; weight gradients are accumulated into g
+int trunk_bwd(int64_t B, int64_t L, int heads, int layers, const StackParams& p, const StackGrads& g, float* const* X,
+              float* dX, cudaStream_t s);
+
 // ---- fuse.cu ------------------------------------------------------------------------------------
 // weights[b,l,:] = l < n_b ? w_valid[b] : w_pad[b];  ens[b,l] = sum_k weights * float(scores)
 int head_fuse_fwd(int64_t B, int64_t L, int K, const float* w_valid, const float* w_pad, const double* scores,

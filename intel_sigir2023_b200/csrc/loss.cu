@@ -284,10 +284,10 @@ static int launch_loss(int which, LossArgs a, cudaStream_t s) {
     INTEL_REQUIRE(smem <= 200 * 1024, INTEL_ERR_UNSUPPORTED, "loss: list length %lld too long", (long long)a.L);
     dim3 grid((unsigned)ceil_div(a.B, LOSS_WARPS)), block(LOSS_WARPS * 32);
     if (which == 0) {
-        if (smem > 48 * 1024) cudaFuncSetAttribute(loss_pl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        ensure_smem(loss_pl_kernel, smem);
         LAUNCH(loss_pl_kernel, grid, block, smem, s, a);
     } else if (which == 1) {
-        if (smem > 48 * 1024) cudaFuncSetAttribute(loss_bpr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        ensure_smem(loss_bpr_kernel, smem);
         LAUNCH(loss_bpr_kernel, grid, block, smem, s, a);
     } else {
         LAUNCH(loss_mse_kernel, grid, block, 0, s, a);

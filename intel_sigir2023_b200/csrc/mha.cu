@@ -187,7 +187,7 @@ int mha_fwd(int64_t B, int64_t T, int d, int heads, const float* QKV, const int6
 #define INTEL_MHA_FWD(DKV)                                                                                         \
     case DKV: {                                                                                                    \
         auto k = mha_fwd_kernel<DKV>;                                                                              \
-        if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
+        ensure_smem(k, smem);     \
         LAUNCH(k, grid, block, smem, s, T, d, heads, QKV, lens, O);                                                \
     } break;
     switch (d / heads) {
@@ -293,7 +293,7 @@ int mha_bwd(int64_t B, int64_t T, int d, int heads, const float* QKV, const int6
 #define INTEL_MHA_BWD(DKV)                                                                                         \
     case DKV: {                                                                                                    \
         auto k = mha_bwd_kernel<DKV>;                                                                              \
-        if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
+        ensure_smem(k, smem);     \
         LAUNCH(k, grid, block, smem, s, T, d, heads, QKV, lens, dO, dQKV);                                         \
     } break;
     switch (d / heads) {
