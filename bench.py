@@ -232,6 +232,11 @@ def run_b200(a):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
+    # the step creates a few thousand short-lived Python objects (ctypes structs, autograd nodes); a full
+    # gen-2 collection over torch's object graph costs 50-100 ms and would land inside the timed region at random
+    import gc
+    gc.collect()
+    gc.freeze()
     # ---- warm-up, then the timed region (inputs resident in HBM) ----
     for i in range(a.warmup if a.profile_mode else max(a.warmup, 3)):
         train_step(resident[i % len(resident)])

@@ -53,7 +53,8 @@ int stack_fwd(int64_t B, int64_t L, int d, int heads, int layers, const intel_se
     const int64_t R = B * L;
     if (trunk_supported(L, d, heads, layers)) {     // whole stack of a session on chip (trunk.cu)
         const StackParams sp{p.wq, p.wk, p.wv, p.w1, p.b1, p.w2, p.b2, p.lnw, p.lnb};
-        return trunk_fwd(B, L, heads, layers, sp, w.X, s);
+        const StackSaved sv{w.QKV, w.A, w.U, w.Z, w.st};
+        return trunk_fwd(B, L, heads, layers, sp, w.X, sv, s);
     }
     for (int l = 0; l < layers; ++l) {
         INTEL_TRY(linear(R, d, d, w.X[l], d, p.wq, d, nullptr, w.QKV[l], 3 * d, s));
@@ -74,7 +75,8 @@ int stack_bwd(int64_t B, int64_t L, int d, int heads, int layers, const intel_se
     if (trunk_supported(L, d, heads, layers)) {
         const StackParams sp{p.wq, p.wk, p.wv, p.w1, p.b1, p.w2, p.b2, p.lnw, p.lnb};
         const StackGrads sg{g.wq, g.wk, g.wv, g.w1, g.b1, g.w2, g.b2, g.lnw, g.lnb};
-        return trunk_bwd(B, L, heads, layers, sp, sg, w.X, dX, s);
+        const StackSaved sv{w.QKV, w.A, w.U, w.Z, w.st};
+        return trunk_bwd(B, L, heads, layers, sp, sg, w.X, sv, dX, s);
     }
     for (int l = layers - 1; l >= 0; --l) {
         float* dZ = t1;

@@ -194,15 +194,13 @@ __global__ void __launch_bounds__(WM * WN * 32) gemm_tc_kernel(GemmDev g) {
             for (int i = 0; i < TM; ++i)
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
-                    ah[i][c] = to_tf32(af[i][c]);
-                    al[i][c] = to_tf32(af[i][c] - __uint_as_float(ah[i][c]));
+                    split_tf32(af[i][c], ah[i][c], al[i][c]);
                 }
 #pragma unroll
             for (int j = 0; j < TN; ++j)
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
-                    bh[j][c] = to_tf32(bf[j][c]);
-                    bl[j][c] = to_tf32(bf[j][c] - __uint_as_float(bh[j][c]));
+                    split_tf32(bf[j][c], bh[j][c], bl[j][c]);
                 }
             // three passes over independent accumulators: no back-to-back dependent MMAs
 #pragma unroll
@@ -368,8 +366,7 @@ __global__ void __launch_bounds__(256) gemm_stream32_kernel(GemmDev g) {
                 float w = 0.f;
                 if (j < ntiles && n < g.N) w = BT ? g.B[k * g.ldb + n] : g.B[n * g.ldb + k];
                 if (g.relu_b) w = fmaxf(w, 0.f);
-                bh[j][s][c] = to_tf32(w);
-                bl[j][s][c] = to_tf32(w - __uint_as_float(bh[j][s][c]));
+                split_tf32(w, bh[j][s][c], bl[j][s][c]);
             }
         }
     }
@@ -412,8 +409,7 @@ __global__ void __launch_bounds__(256) gemm_stream32_kernel(GemmDev g) {
             uint32_t ah[4], al[4];
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-                ah[c] = to_tf32(af[c]);
-                al[c] = to_tf32(af[c] - __uint_as_float(ah[c]));
+                split_tf32(af[c], ah[c], al[c]);
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {

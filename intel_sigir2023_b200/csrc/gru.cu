@@ -96,11 +96,6 @@ static const int GF_SB = 32;            // sessions per CTA, forward
 static const int GB_SB = 16;            // sessions per CTA, backward
 static const int GD = 3 * GH + 4;       // smem row stride of the dgh tile
 
-__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-    hi = to_tf32(x);
-    lo = to_tf32(x - __uint_as_float(hi));
-}
-
 __device__ __forceinline__ void stage_whh(float* Ws, const float* __restrict__ w_hh) {
     for (int e = threadIdx.x; e < 3 * GH * (GH / 4); e += blockDim.x) {
         const int n = e / (GH / 4), k4 = (e % (GH / 4)) * 4;

@@ -114,12 +114,16 @@ int gru_seq_bwd(int64_t B, int64_t T, int h, const int64_t* lens, const float* w
 // ---- trunk.cu: fused self-attention stack (d = 32, L <= 64): all layers of a session on chip -----
 struct StackParams { const float *wq, *wk, *wv, *w1, *b1, *w2, *b2, *lnw, *lnb; };
 struct StackGrads { float *wq, *wk, *wv, *w1, *b1, *w2, *b2, *lnw, *lnb; };
+// per-layer activations the forward kernel leaves for the backward kernel: q|k|v [B*L,96], attention output,
+// FFN hidden (pre-relu), pre-LN sum [B*L,32] each, LN mean / rstd [B*L,2]
+struct StackSaved { float* const* QKV; float* const* A; float* const* U; float* const* Z; float* const* ST; };
 bool trunk_supported(int64_t L, int d, int heads, int layers);
 // X[0] = stack input [B*L,32]; X[l+1] receives the output of layer l
-int trunk_fwd(int64_t B, int64_t L, int heads, int layers, const StackParams& p, float* const* X, cudaStream_t s);
+int trunk_fwd(int64_t B, int64_t L, int heads, int layers, const StackParams& p, float* const* X, const StackSaved& sv,
+              cudaStream_t s);
 // dX: d loss / d X[layers] on entry, d loss / d X[0] on return; weight gradients are accumulated into g
 int trunk_bwd(int64_t B, int64_t L, int heads, int layers, const StackParams& p, const StackGrads& g, float* const* X,
-              float* dX, cudaStream_t s);
+              const StackSaved& sv, float* dX, cudaStream_t s);
 
 // ---- fuse.cu ------------------------------------------------------------------------------------
 // weights[b,l,:] = l < n_b ? w_valid[b] : w_pad[b];  ens[b,l] = sum_k weights * float(scores)

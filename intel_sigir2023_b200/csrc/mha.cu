@@ -39,8 +39,7 @@ __device__ __forceinline__ void warp_mma(const float* __restrict__ A, int a_rs, 
             uint32_t ah[4], al[4];
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-                ah[c] = to_tf32(af[c]);
-                al[c] = to_tf32(af[c] - __uint_as_float(ah[c]));
+                split_tf32(af[c], ah[c], al[c]);
             }
             uint32_t bh[4][2], bl[4][2];
 #pragma unroll
@@ -48,8 +47,8 @@ __device__ __forceinline__ void warp_mma(const float* __restrict__ A, int a_rs, 
                 // tiles past n_tiles read column 0 of B (always mapped) and are never stored
                 const int n = (nt0 + j < n_tiles) ? (nt0 + j) * 8 + gq : gq;
                 const float b0 = B[k0 * b_ks + n * b_ns], b1 = B[(k0 + 4) * b_ks + n * b_ns];
-                bh[j][0] = to_tf32(b0); bl[j][0] = to_tf32(b0 - __uint_as_float(bh[j][0]));
-                bh[j][1] = to_tf32(b1); bl[j][1] = to_tf32(b1 - __uint_as_float(bh[j][1]));
+                split_tf32(b0, bh[j][0], bl[j][0]);
+                split_tf32(b1, bh[j][1], bl[j][1]);
             }
             // three independent passes over the four accumulators: no back-to-back dependent MMAs
 #pragma unroll

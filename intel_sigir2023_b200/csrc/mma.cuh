@@ -51,19 +51,23 @@ static inline void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_
 }
 #endif
 
+// Operand split for 3xTF32.  cvt.rna.tf32.f32 expands to a ~5-instruction sequence on sm_100a and made the
+// MMA kernels issue-bound (profiles/r01_summary.md), so the split is done with integer ops on the bit pattern:
+//   hi = round-to-nearest of x to 10 mantissa bits  ((bits + 0x1000) & ~0x1fff; operands are finite)
+//   lo = x - hi (exact in fp32), low 13 bits cleared - the tensor core would ignore them anyway.
+// |x - hi - lo| <= 2^-21 |x|.
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+    hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
+    lo = __float_as_uint(x - __uint_as_float(hi)) & 0xffffe000u;
+}
+
 // d += a * b at ~fp32 accuracy from three TF32 MMAs; af / bf are fp32 fragment values
 __device__ __forceinline__ void mma_3xtf32(float (&d)[4], const float (&af)[4], const float (&bf)[2]) {
     uint32_t ah[4], al[4], bh[2], bl[2];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        ah[i] = to_tf32(af[i]);
-        al[i] = to_tf32(af[i] - __uint_as_float(ah[i]));
-    }
+    for (int i = 0; i < 4; ++i) split_tf32(af[i], ah[i], al[i]);
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        bh[i] = to_tf32(bf[i]);
-        bl[i] = to_tf32(bf[i] - __uint_as_float(bh[i]));
-    }
+    for (int i = 0; i < 2; ++i) split_tf32(bf[i], bh[i], bl[i]);
     mma_tf32(d, al, bh);
     mma_tf32(d, ah, bl);
     mma_tf32(d, ah, bh);

@@ -23,6 +23,9 @@ struct TrunkArgs {
     int L, heads, layers;
     const float *wq, *wk, *wv, *w1, *b1, *w2, *b2, *lnw, *lnb;
     float* X[9];                     // X[0] input, X[l+1] output of layer l, each [B*L, 32]
+    // activations of layer l kept for the backward pass (written by the forward kernel when save != 0):
+    float *QKV[8], *A[8], *U[8], *Z[8], *ST[8];   // [B*L,96] q|k|v, [B*L,32] x3, [B*L,2] LN mean / rstd
+    int save;
     // backward only
     float* dX;                       // [B*L,32]: d loss / d X[layers] on entry, d loss / d X[0] on return
     float *gwq, *gwk, *gwv, *gw1, *gb1, *gw2, *gb2, *glnw, *glnb;
@@ -40,18 +43,18 @@ __device__ __forceinline__ void tile_mma_acc(float (&acc)[NTN][4], const float* 
         {
             const float a0 = A[(m0 + gq) * ARS + k0 * ACS], a1 = A[(m0 + gq + 8) * ARS + k0 * ACS];
             const float a2 = A[(m0 + gq) * ARS + (k0 + 4) * ACS], a3 = A[(m0 + gq + 8) * ARS + (k0 + 4) * ACS];
-            ah[0] = to_tf32(a0); al[0] = to_tf32(a0 - __uint_as_float(ah[0]));
-            ah[1] = to_tf32(a1); al[1] = to_tf32(a1 - __uint_as_float(ah[1]));
-            ah[2] = to_tf32(a2); al[2] = to_tf32(a2 - __uint_as_float(ah[2]));
-            ah[3] = to_tf32(a3); al[3] = to_tf32(a3 - __uint_as_float(ah[3]));
+            split_tf32(a0, ah[0], al[0]);
+            split_tf32(a1, ah[1], al[1]);
+            split_tf32(a2, ah[2], al[2]);
+            split_tf32(a3, ah[3], al[3]);
         }
         uint32_t bh[NTN][2], bl[NTN][2];
 #pragma unroll
         for (int j = 0; j < NTN; ++j) {
             const int n = (nt0 + j) * 8 + gq;
             const float b0 = B[k0 * BKS + n * BNS], b1 = B[(k0 + 4) * BKS + n * BNS];
-            bh[j][0] = to_tf32(b0); bl[j][0] = to_tf32(b0 - __uint_as_float(bh[j][0]));
-            bh[j][1] = to_tf32(b1); bl[j][1] = to_tf32(b1 - __uint_as_float(bh[j][1]));
+            split_tf32(b0, bh[j][0], bl[j][0]);
+            split_tf32(b1, bh[j][1], bl[j][1]);
         }
 #pragma unroll
         for (int j = 0; j < NTN; ++j) mma_tf32(acc[j], al, bh[j]);
@@ -123,8 +126,10 @@ __device__ __forceinline__ void load_tile(float* dst, const float* __restrict__ 
 template <int TP, int DK>
 __device__ __forceinline__ void layer_forward(const float* W, const float* V, const float* Xs, float* Qs, float* Ks, float* Vs,
                                               float* As, float* Us, float* Zs, float* S, float* Xout, float* stats, int L,
-                                              int heads, int lane, int warp) {
+                                              int heads, int lane, int warp, float* gQKV, float* gA, float* gU, float* gZ,
+                                              float* gST) {
     constexpr int SS = TrunkSmem<TP>::SS, WMAT = TrunkSmem<TP>::WMAT, MT = TP / 16;
+    const int TW = blockDim.x >> 5;
     const float scale = 1.0f / sqrtf((float)DK);
     // Q K V = X W^T   (B(k, n) = W[n][k]); work item = (matrix, m-tile, n-half)
     for (int it = warp; it < 3 * MT * 2; it += TW) {
@@ -134,6 +139,13 @@ __device__ __forceinline__ void layer_forward(const float* W, const float* V, co
                                           [&](int r, int c, float v0, float v1) { dst[r * TS + c] = v0; dst[r * TS + c + 1] = v1; });
     }
     __syncthreads();
+    if (gQKV) {
+        for (int e = threadIdx.x; e < L * 3 * (TD / 4); e += blockDim.x) {
+            const int r = e / (3 * TD / 4), q = (e / (TD / 4)) % 3, c = (e % (TD / 4)) * 4;
+            const float* src = q == 0 ? Qs : (q == 1 ? Ks : Vs);
+            *reinterpret_cast<float4*>(gQKV + (int64_t)r * 3 * TD + q * TD + c) = *reinterpret_cast<const float4*>(src + r * TS + c);
+        }
+    }
     for (int hd = 0; hd < heads; ++hd) {
         const int ho = hd * DK;
         // S = scale * Q_h K_h^T over all TP slots (pad slots are live keys: their K rows are W_k * 0 = 0 -> score 0)
@@ -165,6 +177,12 @@ __device__ __forceinline__ void layer_forward(const float* W, const float* V, co
         }
         __syncthreads();
     }
+    if (gA) {
+        for (int e = threadIdx.x; e < L * (TD / 4); e += blockDim.x) {
+            const int r = e / (TD / 4), c = (e % (TD / 4)) * 4;
+            *reinterpret_cast<float4*>(gA + (int64_t)r * TD + c) = *reinterpret_cast<const float4*>(As + r * TS + c);
+        }
+    }
     // U = A W1^T + b1 (kept pre-relu)
     for (int it = warp; it < MT * 2; it += TW) {
         const int mt = it / 2, nh = it & 1;
@@ -174,6 +192,12 @@ __device__ __forceinline__ void layer_forward(const float* W, const float* V, co
         });
     }
     __syncthreads();
+    if (gU) {
+        for (int e = threadIdx.x; e < L * (TD / 4); e += blockDim.x) {
+            const int r = e / (TD / 4), c = (e % (TD / 4)) * 4;
+            *reinterpret_cast<float4*>(gU + (int64_t)r * TD + c) = *reinterpret_cast<const float4*>(Us + r * TS + c);
+        }
+    }
     // Z = relu(U) W2^T + b2 + X
     for (int it = warp; it < MT * 2; it += TW) {
         const int mt = it / 2, nh = it & 1;
@@ -192,17 +216,17 @@ __device__ __forceinline__ void layer_forward(const float* W, const float* V, co
             const float a0 = fmaxf(Us[(m0 + gq) * TS + k0], 0.f), a1 = fmaxf(Us[(m0 + gq + 8) * TS + k0], 0.f);
             const float a2 = fmaxf(Us[(m0 + gq) * TS + k0 + 4], 0.f), a3 = fmaxf(Us[(m0 + gq + 8) * TS + k0 + 4], 0.f);
             uint32_t ah[4], al[4];
-            ah[0] = to_tf32(a0); al[0] = to_tf32(a0 - __uint_as_float(ah[0]));
-            ah[1] = to_tf32(a1); al[1] = to_tf32(a1 - __uint_as_float(ah[1]));
-            ah[2] = to_tf32(a2); al[2] = to_tf32(a2 - __uint_as_float(ah[2]));
-            ah[3] = to_tf32(a3); al[3] = to_tf32(a3 - __uint_as_float(ah[3]));
+            split_tf32(a0, ah[0], al[0]);
+            split_tf32(a1, ah[1], al[1]);
+            split_tf32(a2, ah[2], al[2]);
+            split_tf32(a3, ah[3], al[3]);
             uint32_t bh[2][2], bl[2][2];
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
                 const int n = (nh * 2 + j) * 8 + gq;
                 const float b0 = Bw[n * TS + k0], b1 = Bw[n * TS + k0 + 4];
-                bh[j][0] = to_tf32(b0); bl[j][0] = to_tf32(b0 - __uint_as_float(bh[j][0]));
-                bh[j][1] = to_tf32(b1); bl[j][1] = to_tf32(b1 - __uint_as_float(bh[j][1]));
+                split_tf32(b0, bh[j][0], bl[j][0]);
+                split_tf32(b1, bh[j][1], bl[j][1]);
             }
 #pragma unroll
             for (int j = 0; j < 2; ++j) mma_tf32(acc[j], al, bh[j]);
@@ -232,6 +256,10 @@ __device__ __forceinline__ void layer_forward(const float* W, const float* V, co
         const float rstd = rsqrtf(warp_sum(dlt * dlt) * (1.0f / TD) + 1e-5f);
         Xout[r * TS + lane] = dlt * rstd * V[2 * TD + lane] + V[3 * TD + lane];
         if (stats && lane == 0) { stats[2 * r] = mean; stats[2 * r + 1] = rstd; }
+        if (gZ) {
+            gZ[(int64_t)r * TD + lane] = z;
+            if (lane == 0) { gST[2 * r] = mean; gST[2 * r + 1] = rstd; }
+        }
     }
     __syncthreads();
 }
@@ -256,7 +284,12 @@ __global__ void __launch_bounds__(TW * 32) trunk_fwd_kernel(TrunkArgs a) {
         __syncthreads();
         for (int l = 0; l < a.layers; ++l) {
             // U reuses the Q tile, Z the K tile (both are dead once the attention output exists)
-            layer_forward<TP, DK>(W, V, Xs, Qs, Ks, Vs, As, Qs, Ks, S, Xs, nullptr, a.L, a.heads, lane, warp);
+            const int64_t ro = b * a.L;
+            const bool sv = a.save != 0;
+            layer_forward<TP, DK>(W, V, Xs, Qs, Ks, Vs, As, Qs, Ks, S, Xs, nullptr, a.L, a.heads, lane, warp,
+                                  sv ? a.QKV[l] + ro * 3 * TD : nullptr, sv ? a.A[l] + ro * TD : nullptr,
+                                  sv ? a.U[l] + ro * TD : nullptr, sv ? a.Z[l] + ro * TD : nullptr,
+                                  sv ? a.ST[l] + ro * 2 : nullptr);
             float* out = a.X[l + 1] + b * a.L * TD;
             for (int e = threadIdx.x; e < a.L * (TD / 4); e += blockDim.x) {
                 const int r = e / (TD / 4), c = (e % (TD / 4)) * 4;
@@ -269,7 +302,7 @@ __global__ void __launch_bounds__(TW * 32) trunk_fwd_kernel(TrunkArgs a) {
 // ------------------------------------------------------------------------------------------------
 // backward: for each session, layers in reverse; everything is recomputed from X[l]
 template <int TP, int DK>
-__global__ void __launch_bounds__(TW * 32) trunk_bwd_kernel(TrunkArgs a) {
+__global__ void __launch_bounds__(512) trunk_bwd_kernel(TrunkArgs a) {
     DYN_SMEM(float, sm);
     using SMP = TrunkSmem<TP>;
     constexpr int SS = SMP::SS, TILE = SMP::TILE, WMAT = SMP::WMAT, MT = TP / 16;
@@ -293,6 +326,10 @@ __global__ void __launch_bounds__(TW * 32) trunk_bwd_kernel(TrunkArgs a) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gq = lane >> 2, tq = lane & 3;
     const float scale = 1.0f / sqrtf((float)DK);
+    const int TW = blockDim.x >> 5;                 // 16 warps: the weight-gradient blocks split the tokens in halves
+    const int w8 = warp & 7, kh = warp >> 3, KH = TW >> 3;
+    constexpr int KSTEPS = TP / 8;
+    const int ks_beg = kh * (KSTEPS / KH), ks_end = (kh == KH - 1) ? KSTEPS : (kh + 1) * (KSTEPS / KH);
     stage_weights(sm, a);
     for (int e = threadIdx.x; e < 5 * WMAT + 4 * TD; e += blockDim.x) GW[e] = 0.f;
     const int L = a.L;
@@ -302,10 +339,24 @@ __global__ void __launch_bounds__(TW * 32) trunk_bwd_kernel(TrunkArgs a) {
         load_tile<TP>(Gs, a.dX + b * L * TD, L);
         for (int l = a.layers - 1; l >= 0; --l) {
             __syncthreads();
-            load_tile<TP>(Xs, a.X[l] + b * L * TD, L);
+            // ---- reload the layer's activations saved by the forward kernel ----
+            {
+                const int64_t ro = b * L;
+                load_tile<TP>(Xs, a.X[l] + ro * TD, L);
+                load_tile<TP>(As, a.A[l] + ro * TD, L);
+                load_tile<TP>(Us, a.U[l] + ro * TD, L);
+                load_tile<TP>(Zs, a.Z[l] + ro * TD, L);
+                const float* gq = a.QKV[l] + ro * 3 * TD;
+                for (int e = threadIdx.x; e < TP * 3 * (TD / 4); e += blockDim.x) {
+                    const int r = e / (3 * TD / 4), q = (e / (TD / 4)) % 3, c = (e % (TD / 4)) * 4;
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (r < L) v = *reinterpret_cast<const float4*>(gq + (int64_t)r * 3 * TD + q * TD + c);
+                    float* dst = q == 0 ? Qs : (q == 1 ? Ks : Vs);
+                    *reinterpret_cast<float4*>(dst + r * TS + c) = v;
+                }
+                for (int e = threadIdx.x; e < 2 * L; e += blockDim.x) stats[e] = a.ST[l][ro * 2 + e];
+            }
             __syncthreads();
-            // ---- recompute the layer (LN output goes to the dead dQ tile; only its statistics are needed) ----
-            layer_forward<TP, DK>(W, V, Xs, Qs, Ks, Vs, As, Us, Zs, P, dQs, stats, L, a.heads, lane, warp);
             // ---- LayerNorm backward: dZ (into Zs), d gamma / d beta ----
             {
                 float pg = 0.f, pb = 0.f;
@@ -326,10 +377,10 @@ __global__ void __launch_bounds__(TW * 32) trunk_bwd_kernel(TrunkArgs a) {
             // ---- FFN backward ----
             // dW2 += dZ^T relu(U), db2 += colsum(dZ); dU = (dZ W2) * (U > 0); 8 (m,n) tile pairs -> one per warp
             {
-                const int mt = warp & 1, np = warp >> 1;            // output rows 16*mt.., n-tile np
+                const int mt = w8 & 1, np = w8 >> 1;                // output rows 16*mt.., n-tile np
                 float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 2
-                for (int ks = 0; ks < TP / 8; ++ks) {
+                for (int ks = ks_beg; ks < ks_end; ++ks) {
                     const int k0 = ks * 8 + tq;
                     float af[4] = {Zs[k0 * TS + mt * 16 + gq], Zs[k0 * TS + mt * 16 + gq + 8], Zs[(k0 + 4) * TS + mt * 16 + gq],
                                    Zs[(k0 + 4) * TS + mt * 16 + gq + 8]};
@@ -338,8 +389,8 @@ __global__ void __launch_bounds__(TW * 32) trunk_bwd_kernel(TrunkArgs a) {
                 }
                 float* g2 = GW + 4 * WMAT;
                 const int r = mt * 16 + gq, c = np * 8 + 2 * tq;
-                g2[r * TS + c] += acc[0]; g2[r * TS + c + 1] += acc[1];
-                g2[(r + 8) * TS + c] += acc[2]; g2[(r + 8) * TS + c + 1] += acc[3];
+                atomicAdd(g2 + r * TS + c, acc[0]); atomicAdd(g2 + r * TS + c + 1, acc[1]);
+                atomicAdd(g2 + (r + 8) * TS + c, acc[2]); atomicAdd(g2 + (r + 8) * TS + c + 1, acc[3]);
                 if (warp == 0) {
                     float sb = 0.f;
                     for (int r2 = 0; r2 < L; ++r2) sb += Zs[r2 * TS + lane];
@@ -356,10 +407,10 @@ __global__ void __launch_bounds__(TW * 32) trunk_bwd_kernel(TrunkArgs a) {
             }
             __syncthreads();
             {   // dW1 += dU^T A, db1 += colsum(dU)
-                const int mt = warp & 1, np = warp >> 1;
+                const int mt = w8 & 1, np = w8 >> 1;
                 float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 2
-                for (int ks = 0; ks < TP / 8; ++ks) {
+                for (int ks = ks_beg; ks < ks_end; ++ks) {
                     const int k0 = ks * 8 + tq;
                     float af[4] = {Us[k0 * TS + mt * 16 + gq], Us[k0 * TS + mt * 16 + gq + 8], Us[(k0 + 4) * TS + mt * 16 + gq],
                                    Us[(k0 + 4) * TS + mt * 16 + gq + 8]};
@@ -368,8 +419,8 @@ __global__ void __launch_bounds__(TW * 32) trunk_bwd_kernel(TrunkArgs a) {
                 }
                 float* g1 = GW + 3 * WMAT;
                 const int r = mt * 16 + gq, c = np * 8 + 2 * tq;
-                g1[r * TS + c] += acc[0]; g1[r * TS + c + 1] += acc[1];
-                g1[(r + 8) * TS + c] += acc[2]; g1[(r + 8) * TS + c + 1] += acc[3];
+                atomicAdd(g1 + r * TS + c, acc[0]); atomicAdd(g1 + r * TS + c + 1, acc[1]);
+                atomicAdd(g1 + (r + 8) * TS + c, acc[2]); atomicAdd(g1 + (r + 8) * TS + c + 1, acc[3]);
                 if (warp == 0) {
                     float sb = 0.f;
                     for (int r2 = 0; r2 < L; ++r2) sb += Us[r2 * TS + lane];
@@ -432,14 +483,14 @@ __global__ void __launch_bounds__(TW * 32) trunk_bwd_kernel(TrunkArgs a) {
             }
             // ---- projections backward: dWq += dQ^T X (same for k, v);  dX = dQ Wq + dK Wk + dV Wv + dZ ----
             {
-                const int mt = warp & 1, np = warp >> 1;
+                const int mt = w8 & 1, np = w8 >> 1;
                 const int r = mt * 16 + gq, c = np * 8 + 2 * tq;
                 const float* src[3] = {dQs, dKs, dVs};
 #pragma unroll
                 for (int m = 0; m < 3; ++m) {
                     float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 2
-                    for (int ks = 0; ks < TP / 8; ++ks) {
+                    for (int ks = ks_beg; ks < ks_end; ++ks) {
                         const int k0 = ks * 8 + tq;
                         const float* G = src[m];
                         float af[4] = {G[k0 * TS + mt * 16 + gq], G[k0 * TS + mt * 16 + gq + 8], G[(k0 + 4) * TS + mt * 16 + gq],
@@ -448,8 +499,8 @@ __global__ void __launch_bounds__(TW * 32) trunk_bwd_kernel(TrunkArgs a) {
                         mma_3xtf32(acc, af, bf);
                     }
                     float* gm = GW + m * WMAT;
-                    gm[r * TS + c] += acc[0]; gm[r * TS + c + 1] += acc[1];
-                    gm[(r + 8) * TS + c] += acc[2]; gm[(r + 8) * TS + c + 1] += acc[3];
+                    atomicAdd(gm + r * TS + c, acc[0]); atomicAdd(gm + r * TS + c + 1, acc[1]);
+                    atomicAdd(gm + (r + 8) * TS + c, acc[2]); atomicAdd(gm + (r + 8) * TS + c + 1, acc[3]);
                 }
             }
             for (int it = warp; it < MT * 2; it += TW) {
@@ -505,7 +556,7 @@ static int trunk_launch(const TrunkArgs& a, bool bwd, cudaStream_t s) {
     if (bwd) {
         auto k = trunk_bwd_kernel<TP, DK>;
         ensure_smem(k, smem);
-        LAUNCH(k, dim3(grid), dim3(TW * 32), smem, s, a);
+        LAUNCH(k, dim3(grid), dim3(512), smem, s, a);
     } else {
         auto k = trunk_fwd_kernel<TP, DK>;
         ensure_smem(k, smem);
@@ -532,23 +583,29 @@ int trunk_run(const TrunkArgs& a, bool bwd, cudaStream_t s) {
     return INTEL_ERR_UNSUPPORTED;
 }
 
-static TrunkArgs trunk_args(int64_t B, int64_t L, int heads, int layers, const StackParams& p, float* const* X) {
+static TrunkArgs trunk_args(int64_t B, int64_t L, int heads, int layers, const StackParams& p, float* const* X,
+                            const StackSaved& sv) {
     TrunkArgs a;
     memset(&a, 0, sizeof(a));
+    for (int l = 0; l < layers && l < 8; ++l) {
+        a.QKV[l] = sv.QKV[l]; a.A[l] = sv.A[l]; a.U[l] = sv.U[l]; a.Z[l] = sv.Z[l]; a.ST[l] = sv.ST[l];
+    }
+    a.save = 1;
     a.B = B; a.L = (int)L; a.heads = heads; a.layers = layers;
     a.wq = p.wq; a.wk = p.wk; a.wv = p.wv; a.w1 = p.w1; a.b1 = p.b1; a.w2 = p.w2; a.b2 = p.b2; a.lnw = p.lnw; a.lnb = p.lnb;
     for (int l = 0; l <= layers && l < 9; ++l) a.X[l] = X[l];
     return a;
 }
 
-int trunk_fwd(int64_t B, int64_t L, int heads, int layers, const StackParams& p, float* const* X, cudaStream_t s) {
-    TrunkArgs a = trunk_args(B, L, heads, layers, p, X);
+int trunk_fwd(int64_t B, int64_t L, int heads, int layers, const StackParams& p, float* const* X, const StackSaved& sv,
+              cudaStream_t s) {
+    TrunkArgs a = trunk_args(B, L, heads, layers, p, X, sv);
     return trunk_run(a, false, s);
 }
 
 int trunk_bwd(int64_t B, int64_t L, int heads, int layers, const StackParams& p, const StackGrads& g, float* const* X,
-              float* dX, cudaStream_t s) {
-    TrunkArgs a = trunk_args(B, L, heads, layers, p, X);
+              const StackSaved& sv, float* dX, cudaStream_t s) {
+    TrunkArgs a = trunk_args(B, L, heads, layers, p, X, sv);
     a.dX = dX;
     a.gwq = g.wq; a.gwk = g.wk; a.gwv = g.wv; a.gw1 = g.w1; a.gb1 = g.b1; a.gw2 = g.w2; a.gb2 = g.b2; a.glnw = g.lnw; a.glnb = g.lnb;
     return trunk_run(a, true, s);

@@ -11,7 +11,10 @@ model = IntEL(argparse.Namespace(device=dev, model_path="", buffer=1), cfg=cfg).
 crit = losses.IntListloss(loss_args)
 batch = synthetic.make_batch(corpus, synthetic.BatchSpec(batch_size=a.batch, max_len=a.list_len, min_len=a.list_len), seed=1, device=dev)
 def ev(): return torch.cuda.Event(enable_timing=True)
-for it in range(6):
+import gc
+if os.environ.get('NOGC'): gc.disable()
+if os.environ.get('FREEZE'): gc.collect(); gc.freeze()
+for it in range(16):
     for p in model.parameters(): p.grad = None
     torch.cuda.synchronize()
     t0 = time.perf_counter()
