@@ -121,7 +121,7 @@ def run_reference(a):
         "impl": "reference", "metric": "sessions/sec (train fwd+bwd)", "value": rate, "unit": "sessions/s",
         "n_gpus": a.gpus, "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(a, cfg, loss_kind, a.cpu_batch),
+        "config": workload_config(a, cfg, loss_kind, a.batch),
         "cpu_baseline": {"value": rate, "unit": "sessions/s", "cores": ncores, "kind": "port", "sample": sample},
         "e2e": {"value": rate, "unit": "sessions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,

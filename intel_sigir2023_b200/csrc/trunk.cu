@@ -36,25 +36,21 @@ template <int NTN, int KS, int ARS, int ACS, int BKS, int BNS>
 __device__ __forceinline__ void tile_mma_acc(float (&acc)[NTN][4], const float* __restrict__ A, const float* __restrict__ B,
                                              int m0, int nt0, int lane) {
     const int gq = lane >> 2, tq = lane & 3;
-#pragma unroll 2
+    // per-lane base pointers; every further offset is a compile-time constant once the k loop is unrolled
+    const float* pa = A + (m0 + gq) * ARS + tq * ACS;
+    const float* pb = B + tq * BKS + (nt0 * 8 + gq) * BNS;
+#pragma unroll
     for (int ks = 0; ks < KS; ++ks) {
-        const int k0 = ks * 8 + tq;
         uint32_t ah[4], al[4];
-        {
-            const float a0 = A[(m0 + gq) * ARS + k0 * ACS], a1 = A[(m0 + gq + 8) * ARS + k0 * ACS];
-            const float a2 = A[(m0 + gq) * ARS + (k0 + 4) * ACS], a3 = A[(m0 + gq + 8) * ARS + (k0 + 4) * ACS];
-            split_tf32(a0, ah[0], al[0]);
-            split_tf32(a1, ah[1], al[1]);
-            split_tf32(a2, ah[2], al[2]);
-            split_tf32(a3, ah[3], al[3]);
-        }
+        split_tf32(pa[(ks * 8) * ACS], ah[0], al[0]);
+        split_tf32(pa[8 * ARS + (ks * 8) * ACS], ah[1], al[1]);
+        split_tf32(pa[(ks * 8 + 4) * ACS], ah[2], al[2]);
+        split_tf32(pa[8 * ARS + (ks * 8 + 4) * ACS], ah[3], al[3]);
         uint32_t bh[NTN][2], bl[NTN][2];
 #pragma unroll
         for (int j = 0; j < NTN; ++j) {
-            const int n = (nt0 + j) * 8 + gq;
-            const float b0 = B[k0 * BKS + n * BNS], b1 = B[(k0 + 4) * BKS + n * BNS];
-            split_tf32(b0, bh[j][0], bl[j][0]);
-            split_tf32(b1, bh[j][1], bl[j][1]);
+            split_tf32(pb[(ks * 8) * BKS + (j * 8) * BNS], bh[j][0], bl[j][0]);
+            split_tf32(pb[(ks * 8 + 4) * BKS + (j * 8) * BNS], bh[j][1], bl[j][1]);
         }
 #pragma unroll
         for (int j = 0; j < NTN; ++j) mma_tf32(acc[j], al, bh[j]);

@@ -1,0 +1,121 @@
+"""Size-independent properties at BASELINE.json's full per-step sizes (the oracle cannot run these in seconds):
+shard additivity of the evaluation sums, batch-split invariance of the forward pass, linearity of the fusion,
+a directional finite-difference check of the fused loss gradients, permutation invariance of NDCG."""
+import argparse
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _model(cfg_kw, corpus_kw, seed=0):
+    from intel_sigir2023_b200 import synthetic
+    from intel_sigir2023_b200.config import IntelConfig
+    from intel_sigir2023_b200.IntEL import IntEL
+    corpus = synthetic.CorpusSpec(**corpus_kw)
+    cfg = IntelConfig(item_rows=corpus.item_rows, class_rows=corpus.n_class, user_rows=corpus.user_rows,
+                      ctx_rows=corpus.n_ctx, intent_num=corpus.intent_num, model_num=corpus.model_num,
+                      history_max=corpus.history_max, **cfg_kw)
+    torch.manual_seed(seed)
+    model = IntEL(argparse.Namespace(device=torch.device(DEV), model_path="", buffer=1), cfg=cfg).to(DEV)
+    return corpus, cfg, model
+
+
+C2 = dict(n_item=100_000, n_class=357, n_user=10_000, n_ctx=931, model_num=4, intent_num=1071, history_max=20)
+PL = dict(encoder="GRU4Rec", context_emb_size=32, intent_emb_size=32, cross_attn_qsize=64, num_heads=2, num_layers=2)
+
+
+def test_eval_sums_are_additive_over_shards_1m_sessions():
+    """configs[1] size: 1M sessions x 50 candidates; sum over 4 shards == one pass; shuffling sessions changes nothing."""
+    from intel_sigir2023_b200 import evaluate, synthetic
+    N, L = 1_000_000, 50
+    pred, ranking, pos, slen = synthetic.eval_set(N, L, 25, seed=3, device=DEV)
+    topk = [3, 1, 5, 10]
+    args = lambda sl: (pred[sl], ranking[sl], slen[sl], pos["c_paynum_i"][sl], pos["c_favnum_i"][sl], pos["c_clicknum_i"][sl], L, topk)
+    full_s, full_c = evaluate.ndcg_sums(*args(slice(None)))
+    parts = [evaluate.ndcg_sums(*args(slice(i * N // 4, (i + 1) * N // 4))) for i in range(4)]
+    ps, pc = sum(p[0] for p in parts), sum(p[1] for p in parts)
+    assert torch.equal(full_c, pc)
+    assert torch.allclose(full_s, ps, rtol=1e-12, atol=0)
+    perm = torch.randperm(N, device=DEV)
+    sh_s, sh_c = evaluate.ndcg_sums(pred[perm], ranking[perm], slen[perm], pos["c_paynum_i"][perm], pos["c_favnum_i"][perm],
+                                    pos["c_clicknum_i"][perm], L, topk)
+    assert torch.equal(full_c, sh_c) and torch.allclose(full_s, sh_s, rtol=1e-12, atol=0)
+    res = evaluate.metrics_from_sums(full_s.cpu().numpy(), full_c.cpu().numpy(), topk, ["NDCG", "HR"])
+    assert 0.0 < res["NDCG@3"] < 1.0 and res["click_HR@10"] <= 1.0
+    # a perfect scorer (score = gain) has NDCG@k = 1 for every k
+    perfect = ranking.clamp(min=0).float() + 0.01 * torch.rand(N, L, device=DEV)
+    valid = torch.arange(L, device=DEV)[None, :] < slen[:, None]
+    s2, c2 = evaluate.ndcg_sums(perfect * valid, ranking, slen, pos["c_paynum_i"], pos["c_favnum_i"], pos["c_clicknum_i"], L, topk)
+    r2 = evaluate.metrics_from_sums(s2.cpu().numpy(), c2.cpu().numpy(), topk, ["NDCG", "HR"])
+    assert all(abs(r2[f"NDCG@{k}"] - 1.0) < 1e-12 for k in topk)
+
+
+def test_eval_long_lists_config4_shape():
+    """configs[3] shape: 200 candidates (a 100k-session slice); additivity + perfect scorer."""
+    from intel_sigir2023_b200 import evaluate, synthetic
+    N, L = 100_000, 200
+    pred, ranking, pos, slen = synthetic.eval_set(N, L, 100, seed=5, device=DEV)
+    topk = [3, 1, 5, 10]
+    a, ac = evaluate.ndcg_sums(pred, ranking, slen, pos["c_paynum_i"], pos["c_favnum_i"], pos["c_clicknum_i"], L, topk)
+    h = N // 2
+    b1 = evaluate.ndcg_sums(pred[:h], ranking[:h], slen[:h], pos["c_paynum_i"][:h], pos["c_favnum_i"][:h], pos["c_clicknum_i"][:h], L, topk)
+    b2 = evaluate.ndcg_sums(pred[h:], ranking[h:], slen[h:], pos["c_paynum_i"][h:], pos["c_favnum_i"][h:], pos["c_clicknum_i"][h:], L, topk)
+    assert torch.allclose(a, b1[0] + b2[0], rtol=1e-12, atol=0) and torch.equal(ac, b1[1] + b2[1])
+
+
+def test_forward_is_invariant_to_batch_split_full_step():
+    """one bench-sized step (4096 sessions x 50 x K=4, I=1071): the two halves give the same rows as the whole."""
+    from intel_sigir2023_b200 import synthetic
+    corpus, cfg, model = _model(PL, C2)
+    model.eval()
+    batch = synthetic.make_batch(corpus, synthetic.BatchSpec(batch_size=4096, max_len=50, min_len=20), seed=1, device=DEV)
+    with torch.no_grad():
+        whole = model(batch)
+        halves = [model(synthetic.shard_batch(batch, r, 2)) for r in range(2)]
+    for k in ("weights", "ens_score", "intents"):
+        cat = torch.cat([h[k] for h in halves], dim=0)
+        assert torch.allclose(whole[k], cat, rtol=1e-6, atol=1e-7), k
+    assert torch.isfinite(whole["ens_score"]).all()
+    # pad slots carry score 0 -> ens 0; intents are distributions
+    valid = torch.arange(50, device=DEV)[None, :] < batch["session_len"][:, None]
+    assert (whole["ens_score"][~valid] == 0).all()
+    assert torch.allclose(whole["intents"].sum(-1), torch.ones(4096, device=DEV), atol=1e-5)
+
+
+def test_fusion_is_linear_in_the_weights():
+    from intel_sigir2023_b200 import baselines
+    g = torch.Generator(device=DEV).manual_seed(0)
+    x = torch.rand(4096, 50, 4, generator=g, device=DEV, dtype=torch.float64)
+    w1 = torch.randn(4096, 50, 4, generator=g, device=DEV)
+    w2 = torch.randn(4096, 50, 4, generator=g, device=DEV)
+    lhs = baselines.fuse(2.0 * w1 + w2, x)
+    rhs = 2.0 * baselines.fuse(w1, x) + baselines.fuse(w2, x)
+    assert torch.allclose(lhs, rhs, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("kind", ["list", "bpr", "mse"])
+def test_loss_gradient_matches_finite_difference_full_batch(kind):
+    """directional derivative of the fused loss kernels at B=4096, L=50, K=4 (float32 central difference)."""
+    from intel_sigir2023_b200 import losses, synthetic
+    corpus = synthetic.CorpusSpec(**C2)
+    batch = synthetic.make_batch(corpus, synthetic.BatchSpec(batch_size=4096, max_len=50, min_len=20), seed=2, device=DEV)
+    g = torch.Generator(device=DEV).manual_seed(1)
+    ens = torch.randn(4096, 50, generator=g, device=DEV)
+    w = 0.3 * torch.randn(4096, 50, 4, generator=g, device=DEV)
+    cls = {"list": losses.Listloss, "bpr": losses.BPRloss, "mse": losses.MSEloss}[kind]
+    crit = cls(argparse.Namespace(cal_diversity=1, diversity_alpha=0.05, intent_weight=0.1, ensemble_weight=1.0, kl_temp=2.0, kl_weight=0.5))
+    crit.bpr_noise = torch.rand(4096, 50, 50, generator=g, device=DEV)
+
+    def f(e, ww):
+        return crit({"ens_score": e, "weights": ww}, batch)[0]
+    e0, w0 = ens.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    f(e0, w0).backward()
+    de, dw = torch.randn_like(ens), torch.randn_like(w)
+    analytic = (e0.grad.double() * de.double()).sum() + (w0.grad.double() * dw.double()).sum()
+    eps = 1e-2
+    num = (f(ens + eps * de, w + eps * dw).double() - f(ens - eps * de, w - eps * dw).double()) / (2 * eps)
+    assert abs(analytic.item() - num.item()) <= 2e-2 * abs(num.item()) + 1e-4, (analytic.item(), num.item())
