@@ -279,10 +279,8 @@ def run_b200(a):
                                for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}}
 
     # ---- end to end: host (pinned) batch -> H2D -> step -> loss D2H, every step ----
-    e2e = None
-    if not a.no_e2e:
-        host = [{k: (v.cpu().pin_memory() if torch.is_tensor(v) else v) for k, v in resident[i].items()}
-                for i in range(min(2, len(resident)))]
+    def run_e2e(dev_batches):
+        host = [{k: (v.cpu().pin_memory() if torch.is_tensor(v) else v) for k, v in b.items()} for b in dev_batches]
         h2d = batch_bytes(host[0])
         loss_host = torch.zeros(1, dtype=torch.float64).pin_memory()
 
@@ -290,12 +288,27 @@ def run_b200(a):
             b = synthetic.batch_to(host[i % len(host)], dev, non_blocking=True)
             loss = train_step(b)
             loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
-        for i in range(2):
+        for i in range(3):
             e2e_step(i)
-        n_e2e = max(3, min(a.steps, 6))
-        ms_e2e = timed(e2e_step, n_e2e) / n_e2e
-        e2e = {"value": world * B / (ms_e2e * 1e-3), "unit": "sessions/s", "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": 8, "ms_per_step": ms_e2e}
+        n_e2e = max(5, min(a.steps, 10))
+        ms = min(timed(e2e_step, n_e2e) / n_e2e for _ in range(2))      # best of two passes: PCIe is shared on the box
+        return {"value": world * B / (ms * 1e-3), "unit": "sessions/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": 8, "ms_per_step": ms}
+
+    e2e = e2e_compact = None
+    if not a.no_e2e:
+        e2e = run_e2e(resident[:2])
+        e2e["input_layout"] = "dense reference API"
+        # the opt-in index form of his_intents / his_item_int (what a device-side batch builder would emit,
+        # SURVEY.md 8f-2): same sessions, same math, 70x fewer bytes over PCIe
+        compact = [synthetic.make_batch(corpus, spec, seed=1000 * rank + i, device=dev, layout="compact") for i in range(2)]
+        for i in range(2):
+            train_step(compact[i])
+        ms_c = timed(lambda i: train_step(compact[i % 2]), a.steps) / a.steps
+        e2e_compact = run_e2e(compact)
+        e2e_compact["input_layout"] = "compact (index/value) history intents, opt-in extension"
+        e2e_compact["value_resident"] = world * B / (ms_c * 1e-3)
+        del compact
 
     # ---- eval throughput: forward (no_grad) + evaluate_method on device ----
     topk, metrics = [3, 1, 5, 10], ["NDCG", "HR"]
@@ -325,6 +338,7 @@ def run_b200(a):
     }
     if e2e is not None:
         line["e2e"] = e2e
+        line["e2e_compact"] = e2e_compact
     if not a.no_cpu_baseline and world == 1:
         rate, ms, ncores, sample = cpu_reference_rate(a, corpus, cfg, loss_kind, loss_args, 4, 1)
         line["cpu_baseline"] = {"value": rate, "unit": "sessions/s", "cores": ncores, "kind": "port", "sample": sample}

@@ -95,6 +95,13 @@ typedef struct {
     const int64_t *his_item_id;      /* [B,H2]                   */
     const double  *his_item_int;     /* [B,H2,I] float64 one-hot */
     const int64_t *history_item_len; /* [B]                      */
+    /* Opt-in compact form of the two dense history tensors (what a device-side batch builder would emit):
+     * entry e of row (b,h) adds val * W[:, idx].  When the idx pointer is non-NULL the dense tensor is ignored. */
+    const int32_t *his_intents_idx;  /* [B,H1,nz1] */
+    const float   *his_intents_val;  /* [B,H1,nz1] */
+    const int32_t *his_item_int_idx; /* [B,H2,nz2] */
+    const float   *his_item_int_val; /* [B,H2,nz2] */
+    int32_t nz1, nz2;
 } intel_batch_t;
 
 const char* intel_last_error(void);

@@ -54,7 +54,9 @@ class Tensors(C.Structure):
 
 class Batch(C.Structure):
     _fields_ = [(n, _p) for n in ("u_id", "i_id", "i_class", "session_len", "scores", "context_mh", "his_context",
-                                  "his_intents", "history_len", "his_item_id", "his_item_int", "history_item_len")]
+                                  "his_intents", "history_len", "his_item_id", "his_item_int", "history_item_len",
+                                  "his_intents_idx", "his_intents_val", "his_item_int_idx", "his_item_int_val")] + \
+               [("nz1", C.c_int32), ("nz2", C.c_int32)]
 
 
 _lib: Optional[C.CDLL] = None
@@ -221,10 +223,20 @@ def make_batch(batch: Dict[str, object], cfg: IntelConfig) -> Batch:
     b.scores = ptr(batch["scores"], f64)
     b.context_mh = ptr(batch["context_mh"], i64)
     b.his_context = ptr(batch["his_context_mh"], i64)
-    b.his_intents = ptr(batch["his_intents"], f64)
     b.history_len = ptr(batch["history_len"], i64)
     b.his_item_id = ptr(batch["his_item_id"], i64)
-    b.his_item_int = ptr(batch["his_item_int"], f64)
+    if "his_intents_idx" in batch:       # opt-in compact layout (synthetic.make_batch(layout="compact"))
+        b.his_intents_idx = ptr(batch["his_intents_idx"], torch.int32)
+        b.his_intents_val = ptr(batch["his_intents_val"], torch.float32)
+        b.nz1 = batch["his_intents_idx"].shape[2]
+    else:
+        b.his_intents = ptr(batch["his_intents"], f64)
+    if "his_item_int_idx" in batch:
+        b.his_item_int_idx = ptr(batch["his_item_int_idx"], torch.int32)
+        b.his_item_int_val = ptr(batch["his_item_int_val"], torch.float32)
+        b.nz2 = batch["his_item_int_idx"].shape[2]
+    else:
+        b.his_item_int = ptr(batch["his_item_int"], f64)
     b.history_item_len = ptr(batch["history_item_len"], i64)
     return b
 

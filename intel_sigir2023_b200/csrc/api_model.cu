@@ -519,12 +519,24 @@ int intel_intent_fwd(const intel_dims_t* d, const intel_tensors_t* P, const inte
     INTEL_TRY(transpose(dint, I, P->intent_w, w.Wt, 0, s));
     // session history tokens: [context embedding | intent embedding of the dense history intents]
     INTEL_TRY(gather_rows(B * d->H1, dctx, P->ctx_emb, bt->his_context, w.e1.seq, d1, 0, s));
-    INTEL_TRY(dense_rows_linear_fwd(B * d->H1, I, dint, bt->his_intents, w.Wt, P->intent_b, w.e1.seq + dctx, d1,
-                                    w.e1.nz_idx, w.e1.nz_val, w.e1.nz_cnt, NZ_CAP, s));
+    if (bt->his_intents_idx) {
+        INTEL_TRY(sparse_rows_linear_fwd(B * d->H1, bt->nz1, dint, bt->his_intents_idx, bt->his_intents_val, w.Wt,
+                                         P->intent_b, w.e1.seq + dctx, d1, s));
+    } else {
+        INTEL_REQUIRE(bt->his_intents, INTEL_ERR_ARG, "his_intents is null");
+        INTEL_TRY(dense_rows_linear_fwd(B * d->H1, I, dint, bt->his_intents, w.Wt, P->intent_b, w.e1.seq + dctx, d1,
+                                        w.e1.nz_idx, w.e1.nz_val, w.e1.nz_cnt, NZ_CAP, s));
+    }
     // item history tokens: [item id embedding | intent embedding of the one-hot item intents]
     INTEL_TRY(gather_rows(B * d->H2, diid, P->iid_emb, bt->his_item_id, w.e2.seq, d2, 0, s));
-    INTEL_TRY(dense_rows_linear_fwd(B * d->H2, I, dint, bt->his_item_int, w.Wt, P->intent_b, w.e2.seq + diid, d2,
-                                    w.e2.nz_idx, w.e2.nz_val, w.e2.nz_cnt, NZ_CAP, s));
+    if (bt->his_item_int_idx) {
+        INTEL_TRY(sparse_rows_linear_fwd(B * d->H2, bt->nz2, dint, bt->his_item_int_idx, bt->his_item_int_val, w.Wt,
+                                         P->intent_b, w.e2.seq + diid, d2, s));
+    } else {
+        INTEL_REQUIRE(bt->his_item_int, INTEL_ERR_ARG, "his_item_int is null");
+        INTEL_TRY(dense_rows_linear_fwd(B * d->H2, I, dint, bt->his_item_int, w.Wt, P->intent_b, w.e2.seq + diid, d2,
+                                        w.e2.nz_idx, w.e2.nz_val, w.e2.nz_cnt, NZ_CAP, s));
+    }
     if (d->encoder == INTEL_ENCODER_BERT4REC) {
         INTEL_TRY(bert_fwd(d, P->enc, w.e1, bt->history_len, w.feat + off_v1, Dp, s));
         INTEL_TRY(bert_fwd(d, P->item_enc, w.e2, bt->history_item_len, w.feat + off_v2, Dp, s));
@@ -567,12 +579,22 @@ int intel_intent_bwd(const intel_dims_t* d, const intel_tensors_t* P, const inte
     }
     INTEL_TRY(fill_zero(w.dWt, (size_t)I * dint * 4, s));
     INTEL_TRY(scatter_add_rows(B * d->H1, dctx, w.e1.dseq, d1, bt->his_context, G->ctx_emb, nullptr, s));
-    INTEL_TRY(dense_rows_linear_bwd(B * d->H1, I, dint, bt->his_intents, w.e1.dseq + dctx, d1, w.e1.nz_idx, w.e1.nz_val,
-                                    w.e1.nz_cnt, NZ_CAP, w.dWt, s));
+    if (bt->his_intents_idx) {
+        INTEL_TRY(dense_rows_linear_bwd(B * d->H1, I, dint, nullptr, w.e1.dseq + dctx, d1, bt->his_intents_idx,
+                                        bt->his_intents_val, nullptr, bt->nz1, w.dWt, s));
+    } else {
+        INTEL_TRY(dense_rows_linear_bwd(B * d->H1, I, dint, bt->his_intents, w.e1.dseq + dctx, d1, w.e1.nz_idx, w.e1.nz_val,
+                                        w.e1.nz_cnt, NZ_CAP, w.dWt, s));
+    }
     INTEL_TRY(colsum(B * d->H1, dint, w.e1.dseq + dctx, d1, G->intent_b, s));
     INTEL_TRY(scatter_add_rows(B * d->H2, diid, w.e2.dseq, d2, bt->his_item_id, G->iid_emb, nullptr, s));
-    INTEL_TRY(dense_rows_linear_bwd(B * d->H2, I, dint, bt->his_item_int, w.e2.dseq + diid, d2, w.e2.nz_idx, w.e2.nz_val,
-                                    w.e2.nz_cnt, NZ_CAP, w.dWt, s));
+    if (bt->his_item_int_idx) {
+        INTEL_TRY(dense_rows_linear_bwd(B * d->H2, I, dint, nullptr, w.e2.dseq + diid, d2, bt->his_item_int_idx,
+                                        bt->his_item_int_val, nullptr, bt->nz2, w.dWt, s));
+    } else {
+        INTEL_TRY(dense_rows_linear_bwd(B * d->H2, I, dint, bt->his_item_int, w.e2.dseq + diid, d2, w.e2.nz_idx, w.e2.nz_val,
+                                        w.e2.nz_cnt, NZ_CAP, w.dWt, s));
+    }
     INTEL_TRY(colsum(B * d->H2, dint, w.e2.dseq + diid, d2, G->intent_b, s));
     return transpose(I, dint, w.dWt, G->intent_w, 1, s);
 }

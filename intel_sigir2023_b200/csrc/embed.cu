@@ -130,6 +130,33 @@ int dense_rows_linear_fwd(int64_t R, int64_t I, int d, const double* X, const fl
     return check_launch("dense_rows_fwd", (double)R * (8.0 * I + 4.0 * d), 0.0);
 }
 
+// Compact input form of the same layer: row r = sum_e val[r,e] * Wt[idx[r,e], :] + bias (one thread per output).
+__global__ void __launch_bounds__(256) sparse_rows_fwd_kernel(int64_t R, int nz, int d, const int32_t* __restrict__ idx,
+                                                              const float* __restrict__ val, const float* __restrict__ Wt,
+                                                              const float* __restrict__ bias, float* __restrict__ Y,
+                                                              int64_t ldy) {
+    const int64_t total = R * d;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = e / d;
+        const int c = (int)(e % d);
+        float acc = bias ? bias[c] : 0.f;
+        for (int k = 0; k < nz; ++k) {
+            const float v = val[r * nz + k];
+            if (v != 0.f) acc = fmaf(v, Wt[(int64_t)idx[r * nz + k] * d + c], acc);
+        }
+        Y[r * ldy + c] = acc;
+    }
+}
+
+int sparse_rows_linear_fwd(int64_t R, int nz, int d, const int32_t* idx, const float* val, const float* Wt,
+                           const float* bias, float* Y, int64_t ldy, cudaStream_t s) {
+    if (R <= 0) return INTEL_OK;
+    INTEL_REQUIRE(idx && val && Wt && Y && nz > 0, INTEL_ERR_ARG, "sparse_rows_linear_fwd: bad argument");
+    unsigned grid = stream_grid(ceil_div(R * d, 256), 8);
+    LAUNCH(sparse_rows_fwd_kernel, dim3(grid), dim3(256), 0, s, R, nz, d, idx, val, Wt, bias, Y, ldy);
+    return check_launch("sparse_rows_fwd", (double)R * (8.0 * nz + 4.0 * d * (nz + 1)), 2.0 * R * nz * d);
+}
+
 // backward w.r.t. the weight: dWt[i, :] += x[r,i] * dY[r, :]; uses the compacted non-zeros of the
 // forward pass, re-streaming only rows that overflowed the compaction capacity.
 __global__ void __launch_bounds__(256) dense_rows_bwd_kernel(int64_t R, int64_t I, int d, const double* __restrict__ X,
@@ -143,11 +170,12 @@ __global__ void __launch_bounds__(256) dense_rows_bwd_kernel(int64_t R, int64_t 
     for (int64_t r = warp; r < R; r += nwarps) {
         const float g0 = (lane < d) ? dY[r * lddy + lane] : 0.f;
         const float g1 = (lane + 32 < d) ? dY[r * lddy + lane + 32] : 0.f;
-        const int cnt = nz_cnt ? nz_cnt[r] : cap + 1;
+        const int cnt = nz_cnt ? nz_cnt[r] : (X ? cap + 1 : cap);     // X == null: caller-provided compact rows
         if (cnt <= cap) {
             for (int e = 0; e < cnt; ++e) {
                 const int64_t i = nz_idx[r * cap + e];
                 const float fv = nz_val[r * cap + e];
+                if (fv == 0.f) continue;
                 if (lane < d) atomicAdd(dWt + i * d + lane, fv * g0);
                 if (lane + 32 < d) atomicAdd(dWt + i * d + lane + 32, fv * g1);
             }

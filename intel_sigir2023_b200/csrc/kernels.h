@@ -51,6 +51,10 @@ int dense_rows_linear_fwd(int64_t R, int64_t I, int d, const double* X, const fl
 int dense_rows_linear_bwd(int64_t R, int64_t I, int d, const double* X, const float* dY, int64_t lddy,
                           const int32_t* nz_idx, const float* nz_val, const int32_t* nz_cnt, int cap,
                           float* dWt, cudaStream_t s);
+// compact rows: Y[r,:] = sum_e val[r,e] * Wt[idx[r,e],:] + bias.  Its backward is dense_rows_linear_bwd with
+// X = null, nz_idx/nz_val = the caller's arrays, nz_cnt = null, cap = nz.
+int sparse_rows_linear_fwd(int64_t R, int nz, int d, const int32_t* idx, const float* val, const float* Wt,
+                           const float* bias, float* Y, int64_t ldy, cudaStream_t s);
 // out[c, r] (=|+=) in[r, c]
 int transpose(int64_t rows, int64_t cols, const float* in, float* out, int accumulate, cudaStream_t s);
 // scores f64 [R,K] -> Y[R, d] = W[d,K] x + b  (score_embeddings) and the f32 copy xs[R,K]

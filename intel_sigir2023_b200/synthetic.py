@@ -62,25 +62,40 @@ def _poisson(rate: float, shape, gen: torch.Generator, device) -> torch.Tensor:
     return torch.poisson(torch.full(shape, rate, device=device), generator=gen).long()
 
 
-def _intent_rows(rows: int, I: int, max_nnz: int, gen, device) -> torch.Tensor:
-    """Dense float64 [rows, I] vectors with 1..max_nnz positive entries summing to 1."""
-    out = torch.zeros(rows, I, dtype=torch.float64, device=device)
-    if rows == 0:
-        return out
+def _intent_pairs(rows: int, I: int, max_nnz: int, gen, device):
+    """(idx int64 [rows, nnz], val float64 [rows, nnz]): 1..max_nnz positive entries per row summing to 1
+    (an index may repeat inside a row; repeated entries add up)."""
     max_nnz = max(1, min(max_nnz, I))
     nnz = torch.randint(1, max_nnz + 1, (rows,), generator=gen, device=device)
     idx = torch.randint(0, I, (rows, max_nnz), generator=gen, device=device)
     val = torch.rand(rows, max_nnz, generator=gen, device=device, dtype=torch.float64) + 0.05
     keep = torch.arange(max_nnz, device=device)[None, :] < nnz[:, None]
     val = val * keep
-    out.scatter_add_(1, idx, val)
-    out /= out.sum(dim=1, keepdim=True)
+    val = val / val.sum(dim=1, keepdim=True).clamp_min(1e-30)
+    return idx, val
+
+
+def _densify(idx: torch.Tensor, val: torch.Tensor, I: int) -> torch.Tensor:
+    out = torch.zeros(idx.shape[0], I, dtype=torch.float64, device=idx.device)
+    if idx.shape[0]:
+        out.scatter_add_(1, idx, val)
     return out
 
 
+def _intent_rows(rows: int, I: int, max_nnz: int, gen, device) -> torch.Tensor:
+    """Dense float64 [rows, I] vectors with 1..max_nnz positive entries summing to 1."""
+    idx, val = _intent_pairs(rows, I, max_nnz, gen, device)
+    return _densify(idx, val, I)
+
+
 def make_batch(corpus: CorpusSpec, spec: BatchSpec, seed: int = 0,
-               device: str | torch.device = "cpu") -> Dict[str, object]:
-    """One collated batch; same keys as the reference's DataLoader would yield."""
+               device: str | torch.device = "cpu", layout: str = "dense") -> Dict[str, object]:
+    """One collated batch; same keys as the reference's DataLoader would yield.
+
+    layout: "dense" = the reference API (float64 [B,H,I] ``his_intents`` / one-hot ``his_item_int``);
+    "compact" = the opt-in index form of the same two tensors (``his_intents_idx`` int32 [B,H,nz] +
+    ``his_intents_val`` float32, ``his_item_int_idx`` int32 [B,H2,1] + ``his_item_int_val``), which is what a
+    device-side batch builder would emit; "both" = both, from the same draws."""
     dev = torch.device(device)
     gen = torch.Generator(device=dev)
     gen.manual_seed(int(seed))
@@ -141,27 +156,41 @@ def make_batch(corpus: CorpusSpec, spec: BatchSpec, seed: int = 0,
     hv = torch.arange(H, device=dev)[None, :] < h_len[:, None]
     hv2 = torch.arange(H2, device=dev)[None, :] < hi_len[:, None]
     his_ctx = torch.randint(1, corpus.n_ctx, (B, H), generator=gen, device=dev) * hv
-    his_int = _intent_rows(B * H, I, spec.max_nnz, gen, dev).view(B, H, I) * hv[:, :, None]
+    hidx, hval = _intent_pairs(B * H, I, spec.max_nnz, gen, dev)
+    hval = hval * hv.reshape(-1, 1)
     uh = torch.rand(B, H2, generator=gen, device=dev)
     his_item = (1 + (uh * uh * corpus.n_item).long()).clamp_(1, corpus.n_item) * hv2
     hot = torch.randint(0, I, (B, H2), generator=gen, device=dev)
-    his_item_int = torch.zeros(B, H2, I, dtype=torch.float64, device=dev)
-    his_item_int.scatter_(2, hot[:, :, None], hv2[:, :, None].double())
     intents = _intent_rows(B, I, spec.max_nnz, gen, dev)
+    extra: Dict[str, object] = {}
+    if layout in ("dense", "both"):
+        his_item_int = torch.zeros(B, H2, I, dtype=torch.float64, device=dev)
+        his_item_int.scatter_(2, hot[:, :, None], hv2[:, :, None].double())
+        extra["his_intents"] = _densify(hidx, hval, I).view(B, H, I)
+        extra["his_item_int"] = his_item_int
+    if layout in ("compact", "both"):
+        extra["his_intents_idx"] = hidx.view(B, H, -1).to(torch.int32)
+        extra["his_intents_val"] = hval.view(B, H, -1).to(torch.float32)
+        extra["his_item_int_idx"] = hot.view(B, H2, 1).to(torch.int32)
+        extra["his_item_int_val"] = hv2.view(B, H2, 1).to(torch.float32)
+    if layout not in ("dense", "compact", "both"):
+        raise ValueError(layout)
 
-    return {
+    out = {
         "u_id_c": u_id, "c_id_c": c_id, "context_mh": ctx,
         "user_mh": torch.zeros(B, dtype=torch.long, device=dev),
         "c_paynum_i": pay, "c_favnum_i": fav, "c_clicknum_i": clk,
         "i_class_c": i_class, "i_id_s": i_id, "session_len": n,
         "intents": intents, "ranking": ranking,
-        "his_intents": his_int, "his_context_mh": his_ctx,
+        "his_context_mh": his_ctx,
         "position": h_len.clone(), "history_len": h_len,
         "intentloss_w": torch.full((B, I), 1.0 / I, dtype=torch.float64, device=dev),
-        "his_item_id": his_item, "his_item_int": his_item_int,
+        "his_item_id": his_item,
         "history_item_len": hi_len, "scores": scores,
         "batch_size": B, "phase": spec.phase,
     }
+    out.update(extra)
+    return out
 
 
 def batch_to(batch: Dict[str, object], device, non_blocking: bool = False) -> Dict[str, object]:

@@ -284,3 +284,31 @@ def check_against_oracle(device, seed=0, B=70, L=21, min_len=3, kind="list", cor
     for k, p in model.named_parameters():
         ref_g = sd[k].grad.numpy() if sd[k].grad is not None else np.zeros(tuple(p.shape), np.float32)
         assert_grad_close(p.grad.cpu().numpy(), ref_g, gmax, f"{k} {cfg_kw}", rtol=1e-3, afrac=5e-6)
+
+
+def check_compact_layout(device):
+    """the opt-in index form of his_intents / his_item_int gives the same forward and gradients as the dense API"""
+    from intel_sigir2023_b200 import losses, synthetic
+    from intel_sigir2023_b200.config import IntelConfig
+    corpus = synthetic.CorpusSpec(n_item=200, n_class=9, n_user=30, n_ctx=19, model_num=3, intent_num=40, history_max=6)
+    for enc in ("GRU4Rec", "BERT4Rec"):
+        cfg = IntelConfig(item_rows=corpus.item_rows, class_rows=corpus.n_class, user_rows=corpus.user_rows,
+                          ctx_rows=corpus.n_ctx, intent_num=corpus.intent_num, model_num=3, history_max=6, encoder=enc,
+                          num_heads=2)
+        both = synthetic.make_batch(corpus, synthetic.BatchSpec(batch_size=11, max_len=13, min_len=2), seed=5, layout="both")
+        both = {k: (v.to(device) if torch.is_tensor(v) else v) for k, v in both.items()}
+        dense = {k: v for k, v in both.items() if not k.endswith(("_idx", "_val"))}
+        compact = {k: v for k, v in both.items() if k not in ("his_intents", "his_item_int")}
+        state = O.init_state(cfg, seed=3)
+        res = []
+        for b in (dense, compact):
+            model = make_model(cfg, {k: v.to(device) for k, v in state.items()}, device).train()
+            out = model(b)
+            loss, _, _ = losses.IntListloss(loss_args())(out, b)
+            loss.backward()
+            res.append((out, loss, {k: p.grad.clone() for k, p in model.named_parameters()}))
+        for k in ("intents", "weights", "ens_score"):
+            assert rel_err(res[1][0][k].detach().cpu().numpy(), res[0][0][k].detach().cpu().numpy()) < 2e-6, (enc, k)
+        gmax = max(float(g.abs().max()) for g in res[0][2].values())
+        for k, g in res[0][2].items():
+            assert_grad_close(res[1][2][k].cpu().numpy(), g.cpu().numpy(), gmax, f"{enc}/{k}", rtol=1e-4, afrac=2e-6)

@@ -78,3 +78,7 @@ def test_baselines():
 def test_against_oracle_multi_tile():
     P.check_against_oracle("cpu", B=35, L=9, encoder="GRU4Rec", num_heads=2, num_layers=1,
                            corpus_kw=dict(history_max=4, intent_num=24))
+
+
+def test_compact_layout_matches_dense():
+    P.check_compact_layout("cpu")

@@ -83,3 +83,7 @@ def test_baselines():
 ])
 def test_against_oracle(cfg):
     P.check_against_oracle(DEV, **cfg)
+
+
+def test_compact_layout_matches_dense():
+    P.check_compact_layout(DEV)
