@@ -49,6 +49,10 @@ typedef struct {
     int32_t cross_attention; /* 1: CrossAtt pooling (default); 0: intent MLP gate */
     int32_t encoder;         /* INTEL_ENCODER_* */
     int32_t gru_hidden, bert_layers, bert_heads, history_max;
+    /* nn.Dropout of the two self-attention stacks (IntEL.py:187,196), training mode only: p = 0 disables it.
+     * Masks come from a counter-based hash of (seed, stream, layer, row, channel); pass a new seed per step. */
+    float dropout_p;
+    uint64_t dropout_seed;
 } intel_dims_t;
 
 typedef struct {             /* layers.py TransformerLayer, one block of BERT4RecEncoder */
@@ -194,6 +198,10 @@ int intel_profile_enable(int on);
 /* Synchronises the device, then writes one text line per kernel name: "name launches total_ms
  * algorithmic_bytes flops" and clears the records. */
 int intel_profile_report(char* buf, size_t cap);
+
+/* test hook: 0 routes the self-attention stacks through the staged kernels even where the fused per-session
+ * kernel applies (both implement the same math; tests compare them). Default 1. */
+int intel_debug_use_fused_stack(int on);
 
 /* ---- building blocks exposed for unit tests --------------------------------------------- */
 /* out[r, :] = table[idx[r], :]  (nn.Embedding forward) */

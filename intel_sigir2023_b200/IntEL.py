@@ -87,7 +87,10 @@ class _IntelFn(torch.autograd.Function):
         tensors = dict(zip(names, params))
         B, L = batch["i_id_s"].shape
         H1, H2 = batch["his_context_mh"].shape[1], batch["his_item_id"].shape[1]
-        dims = _lib.make_dims(cfg, B, L, H1, H2)
+        p_drop = float(cfg.dropout) if model.training else 0.0
+        if p_drop > 0.0:
+            model._drop_step += 1
+        dims = _lib.make_dims(cfg, B, L, H1, H2, p_drop, model._drop_seed * 1000003 + model._drop_step)
         P = _lib.make_tensors(cfg, tensors)
         bt = _lib.make_batch(batch, cfg)
         stream = _lib.stream_ptr(dev)
@@ -174,6 +177,7 @@ class IntEL(nn.Module):
         self.optimizer, self.scheduler = None, None
         self.check_list = list()
         self._ws_pool = {}
+        self._drop_seed, self._drop_step = int(torch.initial_seed()) & 0x7FFFFFFF, 0
         self.intent_num, self.model_num = c.intent_num, c.model_num
         self.user_num, self.item_num = c.user_rows, c.item_rows
         self.max_his = c.history_max
@@ -211,8 +215,6 @@ class IntEL(nn.Module):
 
     # ---- the hot path ----
     def forward(self, data: Dict[str, object]) -> Dict[str, torch.Tensor]:
-        if self.training and self.cfg.dropout > 0:
-            raise NotImplementedError("dropout > 0 is not implemented in the B200 path (use --dropout 0)")
         params = [p for _, p in self.named_parameters()]
         weights, ens, intents = _IntelFn.apply(self, data, *params)
         return {"weights": weights, "ens_score": ens, "intents": intents}

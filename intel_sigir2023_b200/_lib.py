@@ -25,7 +25,8 @@ class Dims(C.Structure):
     _fields_ = [(n, C.c_int64) for n in ("B", "L", "K", "I", "H1", "H2", "item_rows", "class_rows", "user_rows", "ctx_rows")] + \
                [(n, C.c_int32) for n in ("d_iid", "d_im", "d_u", "d_s", "d_int", "d_ctx", "qsize", "heads", "layers",
                                          "cross_attention", "encoder", "gru_hidden", "bert_layers", "bert_heads",
-                                         "history_max")]
+                                         "history_max")] + \
+               [("dropout_p", C.c_float), ("dropout_seed", C.c_uint64)]
 
 
 class BertLayer(C.Structure):
@@ -94,6 +95,7 @@ def _declare(lib: C.CDLL) -> None:
         "intel_linear_dw": (i32, [i64, i64, i64, _p, _p, _p, _p, _p]),
         "intel_mha_fwd": (i32, [i64, i64, i32, i32, _p, _p, _p, _p]),
         "intel_mha_bwd": (i32, [i64, i64, i32, i32, _p, _p, _p, _p, _p]),
+        "intel_debug_use_fused_stack": (i32, [i32]),
         "intel_profile_enable": (i32, [i32]),
         "intel_profile_report": (i32, [C.c_char_p, sz]),
     }
@@ -110,7 +112,7 @@ EXPORTED = ["intel_last_error", "intel_abi_version", "intel_intent_workspace_byt
             "intel_intent_topk_workspace_bytes", "intel_intent_topk", "intel_fuse_fwd", "intel_select_list",
             "intel_rank_lists", "intel_gather_fwd", "intel_scatter_add_bwd", "intel_linear_fwd",
             "intel_profile_enable", "intel_profile_report", "intel_linear_dx", "intel_linear_dw", "intel_mha_fwd",
-            "intel_mha_bwd"]
+            "intel_mha_bwd", "intel_debug_use_fused_stack"]
 
 
 def load(path: Optional[str] = None) -> C.CDLL:
@@ -155,8 +157,9 @@ def stream_ptr(device: torch.device) -> Optional[int]:
     return torch.cuda.current_stream(device).cuda_stream
 
 
-def make_dims(cfg: IntelConfig, B: int, L: int, H1: int, H2: int) -> Dims:
+def make_dims(cfg: IntelConfig, B: int, L: int, H1: int, H2: int, dropout_p: float = 0.0, seed: int = 0) -> Dims:
     d = Dims()
+    d.dropout_p, d.dropout_seed = float(dropout_p), int(seed) & 0xFFFFFFFFFFFFFFFF
     d.B, d.L, d.K, d.I, d.H1, d.H2 = B, L, cfg.model_num, cfg.intent_num, H1, H2
     d.item_rows, d.class_rows, d.user_rows, d.ctx_rows = cfg.item_rows, cfg.class_rows, cfg.user_rows, cfg.ctx_rows
     d.d_iid, d.d_im = cfg.i_emb_size, (cfg.im_emb_size if cfg.class_rows > 0 else 0)

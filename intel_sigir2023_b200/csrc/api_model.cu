@@ -49,12 +49,15 @@ void stack_layout(Arena& a, int64_t R, int d, int layers, StackWs& w) {
     }
 }
 
-int stack_fwd(int64_t B, int64_t L, int d, int heads, int layers, const intel_selfatt_t& p, StackWs& w, cudaStream_t s) {
+int g_use_fused_stack = 1;
+
+int stack_fwd(int64_t B, int64_t L, int d, int heads, int layers, const intel_selfatt_t& p, StackWs& w, float drop_p,
+              uint64_t drop_seed, int stream_id, cudaStream_t s) {
     const int64_t R = B * L;
-    if (trunk_supported(L, d, heads, layers)) {     // whole stack of a session on chip (trunk.cu)
+    if (g_use_fused_stack && trunk_supported(L, d, heads, layers)) {     // whole stack of a session on chip (trunk.cu)
         const StackParams sp{p.wq, p.wk, p.wv, p.w1, p.b1, p.w2, p.b2, p.lnw, p.lnb};
         const StackSaved sv{w.QKV, w.A, w.U, w.Z, w.st};
-        return trunk_fwd(B, L, heads, layers, sp, w.X, sv, s);
+        return trunk_fwd(B, L, heads, layers, sp, w.X, sv, drop_p, drop_seed, stream_id, s);
     }
     for (int l = 0; l < layers; ++l) {
         INTEL_TRY(linear(R, d, d, w.X[l], d, p.wq, d, nullptr, w.QKV[l], 3 * d, s));
@@ -62,7 +65,12 @@ int stack_fwd(int64_t B, int64_t L, int d, int heads, int layers, const intel_se
         INTEL_TRY(linear(R, d, d, w.X[l], d, p.wv, d, nullptr, w.QKV[l] + 2 * d, 3 * d, s));
         INTEL_TRY(mha_fwd(B, L, d, heads, w.QKV[l], nullptr, w.A[l], s));
         INTEL_TRY(linear(R, d, d, w.A[l], d, p.w1, d, p.b1, w.U[l], d, s));
-        INTEL_TRY(linear(R, d, d, w.U[l], d, p.w2, d, p.b2, w.Z[l], d, s, /*relu_a=*/true, false, w.X[l], d));
+        if (drop_p > 0.f) {      // Z = dropout(relu(U) W2^T + b2) + X
+            INTEL_TRY(linear(R, d, d, w.U[l], d, p.w2, d, p.b2, w.Z[l], d, s, /*relu_a=*/true));
+            INTEL_TRY(dropout_apply(R, d, w.Z[l], w.X[l], w.Z[l], make_dropout(drop_p, drop_seed, stream_id, l), s));
+        } else {
+            INTEL_TRY(linear(R, d, d, w.U[l], d, p.w2, d, p.b2, w.Z[l], d, s, /*relu_a=*/true, false, w.X[l], d));
+        }
         INTEL_TRY(layernorm_fwd(R, d, w.Z[l], p.lnw, p.lnb, w.X[l + 1], w.st[l], s));
     }
     return INTEL_OK;
@@ -70,20 +78,26 @@ int stack_fwd(int64_t B, int64_t L, int d, int heads, int layers, const intel_se
 
 // dX holds d(loss)/d X[layers] on entry and d(loss)/d X[0] on return.  t1, t2: [R,d] scratch; dqkv: [R,3d].
 int stack_bwd(int64_t B, int64_t L, int d, int heads, int layers, const intel_selfatt_t& p, intel_selfatt_t& g,
-              StackWs& w, float* dX, float* t1, float* t2, float* dqkv, cudaStream_t s) {
+              StackWs& w, float* dX, float* t1, float* t2, float* dqkv, float drop_p, uint64_t drop_seed, int stream_id,
+              cudaStream_t s) {
     const int64_t R = B * L;
-    if (trunk_supported(L, d, heads, layers)) {
+    if (g_use_fused_stack && trunk_supported(L, d, heads, layers)) {
         const StackParams sp{p.wq, p.wk, p.wv, p.w1, p.b1, p.w2, p.b2, p.lnw, p.lnb};
         const StackGrads sg{g.wq, g.wk, g.wv, g.w1, g.b1, g.w2, g.b2, g.lnw, g.lnb};
         const StackSaved sv{w.QKV, w.A, w.U, w.Z, w.st};
-        return trunk_bwd(B, L, heads, layers, sp, sg, w.X, sv, dX, s);
+        return trunk_bwd(B, L, heads, layers, sp, sg, w.X, sv, dX, drop_p, drop_seed, stream_id, s);
     }
     for (int l = layers - 1; l >= 0; --l) {
         float* dZ = t1;
         INTEL_TRY(layernorm_bwd(R, d, dX, w.Z[l], w.st[l], p.lnw, dZ, g.lnw, g.lnb, s));
-        INTEL_TRY(linear_dw(R, d, d, dZ, d, w.U[l], d, g.w2, d, g.b2, s, /*relu_x=*/true));
+        const float* dF = dZ;        // gradient of the FFN branch: dZ through the dropout mask (scratch: dqkv)
+        if (drop_p > 0.f) {
+            INTEL_TRY(dropout_apply(R, d, dZ, nullptr, dqkv, make_dropout(drop_p, drop_seed, stream_id, l), s));
+            dF = dqkv;
+        }
+        INTEL_TRY(linear_dw(R, d, d, dF, d, w.U[l], d, g.w2, d, g.b2, s, /*relu_x=*/true));
         float* dU = t2;
-        INTEL_TRY(linear_dx(R, d, d, dZ, d, p.w2, d, dU, d, s, 0, w.U[l], d));
+        INTEL_TRY(linear_dx(R, d, d, dF, d, p.w2, d, dU, d, s, 0, w.U[l], d));
         INTEL_TRY(linear_dw(R, d, d, dU, d, w.A[l], d, g.w1, d, g.b1, s));
         float* dA = dX;   // dX is consumed
         INTEL_TRY(linear_dx(R, d, d, dU, d, p.w1, d, dA, d, s));
@@ -327,6 +341,11 @@ int gru_bwd(const intel_dims_t* d, const intel_encoder_t& p, intel_encoder_t& g,
 
 extern "C" {
 
+int intel_debug_use_fused_stack(int on) {
+    g_use_fused_stack = on ? 1 : 0;
+    return INTEL_OK;
+}
+
 // ================================================================================================
 size_t intel_ensemble_workspace_bytes(const intel_dims_t* d) {
     if (check_dims(d) != INTEL_OK) return 0;
@@ -356,8 +375,8 @@ int intel_ensemble_fwd(const intel_dims_t* d, const intel_tensors_t* P, const in
     INTEL_TRY(gather_rows(R, d->d_iid, P->iid_emb, bt->i_id, w.item.X[0], di, 0, s));
     if (d->d_im > 0) INTEL_TRY(gather_rows(R, d->d_im, P->item_emb, bt->i_class, w.item.X[0] + d->d_iid, di, 0, s));
     INTEL_TRY(score_embed_fwd(R, K, ds, bt->scores, P->score_w, P->score_b, w.score.X[0], w.xs, s));
-    INTEL_TRY(stack_fwd(B, L, di, d->heads, d->layers, P->item, w.item, s));
-    INTEL_TRY(stack_fwd(B, L, ds, d->heads, d->layers, P->score, w.score, s));
+    INTEL_TRY(stack_fwd(B, L, di, d->heads, d->layers, P->item, w.item, d->dropout_p, d->dropout_seed, 0, s));
+    INTEL_TRY(stack_fwd(B, L, ds, d->heads, d->layers, P->score, w.score, d->dropout_p, d->dropout_seed, 1, s));
     float* Xi = w.item.X[d->layers];
     float* Xs = w.score.X[d->layers];
 
@@ -446,11 +465,13 @@ int intel_ensemble_bwd(const intel_dims_t* d, const intel_tensors_t* P, const in
             INTEL_TRY(linear_dw(B, dd, I, w.dq, dd, intents, I, gxq, I, nullptr, s));
             INTEL_TRY(linear_dx(B, dd, I, w.dq, dd, xq, I, d_intents_out, I, s, 1));
             if (st == 0) {
-                INTEL_TRY(stack_bwd(B, L, di, d->heads, d->layers, P->item, G->item, w.item, w.dXa, w.t1, w.t2, w.dqkv, s));
+                INTEL_TRY(stack_bwd(B, L, di, d->heads, d->layers, P->item, G->item, w.item, w.dXa, w.t1, w.t2, w.dqkv, d->dropout_p,
+                                    d->dropout_seed, 0, s));
                 INTEL_TRY(scatter_add_rows(R, d->d_iid, w.dXa, di, bt->i_id, G->iid_emb, nullptr, s));
                 if (d->d_im > 0) INTEL_TRY(scatter_add_rows(R, d->d_im, w.dXa + d->d_iid, di, bt->i_class, G->item_emb, nullptr, s));
             } else {
-                INTEL_TRY(stack_bwd(B, L, ds, d->heads, d->layers, P->score, G->score, w.score, w.dXa, w.t1, w.t2, w.dqkv, s));
+                INTEL_TRY(stack_bwd(B, L, ds, d->heads, d->layers, P->score, G->score, w.score, w.dXa, w.t1, w.t2, w.dqkv, d->dropout_p,
+                                    d->dropout_seed, 1, s));
                 INTEL_TRY(linear_dw(R, ds, K, w.dXa, ds, w.xs, K, G->score_w, K, G->score_b, s));
             }
         }
@@ -480,11 +501,13 @@ int intel_ensemble_bwd(const intel_dims_t* d, const intel_tensors_t* P, const in
             INTEL_TRY(linear_dw(B, q, I, w.dt, q, intents, I, gw0, I, gb0, s));
             INTEL_TRY(linear_dx(B, q, I, w.dt, q, w0, I, d_intents_out, I, s, 1));
             if (st == 0) {
-                INTEL_TRY(stack_bwd(B, L, di, d->heads, d->layers, P->item, G->item, w.item, w.dXa, w.t1, w.t2, w.dqkv, s));
+                INTEL_TRY(stack_bwd(B, L, di, d->heads, d->layers, P->item, G->item, w.item, w.dXa, w.t1, w.t2, w.dqkv, d->dropout_p,
+                                    d->dropout_seed, 0, s));
                 INTEL_TRY(scatter_add_rows(R, d->d_iid, w.dXa, di, bt->i_id, G->iid_emb, nullptr, s));
                 if (d->d_im > 0) INTEL_TRY(scatter_add_rows(R, d->d_im, w.dXa + d->d_iid, di, bt->i_class, G->item_emb, nullptr, s));
             } else {
-                INTEL_TRY(stack_bwd(B, L, ds, d->heads, d->layers, P->score, G->score, w.score, w.dXa, w.t1, w.t2, w.dqkv, s));
+                INTEL_TRY(stack_bwd(B, L, ds, d->heads, d->layers, P->score, G->score, w.score, w.dXa, w.t1, w.t2, w.dqkv, d->dropout_p,
+                                    d->dropout_seed, 1, s));
                 INTEL_TRY(linear_dw(R, ds, K, w.dXa, ds, w.xs, K, G->score_w, K, G->score_b, s));
             }
         }

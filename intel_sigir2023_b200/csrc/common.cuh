@@ -85,6 +85,33 @@ template <class K> inline void ensure_smem(K kernel, size_t smem) {
 template <class K> inline void ensure_smem(K, size_t) {}
 #endif
 
+// counter-based uniform 32-bit hash (splitmix64 finaliser): BPR negative draw, dropout masks
+__device__ __forceinline__ uint32_t hash_u32(uint64_t seed, uint64_t idx) {
+    uint64_t z = seed + idx * 0x9E3779B97F4A7C15ull + 0x632BE59BD9B4E019ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return (uint32_t)((z ^ (z >> 31)) >> 32);
+}
+struct Dropout {
+    float p, inv;          // drop probability, 1 / (1 - p)
+    uint32_t thr;          // keep iff hash >= thr
+    uint64_t seed;         // already mixed with (stream, layer)
+};
+static inline Dropout make_dropout(float p, uint64_t seed, int stream, int layer) {
+    Dropout d;
+    d.p = p;
+    d.inv = p > 0.f ? 1.0f / (1.0f - p) : 1.0f;
+    double t = (double)p * 4294967296.0;
+    d.thr = p > 0.f ? (uint32_t)(t > 4294967295.0 ? 4294967295.0 : t) : 0u;
+    d.seed = seed * 0x100000001B3ull + (uint64_t)(stream * 64 + layer + 1) * 0xD6E8FEB86659FD93ull;
+    return d;
+}
+// multiplier of element (row, col) of a [rows, width] activation: 0 or 1/(1-p)
+__device__ __forceinline__ float dropout_scale(const Dropout& d, int64_t row, int col, int width) {
+    if (d.p <= 0.f) return 1.0f;
+    return hash_u32(d.seed, (uint64_t)(row * width + col)) >= d.thr ? d.inv : 0.0f;
+}
+
 // ---- warp helpers ----
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

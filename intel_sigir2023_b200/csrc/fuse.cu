@@ -231,6 +231,22 @@ int relu_bwd(int64_t rows, int cols, const float* dy, int64_t lddy, const float*
     return check_launch("relu_bwd");
 }
 
+// staged path of the stacks: y[r,c] = x[r,c] * dropout_scale(r,c) (+ add[r,c]); y may alias x
+__global__ void __launch_bounds__(256) dropout_kernel(int64_t rows, int width, const float* x, const float* __restrict__ add,
+                                                      float* y, Dropout dr) {
+    const int64_t n = rows * width;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        const float v = x[e] * dropout_scale(dr, e / width, (int)(e % width), width);
+        y[e] = add ? v + add[e] : v;
+    }
+}
+int dropout_apply(int64_t rows, int width, const float* x, const float* add, float* y, const Dropout& dr, cudaStream_t s) {
+    if (rows * width <= 0) return INTEL_OK;
+    unsigned grid = stream_grid(ceil_div(rows * width, 256), 8);
+    LAUNCH(dropout_kernel, dim3(grid), dim3(256), 0, s, rows, width, x, add, y, dr);
+    return check_launch("dropout", 12.0 * rows * width, 0.0);
+}
+
 __global__ void __launch_bounds__(256) add_inplace_kernel(int64_t n, float* y, const float* __restrict__ x) {
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x)
         y[e] += x[e];

@@ -124,10 +124,10 @@ struct StackSaved { float* const* QKV; float* const* A; float* const* U; float* 
 bool trunk_supported(int64_t L, int d, int heads, int layers);
 // X[0] = stack input [B*L,32]; X[l+1] receives the output of layer l
 int trunk_fwd(int64_t B, int64_t L, int heads, int layers, const StackParams& p, float* const* X, const StackSaved& sv,
-              cudaStream_t s);
+              float drop_p, uint64_t drop_seed, int stream_id, cudaStream_t s);
 // dX: d loss / d X[layers] on entry, d loss / d X[0] on return; weight gradients are accumulated into g
 int trunk_bwd(int64_t B, int64_t L, int heads, int layers, const StackParams& p, const StackGrads& g, float* const* X,
-              const StackSaved& sv, float* dX, cudaStream_t s);
+              const StackSaved& sv, float* dX, float drop_p, uint64_t drop_seed, int stream_id, cudaStream_t s);
 
 // ---- fuse.cu ------------------------------------------------------------------------------------
 // weights[b,l,:] = l < n_b ? w_valid[b] : w_pad[b];  ens[b,l] = sum_k weights * float(scores)
@@ -152,5 +152,7 @@ int bcast_rows_bwd(int64_t B, int64_t L, int d, const float* dout, int64_t ldo, 
 int relu_bwd(int64_t rows, int cols, const float* dy, int64_t lddy, const float* v, int64_t ldv, float* dx,
              int64_t lddx, cudaStream_t s);
 int add_inplace(int64_t n, float* y, const float* x, cudaStream_t s);
+// y = x * dropout mask/(1-p) (+ add); used by the staged path of the stacks, forward and backward
+int dropout_apply(int64_t rows, int width, const float* x, const float* add, float* y, const Dropout& dr, cudaStream_t s);
 
 }  // namespace intel

@@ -148,12 +148,7 @@ __global__ void __launch_bounds__(LOSS_WARPS * 32) loss_pl_kernel(LossArgs a) {
 // BPR (BPRloss.py:12-56): for each positive i pick one j among the valid items of the closest lower
 // rank (argmax of the injected noise, BPRloss.py:26-28); with no candidate the argmax falls on pure
 // noise over all L slots.  l_i = -log sigmoid(s_i - s_j);  div_i = sum_k w_ik sig'(D) ((x_ik-x_jk) - D)^2
-__device__ __forceinline__ uint32_t bpr_hash(uint64_t seed, uint64_t idx) {
-    uint64_t z = seed + idx * 0x9E3779B97F4A7C15ull + 0x632BE59BD9B4E019ull;
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    return (uint32_t)((z ^ (z >> 31)) >> 32);
-}
+__device__ __forceinline__ uint32_t bpr_hash(uint64_t seed, uint64_t idx) { return hash_u32(seed, idx); }
 
 __global__ void __launch_bounds__(LOSS_WARPS * 32) loss_bpr_kernel(LossArgs a) {
     DYN_SMEM(float, sm);

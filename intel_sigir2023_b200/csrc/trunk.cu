@@ -26,6 +26,7 @@ struct TrunkArgs {
     // activations of layer l kept for the backward pass (written by the forward kernel when save != 0):
     float *QKV[8], *A[8], *U[8], *Z[8], *ST[8];   // [B*L,96] q|k|v, [B*L,32] x3, [B*L,2] LN mean / rstd
     int save;
+    Dropout drop[8];                 // per layer (p = 0: off)
     // backward only
     float* dX;                       // [B*L,32]: d loss / d X[layers] on entry, d loss / d X[0] on return
     float *gwq, *gwk, *gwv, *gw1, *gb1, *gw2, *gb2, *glnw, *glnb;
@@ -123,7 +124,7 @@ template <int TP, int DK>
 __device__ __forceinline__ void layer_forward(const float* W, const float* V, const float* Xs, float* Qs, float* Ks, float* Vs,
                                               float* As, float* Us, float* Zs, float* S, float* Xout, float* stats, int L,
                                               int heads, int lane, int warp, float* gQKV, float* gA, float* gU, float* gZ,
-                                              float* gST) {
+                                              float* gST, const Dropout& dr, int64_t row0) {
     constexpr int SS = TrunkSmem<TP>::SS, WMAT = TrunkSmem<TP>::WMAT, MT = TP / 16;
     const int TW = blockDim.x >> 5;
     const float scale = 1.0f / sqrtf((float)DK);
@@ -237,8 +238,10 @@ __device__ __forceinline__ void layer_forward(const float* W, const float* V, co
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
                 const int r = mt * 16 + gq + 8 * hh;
-                Zs[r * TS + c] = (r < L) ? acc[j][2 * hh] + V[TD + c] + Xs[r * TS + c] : 0.f;
-                Zs[r * TS + c + 1] = (r < L) ? acc[j][2 * hh + 1] + V[TD + c + 1] + Xs[r * TS + c + 1] : 0.f;
+                // dropout acts on the FFN output before the residual (IntEL.py:187-188)
+                Zs[r * TS + c] = (r < L) ? (acc[j][2 * hh] + V[TD + c]) * dropout_scale(dr, row0 + r, c, TD) + Xs[r * TS + c] : 0.f;
+                Zs[r * TS + c + 1] =
+                    (r < L) ? (acc[j][2 * hh + 1] + V[TD + c + 1]) * dropout_scale(dr, row0 + r, c + 1, TD) + Xs[r * TS + c + 1] : 0.f;
             }
         }
     }
@@ -285,7 +288,7 @@ __global__ void __launch_bounds__(TW * 32) trunk_fwd_kernel(TrunkArgs a) {
             layer_forward<TP, DK>(W, V, Xs, Qs, Ks, Vs, As, Qs, Ks, S, Xs, nullptr, a.L, a.heads, lane, warp,
                                   sv ? a.QKV[l] + ro * 3 * TD : nullptr, sv ? a.A[l] + ro * TD : nullptr,
                                   sv ? a.U[l] + ro * TD : nullptr, sv ? a.Z[l] + ro * TD : nullptr,
-                                  sv ? a.ST[l] + ro * 2 : nullptr);
+                                  sv ? a.ST[l] + ro * 2 : nullptr, a.drop[l], ro);
             float* out = a.X[l + 1] + b * a.L * TD;
             for (int e = threadIdx.x; e < a.L * (TD / 4); e += blockDim.x) {
                 const int r = e / (TD / 4), c = (e % (TD / 4)) * 4;
@@ -370,6 +373,17 @@ __global__ void __launch_bounds__(512) trunk_bwd_kernel(TrunkArgs a) {
                 atomicAdd(GV + 3 * TD + lane, pb);
             }
             __syncthreads();
+            // dropout sits between the FFN output and the residual: the FFN branch sees dZ * mask / (1-p),
+            // the residual branch the plain dZ.  The masked copy lives in the (still unused) dQ tile.
+            const float* Fs = Zs;
+            if (a.drop[l].p > 0.f) {
+                for (int e = threadIdx.x; e < TP * TD; e += blockDim.x) {
+                    const int r = e / TD, c = e % TD;
+                    dQs[r * TS + c] = (r < L) ? Zs[r * TS + c] * dropout_scale(a.drop[l], b * L + r, c, TD) : 0.f;
+                }
+                Fs = dQs;
+                __syncthreads();
+            }
             // ---- FFN backward ----
             // dW2 += dZ^T relu(U), db2 += colsum(dZ); dU = (dZ W2) * (U > 0); 8 (m,n) tile pairs -> one per warp
             {
@@ -378,8 +392,8 @@ __global__ void __launch_bounds__(512) trunk_bwd_kernel(TrunkArgs a) {
 #pragma unroll 2
                 for (int ks = ks_beg; ks < ks_end; ++ks) {
                     const int k0 = ks * 8 + tq;
-                    float af[4] = {Zs[k0 * TS + mt * 16 + gq], Zs[k0 * TS + mt * 16 + gq + 8], Zs[(k0 + 4) * TS + mt * 16 + gq],
-                                   Zs[(k0 + 4) * TS + mt * 16 + gq + 8]};
+                    float af[4] = {Fs[k0 * TS + mt * 16 + gq], Fs[k0 * TS + mt * 16 + gq + 8], Fs[(k0 + 4) * TS + mt * 16 + gq],
+                                   Fs[(k0 + 4) * TS + mt * 16 + gq + 8]};
                     float bf[2] = {fmaxf(Us[k0 * TS + np * 8 + gq], 0.f), fmaxf(Us[(k0 + 4) * TS + np * 8 + gq], 0.f)};
                     mma_3xtf32(acc, af, bf);
                 }
@@ -389,14 +403,14 @@ __global__ void __launch_bounds__(512) trunk_bwd_kernel(TrunkArgs a) {
                 atomicAdd(g2 + (r + 8) * TS + c, acc[2]); atomicAdd(g2 + (r + 8) * TS + c + 1, acc[3]);
                 if (warp == 0) {
                     float sb = 0.f;
-                    for (int r2 = 0; r2 < L; ++r2) sb += Zs[r2 * TS + lane];
+                    for (int r2 = 0; r2 < L; ++r2) sb += Fs[r2 * TS + lane];
                     GV[TD + lane] += sb;
                 }
             }
             __syncthreads();
             for (int it = warp; it < MT * 2; it += TW) {            // dU = (dZ W2) * (U > 0), in place over U
                 const int mt = it / 2, nh = it & 1;
-                tile_mma<2, TD / 8, TS, 1, TS, 1>(Zs, W + 4 * WMAT, mt * 16, nh * 2, lane, [&](int r, int c, float v0, float v1) {
+                tile_mma<2, TD / 8, TS, 1, TS, 1>(Fs, W + 4 * WMAT, mt * 16, nh * 2, lane, [&](int r, int c, float v0, float v1) {
                     Us[r * TS + c] = Us[r * TS + c] > 0.f ? v0 : 0.f;
                     Us[r * TS + c + 1] = Us[r * TS + c + 1] > 0.f ? v1 : 0.f;
                 });
@@ -580,9 +594,10 @@ int trunk_run(const TrunkArgs& a, bool bwd, cudaStream_t s) {
 }
 
 static TrunkArgs trunk_args(int64_t B, int64_t L, int heads, int layers, const StackParams& p, float* const* X,
-                            const StackSaved& sv) {
+                            const StackSaved& sv, float drop_p, uint64_t drop_seed, int stream_id) {
     TrunkArgs a;
     memset(&a, 0, sizeof(a));
+    for (int l = 0; l < 8; ++l) a.drop[l] = make_dropout(drop_p, drop_seed, stream_id, l);
     for (int l = 0; l < layers && l < 8; ++l) {
         a.QKV[l] = sv.QKV[l]; a.A[l] = sv.A[l]; a.U[l] = sv.U[l]; a.Z[l] = sv.Z[l]; a.ST[l] = sv.ST[l];
     }
@@ -594,14 +609,14 @@ static TrunkArgs trunk_args(int64_t B, int64_t L, int heads, int layers, const S
 }
 
 int trunk_fwd(int64_t B, int64_t L, int heads, int layers, const StackParams& p, float* const* X, const StackSaved& sv,
-              cudaStream_t s) {
-    TrunkArgs a = trunk_args(B, L, heads, layers, p, X, sv);
+              float drop_p, uint64_t drop_seed, int stream_id, cudaStream_t s) {
+    TrunkArgs a = trunk_args(B, L, heads, layers, p, X, sv, drop_p, drop_seed, stream_id);
     return trunk_run(a, false, s);
 }
 
 int trunk_bwd(int64_t B, int64_t L, int heads, int layers, const StackParams& p, const StackGrads& g, float* const* X,
-              const StackSaved& sv, float* dX, cudaStream_t s) {
-    TrunkArgs a = trunk_args(B, L, heads, layers, p, X, sv);
+              const StackSaved& sv, float* dX, float drop_p, uint64_t drop_seed, int stream_id, cudaStream_t s) {
+    TrunkArgs a = trunk_args(B, L, heads, layers, p, X, sv, drop_p, drop_seed, stream_id);
     a.dX = dX;
     a.gwq = g.wq; a.gwk = g.wk; a.gwv = g.wv; a.gw1 = g.w1; a.gb1 = g.b1; a.gw2 = g.w2; a.gb2 = g.b2; a.glnw = g.lnw; a.glnb = g.lnb;
     return trunk_run(a, true, s);

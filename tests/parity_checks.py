@@ -312,3 +312,67 @@ def check_compact_layout(device):
         gmax = max(float(g.abs().max()) for g in res[0][2].values())
         for k, g in res[0][2].items():
             assert_grad_close(res[1][2][k].cpu().numpy(), g.cpu().numpy(), gmax, f"{enc}/{k}", rtol=1e-4, afrac=2e-6)
+
+
+def _fresh(cfg, state, device, batch, train=True, fused=True, drop_step=0):
+    from intel_sigir2023_b200 import _lib, losses
+    _lib.check(_lib.load().intel_debug_use_fused_stack(1 if fused else 0))
+    try:
+        model = make_model(cfg, {k: v.to(device) for k, v in state.items()}, device)
+        model.train(train)
+        model._drop_seed, model._drop_step = 1234, drop_step
+        out = model(batch)
+        loss, _, _ = losses.IntListloss(loss_args())(out, batch)
+        loss.backward()
+        return out, loss, {k: p.grad.clone() for k, p in model.named_parameters()}
+    finally:
+        _lib.check(_lib.load().intel_debug_use_fused_stack(1))
+
+
+def check_fused_vs_staged(device, dropout=0.0, B=19, L=23):
+    """the fused per-session stack kernel and the staged kernels implement the same math (also under dropout:
+    both draw the mask from the same counter-based hash)"""
+    from intel_sigir2023_b200 import synthetic
+    from intel_sigir2023_b200.config import IntelConfig
+    corpus = synthetic.CorpusSpec(n_item=200, n_class=9, n_user=30, n_ctx=19, model_num=3, intent_num=40, history_max=6)
+    cfg = IntelConfig(item_rows=corpus.item_rows, class_rows=corpus.n_class, user_rows=corpus.user_rows, ctx_rows=corpus.n_ctx,
+                      intent_num=corpus.intent_num, model_num=3, history_max=6, encoder="GRU4Rec", num_heads=2, num_layers=2,
+                      dropout=dropout)
+    batch = synthetic.make_batch(corpus, synthetic.BatchSpec(batch_size=B, max_len=L, min_len=2), seed=8)
+    batch = {k: (v.to(device) if torch.is_tensor(v) else v) for k, v in batch.items()}
+    state = O.init_state(cfg, seed=4)
+    a = _fresh(cfg, state, device, batch, fused=True)
+    b = _fresh(cfg, state, device, batch, fused=False)
+    for k in ("intents", "weights", "ens_score"):
+        assert rel_err(a[0][k].detach().cpu().numpy(), b[0][k].detach().cpu().numpy()) < 5e-6, (k, dropout)
+    gmax = max(float(g.abs().max()) for g in b[2].values())
+    for k, g in b[2].items():
+        assert_grad_close(a[2][k].cpu().numpy(), g.cpu().numpy(), gmax, f"{k} p={dropout}", rtol=2e-4, afrac=3e-6)
+    return cfg, state, batch, a
+
+
+def check_dropout(device):
+    """training-mode dropout: deterministic per (seed, step), off in eval mode, changes the output, unbiased scale,
+    and the backward pass uses the same mask (directional finite difference with the mask held fixed)."""
+    from intel_sigir2023_b200 import losses
+    cfg, state, batch, a = check_fused_vs_staged(device, dropout=0.3)
+    again = _fresh(cfg, state, device, batch)
+    assert torch.equal(a[0]["ens_score"], again[0]["ens_score"])                      # same seed and step -> same mask
+    other = _fresh(cfg, state, device, batch, drop_step=7)
+    assert not torch.equal(a[0]["ens_score"], other[0]["ens_score"])                  # new step -> new mask
+    ev = _fresh(cfg, state, device, batch, train=False)
+    import dataclasses
+    cfg0 = dataclasses.replace(cfg, dropout=0.0)
+    ref = _fresh(cfg0, state, device, batch)
+    assert torch.equal(ev[0]["ens_score"], ref[0]["ens_score"])                       # eval mode: no dropout
+    assert not torch.equal(a[0]["ens_score"], ref[0]["ens_score"])
+    # finite differences along a random direction of the stack weights, mask fixed by (seed, step)
+    g = torch.Generator().manual_seed(0)
+    keys = [k for k in state if k.startswith(("i_", "s_"))]
+    direction = {k: torch.randn(state[k].shape, generator=g) for k in keys}
+    analytic = sum(float((a[2][k].cpu().double() * direction[k].double()).sum()) for k in keys)
+    eps = 2e-3
+    lp = _fresh(cfg, {k: (v + eps * direction[k] if k in direction else v) for k, v in state.items()}, device, batch)[1]
+    lm = _fresh(cfg, {k: (v - eps * direction[k] if k in direction else v) for k, v in state.items()}, device, batch)[1]
+    num = (lp.item() - lm.item()) / (2 * eps)
+    assert abs(analytic - num) <= 3e-2 * abs(num) + 1e-4, (analytic, num)

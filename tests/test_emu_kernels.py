@@ -82,3 +82,11 @@ def test_against_oracle_multi_tile():
 
 def test_compact_layout_matches_dense():
     P.check_compact_layout("cpu")
+
+
+def test_fused_stack_matches_staged():
+    P.check_fused_vs_staged("cpu")
+
+
+def test_dropout():
+    P.check_dropout("cpu")

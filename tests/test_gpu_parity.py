@@ -87,3 +87,11 @@ def test_against_oracle(cfg):
 
 def test_compact_layout_matches_dense():
     P.check_compact_layout(DEV)
+
+
+def test_fused_stack_matches_staged():
+    P.check_fused_vs_staged(DEV)
+
+
+def test_dropout():
+    P.check_dropout(DEV)
