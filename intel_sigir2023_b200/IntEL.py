@@ -104,8 +104,11 @@ class _IntelFn(torch.autograd.Function):
                                           _lib.ptr(ws_ens), ws_ens.numel(), stream))
         if any(ctx.needs_input_grad):
             ctx.model, ctx.batch, ctx.dims = model, batch, dims
-            ctx.ws_int, ctx.ws_ens, ctx.intents = ws_int, ws_ens, intents
+            ctx.ws_int, ctx.ws_ens = ws_int, ws_ens
             ctx.params = params
+            # `intents` is an output: holding it as a plain attribute would close a ctx -> tensor -> grad_fn -> ctx
+            # cycle that only the cyclic GC frees, and every leaked step costs the allocator a fresh cudaMalloc.
+            ctx.save_for_backward(intents)
         else:                       # inference: nothing is kept for a backward pass
             _give_ws(model, ws_int)
             _give_ws(model, ws_ens)
@@ -116,6 +119,7 @@ class _IntelFn(torch.autograd.Function):
         lib = _lib.load()
         model, cfg, batch, dims = ctx.model, ctx.model.cfg, ctx.batch, ctx.dims
         params = ctx.params
+        (intents,) = ctx.saved_tensors
         dev = params[0].device
         names = model._param_names
         P = _lib.make_tensors(cfg, dict(zip(names, params)))
@@ -125,15 +129,15 @@ class _IntelFn(torch.autograd.Function):
         stream = _lib.stream_ptr(dev)
         d_int_ens: Optional[torch.Tensor] = None
         if d_weights is not None or d_ens is not None:
-            d_int_ens = torch.empty_like(ctx.intents)
+            d_int_ens = torch.empty_like(intents)
             dw = d_weights.contiguous() if d_weights is not None else None
             de = d_ens.contiguous() if d_ens is not None else None
-            _lib.check(lib.intel_ensemble_bwd(dims, P, bt, _lib.ptr(ctx.intents), _lib.ptr(dw), _lib.ptr(de), G,
+            _lib.check(lib.intel_ensemble_bwd(dims, P, bt, _lib.ptr(intents), _lib.ptr(dw), _lib.ptr(de), G,
                                               _lib.ptr(d_int_ens), _lib.ptr(ctx.ws_ens), ctx.ws_ens.numel(), stream))
         first = d_intents.contiguous() if d_intents is not None else d_int_ens
         extra = d_int_ens if d_intents is not None else None
         if first is not None:
-            _lib.check(lib.intel_intent_bwd(dims, P, bt, _lib.ptr(ctx.intents), _lib.ptr(first), _lib.ptr(extra), G,
+            _lib.check(lib.intel_intent_bwd(dims, P, bt, _lib.ptr(intents), _lib.ptr(first), _lib.ptr(extra), G,
                                             _lib.ptr(ctx.ws_int), ctx.ws_int.numel(), stream))
         _give_ws(model, ctx.ws_int)
         _give_ws(model, ctx.ws_ens)

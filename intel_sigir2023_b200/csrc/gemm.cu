@@ -27,64 +27,99 @@ struct GemmDev {
 static const int BK = 32;
 
 // Global -> register staging of one operand tile.  TR = operand stored [K][rows] (rows contiguous),
-// otherwise [rows][K] (k contiguous).  Each thread owns NV float4 chunks.
+// otherwise [rows][K] (k contiguous).  Two modes: 16-byte chunks when the operand is 16-byte aligned with a
+// leading dimension that is a multiple of 4, otherwise element-wise with consecutive lanes on consecutive
+// addresses (I = 1071 makes every operand with that leading dimension misaligned; a per-thread 4-float
+// fallback there cost 4x the transactions).
 template <int ROWS, int NT, bool TR>
 struct TileLoader {
     static constexpr int CH = ROWS * BK / 4;                 // float4 chunks per tile
     static constexpr int NV = (CH + NT - 1) / NT;
+    static constexpr int NE = 4 * NV;                        // scalars per thread
     static constexpr int LD = TR ? ROWS + 8 : BK + 4;       // shared-memory leading dimension
-    float4 v[NV];
+    float f[NE];
 
     __device__ __forceinline__ void load(const float* __restrict__ P, int64_t ld, int64_t r0, int64_t rmax, int64_t k0,
                                          int64_t kend, int vec, int relu, int tid) {
+        if (vec) {
 #pragma unroll
-        for (int i = 0; i < NV; ++i) {
-            const int e = tid + i * NT;
-            float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (e < CH) {
-                if (TR) {
-                    const int kk = e / (ROWS / 4), r4 = (e % (ROWS / 4)) * 4;
-                    const int64_t gk = k0 + kk, gr = r0 + r4;
-                    if (gk < kend) {
-                        const float* p = P + gk * ld + gr;
-                        if (vec && gr + 3 < rmax) x = *reinterpret_cast<const float4*>(p);
-                        else {
-                            if (gr < rmax) x.x = p[0];
-                            if (gr + 1 < rmax) x.y = p[1];
-                            if (gr + 2 < rmax) x.z = p[2];
-                            if (gr + 3 < rmax) x.w = p[3];
+            for (int i = 0; i < NV; ++i) {
+                const int e = tid + i * NT;
+                float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (e < CH) {
+                    if (TR) {
+                        const int kk = e / (ROWS / 4), r4 = (e % (ROWS / 4)) * 4;
+                        const int64_t gk = k0 + kk, gr = r0 + r4;
+                        if (gk < kend) {
+                            const float* p = P + gk * ld + gr;
+                            if (gr + 3 < rmax) x = *reinterpret_cast<const float4*>(p);
+                            else {
+                                if (gr < rmax) x.x = p[0];
+                                if (gr + 1 < rmax) x.y = p[1];
+                                if (gr + 2 < rmax) x.z = p[2];
+                            }
                         }
-                    }
-                } else {
-                    const int rr = e / (BK / 4), k4 = (e % (BK / 4)) * 4;
-                    const int64_t gr = r0 + rr, gk = k0 + k4;
-                    if (gr < rmax) {
-                        const float* p = P + gr * ld + gk;
-                        if (vec && gk + 3 < kend) x = *reinterpret_cast<const float4*>(p);
-                        else {
-                            if (gk < kend) x.x = p[0];
-                            if (gk + 1 < kend) x.y = p[1];
-                            if (gk + 2 < kend) x.z = p[2];
-                            if (gk + 3 < kend) x.w = p[3];
+                    } else {
+                        const int rr = e / (BK / 4), k4 = (e % (BK / 4)) * 4;
+                        const int64_t gr = r0 + rr, gk = k0 + k4;
+                        if (gr < rmax) {
+                            const float* p = P + gr * ld + gk;
+                            if (gk + 3 < kend) x = *reinterpret_cast<const float4*>(p);
+                            else {
+                                if (gk < kend) x.x = p[0];
+                                if (gk + 1 < kend) x.y = p[1];
+                                if (gk + 2 < kend) x.z = p[2];
+                            }
                         }
                     }
                 }
-                if (relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+                f[4 * i] = x.x; f[4 * i + 1] = x.y; f[4 * i + 2] = x.z; f[4 * i + 3] = x.w;
             }
-            v[i] = x;
+        } else {
+#pragma unroll
+            for (int i = 0; i < NE; ++i) {
+                const int e = tid + i * NT;
+                float x = 0.f;
+                if (e < ROWS * BK) {
+                    if (TR) {
+                        const int kk = e / ROWS, r = e % ROWS;
+                        if (k0 + kk < kend && r0 + r < rmax) x = P[(k0 + kk) * ld + r0 + r];
+                    } else {
+                        const int rr = e / BK, k = e % BK;
+                        if (r0 + rr < rmax && k0 + k < kend) x = P[(r0 + rr) * ld + k0 + k];
+                    }
+                }
+                f[i] = x;
+            }
+        }
+        if (relu) {
+#pragma unroll
+            for (int i = 0; i < NE; ++i) f[i] = fmaxf(f[i], 0.f);
         }
     }
-    __device__ __forceinline__ void store(float* s, int tid) const {
+    __device__ __forceinline__ void store(float* s, int vec, int tid) const {
+        if (vec) {
 #pragma unroll
-        for (int i = 0; i < NV; ++i) {
-            const int e = tid + i * NT;
-            if (e < CH) {
-                if (TR) {
-                    const int kk = e / (ROWS / 4), r4 = (e % (ROWS / 4)) * 4;
-                    *reinterpret_cast<float4*>(s + kk * LD + r4) = v[i];
-                } else {
-                    const int rr = e / (BK / 4), k4 = (e % (BK / 4)) * 4;
-                    *reinterpret_cast<float4*>(s + rr * LD + k4) = v[i];
+            for (int i = 0; i < NV; ++i) {
+                const int e = tid + i * NT;
+                if (e < CH) {
+                    const float4 x = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+                    if (TR) {
+                        const int kk = e / (ROWS / 4), r4 = (e % (ROWS / 4)) * 4;
+                        *reinterpret_cast<float4*>(s + kk * LD + r4) = x;
+                    } else {
+                        const int rr = e / (BK / 4), k4 = (e % (BK / 4)) * 4;
+                        *reinterpret_cast<float4*>(s + rr * LD + k4) = x;
+                    }
+                }
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < NE; ++i) {
+                const int e = tid + i * NT;
+                if (e < ROWS * BK) {
+                    if (TR) s[(e / ROWS) * LD + (e % ROWS)] = f[i];
+                    else s[(e / BK) * LD + (e % BK)] = f[i];
                 }
             }
         }
@@ -164,13 +199,23 @@ __global__ void __launch_bounds__(WM * WN * 32) gemm_tc_kernel(GemmDev g) {
         lb.load(g.B, g.ldb, n0, g.N, kbeg, kend, g.vec_b, g.relu_b, tid);
     }
     for (int64_t k0 = kbeg; k0 < kend; k0 += BK) {
-        la.store(sA, tid);
-        lb.store(sB, tid);
+        la.store(sA, g.vec_a, tid);
+        lb.store(sB, g.vec_b, tid);
         __syncthreads();
         if (k0 + BK < kend) {     // prefetch the next k-tile into registers while this one is consumed
             la.load(g.A, g.lda, m0, g.M, k0 + BK, kend, g.vec_a, g.relu_a, tid);
             lb.load(g.B, g.ldb, n0, g.N, k0 + BK, kend, g.vec_b, g.relu_b, tid);
         }
+        // The tensor core adds into its accumulator with truncation, so a long MMA chain drifts towards zero
+        // linearly in K.  Each k-tile is therefore summed from zero in `part` and folded into `acc` with a
+        // round-to-nearest FADD.
+        float part[TM][TN][4];
+#pragma unroll
+        for (int i = 0; i < TM; ++i)
+#pragma unroll
+            for (int j = 0; j < TN; ++j)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) part[i][j][c] = 0.f;
 #pragma unroll
         for (int ks = 0; ks < BK / 8; ++ks) {
             const int kb = ks * 8;
@@ -206,16 +251,22 @@ __global__ void __launch_bounds__(WM * WN * 32) gemm_tc_kernel(GemmDev g) {
 #pragma unroll
             for (int i = 0; i < TM; ++i)
 #pragma unroll
-                for (int j = 0; j < TN; ++j) mma_tf32(acc[i][j], al[i], bh[j]);
+                for (int j = 0; j < TN; ++j) mma_tf32(part[i][j], al[i], bh[j]);
 #pragma unroll
             for (int i = 0; i < TM; ++i)
 #pragma unroll
-                for (int j = 0; j < TN; ++j) mma_tf32(acc[i][j], ah[i], bl[j]);
+                for (int j = 0; j < TN; ++j) mma_tf32(part[i][j], ah[i], bl[j]);
 #pragma unroll
             for (int i = 0; i < TM; ++i)
 #pragma unroll
-                for (int j = 0; j < TN; ++j) mma_tf32(acc[i][j], ah[i], bh[j]);
+                for (int j = 0; j < TN; ++j) mma_tf32(part[i][j], ah[i], bh[j]);
         }
+#pragma unroll
+        for (int i = 0; i < TM; ++i)
+#pragma unroll
+            for (int j = 0; j < TN; ++j)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[i][j][c] += part[i][j][c];
         __syncthreads();
     }
 
@@ -252,50 +303,76 @@ __global__ void __launch_bounds__(WG_WARPS * 32) gemm_wgrad_kernel(GemmDev g) {
 #pragma unroll
             for (int c = 0; c < 4; ++c) acc[i][j][c] = 0.f;
 
-    float4 px[4], py[4];
-    auto fetch = [&](int64_t k0) {
+    // register staging of the next [WG_BK][32] tile of each operand: 16-byte chunks when aligned, else
+    // element-wise with consecutive lanes on consecutive addresses (see TileLoader)
+    float pa[16], pb[16];
+    auto fetch_one = [&](const float* __restrict__ P, int64_t ld, int64_t c0, int64_t cmax, int vec, int relu, int64_t k0,
+                         float (&dst)[16]) {
+        if (vec) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int e = tid + i * (WG_WARPS * 32);
-            const int kk = e >> 3, r4 = (e & 7) * 4;
-            const int64_t gk = k0 + kk;
-            float4 x = make_float4(0.f, 0.f, 0.f, 0.f), y = x;
-            if (gk < kend) {
-                const float* pa = g.A + gk * g.lda + m0 + r4;
-                const float* pb = g.B + gk * g.ldb + n0 + r4;
-                if (g.vec_a && m0 + r4 + 3 < g.M) x = *reinterpret_cast<const float4*>(pa);
-                else {
-                    if (m0 + r4 < g.M) x.x = pa[0];
-                    if (m0 + r4 + 1 < g.M) x.y = pa[1];
-                    if (m0 + r4 + 2 < g.M) x.z = pa[2];
-                    if (m0 + r4 + 3 < g.M) x.w = pa[3];
+            for (int i = 0; i < 4; ++i) {
+                const int e = tid + i * (WG_WARPS * 32);
+                const int kk = e >> 3, r4 = (e & 7) * 4;
+                const int64_t gk = k0 + kk;
+                float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (gk < kend) {
+                    const float* p = P + gk * ld + c0 + r4;
+                    if (c0 + r4 + 3 < cmax) x = *reinterpret_cast<const float4*>(p);
+                    else {
+                        if (c0 + r4 < cmax) x.x = p[0];
+                        if (c0 + r4 + 1 < cmax) x.y = p[1];
+                        if (c0 + r4 + 2 < cmax) x.z = p[2];
+                    }
                 }
-                if (g.vec_b && n0 + r4 + 3 < g.N) y = *reinterpret_cast<const float4*>(pb);
-                else {
-                    if (n0 + r4 < g.N) y.x = pb[0];
-                    if (n0 + r4 + 1 < g.N) y.y = pb[1];
-                    if (n0 + r4 + 2 < g.N) y.z = pb[2];
-                    if (n0 + r4 + 3 < g.N) y.w = pb[3];
-                }
-                if (g.relu_a) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
-                if (g.relu_b) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
+                dst[4 * i] = x.x; dst[4 * i + 1] = x.y; dst[4 * i + 2] = x.z; dst[4 * i + 3] = x.w;
             }
-            px[i] = x;
-            py[i] = y;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int e = tid + i * (WG_WARPS * 32);
+                const int kk = e >> 5, r = e & 31;
+                const int64_t gk = k0 + kk;
+                dst[i] = (gk < kend && c0 + r < cmax) ? P[gk * ld + c0 + r] : 0.f;
+            }
         }
+        if (relu) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) dst[i] = fmaxf(dst[i], 0.f);
+        }
+    };
+    auto stash = [&](float* sdst, int vec, const float (&src)[16]) {
+        if (vec) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int e = tid + i * (WG_WARPS * 32);
+                *reinterpret_cast<float4*>(sdst + (e >> 3) * LD + (e & 7) * 4) =
+                    make_float4(src[4 * i], src[4 * i + 1], src[4 * i + 2], src[4 * i + 3]);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int e = tid + i * (WG_WARPS * 32);
+                sdst[(e >> 5) * LD + (e & 31)] = src[i];
+            }
+        }
+    };
+    auto fetch = [&](int64_t k0) {
+        fetch_one(g.A, g.lda, m0, g.M, g.vec_a, g.relu_a, k0, pa);
+        fetch_one(g.B, g.ldb, n0, g.N, g.vec_b, g.relu_b, k0, pb);
     };
     if (kbeg < kend) fetch(kbeg);
     for (int64_t k0 = kbeg; k0 < kend; k0 += WG_BK) {
-        // stage [WG_BK][32] of both operands: 8 float4 per k-row, 4 chunks per thread and operand
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int e = tid + i * (WG_WARPS * 32);
-            const int kk = e >> 3, r4 = (e & 7) * 4;
-            *reinterpret_cast<float4*>(sA + kk * LD + r4) = px[i];
-            *reinterpret_cast<float4*>(sB + kk * LD + r4) = py[i];
-        }
+        stash(sA, g.vec_a, pa);
+        stash(sB, g.vec_b, pb);
         __syncthreads();
         if (k0 + WG_BK < kend) fetch(k0 + WG_BK);     // next tile in flight while this one is consumed
+        float part[2][4][4];     // per-slab partial sums, folded into acc with a rounded add (see gemm_tc_kernel)
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) part[i][j][c] = 0.f;
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks) {
             const int kb = warp * 16 + ks * 8;
@@ -317,8 +394,14 @@ __global__ void __launch_bounds__(WG_WARPS * 32) gemm_wgrad_kernel(GemmDev g) {
 #pragma unroll
             for (int i = 0; i < 2; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) mma_3xtf32(acc[i][j], af[i], bf[j]);
+                for (int j = 0; j < 4; ++j) mma_3xtf32(part[i][j], af[i], bf[j]);
         }
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[i][j][c] += part[i][j][c];
         __syncthreads();
     }
     // cross-warp reduction through shared memory (8 partial 32x32 tiles fit in the staging buffers)
@@ -340,6 +423,195 @@ __global__ void __launch_bounds__(WG_WARPS * 32) gemm_wgrad_kernel(GemmDev g) {
 #pragma unroll
         for (int w = 0; w < 4; ++w) v += sA[w * 1024 + e] + sB[w * 1024 + e];
         gemm_store(g, m0 + (e >> 5), n0 + (e & 31), v, first);
+    }
+}
+
+// Tall output with few columns and a LONG inner dimension (the intent-side projections:
+// [B x 1071] x [1071 -> 32]): a 128 x 32 tiling leaves 32-64 CTAs walking 34 k-tiles one after the other.  Here a
+// CTA owns 32 rows x 32 columns and its eight warps split every staged 128-wide k slab between them; the eight
+// partial tiles are reduced through shared memory.  A is [M][K] (k contiguous); B is [N][K] or, BT, [K][N].
+static const int SK_BK = 128, SK_LD = SK_BK + 4, SK_LDT = 32 + 8;
+
+// [32 rows][128 k] slab of a k-contiguous operand -> 16 registers per thread (and back to shared memory)
+__device__ __forceinline__ void sk_load_kmajor(const float* __restrict__ P, int64_t ld, int64_t r0, int64_t rmax, int64_t k0,
+                                               int64_t kend, int vec, int relu, int tid, float (&dst)[16]) {
+    if (vec) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int e = tid + i * 256;
+            const int rr = e >> 5, k4 = (e & 31) * 4;
+            float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r0 + rr < rmax) {
+                const float* p = P + (r0 + rr) * ld + k0 + k4;
+                if (k0 + k4 + 3 < kend) x = *reinterpret_cast<const float4*>(p);
+                else {
+                    if (k0 + k4 < kend) x.x = p[0];
+                    if (k0 + k4 + 1 < kend) x.y = p[1];
+                    if (k0 + k4 + 2 < kend) x.z = p[2];
+                }
+            }
+            dst[4 * i] = x.x; dst[4 * i + 1] = x.y; dst[4 * i + 2] = x.z; dst[4 * i + 3] = x.w;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int e = tid + i * 256;
+            const int rr = e >> 7, k = e & 127;
+            dst[i] = (r0 + rr < rmax && k0 + k < kend) ? P[(r0 + rr) * ld + k0 + k] : 0.f;
+        }
+    }
+    if (relu) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) dst[i] = fmaxf(dst[i], 0.f);
+    }
+}
+__device__ __forceinline__ void sk_stash_kmajor(float* s, int vec, int tid, const float (&src)[16]) {
+    if (vec) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int e = tid + i * 256;
+            *reinterpret_cast<float4*>(s + (e >> 5) * SK_LD + (e & 31) * 4) = make_float4(src[4 * i], src[4 * i + 1], src[4 * i + 2], src[4 * i + 3]);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int e = tid + i * 256;
+            s[(e >> 7) * SK_LD + (e & 127)] = src[i];
+        }
+    }
+}
+// [128 k][32 cols] slab of a column-contiguous operand
+__device__ __forceinline__ void sk_load_cmajor(const float* __restrict__ P, int64_t ld, int64_t c0, int64_t cmax, int64_t k0,
+                                               int64_t kend, int vec, int relu, int tid, float (&dst)[16]) {
+    if (vec) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int e = tid + i * 256;
+            const int kk = e >> 3, r4 = (e & 7) * 4;
+            float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (k0 + kk < kend) {
+                const float* p = P + (k0 + kk) * ld + c0 + r4;
+                if (c0 + r4 + 3 < cmax) x = *reinterpret_cast<const float4*>(p);
+                else {
+                    if (c0 + r4 < cmax) x.x = p[0];
+                    if (c0 + r4 + 1 < cmax) x.y = p[1];
+                    if (c0 + r4 + 2 < cmax) x.z = p[2];
+                }
+            }
+            dst[4 * i] = x.x; dst[4 * i + 1] = x.y; dst[4 * i + 2] = x.z; dst[4 * i + 3] = x.w;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int e = tid + i * 256;
+            const int kk = e >> 5, r = e & 31;
+            dst[i] = (k0 + kk < kend && c0 + r < cmax) ? P[(k0 + kk) * ld + c0 + r] : 0.f;
+        }
+    }
+    if (relu) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) dst[i] = fmaxf(dst[i], 0.f);
+    }
+}
+__device__ __forceinline__ void sk_stash_cmajor(float* s, int vec, int tid, const float (&src)[16]) {
+    if (vec) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int e = tid + i * 256;
+            *reinterpret_cast<float4*>(s + (e >> 3) * SK_LDT + (e & 7) * 4) = make_float4(src[4 * i], src[4 * i + 1], src[4 * i + 2], src[4 * i + 3]);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int e = tid + i * 256;
+            s[(e >> 5) * SK_LDT + (e & 31)] = src[i];
+        }
+    }
+}
+
+template <bool BT>
+__global__ void __launch_bounds__(256) gemm_skinny_kernel(GemmDev g) {
+    __shared__ __align__(16) float sm[32 * SK_LD + SK_BK * SK_LDT];     // A slab | B slab; reused for the reduction (>= 8192)
+    float* sA = sm;
+    float* sB = sm + 32 * SK_LD;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int gq = lane >> 2, tq = lane & 3;
+    const int64_t m0 = (int64_t)blockIdx.x * 32, n0 = (int64_t)blockIdx.y * 32;
+    float acc[2][4][4];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[i][j][c] = 0.f;
+    float pa[16], pb[16];
+    auto fetch = [&](int64_t k0) {
+        sk_load_kmajor(g.A, g.lda, m0, g.M, k0, g.K, g.vec_a, g.relu_a, tid, pa);
+        if (BT) sk_load_cmajor(g.B, g.ldb, n0, g.N, k0, g.K, g.vec_b, g.relu_b, tid, pb);
+        else sk_load_kmajor(g.B, g.ldb, n0, g.N, k0, g.K, g.vec_b, g.relu_b, tid, pb);
+    };
+    fetch(0);
+    for (int64_t k0 = 0; k0 < g.K; k0 += SK_BK) {
+        sk_stash_kmajor(sA, g.vec_a, tid, pa);
+        if (BT) sk_stash_cmajor(sB, g.vec_b, tid, pb);
+        else sk_stash_kmajor(sB, g.vec_b, tid, pb);
+        __syncthreads();
+        if (k0 + SK_BK < g.K) fetch(k0 + SK_BK);
+        float part[2][4][4];     // per-slab partial sums, folded into acc with a rounded add (see gemm_tc_kernel)
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) part[i][j][c] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+            const int kb = warp * 16 + ks * 8;
+            float af[2][4], bf[4][2];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int r = i * 16 + gq;
+                af[i][0] = sA[r * SK_LD + kb + tq];
+                af[i][1] = sA[(r + 8) * SK_LD + kb + tq];
+                af[i][2] = sA[r * SK_LD + kb + tq + 4];
+                af[i][3] = sA[(r + 8) * SK_LD + kb + tq + 4];
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int c = j * 8 + gq;
+                bf[j][0] = BT ? sB[(kb + tq) * SK_LDT + c] : sB[c * SK_LD + kb + tq];
+                bf[j][1] = BT ? sB[(kb + tq + 4) * SK_LDT + c] : sB[c * SK_LD + kb + tq + 4];
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) mma_3xtf32(part[i][j], af[i], bf[j]);
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[i][j][c] += part[i][j][c];
+        __syncthreads();
+    }
+    float* red = sm + warp * 1024;
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int r = i * 16 + gq, c = j * 8 + 2 * tq;
+            red[r * 32 + c] = acc[i][j][0];
+            red[r * 32 + c + 1] = acc[i][j][1];
+            red[(r + 8) * 32 + c] = acc[i][j][2];
+            red[(r + 8) * 32 + c + 1] = acc[i][j][3];
+        }
+    __syncthreads();
+    for (int e = tid; e < 1024; e += 256) {
+        float v = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) v += sm[w * 1024 + e];
+        gemm_store(g, m0 + (e >> 5), n0 + (e & 31), v, true);
     }
 }
 
@@ -464,7 +736,16 @@ int gemm(const Gemm& g, cudaStream_t s) {
     const bool wgrad = g.a_t && g.b_t;
     // tile choice: the largest tile that still yields ~2 waves of CTAs on the 148 SMs; weight gradients with a
     // small output use the warp-split-K kernel, everything else the tiled kernel (with split-K when allowed)
-    const bool can_split = (g.accumulate == 2 && !g.relu_out && !g.mask && g.splits <= 0);
+    // plain outputs with a long inner dimension and too few tiles to fill the GPU are also split: the output is
+    // cleared first and the partial products are accumulated with atomics
+    const bool prezero = (g.accumulate == 0 && !g.relu_out && !g.mask && g.splits == 1 && g.K >= 512 && g.N > 64 &&
+                          ceil_div(g.M, 128) * ceil_div(g.N, 64) < kNumSMs);
+    if (prezero) {
+        cudaError_t e = cudaMemset2DAsync(g.C, (size_t)g.ldc * 4, 0, (size_t)g.N * 4, (size_t)g.M, s);
+        INTEL_REQUIRE(e == cudaSuccess, INTEL_ERR_CUDA, "cudaMemset2DAsync: %s", cudaGetErrorString(e));
+        d.accumulate = 2;
+    }
+    const bool can_split = ((g.accumulate == 2 && !g.relu_out && !g.mask && g.splits <= 0) || prezero);
     auto ctas = [&](int bm, int bn) { return ceil_div(g.M, bm) * ceil_div(g.N, bn); };
     int cfg;   // 0: 128x64  1: 128x32  2: 64x64  3: 64x32  4: warp-split-K 32x32
     if (wgrad && (g.M < 64 || g.N < 64)) cfg = 4;
@@ -474,7 +755,7 @@ int gemm(const Gemm& g, cudaStream_t s) {
     else cfg = 3;
     const int bm = cfg == 4 ? 32 : (cfg <= 1 ? 128 : 64), bn = (cfg == 0 || cfg == 2) ? 64 : 32;
     const int bk = cfg == 4 ? WG_BK : BK;
-    int splits = g.splits;
+    int splits = prezero ? 0 : g.splits;
     if (splits <= 0) {
         splits = 1;
         if (can_split) {
@@ -485,13 +766,17 @@ int gemm(const Gemm& g, cudaStream_t s) {
             if (splits < 1) splits = 1;
         }
     }
-    INTEL_REQUIRE(splits == 1 || (g.accumulate == 2 && !g.relu_out && !g.mask), INTEL_ERR_ARG,
+    INTEL_REQUIRE(splits == 1 || (d.accumulate == 2 && !g.relu_out && !g.mask), INTEL_ERR_ARG,
                   "gemm: split-K needs atomic accumulation and a linear epilogue");
     INTEL_REQUIRE(splits <= 65535, INTEL_ERR_ARG, "gemm: too many splits");
     d.splits = splits;
     d.kchunk = ceil_div(ceil_div(g.K, splits), bk) * bk;
     if (d.kchunk <= 0) d.kchunk = bk;
-    if (!g.a_t && g.K == 32 && g.N <= 32 && d.vec_a && g.accumulate != 2 && splits == 1 && g.M >= 2048) {
+    if (!g.a_t && splits == 1 && g.N <= 64 && g.K >= 256 && ctas(128, 32) < 2 * kNumSMs) {
+        dim3 grid((unsigned)ceil_div(d.M, 32), (unsigned)ceil_div(d.N, 32));
+        if (g.b_t) { auto k = gemm_skinny_kernel<true>; LAUNCH(k, grid, dim3(256), 0, s, d); }
+        else { auto k = gemm_skinny_kernel<false>; LAUNCH(k, grid, dim3(256), 0, s, d); }
+    } else if (!g.a_t && g.K == 32 && g.N <= 32 && d.vec_a && g.accumulate != 2 && splits == 1 && g.M >= 2048) {
         const unsigned grid = stream_grid(ceil_div(g.M, 16 * 8), 3);
         if (g.b_t) { auto k = gemm_stream32_kernel<true>; LAUNCH(k, dim3(grid), dim3(256), 0, s, d); }
         else { auto k = gemm_stream32_kernel<false>; LAUNCH(k, dim3(grid), dim3(256), 0, s, d); }

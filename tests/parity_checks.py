@@ -32,7 +32,7 @@ def check_linear(device):
     from intel_sigir2023_b200 import _lib
     lib = _lib.load()
     g = torch.Generator().manual_seed(0)
-    for (M, N, K) in [(7, 5, 3), (130, 33, 17), (64, 64, 64), (300, 8, 40), (20, 100, 70), (3001, 32, 32), (2500, 24, 32)]:
+    for (M, N, K) in [(7, 5, 3), (130, 33, 17), (64, 64, 64), (300, 8, 40), (20, 100, 70), (3001, 32, 32), (2500, 24, 32), (200, 32, 1071), (130, 48, 300), (77, 9, 515), (300, 176, 600)]:
         A = torch.randn(M, K, generator=g).to(device)
         W = torch.randn(N, K, generator=g).to(device)
         b = torch.randn(N, generator=g).to(device)
@@ -47,7 +47,7 @@ def check_linear_grads(device):
     from intel_sigir2023_b200 import _lib
     lib = _lib.load()
     g = torch.Generator().manual_seed(2)
-    for (M, N, K) in [(9, 5, 3), (1000, 33, 17), (4100, 32, 32), (257, 96, 40), (70, 130, 50)]:
+    for (M, N, K) in [(9, 5, 3), (1000, 33, 17), (4100, 32, 32), (257, 96, 40), (70, 130, 50), (150, 1071, 32), (90, 300, 24), (300, 600, 176)]:
         dY = torch.randn(M, N, generator=g).to(device)
         X = torch.randn(M, K, generator=g).to(device)
         W = torch.randn(N, K, generator=g).to(device)

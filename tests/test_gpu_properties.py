@@ -119,3 +119,38 @@ def test_loss_gradient_matches_finite_difference_full_batch(kind):
     eps = 1e-2
     num = (f(ens + eps * de, w + eps * dw).double() - f(ens - eps * de, w - eps * dw).double()) / (2 * eps)
     assert abs(analytic.item() - num.item()) <= 2e-2 * abs(num.item()) + 1e-4, (analytic.item(), num.item())
+
+
+def test_train_step_holds_no_reference_cycles_on_device_memory():
+    """A ctx -> output -> grad_fn -> ctx cycle keeps a step's tensors alive until the cyclic GC runs; the caching
+    allocator then has to cudaMalloc fresh segments inside the step (tens of ms of host stall).  With the GC off,
+    steady-state steps must not grow the allocator at all."""
+    import gc
+    from intel_sigir2023_b200 import losses, synthetic
+    corpus, cfg, model = _model(PL, C2)
+    crit = losses.IntListloss(argparse.Namespace(cal_diversity=1, diversity_alpha=1e-6, intent_weight=0.001,
+                                                 ensemble_weight=1.0, kl_weight=1.0, kl_temp=2.0))
+    batch = synthetic.make_batch(corpus, synthetic.BatchSpec(batch_size=512, max_len=50, min_len=50), seed=1, device=DEV)
+
+    def step():
+        for p in model.parameters():
+            p.grad = None
+        out = model(batch)
+        loss, _, _ = crit(out, batch)
+        loss.backward()
+
+    gc.collect()
+    gc.disable()
+    try:
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        seg0 = torch.cuda.memory_stats()["segment.all.allocated"]
+        live0 = torch.cuda.memory_allocated()
+        for _ in range(12):
+            step()
+        torch.cuda.synchronize()
+        assert torch.cuda.memory_stats()["segment.all.allocated"] == seg0
+        assert torch.cuda.memory_allocated() == live0
+    finally:
+        gc.enable()
