@@ -113,6 +113,14 @@ __device__ __forceinline__ float dropout_scale(const Dropout& d, int64_t row, in
 }
 
 // ---- warp helpers ----
+// barrier over a subset of the CTA's warps (bar.sync id, nthreads): id 1..15, nthreads a multiple of 32
+__device__ __forceinline__ void bar_sync(int id, int nthreads) {
+#ifdef INTEL_EMU
+    emu::named_barrier(id, nthreads);
+#else
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+#endif
+}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

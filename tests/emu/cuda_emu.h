@@ -75,7 +75,7 @@ struct Fiber {
     char* stack = nullptr;
     uint3 tid{0, 0, 0};
     int lin = 0;       // linear thread id in the block
-    int state = 0;     // 0 runnable, 1 waiting block barrier, 2 waiting warp barrier, 3 done
+    int state = 0;     // 0 runnable, 1 waiting block barrier, 2 waiting warp barrier, 3 done, 16+id waiting named barrier id
 };
 
 static const size_t kStack = 192 * 1024;
@@ -109,6 +109,7 @@ struct Sched {
     void* main_sp = nullptr;
     Fiber* cur = nullptr;
     int nthreads = 0, alive = 0, block_arrived = 0;
+    int named_arrived[16] = {0}, named_expect[16] = {0};   // bar.sync id, count
     std::vector<int> warp_alive, warp_arrived;
     std::vector<uint64_t> slots;           // per-thread exchange slot for collectives
     std::function<void()> body;
@@ -134,6 +135,13 @@ inline void release_checks() {
     if (s.alive > 0 && s.block_arrived == s.alive) {
         for (auto& f : s.fibers) if (f.state == 1) f.state = 0;
         s.block_arrived = 0;
+    }
+    for (int id = 0; id < 16; ++id) {
+        if (s.named_expect[id] > 0 && s.named_arrived[id] >= s.named_expect[id]) {
+            for (auto& f : s.fibers) if (f.state == 16 + id) f.state = 0;
+            s.named_arrived[id] = 0;
+            s.named_expect[id] = 0;
+        }
     }
     for (size_t w = 0; w < s.warp_alive.size(); ++w) {
         if (s.warp_alive[w] > 0 && s.warp_arrived[w] == s.warp_alive[w]) {
@@ -177,6 +185,7 @@ inline void run_block() {
     }
     s.alive = n;
     s.block_arrived = 0;
+    for (int id = 0; id < 16; ++id) s.named_arrived[id] = s.named_expect[id] = 0;
     static int order = -1;
     if (order < 0) {
         const char* e = getenv("INTEL_EMU_ORDER");
@@ -221,6 +230,16 @@ inline void block_barrier() {
     Sched& s = S();
     s.cur->state = 1;
     s.block_arrived++;
+    yield_to_main();
+}
+// bar.sync id, count: the first `count` threads to arrive at barrier `id` are released together
+inline void named_barrier(int id, int count) {
+    Sched& s = S();
+    if (id < 0 || id >= 16 || (count & 31)) { fprintf(stderr, "emu: bad named barrier %d/%d\n", id, count); abort(); }
+    if (s.named_expect[id] != 0 && s.named_expect[id] != count) { fprintf(stderr, "emu: named barrier %d count mismatch\n", id); abort(); }
+    s.named_expect[id] = count;
+    s.cur->state = 16 + id;
+    s.named_arrived[id]++;
     yield_to_main();
 }
 inline void warp_barrier() {

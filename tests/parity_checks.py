@@ -329,19 +329,24 @@ def _fresh(cfg, state, device, batch, train=True, fused=True, drop_step=0):
         _lib.check(_lib.load().intel_debug_use_fused_stack(1))
 
 
-def check_fused_vs_staged(device, dropout=0.0, B=19, L=23):
+def check_fused_vs_staged(device, dropout=0.0, B=19, L=23, heads=2, layers=2, sessions_per_cta=3):
     """the fused per-session stack kernel and the staged kernels implement the same math (also under dropout:
     both draw the mask from the same counter-based hash)"""
     from intel_sigir2023_b200 import synthetic
     from intel_sigir2023_b200.config import IntelConfig
     corpus = synthetic.CorpusSpec(n_item=200, n_class=9, n_user=30, n_ctx=19, model_num=3, intent_num=40, history_max=6)
     cfg = IntelConfig(item_rows=corpus.item_rows, class_rows=corpus.n_class, user_rows=corpus.user_rows, ctx_rows=corpus.n_ctx,
-                      intent_num=corpus.intent_num, model_num=3, history_max=6, encoder="GRU4Rec", num_heads=2, num_layers=2,
-                      dropout=dropout)
-    batch = synthetic.make_batch(corpus, synthetic.BatchSpec(batch_size=B, max_len=L, min_len=2), seed=8)
+                      intent_num=corpus.intent_num, model_num=3, history_max=6, encoder="GRU4Rec", num_heads=heads,
+                      num_layers=layers, dropout=dropout)
+    batch = synthetic.make_batch(corpus, synthetic.BatchSpec(batch_size=B, max_len=L, min_len=min(2, L)), seed=8)
     batch = {k: (v.to(device) if torch.is_tensor(v) else v) for k, v in batch.items()}
     state = O.init_state(cfg, seed=4)
-    a = _fresh(cfg, state, device, batch, fused=True)
+    from intel_sigir2023_b200 import _lib
+    _lib.check(_lib.load().intel_debug_stack_sessions_per_cta(sessions_per_cta))
+    try:
+        a = _fresh(cfg, state, device, batch, fused=True)
+    finally:
+        _lib.check(_lib.load().intel_debug_stack_sessions_per_cta(3))
     b = _fresh(cfg, state, device, batch, fused=False)
     for k in ("intents", "weights", "ens_score"):
         assert rel_err(a[0][k].detach().cpu().numpy(), b[0][k].detach().cpu().numpy()) < 5e-6, (k, dropout)
@@ -349,6 +354,13 @@ def check_fused_vs_staged(device, dropout=0.0, B=19, L=23):
     for k, g in b[2].items():
         assert_grad_close(a[2][k].cpu().numpy(), g.cpu().numpy(), gmax, f"{k} p={dropout}", rtol=2e-4, afrac=3e-6)
     return cfg, state, batch, a
+
+
+def check_fused_shapes(device, cases=((5, 7, 2, 1, 1), (9, 16, 1, 2, 2), (7, 40, 2, 1, 4), (6, 50, 2, 2, 3), (5, 64, 1, 1, 2))):
+    """every padded-length / head-count instantiation of the fused stack kernels, and every sessions-per-CTA
+    setting, against the staged kernels: cases are (B, L, heads, layers, sessions per CTA)"""
+    for (B, L, heads, layers, ns) in cases:
+        check_fused_vs_staged(device, B=B, L=L, heads=heads, layers=layers, sessions_per_cta=ns)
 
 
 def check_dropout(device):

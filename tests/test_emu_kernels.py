@@ -88,5 +88,9 @@ def test_fused_stack_matches_staged():
     P.check_fused_vs_staged("cpu")
 
 
+def test_fused_stack_shapes():
+    P.check_fused_shapes("cpu")
+
+
 def test_dropout():
     P.check_dropout("cpu")

@@ -93,5 +93,9 @@ def test_fused_stack_matches_staged():
     P.check_fused_vs_staged(DEV)
 
 
+def test_fused_stack_shapes():
+    P.check_fused_shapes(DEV)
+
+
 def test_dropout():
     P.check_dropout(DEV)
