@@ -202,6 +202,8 @@ int intel_profile_report(char* buf, size_t cap);
 /* test hook: 0 routes the self-attention stacks through the staged kernels even where the fused per-session
  * kernel applies (both implement the same math; tests compare them). Default 1. */
 int intel_debug_use_fused_stack(int on);
+/* test hook: 0 keeps large GEMMs on the mma.sync kernels instead of the tcgen05 / TMEM kernel. Default 1. */
+int intel_debug_use_tcgen05_gemm(int on);
 /* tuning / test hook: sessions that share one CTA (and one staged copy of the weights) in the fused stack
  * kernels, 1..4. */
 int intel_debug_stack_sessions_per_cta(int n);

@@ -97,6 +97,7 @@ def _declare(lib: C.CDLL) -> None:
         "intel_mha_bwd": (i32, [i64, i64, i32, i32, _p, _p, _p, _p, _p]),
         "intel_debug_use_fused_stack": (i32, [i32]),
         "intel_debug_stack_sessions_per_cta": (i32, [i32]),
+        "intel_debug_use_tcgen05_gemm": (i32, [i32]),
         "intel_profile_enable": (i32, [i32]),
         "intel_profile_report": (i32, [C.c_char_p, sz]),
     }
@@ -113,7 +114,7 @@ EXPORTED = ["intel_last_error", "intel_abi_version", "intel_intent_workspace_byt
             "intel_intent_topk_workspace_bytes", "intel_intent_topk", "intel_fuse_fwd", "intel_select_list",
             "intel_rank_lists", "intel_gather_fwd", "intel_scatter_add_bwd", "intel_linear_fwd",
             "intel_profile_enable", "intel_profile_report", "intel_linear_dx", "intel_linear_dw", "intel_mha_fwd",
-            "intel_mha_bwd", "intel_debug_use_fused_stack", "intel_debug_stack_sessions_per_cta"]
+            "intel_mha_bwd", "intel_debug_use_fused_stack", "intel_debug_stack_sessions_per_cta", "intel_debug_use_tcgen05_gemm"]
 
 
 def load(path: Optional[str] = None) -> C.CDLL:
@@ -131,6 +132,8 @@ def load(path: Optional[str] = None) -> C.CDLL:
         raise RuntimeError("libintel_b200 ABI version mismatch")
     if os.environ.get("INTEL_STACK_SESSIONS"):       # tuning knob for the fused stack kernels (1..4 sessions per CTA)
         lib.intel_debug_stack_sessions_per_cta(int(os.environ["INTEL_STACK_SESSIONS"]))
+    if os.environ.get("INTEL_TCGEN05_GEMM"):
+        lib.intel_debug_use_tcgen05_gemm(int(os.environ["INTEL_TCGEN05_GEMM"]))
     _lib = lib
     return lib
 
@@ -247,8 +250,9 @@ def make_batch(batch: Dict[str, object], cfg: IntelConfig) -> Batch:
     return b
 
 
-def profile(on: bool) -> None:
-    check(load().intel_profile_enable(1 if on else 0))
+def profile(on) -> None:
+    """True/1: per-kernel CUDA-event timing; 2: additionally one line per GEMM shape; False/0: off."""
+    check(load().intel_profile_enable(int(on)))
 
 
 def profile_report() -> Dict[str, Dict[str, float]]:

@@ -2,6 +2,7 @@
 #include <stdarg.h>
 
 #include <map>
+#include <set>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -27,13 +28,18 @@ void ensure_smem_impl(const void* kernel, size_t smem) {
     std::lock_guard<std::mutex> lock(mu);
     auto it = done.find(kernel);
     if (it != done.end() && it->second >= smem) return;
-    const size_t want = 227 * 1024;      // opt in to the B200 maximum once
+    // opt in to the B200 maximum once (227 KB per CTA, shared between the kernel's static and dynamic parts)
+    cudaFuncAttributes fa;
+    size_t want = 227 * 1024;
+    if (cudaFuncGetAttributes(&fa, kernel) == cudaSuccess && fa.sharedSizeBytes < want) want -= fa.sharedSizeBytes;
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > want ? smem : want));
+    // ask for the largest shared-memory carve-out so that as many CTAs as the request allows are co-resident
+    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
     done[kernel] = smem > want ? smem : want;
 }
 
 struct ProfRec { cudaEvent_t a, b; const char* what; double bytes, flops; };
-static bool g_prof_on = false, g_prof_pending = false;
+static bool g_prof_on = false, g_prof_pending = false, g_prof_detail = false;
 static cudaEvent_t g_pa, g_pb;
 static std::vector<ProfRec> g_recs;
 
@@ -52,10 +58,17 @@ static void prof_commit(const char* what, double bytes, double flops) {
     g_recs.push_back({g_pa, g_pb, what, bytes, flops});
     g_prof_pending = false;
 }
+bool prof_detail() { return g_prof_on && g_prof_detail; }
+const char* prof_intern(const char* name) {
+    static std::set<std::string> names;
+    return names.insert(name).first->c_str();
+}
 #else
 void prof_before(cudaStream_t) {}
 void prof_mark(cudaStream_t) {}
 static void prof_commit(const char*, double, double) {}
+bool prof_detail() { return false; }
+const char* prof_intern(const char* name) { return name; }
 #endif
 
 int check_launch(const char* what, double bytes, double flops) {
@@ -80,6 +93,7 @@ int intel_abi_version(void) { return INTEL_ABI_VERSION; }
 int intel_profile_enable(int on) {
 #ifndef INTEL_EMU
     g_prof_on = on != 0;
+    g_prof_detail = on == 2;       // 2: GEMM launches are reported per shape
     g_prof_pending = false;
 #endif
     (void)on;

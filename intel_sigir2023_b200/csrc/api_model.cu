@@ -346,6 +346,11 @@ int intel_debug_use_fused_stack(int on) {
     return INTEL_OK;
 }
 
+int intel_debug_use_tcgen05_gemm(int on) {
+    gemm_debug_use_umma(on);
+    return INTEL_OK;
+}
+
 int intel_debug_stack_sessions_per_cta(int n) {
     trunk_debug_sessions_per_cta(n);
     return INTEL_OK;

@@ -29,6 +29,10 @@ namespace intel {
 // attributed by check_launch(name, algorithmic bytes, flops).  Off by default; no-ops in the emulator.
 void prof_before(cudaStream_t s);
 void prof_mark(cudaStream_t s);
+bool prof_detail();                              // per-shape GEMM names requested (intel_profile_enable(2))
+const char* prof_intern(const char* name);
+bool prof_detail();                              // per-shape GEMM names requested (intel_profile_enable(2))
+const char* prof_intern(const char* name);
 
 // ---- error plumbing: no exceptions across the C ABI, int status + thread-local message ----
 enum { INTEL_OK = 0, INTEL_ERR_ARG = 1, INTEL_ERR_WORKSPACE = 2, INTEL_ERR_CUDA = 3, INTEL_ERR_UNSUPPORTED = 4 };

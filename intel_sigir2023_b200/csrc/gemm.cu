@@ -25,6 +25,8 @@ struct GemmDev {
 };
 
 static const int BK = 32;
+static int g_use_umma = 1;
+void gemm_debug_use_umma(int on) { g_use_umma = on ? 1 : 0; }
 
 // Global -> register staging of one operand tile.  TR = operand stored [K][rows] (rows contiguous),
 // otherwise [rows][K] (k contiguous).  Two modes: 16-byte chunks when the operand is 16-byte aligned with a
@@ -167,6 +169,10 @@ __device__ __forceinline__ void gemm_store2(const GemmDev& g, int64_t gm, int64_
     else if (g.accumulate == 1) { float2 o = *reinterpret_cast<float2*>(c); *reinterpret_cast<float2*>(c) = make_float2(o.x + v0, o.y + v1); }
     else { atomicAdd(c, v0); atomicAdd(c + 1, v1); }
 }
+
+}  // namespace intel
+#include "gemm_umma.cuh"
+namespace intel {
 
 template <int BM, int BN, int WM, int WN, bool AT, bool BT>
 __global__ void __launch_bounds__(WM * WN * 32) gemm_tc_kernel(GemmDev g) {
@@ -747,6 +753,61 @@ int gemm(const Gemm& g, cudaStream_t s) {
     }
     const bool can_split = ((g.accumulate == 2 && !g.relu_out && !g.mask && g.splits <= 0) || prezero);
     auto ctas = [&](int bm, int bn) { return ceil_div(g.M, bm) * ceil_div(g.N, bn); };
+    const char* what = wgrad ? "gemm_wgrad" : (g.b_t ? "gemm_dgrad" : "gemm_fwd");
+    const double bytes = 4.0 * ((double)d.M * d.K + (double)d.N * d.K +
+                                (double)d.M * d.N * (1 + (d.add != nullptr) + (d.mask != nullptr)));
+#ifndef INTEL_EMU
+    // large products with 16-byte aligned operands: tcgen05 path (gemm_umma.cuh), 128 x bn tiles, TMEM accumulators
+    if (g_use_umma && d.vec_a && d.vec_b && g.M >= 128 && g.N >= 16 && g.K >= 16 && (double)g.M * g.N * g.K >= 134217728.0) {
+        // short inner dimension: the epilogue dominates, smaller tiles keep two CTAs per SM
+        const int bn_max = g.K <= 128 ? 64 : 128;
+        const int bn = (int)(g.N >= bn_max ? bn_max : ceil_div(g.N, 16) * 16);
+        const int64_t tiles = ceil_div(g.M, umma::UM) * ceil_div(g.N, bn);
+        int splits = prezero ? 0 : g.splits;
+        if (splits <= 0) {
+            splits = 1;
+            if (can_split) {
+                const int64_t want = ceil_div(3 * kNumSMs, tiles), maxs = ceil_div(g.K, 4 * umma::UBK);
+                splits = (int)(want < 1 ? 1 : (want > maxs ? maxs : want));
+            }
+        }
+        INTEL_REQUIRE(splits == 1 || (d.accumulate == 2 && !g.relu_out && !g.mask), INTEL_ERR_ARG,
+                      "gemm: split-K needs atomic accumulation and a linear epilogue");
+        INTEL_REQUIRE(splits <= 65535, INTEL_ERR_ARG, "gemm: too many splits");
+        d.splits = splits;
+        d.kchunk = ceil_div(ceil_div(g.K, splits), umma::UBK) * umma::UBK;
+        size_t smem = (size_t)umma::USTAGES * 2 * (umma::plane_bytes(umma::UM) + umma::plane_bytes(bn)) +
+                      (size_t)umma::URAW * (umma::raw_bytes(umma::UM) + umma::raw_bytes(bn));
+        const size_t tile_bytes = (size_t)umma::UM * (bn + 4) * 4;      // epilogue staging tile reuses the operand stages
+        if (smem < tile_bytes) smem = tile_bytes;
+        dim3 grid((unsigned)ceil_div(g.M, umma::UM), (unsigned)ceil_div(g.N, bn), (unsigned)splits);
+        auto al16 = [](const float* p, int64_t ld) { return p == nullptr || ((((uintptr_t)p) % 16 == 0) && (ld % 4 == 0)); };
+        const int vec_c4 = al16(g.C, g.ldc) && al16(g.add, g.ldadd) && al16(g.mask, g.ldmask) && al16(g.bias, 4);
+        const bool multi = d.kchunk > (int64_t)umma::UCH * umma::UBK;
+#define INTEL_UMMA_N(ATR, BTR, NACC)                                                                                  \
+    do {                                                                                                              \
+        if (multi) { auto k = umma::gemm_umma_kernel<ATR, BTR, NACC, true>; ensure_smem(k, smem); LAUNCH(k, grid, dim3(umma::UTHREADS), smem, s, d, bn, vec_c4); }   \
+        else { auto k = umma::gemm_umma_kernel<ATR, BTR, NACC, false>; ensure_smem(k, smem); LAUNCH(k, grid, dim3(umma::UTHREADS), smem, s, d, bn, vec_c4); }       \
+    } while (0)
+#define INTEL_UMMA(ATR, BTR)                                                                                          \
+    do {                                                                                                              \
+        if (bn <= 32) INTEL_UMMA_N(ATR, BTR, 32);                                                                     \
+        else if (bn <= 64) INTEL_UMMA_N(ATR, BTR, 64);                                                                \
+        else INTEL_UMMA_N(ATR, BTR, 128);                                                                             \
+    } while (0)
+        if (!g.a_t && !g.b_t) INTEL_UMMA(false, false);
+        else if (!g.a_t) INTEL_UMMA(false, true);
+        else INTEL_UMMA(true, true);
+#undef INTEL_UMMA_N
+#undef INTEL_UMMA
+        if (prof_detail()) {
+            char name[128];
+            snprintf(name, sizeof(name), "%s[%lldx%lldx%lld,umma bn%d,splits%d]", what, (long long)d.M, (long long)d.N, (long long)d.K, bn, splits);
+            what = prof_intern(name);
+        }
+        return check_launch(what, bytes, 2.0 * d.M * d.N * d.K);
+    }
+#endif
     int cfg;   // 0: 128x64  1: 128x32  2: 64x64  3: 64x32  4: warp-split-K 32x32
     if (wgrad && (g.M < 64 || g.N < 64)) cfg = 4;
     else if (g.N <= 32) cfg = (ctas(128, 32) >= 2 * kNumSMs || can_split) ? 1 : 3;
@@ -792,9 +853,13 @@ int gemm(const Gemm& g, cudaStream_t s) {
     } else {
         launch_tc<64, 32, 2, 1>(d, g.a_t, g.b_t, s);
     }
-    const double bytes = 4.0 * ((double)d.M * d.K + (double)d.N * d.K +
-                                (double)d.M * d.N * (1 + (d.add != nullptr) + (d.mask != nullptr)));
-    return check_launch(wgrad ? "gemm_wgrad" : (g.b_t ? "gemm_dgrad" : "gemm_fwd"), bytes, 2.0 * d.M * d.N * d.K);
+    if (prof_detail()) {
+        char name[128];
+        snprintf(name, sizeof(name), "%s[%lldx%lldx%lld,cfg%d,splits%d,vec%d%d%d]", what, (long long)d.M, (long long)d.N,
+                 (long long)d.K, cfg, splits, d.vec_a, d.vec_b, d.vec_c);
+        what = prof_intern(name);
+    }
+    return check_launch(what, bytes, 2.0 * d.M * d.N * d.K);
 }
 
 int linear(int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* W, int64_t ldw,

@@ -122,6 +122,7 @@ struct StackGrads { float *wq, *wk, *wv, *w1, *b1, *w2, *b2, *lnw, *lnb; };
 // FFN hidden (pre-relu), pre-LN sum [B*L,32] each, LN mean / rstd [B*L,2]
 struct StackSaved { float* const* QKV; float* const* A; float* const* U; float* const* Z; float* const* ST; };
 void trunk_debug_sessions_per_cta(int n);
+void gemm_debug_use_umma(int on);
 bool trunk_supported(int64_t L, int d, int heads, int layers);
 // X[0] = stack input [B*L,32]; X[l+1] receives the output of layer l
 int trunk_fwd(int64_t B, int64_t L, int heads, int layers, const StackParams& p, float* const* X, const StackSaved& sv,

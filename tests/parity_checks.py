@@ -64,6 +64,43 @@ def check_linear_grads(device):
         assert rel_err(db.cpu().numpy(), dY.cpu().sum(0).numpy()) < 3e-6, ("db", M, N, K)
 
 
+def check_linear_large(device):
+    """shapes large enough for the tcgen05 / TMEM kernel (all three passes, tails in every dimension, split-K with
+    atomics, relu / mask / bias epilogues), against float64 and against the mma.sync kernels"""
+    from intel_sigir2023_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(7)
+    st = _lib.stream_ptr(torch.device(device))
+    for (M, N, K) in [(4096, 128, 256), (8192, 100, 176), (20000, 384, 48), (4099, 72, 1000), (4096, 1068, 176)]:
+        X = torch.randn(M, K, generator=g).to(device)
+        W = torch.randn(N, K, generator=g).to(device)
+        b = torch.randn(N, generator=g).to(device)
+        dY = torch.randn(M, N, generator=g).to(device)
+        U = torch.randn(M, K, generator=g).to(device)
+        ref_y = (X.double() @ W.double().t() + b.double()).cpu().numpy()
+        ref_dx = ((dY.double() @ W.double()) * (U > 0)).cpu().numpy()
+        ref_dw = (dY.double().t() @ X.double()).cpu().numpy()
+        outs = []
+        for on in (1, 0):
+            _lib.check(lib.intel_debug_use_tcgen05_gemm(on))
+            try:
+                Y = torch.empty(M, N, device=device)
+                _lib.check(lib.intel_linear_fwd(M, N, K, _lib.ptr(X), _lib.ptr(W), _lib.ptr(b), _lib.ptr(Y), st))
+                dX = torch.empty(M, K, device=device)
+                _lib.check(lib.intel_linear_dx(M, N, K, _lib.ptr(dY), _lib.ptr(W), _lib.ptr(dX), _lib.ptr(U), st))
+                dW = torch.zeros(N, K, device=device)
+                db = torch.zeros(N, device=device)
+                _lib.check(lib.intel_linear_dw(M, N, K, _lib.ptr(dY), _lib.ptr(X), _lib.ptr(dW), _lib.ptr(db), st))
+            finally:
+                _lib.check(lib.intel_debug_use_tcgen05_gemm(1))
+            assert rel_err(Y.cpu().numpy(), ref_y) < 3e-6, ("fwd", M, N, K, on)
+            assert rel_err(dX.cpu().numpy(), ref_dx) < 3e-6, ("dx", M, N, K, on)
+            assert rel_err(dW.cpu().numpy(), ref_dw) < 3e-6, ("dw", M, N, K, on)
+            outs.append((Y, dX, dW))
+        for a, c in zip(*outs):
+            assert rel_err(a.cpu().numpy(), c.cpu().numpy()) < 4e-6
+
+
 def check_mha(device, shapes=((3, 12, 32, 2), (2, 50, 32, 2), (2, 100, 32, 1), (1, 130, 48, 2))):
     """attention core vs torch on list lengths that span several 64-row query blocks, with and without key masks."""
     from intel_sigir2023_b200 import _lib

@@ -89,6 +89,10 @@ def test_compact_layout_matches_dense():
     P.check_compact_layout(DEV)
 
 
+def test_linear_large_tcgen05_vs_mma_sync():
+    P.check_linear_large(DEV)
+
+
 def test_fused_stack_matches_staged():
     P.check_fused_vs_staged(DEV)
 
