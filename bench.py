@@ -181,7 +181,7 @@ class ClockSampler:
 
 def run_b200(a):
     import torch.distributed as dist
-    from intel_sigir2023_b200 import _lib, losses, evaluate, dp
+    from intel_sigir2023_b200 import _lib, losses, evaluate, dp, loader
     from intel_sigir2023_b200.IntEL import IntEL
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -284,16 +284,19 @@ def run_b200(a):
         h2d = batch_bytes(host[0])
         loss_host = torch.zeros(1, dtype=torch.float64).pin_memory()
 
-        def e2e_step(i):
-            b = synthetic.batch_to(host[i % len(host)], dev, non_blocking=True)
-            loss = train_step(b)
-            loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
-        for i in range(3):
-            e2e_step(i)
+        # every step copies its own inputs host -> device inside the timed region; the copy of step i + 1 runs on the
+        # loader's side stream while step i computes (loader.DevicePrefetcher), the loss is read back every step
+        def e2e_pass(n):
+            def run(_):
+                for b in loader.DevicePrefetcher((host[i % len(host)] for i in range(n)), dev):
+                    loss = train_step(b)
+                    loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+            return run
+        timed(e2e_pass(3), 1)
         n_e2e = max(5, min(a.steps, 10))
-        ms = min(timed(e2e_step, n_e2e) / n_e2e for _ in range(2))      # best of two passes: PCIe is shared on the box
+        ms = min(timed(e2e_pass(n_e2e), 1) / n_e2e for _ in range(2))      # best of two passes: PCIe is shared on the box
         return {"value": world * B / (ms * 1e-3), "unit": "sessions/s", "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": 8, "ms_per_step": ms}
+                "d2h_bytes_per_step": 8, "ms_per_step": ms, "overlap": "H2D of step i+1 on a copy stream"}
 
     e2e = e2e_compact = None
     if not a.no_e2e:

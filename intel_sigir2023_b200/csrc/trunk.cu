@@ -884,7 +884,7 @@ bool trunk_supported(int64_t L, int d, int heads, int layers) {
     return d == TD && L >= 1 && L <= 64 && layers >= 1 && layers <= 8 && (heads == 1 || heads == 2);
 }
 
-static int g_fwd_sessions_per_cta = 3;
+static int g_fwd_sessions_per_cta = 4;
 void trunk_debug_sessions_per_cta(int n) { g_fwd_sessions_per_cta = n < 1 ? 1 : (n > 4 ? 4 : n); }
 
 static void trunk_account(const TrunkArgs& a, bool bwd, double& bytes, double& flops) {

@@ -366,7 +366,7 @@ def _fresh(cfg, state, device, batch, train=True, fused=True, drop_step=0):
         _lib.check(_lib.load().intel_debug_use_fused_stack(1))
 
 
-def check_fused_vs_staged(device, dropout=0.0, B=19, L=23, heads=2, layers=2, sessions_per_cta=3):
+def check_fused_vs_staged(device, dropout=0.0, B=19, L=23, heads=2, layers=2, sessions_per_cta=4):
     """the fused per-session stack kernel and the staged kernels implement the same math (also under dropout:
     both draw the mask from the same counter-based hash)"""
     from intel_sigir2023_b200 import synthetic
@@ -383,7 +383,7 @@ def check_fused_vs_staged(device, dropout=0.0, B=19, L=23, heads=2, layers=2, se
     try:
         a = _fresh(cfg, state, device, batch, fused=True)
     finally:
-        _lib.check(_lib.load().intel_debug_stack_sessions_per_cta(3))
+        _lib.check(_lib.load().intel_debug_stack_sessions_per_cta(4))
     b = _fresh(cfg, state, device, batch, fused=False)
     for k in ("intents", "weights", "ens_score"):
         assert rel_err(a[0][k].detach().cpu().numpy(), b[0][k].detach().cpu().numpy()) < 5e-6, (k, dropout)

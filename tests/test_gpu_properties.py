@@ -154,3 +154,25 @@ def test_train_step_holds_no_reference_cycles_on_device_memory():
         assert torch.cuda.memory_allocated() == live0
     finally:
         gc.enable()
+
+
+def test_device_prefetcher_yields_the_same_batches_in_order():
+    """loader.DevicePrefetcher (H2D of batch i+1 overlapped with step i) hands over exactly the tensors a synchronous
+    utils.batch_to_gpu would, in order, and training on them gives the same loss."""
+    from intel_sigir2023_b200 import loader, losses, synthetic
+    corpus, cfg, model = _model(PL, C2)
+    crit = losses.IntListloss(argparse.Namespace(cal_diversity=1, diversity_alpha=1e-6, intent_weight=0.001,
+                                                 ensemble_weight=1.0, kl_weight=1.0, kl_temp=2.0))
+    host = [loader.pin_batch(synthetic.make_batch(corpus, synthetic.BatchSpec(batch_size=256, max_len=50, min_len=3), seed=s))
+            for s in range(5)]
+    direct = []
+    for hb in host:
+        b = synthetic.batch_to(hb, DEV)
+        direct.append(float(crit(model(b), b)[0]))
+    staged = []
+    for hb, b in zip(host, loader.DevicePrefetcher(iter(host), DEV)):
+        for k, v in hb.items():
+            if torch.is_tensor(v):
+                assert torch.equal(b[k].cpu(), v), k
+        staged.append(float(crit(model(b), b)[0]))
+    assert staged == direct
