@@ -133,6 +133,21 @@ __global__ void __launch_bounds__(256, 1) gru_seq_fwd_kernel(int64_t B, int64_t 
     __syncthreads();
 
     for (int64_t t = 0; t < T; ++t) {
+        // this step's input pre-activations: requested before the recurrent product so that the HBM latency is hidden
+        float2 gin[2][2][2][3];             // [m-tile][half][ct][gate]
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                const int64_t b = b0 + i * 16 + hh * 8 + gq;
+                const bool live = (b < B) && (t < len_r[i * 2 + hh]);
+#pragma unroll
+                for (int ct = 0; ct < 2; ++ct)
+#pragma unroll
+                    for (int gte = 0; gte < 3; ++gte)
+                        gin[i][hh][ct][gte] = live ? *reinterpret_cast<const float2*>(gi + (b * T + t) * 3 * GH + gte * GH + 16 * warp + 8 * ct + 2 * tq)
+                                                   : make_float2(0.f, 0.f);
+            }
         float acc[2][6][4];                 // [m-tile][gate*2 + ct][frag]
 #pragma unroll
         for (int i = 0; i < 2; ++i)
@@ -186,10 +201,7 @@ __global__ void __launch_bounds__(256, 1) gru_seq_fwd_kernel(int64_t B, int64_t 
                     const float hp0 = hs[row * GW + c], hp1 = hs[row * GW + c + 1];
                     float o0 = hp0, o1 = hp1;
                     if (live) {
-                        const float* gib = gi + (b * T + t) * 3 * GH;
-                        const float2 ir = *reinterpret_cast<const float2*>(gib + c);
-                        const float2 iz = *reinterpret_cast<const float2*>(gib + GH + c);
-                        const float2 in = *reinterpret_cast<const float2*>(gib + 2 * GH + c);
+                        const float2 ir = gin[i][hh][ct][0], iz = gin[i][hh][ct][1], in = gin[i][hh][ct][2];
                         const float r0 = sigmoidf_(ir.x + acc[i][0 + ct][2 * hh] + bias[0][ct][0]);
                         const float r1 = sigmoidf_(ir.y + acc[i][0 + ct][2 * hh + 1] + bias[0][ct][1]);
                         const float z0 = sigmoidf_(iz.x + acc[i][2 + ct][2 * hh] + bias[1][ct][0]);

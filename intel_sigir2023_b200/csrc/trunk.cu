@@ -514,35 +514,50 @@ __device__ __forceinline__ void colsum_rows(float* slot, const float (&v)[4][4],
         }
 }
 
-// pw (this warp's two 16x8 tiles of a 32x32 weight gradient) += T^T B over the session's tokens.
-// T: shared tile [rows][WS] (m = T column), B: global rows of the session [L][ldb] (n = B column), optional relu.
-template <bool RELU>
-__device__ __forceinline__ void wgrad_tiles(float (&pw)[2][4], const float* T, const float* __restrict__ Bg, int ldb, int L, int nkt,
-                                            int w, int lane) {
+// pw[a] (this warp's two 16x8 tiles of a 32x32 weight gradient) += T[a]^T B over the session's tokens, for NA
+// gradient tiles that share the B operand.  T[a]: shared tile [rows][WS] (m = T column), B: global rows of the
+// session [L][ldb] (n = B column), optional relu.  All B fragments are fetched before the first MMA so that the
+// global-memory latency is paid once, not once per k-step.
+template <int NA, int NKT, bool RELU>
+__device__ __forceinline__ void wgrad_tiles(float (*pw)[2][4], const float* const (&T)[NA], const float* __restrict__ Bg, int ldb,
+                                            int L, int nkt, int w, int lane) {
     const int g = lane >> 2, t = lane & 3;
     const int m0 = (w & 1) * 16 + g, n0 = (w >> 1) * 16 + g;
-    float part[2][4];
+    float bv[NKT][2][2];
 #pragma unroll
-    for (int n = 0; n < 2; ++n)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) part[n][c] = 0.f;
-#pragma unroll 2
-    for (int s = 0; s < nkt; ++s) {
+    for (int s = 0; s < NKT; ++s) {
         const int k0 = 8 * s + t, k1 = k0 + 4;
-        const float af[4] = {T[k0 * WS + m0], T[k0 * WS + m0 + 8], T[k1 * WS + m0], T[k1 * WS + m0 + 8]};
 #pragma unroll
         for (int n = 0; n < 2; ++n) {
-            float b0 = k0 < L ? Bg[(int64_t)k0 * ldb + n0 + 8 * n] : 0.f;
-            float b1 = k1 < L ? Bg[(int64_t)k1 * ldb + n0 + 8 * n] : 0.f;
+            float b0 = (s < nkt && k0 < L) ? Bg[(int64_t)k0 * ldb + n0 + 8 * n] : 0.f;
+            float b1 = (s < nkt && k1 < L) ? Bg[(int64_t)k1 * ldb + n0 + 8 * n] : 0.f;
             if (RELU) { b0 = fmaxf(b0, 0.f); b1 = fmaxf(b1, 0.f); }
-            const float bf[2] = {b0, b1};
-            mma_3xtf32(part[n], af, bf);
+            bv[s][n][0] = b0;
+            bv[s][n][1] = b1;
         }
     }
 #pragma unroll
-    for (int n = 0; n < 2; ++n)
+    for (int a = 0; a < NA; ++a) {
+        float part[2][4];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) pw[n][c] += part[n][c];
+        for (int n = 0; n < 2; ++n)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) part[n][c] = 0.f;
+#pragma unroll
+        for (int s = 0; s < NKT; ++s) {
+            if (s < nkt) {
+                const int k0 = 8 * s + t, k1 = k0 + 4;
+                const float* Ta = T[a];
+                const float af[4] = {Ta[k0 * WS + m0], Ta[k0 * WS + m0 + 8], Ta[k1 * WS + m0], Ta[k1 * WS + m0 + 8]};
+#pragma unroll
+                for (int n = 0; n < 2; ++n) mma_3xtf32(part[n], af, bv[s][n]);
+            }
+        }
+#pragma unroll
+        for (int n = 0; n < 2; ++n)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) pw[a][n][c] += part[n][c];
+    }
 }
 
 template <int MT, int DK>
@@ -689,8 +704,12 @@ __global__ void __launch_bounds__(32 * BWD_NS * BWD_WPS, 1) trunk_bwd_kernel(Tru
                 }
             }
             bar_sync(bar, 32 * BWD_WPS);                                                   // s1: regions A and B are complete
-            wgrad_tiles<true>(pw[0], T_dF, a.U[l] + row0 * TD, TD, L, nkt, w, lane);       // dW2 += dF^T relu(U)
-            wgrad_tiles<false>(pw[1], T_dU, a.A[l] + row0 * TD, TD, L, nkt, w, lane);      // dW1 += dU^T A
+            {
+                const float* const t2[1] = {T_dF};
+                const float* const t1[1] = {T_dU};
+                wgrad_tiles<1, NKT, true>(pw + 0, t2, a.U[l] + row0 * TD, TD, L, nkt, w, lane);      // dW2 += dF^T relu(U)
+                wgrad_tiles<1, NKT, false>(pw + 1, t1, a.A[l] + row0 * TD, TD, L, nkt, w, lane);     // dW1 += dU^T A
+            }
             float dq[4][4], dk[4][4], dv[4][4];
 #pragma unroll
             for (int hd = 0; hd < HEADS; ++hd) {
@@ -844,10 +863,10 @@ __global__ void __launch_bounds__(32 * BWD_NS * BWD_WPS, 1) trunk_bwd_kernel(Tru
                 mma_raw<4, 4>(gx, fh, fl, WT + 2 * TD * WS, WS, 4, lane);
             }
             bar_sync(bar, 32 * BWD_WPS);                                                   // dQ | dK | dV tiles are complete
-            const float* Xl = a.X[l] + row0 * TD;
-            wgrad_tiles<false>(pw[2], T_dQ, Xl, TD, L, nkt, w, lane);
-            wgrad_tiles<false>(pw[3], T_dK, Xl, TD, L, nkt, w, lane);
-            wgrad_tiles<false>(pw[4], T_dV, Xl, TD, L, nkt, w, lane);
+            {
+                const float* const tq[3] = {T_dQ, T_dK, T_dV};
+                wgrad_tiles<3, NKT, false>(pw + 2, tq, a.X[l] + row0 * TD, TD, L, nkt, w, lane);    // dW{q,k,v} += d{Q,K,V}^T X
+            }
         }
         if (rowwarp) {
 #pragma unroll
@@ -887,10 +906,14 @@ bool trunk_supported(int64_t L, int d, int heads, int layers) {
 static int g_fwd_sessions_per_cta = 4;
 void trunk_debug_sessions_per_cta(int n) { g_fwd_sessions_per_cta = n < 1 ? 1 : (n > 4 ? 4 : n); }
 
+// algorithmic HBM bytes per token: the stack input (and dX in / out), and per layer the saved q|k|v (96), attention
+// output, FFN hidden, pre-LN sum, layer output (32 each) and LN statistics (2) that the forward pass writes when it
+// saves for backward and the backward pass reads back
 static void trunk_account(const TrunkArgs& a, bool bwd, double& bytes, double& flops) {
-    const double tok = (double)a.B * a.L * a.layers;
-    flops = tok * (2.0 * 5 * TD * TD + 4.0 * a.L * TD) * (bwd ? 3.0 : 1.0);
-    bytes = (double)a.B * a.L * TD * 4.0 * (a.layers + 1) + (bwd ? 2.0 * a.B * a.L * TD * 4.0 : 0.0);
+    const double tok = (double)a.B * a.L;
+    flops = tok * a.layers * (2.0 * 5 * TD * TD + 4.0 * a.L * TD) * (bwd ? 3.0 : 1.0);
+    const double per_layer = (a.save || bwd) ? 4.0 * (3 * TD + 4 * TD + 2) : 0.0;
+    bytes = tok * (4.0 * TD * (bwd ? 2 : 1) + per_layer * a.layers + ((a.save || bwd) ? 0.0 : 4.0 * TD));
 }
 
 template <int MT, int DK, int NS>
