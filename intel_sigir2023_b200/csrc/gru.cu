@@ -256,7 +256,8 @@ __global__ void __launch_bounds__(256, 1) gru_seq_bwd_kernel(int64_t B, int64_t 
                                                              const float* __restrict__ h_all,
                                                              const float* __restrict__ gates,
                                                              const float* __restrict__ dh_in, float* __restrict__ dgi,
-                                                             float* __restrict__ dgh_all) {
+                                                             float* __restrict__ dgh_all, float* __restrict__ db_ih,
+                                                             float* __restrict__ db_hh) {
     DYN_SMEM(float, sm);
     float* Ws = sm;                          // [384][GW]   W_hh[k = gate column][n = hidden]
     float* ds = Ws + 3 * GH * GW;            // [GB_SB][GD] dgh of the current step
@@ -280,6 +281,38 @@ __global__ void __launch_bounds__(256, 1) gru_seq_bwd_kernel(int64_t B, int64_t 
         }
     }
     __syncthreads();
+    // saved gate values r | z | n | W_hn h + b_hn and the previous state of one step, for the elements this lane owns;
+    // the values of step t - 1 are requested before the recurrent product of step t (latency hidden behind the MMAs)
+    float2 sv[2][2][5];
+    auto fetch = [&](int64_t t, float2 (&v)[2][2][5]) {
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+            const int64_t b = b0 + hh * 8 + gq;
+            const bool live = (b < B) && (t >= 0) && (t < len_r[hh]);
+#pragma unroll
+            for (int ct = 0; ct < 2; ++ct) {
+                const int c = 16 * warp + 8 * ct + 2 * tq;
+#pragma unroll
+                for (int q = 0; q < 5; ++q) v[hh][ct][q] = make_float2(0.f, 0.f);
+                if (live) {
+                    const float* gt = gates + (b * T + t) * 4 * GH;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) v[hh][ct][q] = *reinterpret_cast<const float2*>(gt + q * GH + c);
+                    v[hh][ct][4] = *reinterpret_cast<const float2*>(h_all + (b * (T + 1) + t) * GH + c);
+                }
+            }
+        }
+    };
+    fetch(T - 1, sv);
+    float sum_i[2][3][2], sum_h[2][2];        // bias-gradient partial sums: [ct][gate][e] of dgi, [ct][e] of the n-gate of dgh
+#pragma unroll
+    for (int ct = 0; ct < 2; ++ct)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            sum_h[ct][e] = 0.f;
+#pragma unroll
+            for (int q = 0; q < 3; ++q) sum_i[ct][q][e] = 0.f;
+        }
     for (int64_t t = T - 1; t >= 0; --t) {
         // ---- gate derivatives for the elements this lane owns ----
 #pragma unroll
@@ -292,12 +325,7 @@ __global__ void __launch_bounds__(256, 1) gru_seq_bwd_kernel(int64_t B, int64_t 
                 const int c = 16 * warp + 8 * ct + 2 * tq;
                 float2 dr = make_float2(0.f, 0.f), dz = dr, dn = dr, dnr = dr;
                 if (live) {
-                    const float* gt = gates + (b * T + t) * 4 * GH;
-                    const float2 r = *reinterpret_cast<const float2*>(gt + c);
-                    const float2 z = *reinterpret_cast<const float2*>(gt + GH + c);
-                    const float2 n = *reinterpret_cast<const float2*>(gt + 2 * GH + c);
-                    const float2 gn = *reinterpret_cast<const float2*>(gt + 3 * GH + c);
-                    const float2 hp = *reinterpret_cast<const float2*>(h_all + (b * (T + 1) + t) * GH + c);
+                    const float2 r = sv[hh][ct][0], z = sv[hh][ct][1], n = sv[hh][ct][2], gn = sv[hh][ct][3], hp = sv[hh][ct][4];
                     const float g0 = dh[hh][ct][0], g1 = dh[hh][ct][1];
                     dn.x = g0 * (1.f - z.x) * (1.f - n.x * n.x);
                     dn.y = g1 * (1.f - z.y) * (1.f - n.y * n.y);
@@ -320,12 +348,18 @@ __global__ void __launch_bounds__(256, 1) gru_seq_bwd_kernel(int64_t B, int64_t 
                     *reinterpret_cast<float2*>(dg + GH + c) = dz;
                     *reinterpret_cast<float2*>(dg + 2 * GH + c) = dnr;
                 }
+                sum_i[ct][0][0] += dr.x; sum_i[ct][0][1] += dr.y;
+                sum_i[ct][1][0] += dz.x; sum_i[ct][1][1] += dz.y;
+                sum_i[ct][2][0] += dn.x; sum_i[ct][2][1] += dn.y;
+                sum_h[ct][0] += dnr.x;   sum_h[ct][1] += dnr.y;
                 ds[row * GD + c] = dr.x;            ds[row * GD + c + 1] = dr.y;
                 ds[row * GD + GH + c] = dz.x;       ds[row * GD + GH + c + 1] = dz.y;
                 ds[row * GD + 2 * GH + c] = dnr.x;  ds[row * GD + 2 * GH + c + 1] = dnr.y;
             }
         }
         __syncthreads();
+        float2 nx[2][2][5];
+        fetch(t - 1, nx);
         // ---- dh_prev = dh * z + dgh W_hh : [16 x 384] x [384 x 128], this warp owns 16 output columns ----
         float acc[2][4];
 #pragma unroll
@@ -360,19 +394,41 @@ __global__ void __launch_bounds__(256, 1) gru_seq_bwd_kernel(int64_t B, int64_t 
             for (int ct = 0; ct < 2; ++ct) {
                 dh[hh][ct][0] += acc[ct][2 * hh];
                 dh[hh][ct][1] += acc[ct][2 * hh + 1];
+#pragma unroll
+                for (int q = 0; q < 5; ++q) sv[hh][ct][q] = nx[hh][ct][q];
             }
         __syncthreads();                    // the dgh tile is rewritten by the next step
+    }
+    // ---- bias gradients: db_ih = column sums of dgi, db_hh = column sums of dgh (r and z parts are shared) ----
+    if (db_ih != nullptr || db_hh != nullptr) {
+#pragma unroll
+        for (int ct = 0; ct < 2; ++ct)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                float v[4] = {sum_i[ct][0][e], sum_i[ct][1][e], sum_i[ct][2][e], sum_h[ct][e]};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    v[q] += __shfl_xor_sync(0xffffffffu, v[q], 4);
+                    v[q] += __shfl_xor_sync(0xffffffffu, v[q], 8);
+                    v[q] += __shfl_xor_sync(0xffffffffu, v[q], 16);
+                }
+                if (gq == 0) {
+                    const int c = 16 * warp + 8 * ct + 2 * tq + e;
+                    if (db_ih) { atomicAdd(db_ih + c, v[0]); atomicAdd(db_ih + GH + c, v[1]); atomicAdd(db_ih + 2 * GH + c, v[2]); }
+                    if (db_hh) { atomicAdd(db_hh + c, v[0]); atomicAdd(db_hh + GH + c, v[1]); atomicAdd(db_hh + 2 * GH + c, v[3]); }
+                }
+            }
     }
 }
 
 int gru_seq_bwd(int64_t B, int64_t T, int h, const int64_t* lens, const float* w_hh, const float* h_all,
-                const float* gates, const float* dh_in, float* dgi, float* dgh_all, cudaStream_t s) {
+                const float* gates, const float* dh_in, float* dgi, float* dgh_all, float* db_ih, float* db_hh, cudaStream_t s) {
     if (B <= 0 || T <= 0) return INTEL_OK;
     INTEL_REQUIRE(h == GH, INTEL_ERR_UNSUPPORTED, "fused GRU needs hidden size 128");
     const size_t smem = (size_t)(3 * GH * GW + GB_SB * GD) * 4;
     ensure_smem(gru_seq_bwd_kernel, smem);
     LAUNCH(gru_seq_bwd_kernel, dim3((unsigned)ceil_div(B, GB_SB)), dim3(256), smem, s, B, T, lens, w_hh, h_all, gates,
-           dh_in, dgi, dgh_all);
+           dh_in, dgi, dgh_all, db_ih, db_hh);
     return check_launch("gru_seq_bwd", (double)B * T * (4 + 1 + 3 + 3) * GH * 4.0, 2.0 * B * T * 3 * GH * GH);
 }
 

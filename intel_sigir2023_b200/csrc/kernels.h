@@ -113,7 +113,7 @@ int gru_step_bwd(int64_t B, int64_t T, int h, int t, const int64_t* lens, const 
 int gru_seq_fwd(int64_t B, int64_t T, int h, const int64_t* lens, const float* gi, const float* w_hh,
                 const float* b_hh, float* h_all, float* gates, cudaStream_t s);
 int gru_seq_bwd(int64_t B, int64_t T, int h, const int64_t* lens, const float* w_hh, const float* h_all,
-                const float* gates, const float* dh_in, float* dgi, float* dgh_all, cudaStream_t s);
+                const float* gates, const float* dh_in, float* dgi, float* dgh_all, float* db_ih, float* db_hh, cudaStream_t s);
 
 // ---- trunk.cu: fused self-attention stack (d = 32, L <= 64): all layers of a session on chip -----
 struct StackParams { const float *wq, *wk, *wv, *w1, *b1, *w2, *b2, *lnw, *lnb; };
