@@ -261,6 +261,6 @@ def profile_report() -> Dict[str, Dict[str, float]]:
     check(load().intel_profile_report(buf, len(buf)))
     out: Dict[str, Dict[str, float]] = {}
     for line in buf.value.decode().splitlines():
-        name, n, ms, by, fl = line.split()
+        name, n, ms, by, fl = line.rsplit(None, 4)
         out[name] = {"launches": float(n), "ms": float(ms), "bytes": float(by), "flops": float(fl)}
     return out

@@ -758,10 +758,10 @@ int gemm(const Gemm& g, cudaStream_t s) {
                                 (double)d.M * d.N * (1 + (d.add != nullptr) + (d.mask != nullptr)));
 #ifndef INTEL_EMU
     // large products with 16-byte aligned operands: tcgen05 path (gemm_umma.cuh), 128 x bn tiles, TMEM accumulators
-    if (g_use_umma && d.vec_a && d.vec_b && g.M >= 128 && g.N >= 16 && g.K >= 16 && (double)g.M * g.N * g.K >= 134217728.0) {
-        // short inner dimension: the epilogue dominates, smaller tiles keep two CTAs per SM
-        const int bn_max = g.K <= 128 ? 64 : 128;
-        const int bn = (int)(g.N >= bn_max ? bn_max : ceil_div(g.N, 16) * 16);
+    // (tall outputs with few columns and a long inner dimension fill too few 128-row tiles: the skinny kernel below)
+    const bool skinny = !g.a_t && g.splits == 1 && !prezero && g.N <= 64 && g.K >= 256 && ctas(128, 32) < 2 * kNumSMs;
+    if (g_use_umma && !skinny && g.M >= 128 && g.N >= 16 && g.K >= 16 && (double)g.M * g.N * g.K >= 134217728.0) {
+        const int bn = (int)(g.N >= 128 ? 128 : ceil_div(g.N, 16) * 16);
         const int64_t tiles = ceil_div(g.M, umma::UM) * ceil_div(g.N, bn);
         int splits = prezero ? 0 : g.splits;
         if (splits <= 0) {
@@ -776,8 +776,10 @@ int gemm(const Gemm& g, cudaStream_t s) {
         INTEL_REQUIRE(splits <= 65535, INTEL_ERR_ARG, "gemm: too many splits");
         d.splits = splits;
         d.kchunk = ceil_div(ceil_div(g.K, splits), umma::UBK) * umma::UBK;
+        // short inner dimension: the epilogue dominates; a 2-deep raw ring keeps two CTAs per SM
+        const int nraw = d.kchunk <= 128 ? 2 : 4;
         size_t smem = (size_t)umma::USTAGES * 2 * (umma::plane_bytes(umma::UM) + umma::plane_bytes(bn)) +
-                      (size_t)umma::URAW * (umma::raw_bytes(umma::UM) + umma::raw_bytes(bn));
+                      (size_t)nraw * (umma::raw_bytes(umma::UM) + umma::raw_bytes(bn));
         const size_t tile_bytes = (size_t)umma::UM * (bn + 4) * 4;      // epilogue staging tile reuses the operand stages
         if (smem < tile_bytes) smem = tile_bytes;
         dim3 grid((unsigned)ceil_div(g.M, umma::UM), (unsigned)ceil_div(g.N, bn), (unsigned)splits);
@@ -786,8 +788,8 @@ int gemm(const Gemm& g, cudaStream_t s) {
         const bool multi = d.kchunk > (int64_t)umma::UCH * umma::UBK;
 #define INTEL_UMMA_N(ATR, BTR, NACC)                                                                                  \
     do {                                                                                                              \
-        if (multi) { auto k = umma::gemm_umma_kernel<ATR, BTR, NACC, true>; ensure_smem(k, smem); LAUNCH(k, grid, dim3(umma::UTHREADS), smem, s, d, bn, vec_c4); }   \
-        else { auto k = umma::gemm_umma_kernel<ATR, BTR, NACC, false>; ensure_smem(k, smem); LAUNCH(k, grid, dim3(umma::UTHREADS), smem, s, d, bn, vec_c4); }       \
+        if (multi) { auto k = umma::gemm_umma_kernel<ATR, BTR, NACC, true, 4>; ensure_smem(k, smem); LAUNCH(k, grid, dim3(umma::UTHREADS), smem, s, d, bn, vec_c4); }   \
+        else { auto k = umma::gemm_umma_kernel<ATR, BTR, NACC, false, 2>; ensure_smem(k, smem); LAUNCH(k, grid, dim3(umma::UTHREADS), smem, s, d, bn, vec_c4); }       \
     } while (0)
 #define INTEL_UMMA(ATR, BTR)                                                                                          \
     do {                                                                                                              \
@@ -802,7 +804,7 @@ int gemm(const Gemm& g, cudaStream_t s) {
 #undef INTEL_UMMA
         if (prof_detail()) {
             char name[128];
-            snprintf(name, sizeof(name), "%s[%lldx%lldx%lld,umma bn%d,splits%d]", what, (long long)d.M, (long long)d.N, (long long)d.K, bn, splits);
+            snprintf(name, sizeof(name), "%s[%lldx%lldx%lld,umma,bn%d,splits%d]", what, (long long)d.M, (long long)d.N, (long long)d.K, bn, splits);
             what = prof_intern(name);
         }
         return check_launch(what, bytes, 2.0 * d.M * d.N * d.K);

@@ -1,8 +1,8 @@
 // tcgen05 (5th-generation tensor core) path of the fp32-parity GEMM, included by gemm.cu.
 //
-// One CTA (128 threads) owns a 128 x BN output tile whose accumulator lives in tensor memory (TMEM).
+// One CTA (256 threads) owns a 128 x BN output tile whose accumulator lives in tensor memory (TMEM).
 //   1. cp.async streams the raw fp32 k-tiles (16 wide) of both operands into a ring of shared-memory stages,
-//      URAW - 1 tiles ahead of their use, so the HBM latency is covered by the ring and not by occupancy;
+//      NRAW - 1 tiles ahead of their use, so the HBM latency is covered by the ring and not by occupancy;
 //   2. every thread converts the chunks it copied itself (no barrier needed): each value is split into its TF32
 //      hi / lo parts, written as two planes per operand in the UMMA no-swizzle K-major canonical form (8 x 16-byte
 //      core matrices).  An operand stored [K][rows] is transposed on the way: a thread owns a 4 x 4 block;
@@ -23,10 +23,11 @@ namespace umma {
 static const int UM = 128;           // tile rows = MMA M (cta_group::1)
 static const int UBK = 16;           // k-tile per shared-memory stage (two k = 8 MMA slices)
 static const int USTAGES = 2;          // plane stages (MMA of tile i overlaps the conversion of tile i + 1)
-static const int URAW = 4;             // raw fp32 stages filled by cp.async (prefetch distance URAW - 1)
+// raw fp32 stages filled by cp.async (prefetch distance NRAW - 1) are a template parameter: 4 for long inner
+// dimensions, 2 for short ones (less shared memory, two CTAs per SM for the epilogue-dominated products)
 static const int USBO = 144;           // stride of an 8-row core-matrix group: 128 + 16 keeps the transposing stores conflict-free
 static const int UCH = 8;            // k-tiles per accumulation chunk (drained into registers with rounded adds)
-static const int UTHREADS = 128;
+static const int UTHREADS = 256;       // 8 warps: copy / convert work is spread over all of them, warps w and w + 4 share TMEM lanes
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -83,6 +84,9 @@ __host__ __device__ inline int unit_off(int rows, int r, int c) { return c * lbo
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int bytes) {      // bytes < 16: zero-filled tail
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src, int bytes) {        // bytes = 4 or 0 (zero fill)
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -120,14 +124,19 @@ struct Lane {
     int rowok[4];               // !TR: row of chunk j exists
     const float* src[4];        // global address of chunk j at k-tile 0 (k offset kof[j] included)
     int64_t step;               // elements between consecutive k-tiles
+    int vec;                    // chunks are 16-byte aligned in global memory (else four 4-byte copies per chunk)
 
-    __device__ __forceinline__ void init(const float* P, int64_t ld, int64_t r0, int64_t rmax, int rows, int64_t kbeg, int tid) {
+    // tr_base: first thread of the 4 x 4 transposing blocks (A uses threads 0.., B threads 128.. so that both halves work)
+    __device__ __forceinline__ void init(const float* P, int64_t ld, int64_t r0, int64_t rmax, int rows, int64_t kbeg, int tid,
+                                         int tr_base, int vec_) {
+        vec = vec_;
         n = 0;
         bytes = 16;
         if (TR) {
             step = (int64_t)UBK * ld;
-            if (tid < rows) {
-                const int q = tid % (rows / 4), c = tid / (rows / 4);
+            const int bt = tid - tr_base;
+            if (bt >= 0 && bt < rows) {
+                const int q = bt % (rows / 4), c = bt / (rows / 4);
                 const int64_t gr = r0 + 4 * q, left = rmax - gr;
                 bytes = left >= 4 ? 16 : (left > 0 ? (int)left * 4 : 0);
                 n = 4;
@@ -171,7 +180,12 @@ struct Lane {
                     const int64_t left = kend - (k0 + kof[j]);
                     b = rowok[j] ? (left >= 4 ? 16 : (left > 0 ? (int)left * 4 : 0)) : 0;
                 }
-                cp_async16(rawbase + raw[j], src[j] + (b ? (int64_t)t * step : 0), b);
+                const float* p = src[j] + (b ? (int64_t)t * step : 0);
+                if (vec) cp_async16(rawbase + raw[j], p, b);
+                else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) cp_async4(rawbase + raw[j] + 4 * e, 4 * e < b ? p + e : p, 4 * e < b ? 4 : 0);
+                }
             }
         }
     }
@@ -202,7 +216,7 @@ struct Lane {
 // A: M x K, ATR = stored [K][M];  B: N x K, BTR = stored [K][N];  bn = N-tile (multiple of 16, <= NACC);
 // NACC = TMEM columns (32, 64 or 128); MULTI: the k range spans several accumulation chunks, which are summed in
 // NACC registers per thread (single-chunk launches keep the register budget small: more CTAs per SM)
-template <bool ATR, bool BTR, int NACC, bool MULTI>
+template <bool ATR, bool BTR, int NACC, bool MULTI, int NRAW>
 __global__ void __launch_bounds__(UTHREADS) gemm_umma_kernel(GemmDev g, int bn, int vec_c4) {
     extern __shared__ __align__(128) uint8_t umma_smem[];
     __shared__ __align__(8) uint64_t empty_bar[USTAGES];
@@ -216,7 +230,7 @@ __global__ void __launch_bounds__(UTHREADS) gemm_umma_kernel(GemmDev g, int bn, 
     const int pa = plane_bytes(UM), pb = plane_bytes(bn);
     const int stage_bytes = 2 * pa + 2 * pb;
     const int ra = raw_bytes(UM), rb = raw_bytes(bn);
-    uint8_t* planes = umma_smem + URAW * (ra + rb);
+    uint8_t* planes = umma_smem + NRAW * (ra + rb);
     const uint32_t raw_base = smem_u32(umma_smem);
 
     if (tid == 0) {
@@ -239,18 +253,20 @@ __global__ void __launch_bounds__(UTHREADS) gemm_umma_kernel(GemmDev g, int bn, 
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(UM >> 4) << 24);
     const uint32_t a_lbo = lbo_k(UM), b_lbo = lbo_k(bn);
 
-    float acc[MULTI ? NACC : 1];
+    // warps w and w + 4 read the same 32 TMEM lanes (= output rows) and take alternate 16-column chunks
+    const int lanes0 = (warp & 3) * 32, chalf = warp >> 2;
+    float acc[MULTI ? NACC / 2 : 1];
 #pragma unroll
-    for (int j = 0; j < (MULTI ? NACC : 1); ++j) acc[j] = 0.f;
+    for (int j = 0; j < (MULTI ? NACC / 2 : 1); ++j) acc[j] = 0.f;
     const int nk = (int)((kend - kbeg + UBK - 1) / UBK);
     uint32_t chunk_phase = 0;
     Lane<ATR> la;
     Lane<BTR> lb;
-    la.init(g.A, g.lda, m0, g.M, UM, kbeg, tid);
-    lb.init(g.B, g.ldb, n0, g.N, bn, kbeg, tid);
-    // prologue: the first URAW - 1 k-tiles are on their way (one cp.async group per tile, empty groups keep the count uniform)
+    la.init(g.A, g.lda, m0, g.M, UM, kbeg, tid, 0, g.vec_a);
+    lb.init(g.B, g.ldb, n0, g.N, bn, kbeg, tid, UTHREADS / 2, g.vec_b);
+    // prologue: the first NRAW - 1 k-tiles are on their way (one cp.async group per tile, empty groups keep the count uniform)
 #pragma unroll
-    for (int p = 0; p < URAW - 1; ++p) {
+    for (int p = 0; p < NRAW - 1; ++p) {
         if (p < nk) {
             const int64_t k0 = kbeg + (int64_t)p * UBK;
             la.issue(raw_base + p * (ra + rb), p, k0, kend);
@@ -261,15 +277,15 @@ __global__ void __launch_bounds__(UTHREADS) gemm_umma_kernel(GemmDev g, int bn, 
     for (int i = 0; i < nk; ++i) {
         const int s = i % USTAGES;
         uint8_t* st = planes + s * stage_bytes;
-        cp_async_wait<URAW - 2>();                                                        // this thread's chunks of k-tile i have landed
+        cp_async_wait<NRAW - 2>();                                                        // this thread's chunks of k-tile i have landed
         if (i >= USTAGES) mbar_wait(&empty_bar[s], (uint32_t)((i / USTAGES) - 1) & 1u);   // MMAs of k-tile i - USTAGES are done
-        const uint8_t* rw = umma_smem + (i % URAW) * (ra + rb);
+        const uint8_t* rw = umma_smem + (i % NRAW) * (ra + rb);
         la.convert(rw, st, st + pa, g.relu_a);
         lb.convert(rw + ra, st + 2 * pa, st + 2 * pa + pb, g.relu_b);
-        if (i + URAW - 1 < nk) {        // refill the raw stage this thread emptied in the previous iteration
-            const int t = i + URAW - 1;
+        if (i + NRAW - 1 < nk) {        // refill the raw stage this thread emptied in the previous iteration
+            const int t = i + NRAW - 1;
             const int64_t k0 = kbeg + (int64_t)t * UBK;
-            const uint32_t dst = raw_base + (t % URAW) * (ra + rb);
+            const uint32_t dst = raw_base + (t % NRAW) * (ra + rb);
             la.issue(dst, t, k0, kend);
             lb.issue(dst + ra, t, k0, kend);
         }
@@ -300,12 +316,13 @@ __global__ void __launch_bounds__(UTHREADS) gemm_umma_kernel(GemmDev g, int bn, 
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (MULTI && i != nk - 1) {             // drain: acc += TMEM tile (rounded fp32 adds)
 #pragma unroll
-                for (int c0 = 0; c0 < NACC; c0 += 16) {
+                for (int cc = 0; cc < NACC / 32; ++cc) {
+                    const int c0 = (2 * cc + chalf) * 16;
                     if (c0 < bn) {
                         float v[16];
-                        tmem_ld16(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+                        tmem_ld16(tmem_d + ((uint32_t)lanes0 << 16) + (uint32_t)c0, v);
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) acc[MULTI ? c0 + j : 0] += v[j];
+                        for (int j = 0; j < 16; ++j) acc[MULTI ? cc * 16 + j : 0] += v[j];
                     }
                 }
             }
@@ -317,15 +334,16 @@ __global__ void __launch_bounds__(UTHREADS) gemm_umma_kernel(GemmDev g, int bn, 
     float* tile = reinterpret_cast<float*>(umma_smem);
     const int ts = bn + 4;
     {
-        const int row = warp * 32 + lane;
+        const int row = lanes0 + lane;
 #pragma unroll
-        for (int c0 = 0; c0 < NACC; c0 += 16) {
+        for (int cc = 0; cc < (NACC >= 32 ? NACC / 32 : 1); ++cc) {
+            const int c0 = (2 * cc + chalf) * 16;
             if (c0 < bn) {
                 float v[16];
-                tmem_ld16(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+                tmem_ld16(tmem_d + ((uint32_t)lanes0 << 16) + (uint32_t)c0, v);
                 if (MULTI) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] += acc[MULTI ? c0 + j : 0];
+                    for (int j = 0; j < 16; ++j) v[j] += acc[MULTI ? cc * 16 + j : 0];
                 }
 #pragma unroll
                 for (int j = 0; j < 16; j += 4)
@@ -349,6 +367,10 @@ __global__ void __launch_bounds__(UTHREADS) gemm_umma_kernel(GemmDev g, int bn, 
     for (int r = warp; r < UM; r += UTHREADS / 32) {
         const int64_t gm = m0 + r;
         if (gm >= g.M) break;
+        if (!vec_c4) {          // unaligned rows: lanes on consecutive columns, scalar stores
+            for (int c = lane; c < bn; c += 32) gemm_store(g, gm, n0 + c, tile[r * ts + c], first);
+            continue;
+        }
         if (!lane_on) continue;
         float4 v = *reinterpret_cast<const float4*>(tile + r * ts + 4 * lane);
         if (v4) {
