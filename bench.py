@@ -267,16 +267,41 @@ def run_b200(a):
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    # kernels whose inner loop is tensor-core MMA work (3xTF32: three TF32 MMAs per fp32 product);
+    # everything else streams HBM
+    tensor_kernels = {"trunk_fwd", "trunk_bwd", "gru_seq_fwd", "gru_seq_bwd", "gemm_fwd", "gemm_dgrad", "gemm_wgrad",
+                      "mha_fwd", "mha_bwd"}
+    tc_peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 2250.0)))
+    tc_src = ("measured (MEASURED_PEAKS.json bf16_tflops_sustained; the TF32 rate is half of it)" if peaks
+              else "fallback 2250 TFLOP/s nominal dense bf16 (B200_PROFILING.md)")
+    traffic = {}
+    try:        # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+    except Exception:
+        pass
     name, rec = top
-    achieved = rec["bytes"] / (rec["ms"] * 1e-3) / 1e9 if rec["ms"] > 0 else 0.0
-    roofline = {"kernel": name, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
-                "share_of_step": rec["ms"] / total_ms if total_ms else None,
-                "avg_launch_us": rec["ms"] * 1e3 / rec["launches"],
-                "gflops": rec["flops"] / (rec["ms"] * 1e-3) / 1e9 if rec["ms"] > 0 else 0.0,
-                "per_kernel": {k: {"share": v["ms"] / total_ms, "gbs": (v["bytes"] / (v["ms"] * 1e-3) / 1e9) if v["ms"] > 0 else 0.0,
-                                   "launches_per_step": v["launches"] / prof_steps}
-                               for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}}
+    sec = rec["ms"] * 1e-3
+    gbs = rec["bytes"] / sec / 1e9 if sec > 0 else 0.0
+    if name in tensor_kernels:
+        achieved = 3.0 * rec["flops"] / sec / 1e12 if sec > 0 else 0.0
+        roofline = {"kernel": name, "bound": "tensor", "achieved": achieved, "peak": tc_peak, "unit": "TFLOP/s",
+                    "frac": achieved / tc_peak, "peak_source": tc_src,
+                    "flops_counted": "TF32 MMA flops issued = 3 x the fp32 product's flops (3xTF32 split for 1e-5 parity)",
+                    "hbm_gbs_algorithmic": gbs}
+    else:
+        roofline = {"kernel": name, "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": gbs / hbm_peak, "peak_source": peak_src}
+    tr = traffic.get(name)
+    roofline.update({
+        "traffic": tr.get("dram_bytes_per_launch") if isinstance(tr, dict) else None,
+        "algorithmic_bytes_per_launch": rec["bytes"] / rec["launches"],
+        "share_of_step": rec["ms"] / total_ms if total_ms else None,
+        "avg_launch_us": rec["ms"] * 1e3 / rec["launches"],
+        "per_kernel": {k: {"share": v["ms"] / total_ms,
+                           "gbs": (v["bytes"] / (v["ms"] * 1e-3) / 1e9) if v["ms"] > 0 else 0.0,
+                           "tflops_3xtf32": (3.0 * v["flops"] / (v["ms"] * 1e-3) / 1e12) if (v["ms"] > 0 and k in tensor_kernels) else None,
+                           "launches_per_step": v["launches"] / prof_steps}
+                       for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}})
 
     # ---- end to end: host (pinned) batch -> H2D -> step -> loss D2H, every step ----
     def run_e2e(dev_batches):

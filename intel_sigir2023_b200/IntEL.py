@@ -123,7 +123,14 @@ class _IntelFn(torch.autograd.Function):
         dev = params[0].device
         names = model._param_names
         P = _lib.make_tensors(cfg, dict(zip(names, params)))
-        grads = [torch.zeros_like(p) for p in params]
+        # one zero-filled buffer for all dense gradients (a single fill kernel instead of one per parameter); the
+        # per-parameter gradients are 256-byte aligned views into it
+        offs, total = [], 0
+        for p in params:
+            offs.append(total)
+            total += (p.numel() + 63) // 64 * 64
+        flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        grads = [flat[o:o + p.numel()].view(p.shape) for o, p in zip(offs, params)]
         G = _lib.make_tensors(cfg, dict(zip(names, grads)))
         bt = _lib.make_batch(batch, cfg)
         stream = _lib.stream_ptr(dev)
