@@ -199,6 +199,15 @@ int intel_profile_enable(int on);
  * algorithmic_bytes flops" and clears the records. */
 int intel_profile_report(char* buf, size_t cap);
 
+/* ---- host-side input packing (no GPU work) ---------------------------------------------------
+ * dense float64 [rows, I] host tensor (the reference's his_intents / his_item_int rows, collate_batch) -> the compact
+ * form of intel_batch_t: idx int32 [rows, nz], val float32 [rows, nz], zero padded, both in host memory (pinned for
+ * an asynchronous copy).  Scans with `threads` host threads (<= 0: all cores).  Returns the largest number of
+ * non-zeros of any row: if it exceeds nz the rows were truncated and the caller retries with a larger nz or keeps the
+ * dense layout; negative on error.  row_nnz (nullable) receives the per-row counts. */
+int64_t intel_host_pack_rows(int64_t rows, int64_t I, const double* dense, int32_t nz, int32_t* idx, float* val,
+                             int32_t* row_nnz, int threads);
+
 /* test hook: 0 routes the self-attention stacks through the staged kernels even where the fused per-session
  * kernel applies (both implement the same math; tests compare them). Default 1. */
 int intel_debug_use_fused_stack(int on);

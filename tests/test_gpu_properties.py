@@ -176,3 +176,23 @@ def test_device_prefetcher_yields_the_same_batches_in_order():
                 assert torch.equal(b[k].cpu(), v), k
         staged.append(float(crit(model(b), b)[0]))
     assert staged == direct
+
+
+def test_host_packed_history_gives_the_same_step():
+    """DevicePrefetcher(pack_history=True) ships only the non-zeros of the dense float64 history tensors; the model's
+    outputs and the loss match the dense path (fp32 summation order of the sparse rows aside)."""
+    from intel_sigir2023_b200 import loader, losses, synthetic
+    corpus, cfg, model = _model(PL, C2)
+    crit = losses.IntListloss(argparse.Namespace(cal_diversity=1, diversity_alpha=1e-6, intent_weight=0.001,
+                                                 ensemble_weight=1.0, kl_weight=1.0, kl_temp=2.0))
+    host = [loader.pin_batch(synthetic.make_batch(corpus, synthetic.BatchSpec(batch_size=192, max_len=50, min_len=3), seed=s))
+            for s in range(4)]
+    dense = [(model(b), b) for b in (synthetic.batch_to(hb, DEV) for hb in host)]
+    # a tiny initial capacity forces the grow-and-retry path
+    for (out_d, bd), bp in zip(dense, loader.DevicePrefetcher(iter(host), DEV, pack_history=True, pack_nz=2)):
+        assert "his_intents" not in bp and bp["his_intents_idx"].dtype == torch.int32
+        out_p = model(bp)
+        for k in ("intents", "weights", "ens_score"):
+            a, c = out_d[k].detach().cpu().numpy(), out_p[k].detach().cpu().numpy()
+            assert np.abs(a - c).max() <= 2e-6 * max(1.0, np.abs(a).max()), k
+        assert abs(float(crit(out_d, bd)[0]) - float(crit(out_p, bp)[0])) < 1e-5

@@ -85,3 +85,25 @@ def test_fixed_weight_baselines_match_reference():
     untied = (x > 0).all(axis=2)     # zeros tie with the pad slots: order undefined in the reference
     got = O.borda(batch)["ens_score"].numpy()
     assert np.allclose(got[untied], z["F.borda"][untied])
+
+
+def test_host_pack_rows_roundtrip():
+    """intel_host_pack_rows (host threads, no GPU): scatter(idx, val) reproduces the dense rows; truncation is reported."""
+    import torch
+    from intel_sigir2023_b200 import loader
+    g = torch.Generator().manual_seed(5)
+    dense = torch.zeros(37, 5, 1071, dtype=torch.float64)
+    for r in range(37):
+        for h in range(5):
+            n = int(torch.randint(0, 9, (1,), generator=g))
+            cols = torch.randperm(1071, generator=g)[:n]
+            dense[r, h, cols] = torch.rand(n, generator=g, dtype=torch.float64) - 0.3
+    dense[0, 0, 1070] = -0.0          # negative zero is a zero
+    idx = torch.empty(37, 5, 8, dtype=torch.int32)
+    val = torch.empty(37, 5, 8, dtype=torch.float32)
+    got = loader.pack_rows(dense, 8, idx, val, threads=3)
+    assert got == int((dense != 0).sum(-1).max())
+    back = torch.zeros(37, 5, 1071).scatter_add_(2, idx.long(), val)
+    assert torch.equal(back, dense.float())
+    small_i, small_v = torch.empty(37, 5, 2, dtype=torch.int32), torch.empty(37, 5, 2, dtype=torch.float32)
+    assert loader.pack_rows(dense, 2, small_i, small_v) == got > 2
