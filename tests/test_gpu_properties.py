@@ -196,3 +196,37 @@ def test_host_packed_history_gives_the_same_step():
             a, c = out_d[k].detach().cpu().numpy(), out_p[k].detach().cpu().numpy()
             assert np.abs(a - c).max() <= 2e-6 * max(1.0, np.abs(a).max()), k
         assert abs(float(crit(out_d, bd)[0]) - float(crit(out_p, bp)[0])) < 1e-5
+
+
+@pytest.mark.parametrize("encoder", ["BERT4Rec", "GRU4Rec"])
+def test_full_batch_step_tcgen05_vs_mma_sync(encoder):
+    """At B = 4096 most nn.Linear passes are large enough for the tcgen05 / TMEM GEMM (bias, residual, relu and mask
+    epilogues, split-K weight gradients).  The same step with the large GEMMs forced onto the mma.sync kernels must
+    give the same outputs, loss and gradients."""
+    from intel_sigir2023_b200 import _lib, losses, synthetic
+    kw = dict(PL, encoder=encoder)
+    corpus, cfg, model = _model(kw, C2)
+    crit = losses.IntListloss(argparse.Namespace(cal_diversity=1, diversity_alpha=1e-6, intent_weight=0.001,
+                                                 ensemble_weight=1.0, kl_weight=1.0, kl_temp=2.0))
+    batch = synthetic.make_batch(corpus, synthetic.BatchSpec(batch_size=4096, max_len=50, min_len=5), seed=2, device=DEV)
+    res = []
+    for on in (1, 0):
+        _lib.check(_lib.load().intel_debug_use_tcgen05_gemm(on))
+        try:
+            for p in model.parameters():
+                p.grad = None
+            out = model(batch)
+            loss = crit(out, batch)[0]
+            loss.backward()
+            res.append((out, float(loss), {k: p.grad.clone() for k, p in model.named_parameters()}))
+        finally:
+            _lib.check(_lib.load().intel_debug_use_tcgen05_gemm(1))
+    (oa, la, ga), (ob, lb, gb) = res
+    assert abs(la - lb) <= 1e-6 * abs(lb)
+    for k in ("intents", "weights", "ens_score"):
+        a, b = oa[k].detach().cpu().numpy(), ob[k].detach().cpu().numpy()
+        assert np.abs(a - b).max() <= 5e-6 * max(1.0, np.abs(b).max()), k
+    gmax = max(float(g.abs().max()) for g in gb.values())
+    for k, g in gb.items():
+        d = float((ga[k] - g).abs().max())
+        assert d <= 2e-4 * float(g.abs().max()) + 3e-6 * gmax, (k, d)
