@@ -131,6 +131,7 @@ class _IntelFn(torch.autograd.Function):
             total += (p.numel() + 63) // 64 * 64
         flat = torch.zeros(total, dtype=torch.float32, device=dev)
         grads = [flat[o:o + p.numel()].view(p.shape) for o, p in zip(offs, params)]
+        model._flat_grad = flat         # dp.GradReducer all-reduces this one buffer when the .grad tensors still alias it
         G = _lib.make_tensors(cfg, dict(zip(names, grads)))
         bt = _lib.make_batch(batch, cfg)
         stream = _lib.stream_ptr(dev)

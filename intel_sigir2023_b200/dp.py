@@ -23,6 +23,7 @@ class GradReducer:
     flatten/unflatten copies of ~100 MB are made; the many small weights travel in one flat bucket."""
 
     def __init__(self, model: torch.nn.Module, world: int, small_numel: int = 1 << 16):
+        self.model = model
         self.params: List[torch.nn.Parameter] = [p for p in model.parameters() if p.requires_grad]
         self.world = world
         self.small_numel = small_numel
@@ -34,6 +35,16 @@ class GradReducer:
         if self.world <= 1:
             return
         grads = [p.grad for p in self.params if p.grad is not None]
+        # the backward pass writes all gradients into one zero-filled buffer (IntEL._IntelFn.backward): if every .grad
+        # still aliases it (autograd adopted the views instead of copying them), one collective covers everything
+        flat = getattr(self.model, "_flat_grad", None)
+        if flat is not None and grads and len(grads) == len(self.params):
+            base = flat.untyped_storage().data_ptr()
+            if all(g.untyped_storage().data_ptr() == base for g in grads):
+                dist.all_reduce(flat, op=self.avg_op)
+                if self.post_scale != 1.0:
+                    flat.mul_(self.post_scale)
+                return
         big = [g for g in grads if g.numel() > self.small_numel]
         small = [g for g in grads if g.numel() <= self.small_numel]
         works = [dist.all_reduce(g, op=self.avg_op, async_op=True) for g in big]
