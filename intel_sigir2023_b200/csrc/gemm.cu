@@ -7,6 +7,8 @@
 // All shapes here have a tiny inner dimension (32..384, 1071 at most) or a tiny output, so tiles are
 // 128 x {32,64} x 32 with register-staged prefetch of the next k-tile; operands may be stored k-major or
 // row-major (the three nn.Linear passes), selected at compile time.
+#include <stdlib.h>
+
 #include "kernels.h"
 #include "mma.cuh"
 
@@ -761,7 +763,9 @@ int gemm(const Gemm& g, cudaStream_t s) {
     // (tall outputs with few columns and a long inner dimension fill too few 128-row tiles: the skinny kernel below)
     const bool skinny = !g.a_t && g.splits == 1 && !prezero && g.N <= 64 && g.K >= 256 && ctas(128, 32) < 2 * kNumSMs;
     if (g_use_umma && !skinny && g.M >= 128 && g.N >= 16 && g.K >= 16 && (double)g.M * g.N * g.K >= 134217728.0) {
-        const int bn = (int)(g.N >= 128 ? 128 : ceil_div(g.N, 16) * 16);
+        static const int bn_cap = getenv("INTEL_UMMA_BN") ? atoi(getenv("INTEL_UMMA_BN")) : 128;      // tuning knob
+        const int bn_max = (g.K > 128 && bn_cap < 128) ? bn_cap : 128;
+        const int bn = (int)(g.N >= bn_max ? bn_max : ceil_div(g.N, 16) * 16);
         const int64_t tiles = ceil_div(g.M, umma::UM) * ceil_div(g.N, bn);
         int splits = prezero ? 0 : g.splits;
         if (splits <= 0) {
