@@ -115,7 +115,8 @@ def run_reference(a):
     if rank != 0:
         return
     corpus, cfg, loss_kind, loss_args = make_cfg(a)
-    steps, warmup = max(1, min(a.steps, 8)), max(1, min(a.warmup, 2))
+    # a step of this arm is a 512-session sample of the same workload (~0.13 s on 16 cores): K <= 100 keeps the run short
+    steps, warmup = max(1, min(a.steps, 100)), max(1, min(a.warmup, 5))
     rate, ms, ncores, sample = cpu_reference_rate(a, corpus, cfg, loss_kind, loss_args, steps, warmup)
     line = {
         "impl": "reference", "metric": "sessions/sec (train fwd+bwd)", "value": rate, "unit": "sessions/s",
@@ -378,7 +379,7 @@ def run_b200(a):
         line["e2e"] = e2e
         line["e2e_compact"] = e2e_compact
     if not a.no_cpu_baseline and world == 1:
-        rate, ms, ncores, sample = cpu_reference_rate(a, corpus, cfg, loss_kind, loss_args, 4, 1)
+        rate, ms, ncores, sample = cpu_reference_rate(a, corpus, cfg, loss_kind, loss_args, 60, 2)     # ~10 s of CPU work
         line["cpu_baseline"] = {"value": rate, "unit": "sessions/s", "cores": ncores, "kind": "port", "sample": sample}
     print(json.dumps(line), flush=True)
     if world > 1:
