@@ -95,7 +95,11 @@ Reading:
   hoisting all loads of a phase (no change: ptxas already overlaps them).
 * `gemm_umma_kernel` (tcgen05): the UTCHMMA pipe is ~12 % active; the kernel is paced by the cp.async -> split -> plane
   conversion loop (issue active 52 %, short-scoreboard stalls on shared memory) - the next thing to restructure
-  (warp-specialised, persistent).  64-wide tiles for two CTAs per SM were measured: no gain.
+  (persistent CTAs with the epilogue of one tile overlapping the main loop of the next).  Measured and dropped:
+  64-wide tiles for two CTAs per SM (no gain), an 8-deep cp.async ring (slower: the bottleneck is not memory-level
+  parallelism), a dedicated MMA-issuer warp with mbarrier hand-offs (long-K shapes 20-50 % slower: the chunk drain
+  serialises harder), pointer-advancing address arithmetic with a full-tile fast path (slower despite fewer
+  instructions).  ncu source-level sampling shows no hot spot: stall samples are spread over the whole k-tile body.
 * `dense_rows_fwd` streams the float64 [B,H,I] history intents at 5.9 TB/s algorithmic = 0.90 of the measured HBM peak
   (707 MB DRAM read per launch for 702 MB of input).
 

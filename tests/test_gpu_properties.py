@@ -230,3 +230,15 @@ def test_full_batch_step_tcgen05_vs_mma_sync(encoder):
     for k, g in gb.items():
         d = float((ga[k] - g).abs().max())
         assert d <= 2e-4 * float(g.abs().max()) + 3e-6 * gmax, (k, d)
+
+
+@pytest.mark.parametrize("kind,encoder", [("list", "GRU4Rec"), ("bpr", "GRU4Rec"), ("mse", "BERT4Rec")])
+def test_c2_shapes_against_the_oracle(kind, encoder):
+    """BASELINE.json configs[1] shapes (L = 50, K = 4, I = 1071, H = 20, the script's model flags) at B = 1024 - large
+    enough for the tcgen05 GEMMs and for every CTA-level path of the fused kernels - against the CPU oracle: outputs,
+    loss and all parameter gradients."""
+    import parity_checks as P
+    kw = dict(PL, encoder=encoder)
+    P.check_against_oracle(DEV, seed=11, B=1024, L=50, min_len=4, kind=kind,
+                           corpus_kw=dict(n_item=5000, n_class=357, n_user=2000, n_ctx=931, model_num=4, intent_num=1071,
+                                          history_max=20), **kw)
