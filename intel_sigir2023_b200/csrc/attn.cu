@@ -9,6 +9,11 @@ namespace intel {
 static const int LN_MAX_PER_LANE = 8;   // d <= 256
 
 // ------------------------------------------------------------------------------------------------
+// LayerNorm forward / backward: one warp per row, P = ceil(d / 32) values per lane (compile time), RB rows in flight
+// per warp so that the two dependent warp reductions of a row overlap with those of its neighbours.
+static const int LN_RB = 4;
+
+template <int P>
 __global__ void __launch_bounds__(256) layernorm_fwd_kernel(int64_t R, int d, const float* __restrict__ Z,
                                                             const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, float* __restrict__ Y,
@@ -16,30 +21,49 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(int64_t R, int d, co
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t r = warp; r < R; r += nwarps) {
-        float v[LN_MAX_PER_LANE];
-        float sum = 0.f;
+    float gm[P], bt[P];
 #pragma unroll
-        for (int i = 0; i < LN_MAX_PER_LANE; ++i) {
-            int c = lane + 32 * i;
-            v[i] = (c < d) ? Z[r * d + c] : 0.f;
-            sum += v[i];
-        }
-        const float mean = warp_sum(sum) / (float)d;
-        float sq = 0.f;
+    for (int i = 0; i < P; ++i) {
+        const int c = lane + 32 * i;
+        gm[i] = (c < d) ? gamma[c] : 0.f;
+        bt[i] = (c < d) ? beta[c] : 0.f;
+    }
+    for (int64_t r0 = warp * LN_RB; r0 < R; r0 += nwarps * LN_RB) {
+        float v[LN_RB][P], sum[LN_RB], sq[LN_RB];
 #pragma unroll
-        for (int i = 0; i < LN_MAX_PER_LANE; ++i) {
-            int c = lane + 32 * i;
-            float t = (c < d) ? v[i] - mean : 0.f;
-            sq += t * t;
-        }
-        const float rstd = rsqrtf(warp_sum(sq) / (float)d + 1e-5f);
+        for (int q = 0; q < LN_RB; ++q) {
+            sum[q] = 0.f;
 #pragma unroll
-        for (int i = 0; i < LN_MAX_PER_LANE; ++i) {
-            int c = lane + 32 * i;
-            if (c < d) Y[r * d + c] = (v[i] - mean) * rstd * gamma[c] + beta[c];
+            for (int i = 0; i < P; ++i) {
+                const int c = lane + 32 * i;
+                v[q][i] = (c < d && r0 + q < R) ? Z[(r0 + q) * d + c] : 0.f;
+                sum[q] += v[q][i];
+            }
         }
-        if (lane == 0) { stats[2 * r] = mean; stats[2 * r + 1] = rstd; }
+#pragma unroll
+        for (int q = 0; q < LN_RB; ++q) sum[q] = warp_sum(sum[q]) / (float)d;
+#pragma unroll
+        for (int q = 0; q < LN_RB; ++q) {
+            sq[q] = 0.f;
+#pragma unroll
+            for (int i = 0; i < P; ++i) {
+                const float t = (lane + 32 * i < d) ? v[q][i] - sum[q] : 0.f;
+                sq[q] += t * t;
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < LN_RB; ++q) sq[q] = rsqrtf(warp_sum(sq[q]) / (float)d + 1e-5f);
+#pragma unroll
+        for (int q = 0; q < LN_RB; ++q) {
+            if (r0 + q < R) {
+#pragma unroll
+                for (int i = 0; i < P; ++i) {
+                    const int c = lane + 32 * i;
+                    if (c < d) Y[(r0 + q) * d + c] = (v[q][i] - sum[q]) * sq[q] * gm[i] + bt[i];
+                }
+                if (lane == 0) { stats[2 * (r0 + q)] = sum[q]; stats[2 * (r0 + q) + 1] = sq[q]; }
+            }
+        }
     }
 }
 
@@ -47,50 +71,69 @@ int layernorm_fwd(int64_t R, int d, const float* Z, const float* gamma, const fl
                   cudaStream_t s) {
     if (R <= 0) return INTEL_OK;
     INTEL_REQUIRE(d <= 32 * LN_MAX_PER_LANE, INTEL_ERR_UNSUPPORTED, "layernorm width %d > 256", d);
-    unsigned grid = stream_grid(ceil_div(R, 8), 8);
-    LAUNCH(layernorm_fwd_kernel, dim3(grid), dim3(256), 0, s, R, d, Z, gamma, beta, Y, stats);
+    unsigned grid = stream_grid(ceil_div(R, 8 * LN_RB), 8);
+    if (d <= 32) LAUNCH(layernorm_fwd_kernel<1>, dim3(grid), dim3(256), 0, s, R, d, Z, gamma, beta, Y, stats);
+    else if (d <= 64) LAUNCH(layernorm_fwd_kernel<2>, dim3(grid), dim3(256), 0, s, R, d, Z, gamma, beta, Y, stats);
+    else if (d <= 128) LAUNCH(layernorm_fwd_kernel<4>, dim3(grid), dim3(256), 0, s, R, d, Z, gamma, beta, Y, stats);
+    else LAUNCH(layernorm_fwd_kernel<8>, dim3(grid), dim3(256), 0, s, R, d, Z, gamma, beta, Y, stats);
     return check_launch("layernorm_fwd", 8.0 * R * d, 8.0 * R * d);
 }
 
+template <int P>
 __global__ void __launch_bounds__(256) layernorm_bwd_kernel(int64_t R, int d, const float* __restrict__ dY,
                                                             const float* __restrict__ Z, const float* __restrict__ stats,
                                                             const float* __restrict__ gamma, float* __restrict__ dZ,
                                                             float* dgamma, float* dbeta) {
-    __shared__ float red_g[8][32 * LN_MAX_PER_LANE];
-    __shared__ float red_b[8][32 * LN_MAX_PER_LANE];
+    __shared__ float red_g[8][32 * P];
+    __shared__ float red_b[8][32 * P];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    float pg[LN_MAX_PER_LANE], pb[LN_MAX_PER_LANE];
+    float pg[P], pb[P], gm[P];
 #pragma unroll
-    for (int i = 0; i < LN_MAX_PER_LANE; ++i) { pg[i] = 0.f; pb[i] = 0.f; }
-    for (int64_t r = warp; r < R; r += nwarps) {
-        const float mean = stats[2 * r], rstd = stats[2 * r + 1];
-        float xh[LN_MAX_PER_LANE], g[LN_MAX_PER_LANE];
-        float s1 = 0.f, s2 = 0.f;
+    for (int i = 0; i < P; ++i) {
+        pg[i] = 0.f;
+        pb[i] = 0.f;
+        gm[i] = (lane + 32 * i < d) ? gamma[lane + 32 * i] : 0.f;
+    }
+    for (int64_t r0 = warp * LN_RB; r0 < R; r0 += nwarps * LN_RB) {
+        float xh[LN_RB][P], g[LN_RB][P], s1[LN_RB], s2[LN_RB], rstd[LN_RB];
 #pragma unroll
-        for (int i = 0; i < LN_MAX_PER_LANE; ++i) {
-            int c = lane + 32 * i;
-            if (c < d) {
-                const float dy = dY[r * d + c];
-                xh[i] = (Z[r * d + c] - mean) * rstd;
-                g[i] = dy * gamma[c];
-                pg[i] += dy * xh[i];
-                pb[i] += dy;
-            } else { xh[i] = 0.f; g[i] = 0.f; }
-            s1 += g[i];
-            s2 += g[i] * xh[i];
+        for (int q = 0; q < LN_RB; ++q) {
+            const bool ok = r0 + q < R;
+            const float mean = ok ? stats[2 * (r0 + q)] : 0.f;
+            rstd[q] = ok ? stats[2 * (r0 + q) + 1] : 0.f;
+            s1[q] = 0.f;
+            s2[q] = 0.f;
+#pragma unroll
+            for (int i = 0; i < P; ++i) {
+                const int c = lane + 32 * i;
+                if (ok && c < d) {
+                    const float dy = dY[(r0 + q) * d + c];
+                    xh[q][i] = (Z[(r0 + q) * d + c] - mean) * rstd[q];
+                    g[q][i] = dy * gm[i];
+                    pg[i] += dy * xh[q][i];
+                    pb[i] += dy;
+                } else { xh[q][i] = 0.f; g[q][i] = 0.f; }
+                s1[q] += g[q][i];
+                s2[q] += g[q][i] * xh[q][i];
+            }
         }
-        s1 = warp_sum(s1) / (float)d;
-        s2 = warp_sum(s2) / (float)d;
 #pragma unroll
-        for (int i = 0; i < LN_MAX_PER_LANE; ++i) {
-            int c = lane + 32 * i;
-            if (c < d) dZ[r * d + c] = rstd * (g[i] - s1 - xh[i] * s2);
+        for (int q = 0; q < LN_RB; ++q) { s1[q] = warp_sum(s1[q]) / (float)d; s2[q] = warp_sum(s2[q]) / (float)d; }
+#pragma unroll
+        for (int q = 0; q < LN_RB; ++q) {
+            if (r0 + q < R) {
+#pragma unroll
+                for (int i = 0; i < P; ++i) {
+                    const int c = lane + 32 * i;
+                    if (c < d) dZ[(r0 + q) * d + c] = rstd[q] * (g[q][i] - s1[q] - xh[q][i] * s2[q]);
+                }
+            }
         }
     }
 #pragma unroll
-    for (int i = 0; i < LN_MAX_PER_LANE; ++i) { red_g[wib][lane + 32 * i] = pg[i]; red_b[wib][lane + 32 * i] = pb[i]; }
+    for (int i = 0; i < P; ++i) { red_g[wib][lane + 32 * i] = pg[i]; red_b[wib][lane + 32 * i] = pb[i]; }
     __syncthreads();
     for (int c = threadIdx.x; c < d; c += blockDim.x) {
         float tg = 0.f, tb = 0.f;
@@ -105,8 +148,11 @@ int layernorm_bwd(int64_t R, int d, const float* dY, const float* Z, const float
                   float* dgamma, float* dbeta, cudaStream_t s) {
     if (R <= 0) return INTEL_OK;
     INTEL_REQUIRE(d <= 32 * LN_MAX_PER_LANE, INTEL_ERR_UNSUPPORTED, "layernorm width %d > 256", d);
-    unsigned grid = stream_grid(ceil_div(R, 8), 4);
-    LAUNCH(layernorm_bwd_kernel, dim3(grid), dim3(256), 0, s, R, d, dY, Z, stats, gamma, dZ, dgamma, dbeta);
+    unsigned grid = stream_grid(ceil_div(R, 8 * LN_RB), 4);
+    if (d <= 32) LAUNCH(layernorm_bwd_kernel<1>, dim3(grid), dim3(256), 0, s, R, d, dY, Z, stats, gamma, dZ, dgamma, dbeta);
+    else if (d <= 64) LAUNCH(layernorm_bwd_kernel<2>, dim3(grid), dim3(256), 0, s, R, d, dY, Z, stats, gamma, dZ, dgamma, dbeta);
+    else if (d <= 128) LAUNCH(layernorm_bwd_kernel<4>, dim3(grid), dim3(256), 0, s, R, d, dY, Z, stats, gamma, dZ, dgamma, dbeta);
+    else LAUNCH(layernorm_bwd_kernel<8>, dim3(grid), dim3(256), 0, s, R, d, dY, Z, stats, gamma, dZ, dgamma, dbeta);
     return check_launch("layernorm_bwd", 12.0 * R * d, 12.0 * R * d);
 }
 
