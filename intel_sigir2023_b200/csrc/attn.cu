@@ -178,12 +178,34 @@ __global__ void __launch_bounds__(XP_WARPS * 32) cross_pool_fwd_kernel(int64_t B
     const float* x = X + b * L * d;
     const float* q = qk + b * d;
     float mx = -INFINITY;
-    for (int64_t j = lane; j < L; j += 32) {
-        float a = 0.f;
-        for (int c = 0; c < d; ++c) a = fmaf(x[j * d + c], q[c], a);
-        a *= scale;
-        pb[j] = a;
-        mx = fmaxf(mx, a);             // row max over ALL slots, pads included (attention.py:57)
+    if (d == 32 || d == 64) {
+        // d / 4 lanes per row, one 16-byte load each: a warp reads 512 contiguous bytes per pass
+        const int lpr = d >> 2, rpp = 32 / lpr;                 // lanes per row, rows per pass
+        const int sub = lane % lpr, rr = lane / lpr;
+        const float4 qv = *reinterpret_cast<const float4*>(q + 4 * sub);
+        for (int64_t j0 = 0; j0 < L; j0 += rpp) {
+            const int64_t j = j0 + rr;
+            float a = 0.f;
+            if (j < L) {
+                const float4 xv = *reinterpret_cast<const float4*>(x + j * d + 4 * sub);
+                a = fmaf(xv.x, qv.x, fmaf(xv.y, qv.y, fmaf(xv.z, qv.z, xv.w * qv.w)));
+            }
+            for (int o = lpr >> 1; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+            a *= scale;
+            if (j < L) {
+                if (sub == 0) pb[j] = a;
+                mx = fmaxf(mx, a);         // row max over ALL slots, pads included (attention.py:57)
+            }
+        }
+        __syncwarp();
+    } else {
+        for (int64_t j = lane; j < L; j += 32) {
+            float a = 0.f;
+            for (int c = 0; c < d; ++c) a = fmaf(x[j * d + c], q[c], a);
+            a *= scale;
+            pb[j] = a;
+            mx = fmaxf(mx, a);             // row max over ALL slots, pads included (attention.py:57)
+        }
     }
     mx = warp_max(mx);
     float sum = 0.f;
@@ -230,11 +252,31 @@ __global__ void __launch_bounds__(XP_WARPS * 32) cross_pool_bwd_kernel(int64_t B
     const float* x = X + b * L * d;
     const float* g = dxbar + b * d;
     float delta = 0.f;
-    for (int64_t j = lane; j < n; j += 32) {
-        float a = 0.f;
-        for (int c = 0; c < d; ++c) a = fmaf(x[j * d + c], g[c], a);
-        ab[j] = a;                                // dp_j
-        delta = fmaf(p[b * L + j], a, delta);
+    if (d == 32 || d == 64) {
+        const int lpr = d >> 2, rpp = 32 / lpr;
+        const int sub = lane % lpr, rr = lane / lpr;
+        const float4 gv = *reinterpret_cast<const float4*>(g + 4 * sub);
+        for (int64_t j0 = 0; j0 < n; j0 += rpp) {
+            const int64_t j = j0 + rr;
+            float a = 0.f;
+            if (j < n) {
+                const float4 xv = *reinterpret_cast<const float4*>(x + j * d + 4 * sub);
+                a = fmaf(xv.x, gv.x, fmaf(xv.y, gv.y, fmaf(xv.z, gv.z, xv.w * gv.w)));
+            }
+            for (int o = lpr >> 1; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+            if (j < n && sub == 0) {
+                ab[j] = a;                            // dp_j
+                delta = fmaf(p[b * L + j], a, delta);
+            }
+        }
+        __syncwarp();
+    } else {
+        for (int64_t j = lane; j < n; j += 32) {
+            float a = 0.f;
+            for (int c = 0; c < d; ++c) a = fmaf(x[j * d + c], g[c], a);
+            ab[j] = a;                                // dp_j
+            delta = fmaf(p[b * L + j], a, delta);
+        }
     }
     delta = warp_sum(delta);
     for (int64_t j = lane; j < n; j += 32) ab[j] = p[b * L + j] * (ab[j] - delta) * scale;   // datt_j * scale
