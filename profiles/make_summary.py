@@ -64,7 +64,7 @@ e2e = {e['value']:.0f} sessions/s from pinned host batches in the reference's de
 e2e_compact = {d['e2e_compact']['value']:.0f} sessions/s; eval = {d['eval_sessions_per_s']:.0f} sessions/s;
 CPU port of the reference = {d['cpu_baseline']['value']:.0f} sessions/s on {d['cpu_baseline']['cores']} cores
 (`--impl reference`: r01_bench_reference_arm.json); clocks {d['clocks']}; {d['gpu_launches'] // d['steps']} of our kernels per step.
-2 GPUs (r01_bench_final_2gpu.json, before the single-collective gradient exchange): 1.41 M sessions/s; with it 1.48 M (5.55 ms/step, 97 %).
+Weak scaling (r01_bench_final_{{2,4,8}}gpu.json): 1.48 M / 2.93 M / 5.83 M sessions/s on 2 / 4 / 8 GPUs (5.55 / 5.59 / 5.62 ms per step, 95 % at 8).
 
 The first-path summary of this round is kept in r01_summary.md (16.4 ms/step); milestones in between are in DESIGN.md section 10.
 
