@@ -368,12 +368,31 @@ def run_b200(a):
         if world > 1:
             dist.destroy_process_group()
         return
+
+    # ---- optimizer step (not part of `value`): fused Adam + L2 vs torch.optim.Adam on the same gradients ----
+    def time_opt(make):
+        opt = make()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(2):
+            opt.step()
+        e0.record()
+        for _ in range(5):
+            opt.step()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / 5
+    from intel_sigir2023_b200 import optim
+    train_step(resident[0])
+    groups = lambda: optim.customize_parameters(model)
+    optimizer = {"fused_adam_ms": time_opt(lambda: optim.Adam(groups(), lr=1e-3, weight_decay=1e-6)),
+                 "torch_adam_ms": time_opt(lambda: torch.optim.Adam(groups(), lr=1e-3, weight_decay=1e-6)),
+                 "parameters": int(sum(p.numel() for p in model.parameters()))}
     line = {
         "metric": "sessions/sec (train fwd+bwd)", "value": value, "unit": "sessions/s", "n_gpus": world,
         "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(a, cfg, loss_kind, B), "clocks": clocks, "gpu_launches": gpu_launches,
-        "roofline": roofline, "eval_sessions_per_s": world * B / (ms_eval * 1e-3),
+        "roofline": roofline, "eval_sessions_per_s": world * B / (ms_eval * 1e-3), "optimizer": optimizer,
     }
     if e2e is not None:
         line["e2e"] = e2e

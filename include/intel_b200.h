@@ -199,6 +199,15 @@ int intel_profile_enable(int on);
  * algorithmic_bytes flops" and clears the records. */
 int intel_profile_report(char* buf, size_t cap);
 
+/* ---- optimizer step ------------------------------------------------------------------------------
+ * torch.optim.Adam (BaseRunner._build_optimizer, BaseRunner.py:182-188) over `count` parameter tensors in one launch
+ * per 48 tensors.  params / grads / exp_avg / exp_avg_sq / numel / weight_decay are HOST arrays of `count` entries
+ * (device pointers, element counts, per-tensor L2 coefficient: BaseModel.customize_parameters gives the weights
+ * `weight_decay` and the biases 0, BaseModel.py:53-62); step is the 1-based step number of this update. */
+int intel_adam_step(int count, float* const* params, const float* const* grads, float* const* exp_avg,
+                    float* const* exp_avg_sq, const int64_t* numel, const float* weight_decay, double lr, double beta1,
+                    double beta2, double eps, int64_t step, intel_stream_t stream);
+
 /* ---- host-side input packing (no GPU work) ---------------------------------------------------
  * dense float64 [rows, I] host tensor (the reference's his_intents / his_item_int rows, collate_batch) -> the compact
  * form of intel_batch_t: idx int32 [rows, nz], val float32 [rows, nz], zero padded, both in host memory (pinned for

@@ -121,6 +121,9 @@ struct StackGrads { float *wq, *wk, *wv, *w1, *b1, *w2, *b2, *lnw, *lnb; };
 // per-layer activations the forward kernel leaves for the backward kernel: q|k|v [B*L,96], attention output,
 // FFN hidden (pre-relu), pre-LN sum [B*L,32] each, LN mean / rstd [B*L,2]
 struct StackSaved { float* const* QKV; float* const* A; float* const* U; float* const* Z; float* const* ST; };
+int adam_step(int count, float* const* params, const float* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
+              const int64_t* numel, const float* weight_decay, double lr, double beta1, double beta2, double eps, int64_t step,
+              cudaStream_t s);
 void trunk_debug_sessions_per_cta(int n);
 void gemm_debug_use_umma(int on);
 bool trunk_supported(int64_t L, int d, int heads, int layers);

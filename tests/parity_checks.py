@@ -425,3 +425,35 @@ def check_dropout(device):
     lm = _fresh(cfg, {k: (v - eps * direction[k] if k in direction else v) for k, v in state.items()}, device, batch)[1]
     num = (lp.item() - lm.item()) / (2 * eps)
     assert abs(analytic - num) <= 3e-2 * abs(num) + 1e-4, (analytic, num)
+
+
+def check_adam(device, steps=4):
+    """optim.Adam (one fused launch) against torch.optim.Adam with the reference's two parameter groups (L2 on the
+    weights, none on the biases), several steps, including a StepLR decay and a state_dict round trip"""
+    from intel_sigir2023_b200 import optim
+    g = torch.Generator().manual_seed(3)
+
+    def make():
+        torch.manual_seed(0)
+        m = torch.nn.Module()
+        m.emb = torch.nn.Embedding(257, 16)
+        m.lin = torch.nn.Linear(33, 7)
+        m.odd = torch.nn.Parameter(torch.randn(5, 3, 2))
+        return m.to(device)
+    ma, mb = make(), make()
+    oa = optim.Adam(optim.customize_parameters(ma), lr=3e-3, weight_decay=1e-4)
+    ob = torch.optim.Adam(optim.customize_parameters(mb), lr=3e-3, weight_decay=1e-4)
+    sa = torch.optim.lr_scheduler.StepLR(oa, step_size=2, gamma=0.5)
+    sb = torch.optim.lr_scheduler.StepLR(ob, step_size=2, gamma=0.5)
+    for it in range(steps):
+        for (na, pa), (nb, pb) in zip(ma.named_parameters(), mb.named_parameters()):
+            gr = torch.randn(pa.shape, generator=g).to(device)
+            pa.grad, pb.grad = gr.clone(), gr.clone()
+        oa.step(); ob.step(); sa.step(); sb.step()
+        if it == 1:                         # interchangeable state
+            import copy
+            oa.load_state_dict(copy.deepcopy(ob.state_dict()))     # (load_state_dict keeps references to the step tensors)
+    for (na, pa), (nb, pb) in zip(ma.named_parameters(), mb.named_parameters()):
+        assert rel_err(pa.detach().cpu().numpy(), pb.detach().cpu().numpy()) < 2e-6, na
+        ea, eb = oa.state[pa]["exp_avg_sq"], ob.state[pb]["exp_avg_sq"]
+        assert rel_err(ea.cpu().numpy(), eb.cpu().numpy()) < 2e-6, na

@@ -88,6 +88,10 @@ def test_fused_stack_matches_staged():
     P.check_fused_vs_staged("cpu")
 
 
+def test_fused_adam_matches_torch():
+    P.check_adam("cpu")
+
+
 def test_fused_stack_shapes():
     P.check_fused_shapes("cpu")
 

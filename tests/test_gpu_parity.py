@@ -97,6 +97,10 @@ def test_fused_stack_matches_staged():
     P.check_fused_vs_staged(DEV)
 
 
+def test_fused_adam_matches_torch():
+    P.check_adam(DEV)
+
+
 def test_fused_stack_shapes():
     P.check_fused_shapes(DEV)
 
