@@ -199,6 +199,16 @@ int intel_profile_enable(int on);
  * algorithmic_bytes flops" and clears the records. */
 int intel_profile_report(char* buf, size_t cap);
 
+/* ---- aWELv baseline (models/supervise/aWELv.py:28-39; script/baselines.sh:33) -----------------------------
+ * w[b,:] = softmax_k <user_table[u_id[b]], model_table[k]>, weights[b,l,:] = w[b,:], ens[b,l] = sum_k w[b,k] scores[b,l,k].
+ * user_table [users, h], model_table [K, h] (K <= 16), scores float64 [B,L,K]; w_user [B,K] is kept for the backward call,
+ * which accumulates (+=) into the dense g_user_table / g_model_table; d_weights (nullable) [B,L,K], d_ens [B,L]. */
+int intel_awelv_fwd(int64_t B, int64_t L, int K, int h, const float* user_table, const float* model_table, const int64_t* u_id,
+                    const double* scores, float* weights, float* ens_score, float* w_user, intel_stream_t stream);
+int intel_awelv_bwd(int64_t B, int64_t L, int K, int h, const float* user_table, const float* model_table, const int64_t* u_id,
+                    const double* scores, const float* w_user, const float* d_weights, const float* d_ens, float* g_user_table,
+                    float* g_model_table, intel_stream_t stream);
+
 /* ---- optimizer step ------------------------------------------------------------------------------
  * torch.optim.Adam (BaseRunner._build_optimizer, BaseRunner.py:182-188) over `count` parameter tensors in one launch
  * per 48 tensors.  params / grads / exp_avg / exp_avg_sq / numel / weight_decay are HOST arrays of `count` entries

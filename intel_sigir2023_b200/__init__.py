@@ -16,7 +16,7 @@ def __getattr__(name):
     if name in ("evaluate_method", "evaluate_intents"):
         from . import evaluate
         return getattr(evaluate, name)
-    if name in ("SingleSort", "Borda", "RandomFusion"):
+    if name in ("SingleSort", "Borda", "RandomFusion", "aWELv"):
         from . import baselines
         return getattr(baselines, name)
     raise AttributeError(name)

@@ -69,3 +69,65 @@ class RandomFusion(nn.Module):
             raw_weights = torch.rand(x.shape, device=x.device)
         w = torch.softmax(raw_weights.float(), dim=2)
         return {"weights": w, "ens_score": fuse(w, x)}
+
+
+class _AWELvFn(torch.autograd.Function):
+    """(user table, model table) -> (weights [B,L,K], ens_score [B,L]) through intel_awelv_fwd / intel_awelv_bwd."""
+
+    @staticmethod
+    def forward(ctx, user_table, model_table, u_id, scores):
+        lib = _lib.load()
+        B, L, K = scores.shape
+        h = user_table.shape[1]
+        dev = scores.device
+        weights = torch.empty(B, L, K, dtype=torch.float32, device=dev)
+        ens = torch.empty(B, L, dtype=torch.float32, device=dev)
+        w_user = torch.empty(B, K, dtype=torch.float32, device=dev)
+        _lib.check(lib.intel_awelv_fwd(B, L, K, h, _lib.ptr(user_table, torch.float32), _lib.ptr(model_table, torch.float32),
+                                       _lib.ptr(u_id, torch.int64), _lib.ptr(scores, torch.float64), _lib.ptr(weights),
+                                       _lib.ptr(ens), _lib.ptr(w_user), _lib.stream_ptr(dev)))
+        ctx.save_for_backward(user_table, model_table, u_id, scores, w_user)
+        return weights, ens
+
+    @staticmethod
+    def backward(ctx, d_weights, d_ens):
+        lib = _lib.load()
+        user_table, model_table, u_id, scores, w_user = ctx.saved_tensors
+        B, L, K = scores.shape
+        g_user, g_model = torch.zeros_like(user_table), torch.zeros_like(model_table)
+        dw = d_weights.contiguous() if d_weights is not None else None
+        de = d_ens.contiguous() if d_ens is not None else None
+        _lib.check(lib.intel_awelv_bwd(B, L, K, user_table.shape[1], _lib.ptr(user_table), _lib.ptr(model_table),
+                                       _lib.ptr(u_id), _lib.ptr(scores), _lib.ptr(w_user), _lib.ptr(dw), _lib.ptr(de),
+                                       _lib.ptr(g_user), _lib.ptr(g_model), _lib.stream_ptr(scores.device)))
+        return g_user, g_model, None, None
+
+
+class aWELv(nn.Module):
+    """Per-user softmax fusion weights (models/supervise/aWELv.py; script/baselines.sh:33): same parameter names
+    (`uid_embeddings.weight`, `model_embeddings.weight`), flags (`--hidden_size`, `--model_num`) and output dict."""
+    reader, runner = "BaseReader", "BaseRunner"
+    extra_log_args: list = []
+
+    @staticmethod
+    def parse_model_args(parser):
+        parser.add_argument('--hidden_size', type=int, default=32)
+        parser.add_argument('--model_path', type=str, default='', help='Model save path.')
+        parser.add_argument('--buffer', type=int, default=1, help='Whether to buffer feed dicts for dev/test')
+        parser.add_argument('--model_num', type=int, default=2, help='Number of base models.')
+        return parser
+
+    def __init__(self, args, corpus=None, user_num: int = None):
+        super().__init__()
+        self.device = getattr(args, "device", None)
+        self.user_num = int(user_num if user_num is not None else corpus.max_uid + 1)
+        self.uid_embeddings = nn.Embedding(self.user_num, args.hidden_size)
+        self.model_embeddings = nn.Embedding(args.model_num, args.hidden_size)
+
+    def customize_parameters(self, define_dict=None) -> list:
+        from .optim import customize_parameters
+        return customize_parameters(self)
+
+    def forward(self, data: Dict[str, object]) -> Dict[str, torch.Tensor]:
+        w, ens = _AWELvFn.apply(self.uid_embeddings.weight, self.model_embeddings.weight, data['u_id_c'], data['scores'])
+        return {"weights": w, "ens_score": ens}

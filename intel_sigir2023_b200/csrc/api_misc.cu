@@ -130,6 +130,18 @@ int intel_profile_report(char* buf, size_t cap) {
     return INTEL_OK;
 }
 
+int intel_awelv_fwd(int64_t B, int64_t L, int K, int h, const float* user_table, const float* model_table, const int64_t* u_id,
+                    const double* scores, float* weights, float* ens_score, float* w_user, intel_stream_t stream) {
+    return awelv_fwd(B, L, K, h, user_table, model_table, u_id, scores, weights, ens_score, w_user, (cudaStream_t)stream);
+}
+
+int intel_awelv_bwd(int64_t B, int64_t L, int K, int h, const float* user_table, const float* model_table, const int64_t* u_id,
+                    const double* scores, const float* w_user, const float* d_weights, const float* d_ens, float* g_user_table,
+                    float* g_model_table, intel_stream_t stream) {
+    return awelv_bwd(B, L, K, h, user_table, model_table, u_id, scores, w_user, d_weights, d_ens, g_user_table, g_model_table,
+                     (cudaStream_t)stream);
+}
+
 int intel_gather_fwd(int64_t rows, int d, const float* table, const int64_t* idx, float* out, int ld_out, int relu,
                      intel_stream_t stream) {
     return gather_rows(rows, d, table, idx, out, ld_out, relu, (cudaStream_t)stream);

@@ -259,3 +259,112 @@ int add_inplace(int64_t n, float* y, const float* x, cudaStream_t s) {
 }
 
 }  // namespace intel
+
+// ------------------------------------------------------------------------------------------------
+// aWELv (models/supervise/aWELv.py:28-39): per-user fusion weights w = softmax_k <U[u], M[k]>, the same for every
+// slot of the list; ens = sum_k w_k score_k.  One warp per session, forward and backward.
+namespace intel {
+
+static const int AW_MAX_K = 16;
+
+__global__ void __launch_bounds__(256) awelv_fwd_kernel(int64_t B, int64_t L, int K, int h, const float* __restrict__ U,
+                                                        const float* __restrict__ M, const int64_t* __restrict__ uid,
+                                                        const double* __restrict__ scores, float* __restrict__ weights,
+                                                        float* __restrict__ ens, float* __restrict__ wsmall) {
+    const int lane = threadIdx.x & 31;
+    const int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (b >= B) return;
+    const float* u = U + uid[b] * h;
+    float w[AW_MAX_K];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < AW_MAX_K; ++k) {
+        w[k] = 0.f;
+        if (k < K) {
+            float a = 0.f;
+            for (int c = lane; c < h; c += 32) a = fmaf(u[c], M[k * h + c], a);
+            w[k] = warp_sum(a);
+            mx = fmaxf(mx, w[k]);
+        }
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < AW_MAX_K; ++k)
+        if (k < K) { w[k] = expf(w[k] - mx); sum += w[k]; }
+    const float inv = 1.0f / sum;
+#pragma unroll
+    for (int k = 0; k < AW_MAX_K; ++k)
+        if (k < K) {
+            w[k] *= inv;
+            if (lane == 0) wsmall[b * K + k] = w[k];
+        }
+    for (int64_t l = lane; l < L; l += 32) {
+        float e = 0.f;
+#pragma unroll
+        for (int k = 0; k < AW_MAX_K; ++k)
+            if (k < K) {
+                weights[(b * L + l) * K + k] = w[k];
+                e = __fadd_rn(e, __fmul_rn(w[k], (float)scores[(b * L + l) * K + k]));    // torch.mul(w, s).sum(dim=2)
+            }
+        ens[b * L + l] = e;
+    }
+}
+
+__global__ void __launch_bounds__(256) awelv_bwd_kernel(int64_t B, int64_t L, int K, int h, const float* __restrict__ U,
+                                                        const float* __restrict__ M, const int64_t* __restrict__ uid,
+                                                        const double* __restrict__ scores, const float* __restrict__ wsmall,
+                                                        const float* __restrict__ d_weights, const float* __restrict__ d_ens,
+                                                        float* gU, float* gM) {
+    const int lane = threadIdx.x & 31;
+    const int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (b >= B) return;
+    float dw[AW_MAX_K], w[AW_MAX_K];
+#pragma unroll
+    for (int k = 0; k < AW_MAX_K; ++k) { dw[k] = 0.f; w[k] = (k < K) ? wsmall[b * K + k] : 0.f; }
+    for (int64_t l = lane; l < L; l += 32) {
+        const float de = d_ens ? d_ens[b * L + l] : 0.f;
+#pragma unroll
+        for (int k = 0; k < AW_MAX_K; ++k)
+            if (k < K) {
+                float g = de * (float)scores[(b * L + l) * K + k];
+                if (d_weights) g += d_weights[(b * L + l) * K + k];
+                dw[k] += g;
+            }
+    }
+    float dot = 0.f;
+#pragma unroll
+    for (int k = 0; k < AW_MAX_K; ++k)
+        if (k < K) { dw[k] = warp_sum(dw[k]); dot = fmaf(dw[k], w[k], dot); }
+    const int64_t u = uid[b];
+    for (int c = lane; c < h; c += 32) {
+        const float uc = U[u * h + c];
+        float gu = 0.f;
+#pragma unroll
+        for (int k = 0; k < AW_MAX_K; ++k)
+            if (k < K) {
+                const float dl = w[k] * (dw[k] - dot);             // softmax backward
+                gu = fmaf(dl, M[k * h + c], gu);
+                atomicAdd(gM + k * h + c, dl * uc);
+            }
+        atomicAdd(gU + u * h + c, gu);
+    }
+}
+
+int awelv_fwd(int64_t B, int64_t L, int K, int h, const float* U, const float* M, const int64_t* uid, const double* scores,
+              float* weights, float* ens, float* wsmall, cudaStream_t s) {
+    if (B <= 0) return INTEL_OK;
+    INTEL_REQUIRE(K >= 1 && K <= AW_MAX_K && h >= 1, INTEL_ERR_UNSUPPORTED, "aWELv: model_num %d > %d", K, AW_MAX_K);
+    LAUNCH(awelv_fwd_kernel, dim3((unsigned)ceil_div(B, 8)), dim3(256), 0, s, B, L, K, h, U, M, uid, scores, weights, ens, wsmall);
+    return check_launch("awelv_fwd", (double)B * L * K * 12.0 + (double)B * L * 4.0, 2.0 * B * L * K);
+}
+
+int awelv_bwd(int64_t B, int64_t L, int K, int h, const float* U, const float* M, const int64_t* uid, const double* scores,
+              const float* wsmall, const float* d_weights, const float* d_ens, float* gU, float* gM, cudaStream_t s) {
+    if (B <= 0) return INTEL_OK;
+    INTEL_REQUIRE(K >= 1 && K <= AW_MAX_K && h >= 1, INTEL_ERR_UNSUPPORTED, "aWELv: model_num %d > %d", K, AW_MAX_K);
+    LAUNCH(awelv_bwd_kernel, dim3((unsigned)ceil_div(B, 8)), dim3(256), 0, s, B, L, K, h, U, M, uid, scores, wsmall, d_weights,
+           d_ens, gU, gM);
+    return check_launch("awelv_bwd", (double)B * L * K * 12.0 + (double)B * L * 4.0, 4.0 * B * L * K);
+}
+
+}  // namespace intel

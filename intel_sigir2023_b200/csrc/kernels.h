@@ -124,6 +124,10 @@ struct StackSaved { float* const* QKV; float* const* A; float* const* U; float* 
 int adam_step(int count, float* const* params, const float* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
               const int64_t* numel, const float* weight_decay, double lr, double beta1, double beta2, double eps, int64_t step,
               cudaStream_t s);
+int awelv_fwd(int64_t B, int64_t L, int K, int h, const float* U, const float* M, const int64_t* uid, const double* scores,
+              float* weights, float* ens, float* wsmall, cudaStream_t s);
+int awelv_bwd(int64_t B, int64_t L, int K, int h, const float* U, const float* M, const int64_t* uid, const double* scores,
+              const float* wsmall, const float* d_weights, const float* d_ens, float* gU, float* gM, cudaStream_t s);
 void trunk_debug_sessions_per_cta(int n);
 void gemm_debug_use_umma(int on);
 bool trunk_supported(int64_t L, int d, int heads, int layers);

@@ -405,6 +405,16 @@ def borda(batch: Dict[str, object]) -> Dict[str, Tensor]:
     return {"weights": w, "ens_score": (w * rank).sum(dim=2)}
 
 
+def awelv(sd: State, batch: Dict[str, object]) -> Dict[str, Tensor]:
+    """models/supervise/aWELv.py:28-39: per-user softmax over <h_u, h_m>, broadcast over the list."""
+    scores = batch["scores"].float()
+    h_u = sd["uid_embeddings.weight"][batch["u_id_c"]]                      # [B, h]
+    logits = torch.stack([(h_u * sd["model_embeddings.weight"][m][None, :]).sum(dim=1)
+                          for m in range(scores.size(2))], dim=1)           # [B, K]
+    w = logits.unsqueeze(1).repeat(1, scores.size(1), 1).softmax(dim=-1)
+    return {"weights": w, "ens_score": (w * scores).sum(dim=2)}
+
+
 def random_fusion(batch: Dict[str, object], raw_weights: Tensor) -> Dict[str, Tensor]:
     """GeneralSeq.py:23-32 with the uniform draw passed in."""
     x = batch["scores"].float()

@@ -47,9 +47,10 @@ def import_reference():
     sys.path.insert(0, REF_SRC)
     from models.IntEL import IntEL as ref_intel
     from models.unsupervise import SingleSort as ref_single, Borda as ref_borda
-    from loss import IntListloss, IntBPRloss, IntMSEloss
+    from models.supervise import aWELv as ref_awelv
+    from loss import IntListloss, IntBPRloss, IntMSEloss, Listloss
     from helpers import BaseRunner
-    return dict(IntEL=ref_intel.IntEL, SingleSort=ref_single.SingleSort, Borda=ref_borda.Borda,
+    return dict(aWELv=ref_awelv.aWELv, Listloss=Listloss.Listloss, IntEL=ref_intel.IntEL, SingleSort=ref_single.SingleSort, Borda=ref_borda.Borda,
                 list=IntListloss.IntListloss, bpr=IntBPRloss.IntBPRloss, mse=IntMSEloss.IntMSEloss,
                 BaseRunner=BaseRunner.BaseRunner)
 
@@ -200,9 +201,43 @@ def make_eval(ref):
     print("eval:", os.path.getsize(path) // 1024, "KiB", {k: float(v) for k, v in out.items() if k.startswith("A.metric.NDCG")})
 
 
+def make_awelv(ref):
+    """aWELv.forward (models/supervise/aWELv.py:28-39) + Listloss with the diversity term (script/baselines.sh:33)."""
+    corpus = synthetic.CorpusSpec(n_item=90, n_class=7, n_user=23, n_ctx=11, model_num=3, intent_num=20)
+    cfg = IntelConfig(item_rows=corpus.item_rows, class_rows=corpus.n_class, user_rows=corpus.user_rows,
+                      ctx_rows=corpus.n_ctx, intent_num=corpus.intent_num, model_num=corpus.model_num,
+                      history_max=corpus.history_max)
+    batch = synthetic.make_batch(corpus, synthetic.BatchSpec(batch_size=13, max_len=17, min_len=2), seed=5)
+    args = _args(cfg, hidden_size=32, diversity_alpha=0.05)
+    torch.manual_seed(77)
+    model = ref["aWELv"](args, _Corpus(cfg))
+    out = {"user_rows": np.array([cfg.user_rows]), "model_num": np.array([cfg.model_num]), "hidden_size": np.array([32])}
+    for k, v in batch.items():
+        if torch.is_tensor(v):
+            out["batch." + k] = v.numpy()
+    for k, v in model.state_dict().items():
+        out["state." + k] = v.detach().numpy().copy()
+    res = model(dict(batch))
+    loss = ref["Listloss"](args)(res, batch)
+    loss = loss[0] if isinstance(loss, (tuple, list)) else loss
+    loss.backward()
+    out["out.weights"] = res["weights"].detach().numpy().copy()
+    out["out.ens_score"] = res["ens_score"].detach().numpy().copy()
+    out["loss.list"] = np.array([loss.item()], dtype=np.float64)
+    for n, p in model.named_parameters():
+        out["grad.list." + n] = p.grad.numpy().copy()
+    path = os.path.join(ROOT, "tests", "golden", "awelv.npz")
+    np.savez_compressed(path, **out)
+    print(f"awelv: {os.path.getsize(path) / 1024:.0f} KiB  loss(list)=", out["loss.list"][0])
+
+
 if __name__ == "__main__":
     ref = import_reference()
     torch.set_num_threads(4)
+    if "--awelv-only" in sys.argv:
+        make_awelv(ref)
+        sys.exit(0)
     for name in CASES:
         make_case(ref, name)
     make_eval(ref)
+    make_awelv(ref)

@@ -2,6 +2,7 @@
 Every check drives the product's Python host layer -> C ABI -> kernels and compares with the golden
 vectors of the unmodified reference and with the CPU oracle."""
 import argparse
+import os
 
 import numpy as np
 import torch
@@ -457,3 +458,35 @@ def check_adam(device, steps=4):
         assert rel_err(pa.detach().cpu().numpy(), pb.detach().cpu().numpy()) < 2e-6, na
         ea, eb = oa.state[pa]["exp_avg_sq"], ob.state[pb]["exp_avg_sq"]
         assert rel_err(ea.cpu().numpy(), eb.cpu().numpy()) < 2e-6, na
+
+
+def load_awelv_case(device="cpu"):
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "awelv.npz"))
+    batch = {k[6:]: torch.from_numpy(z[k]).to(device) for k in z.files if k.startswith("batch.")}
+    batch["batch_size"] = int(batch["i_id_s"].shape[0])
+    state = {k[6:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("state.")}
+    return z, batch, state
+
+
+def check_awelv(device):
+    """baselines.aWELv (one fused kernel per direction) + Listloss with the diversity term against arrays produced by the
+    unmodified reference model (oracle/make_golden.py:make_awelv)"""
+    import argparse
+    from intel_sigir2023_b200 import baselines, losses
+    z, batch, state = load_awelv_case(device)
+    args = argparse.Namespace(hidden_size=int(z["hidden_size"][0]), model_num=int(z["model_num"][0]), device=device)
+    model = baselines.aWELv(args, user_num=int(z["user_rows"][0]))
+    model.load_state_dict(state)
+    model = model.to(device)
+    out = model(batch)
+    assert rel_err(out["weights"].detach().cpu().numpy(), z["out.weights"]) < TOL
+    assert rel_err(out["ens_score"].detach().cpu().numpy(), z["out.ens_score"]) < TOL
+    crit = losses.Listloss(argparse.Namespace(cal_diversity=1, diversity_alpha=0.05, intent_weight=0.1, ensemble_weight=1.0,
+                                              kl_weight=0.5, kl_temp=2.0))
+    loss = crit(out, batch)
+    loss = loss[0] if isinstance(loss, (tuple, list)) else loss
+    assert abs(float(loss) - float(z["loss.list"][0])) <= TOL * abs(float(z["loss.list"][0]))
+    loss.backward()
+    gmax = max(float(np.abs(z["grad.list." + n]).max()) for n, _ in model.named_parameters())
+    for n, p in model.named_parameters():
+        assert_grad_close(p.grad.cpu().numpy(), z["grad.list." + n], gmax, n, rtol=1e-4, afrac=2e-6)

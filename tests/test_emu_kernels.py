@@ -88,6 +88,10 @@ def test_fused_stack_matches_staged():
     P.check_fused_vs_staged("cpu")
 
 
+def test_awelv_matches_reference_golden():
+    P.check_awelv("cpu")
+
+
 def test_fused_adam_matches_torch():
     P.check_adam("cpu")
 

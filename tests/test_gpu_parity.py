@@ -97,6 +97,10 @@ def test_fused_stack_matches_staged():
     P.check_fused_vs_staged(DEV)
 
 
+def test_awelv_matches_reference_golden():
+    P.check_awelv(DEV)
+
+
 def test_fused_adam_matches_torch():
     P.check_adam(DEV)
 

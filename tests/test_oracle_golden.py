@@ -107,3 +107,21 @@ def test_host_pack_rows_roundtrip():
     assert torch.equal(back, dense.float())
     small_i, small_v = torch.empty(37, 5, 2, dtype=torch.int32), torch.empty(37, 5, 2, dtype=torch.float32)
     assert loader.pack_rows(dense, 2, small_i, small_v) == got > 2
+
+
+def test_oracle_awelv_matches_reference():
+    """oracle.awelv + oracle.list_loss against the unmodified reference aWELv model + Listloss (tests/golden/awelv.npz)"""
+    import torch
+    import parity_checks as P
+    from oracle import intel_oracle as O
+    z, batch, state = P.load_awelv_case()
+    sd = {k: v.clone().requires_grad_(True) for k, v in state.items()}
+    out = O.awelv(sd, batch)
+    assert np.abs(out["weights"].detach().numpy() - z["out.weights"]).max() < 1e-6
+    assert np.abs(out["ens_score"].detach().numpy() - z["out.ens_score"]).max() < 1e-6
+    loss = O.list_loss(out, batch, 1, 0.05)
+    assert abs(loss.item() - float(z["loss.list"][0])) < 1e-6
+    loss.backward()
+    for k, v in sd.items():
+        ref = z["grad.list." + k]
+        assert np.abs(v.grad.numpy() - ref).max() <= 1e-5 * max(1e-6, np.abs(ref).max()) + 1e-8, k
