@@ -438,6 +438,7 @@ def check_adam(device, steps=4):
         torch.manual_seed(0)
         m = torch.nn.Module()
         m.emb = torch.nn.Embedding(257, 16)
+        m.table = torch.nn.Embedding(9001, 32)          # > 2^18 elements: the one-launch-per-table path
         m.lin = torch.nn.Linear(33, 7)
         m.odd = torch.nn.Parameter(torch.randn(5, 3, 2))
         return m.to(device)
