@@ -223,9 +223,11 @@ int intel_adam_step(int count, float* const* params, const float* const* grads, 
  * form of intel_batch_t: idx int32 [rows, nz], val float32 [rows, nz], zero padded, both in host memory (pinned for
  * an asynchronous copy).  Scans with `threads` host threads (<= 0: all cores).  Returns the largest number of
  * non-zeros of any row: if it exceeds nz the rows were truncated and the caller retries with a larger nz or keeps the
- * dense layout; negative on error.  row_nnz (nullable) receives the per-row counts. */
+ * dense layout; negative on error.  row_nnz (nullable) receives the per-row counts.
+ * group > 0: rows come in groups of `group` (the H history slots of a session) and only the first group_len[g] rows of
+ * group g are real (history_len / history_item_len); the padding rows behind them are emitted empty without being read. */
 int64_t intel_host_pack_rows(int64_t rows, int64_t I, const double* dense, int32_t nz, int32_t* idx, float* val,
-                             int32_t* row_nnz, int threads);
+                             int32_t* row_nnz, int threads, int64_t group, const int64_t* group_len);
 
 /* test hook: 0 routes the self-attention stacks through the staged kernels even where the fused per-session
  * kernel applies (both implement the same math; tests compare them). Default 1. */

@@ -98,7 +98,7 @@ def _declare(lib: C.CDLL) -> None:
         "intel_debug_use_fused_stack": (i32, [i32]),
         "intel_debug_stack_sessions_per_cta": (i32, [i32]),
         "intel_debug_use_tcgen05_gemm": (i32, [i32]),
-        "intel_host_pack_rows": (i64, [i64, i64, _p, i32, _p, _p, _p, i32]),
+        "intel_host_pack_rows": (i64, [i64, i64, _p, i32, _p, _p, _p, i32, i64, _p]),
         "intel_awelv_fwd": (i32, [i64, i64, i32, i32, _p, _p, _p, _p, _p, _p, _p, _p]),
         "intel_awelv_bwd": (i32, [i64, i64, i32, i32, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
         "intel_adam_step": (i32, [i32, _p, _p, _p, _p, _p, _p, dbl, dbl, dbl, dbl, i64, _p]),

@@ -34,7 +34,8 @@ __attribute__((target("avx2"))) int64_t skip_zero_blocks_avx2(const uint64_t* ro
 #endif
 
 // rows [r0, r1): returns the largest non-zero count seen
-int32_t pack_block(int64_t r0, int64_t r1, int64_t I, const double* dense, int32_t nz, int32_t* idx, float* val, int32_t* row_nnz) {
+int32_t pack_block(int64_t r0, int64_t r1, int64_t I, const double* dense, int32_t nz, int32_t* idx, float* val, int32_t* row_nnz,
+                   int64_t group, const int64_t* group_len) {
     int32_t worst = 0;
     const uint64_t* bits = reinterpret_cast<const uint64_t*>(dense);
     for (int64_t r = r0; r < r1; ++r) {
@@ -44,6 +45,7 @@ int32_t pack_block(int64_t r0, int64_t r1, int64_t I, const double* dense, int32
         float* ov = val + r * nz;
         int32_t n = 0;
         int64_t c = 0;
+        if (group > 0 && (r % group) >= group_len[r / group]) c = I;     // padding row of a ragged group: not read at all
 #ifdef INTEL_HOST_AVX2
         static const bool avx2 = __builtin_cpu_supports("avx2");
 #endif
@@ -83,8 +85,15 @@ extern "C" {
 // dense [rows, I] float64 (host) -> idx int32 [rows, nz], val float32 [rows, nz] (host, zero padded).
 // Returns the largest number of non-zeros found in a row (>= 0): if it exceeds nz the output is truncated and the
 // caller must retry with a larger nz (or keep the dense layout).  Negative: error.  threads <= 0: all cores.
+// group > 0: the rows form groups of `group` consecutive rows (the H history slots of a session) of which only the
+// first group_len[g] are real; the padding rows behind them (zeros by construction of collate_batch, and never read by
+// the model: the encoders stop at history_len) are emitted empty without being scanned.
 int64_t intel_host_pack_rows(int64_t rows, int64_t I, const double* dense, int32_t nz, int32_t* idx, float* val, int32_t* row_nnz,
-                             int threads) {
+                             int threads, int64_t group, const int64_t* group_len) {
+    if (group > 0 && (!group_len || rows % group != 0)) {
+        set_error("host_pack_rows: bad group arguments");
+        return -1;
+    }
     if (rows < 0 || I <= 0 || nz <= 0 || !dense || !idx || !val) {
         set_error("host_pack_rows: bad argument");
         return -1;
@@ -103,7 +112,7 @@ int64_t intel_host_pack_rows(int64_t rows, int64_t I, const double* dense, int32
             const int64_t r0 = next.fetch_add(chunk);
             if (r0 >= rows) break;
             const int64_t r1 = r0 + chunk < rows ? r0 + chunk : rows;
-            const int32_t b = pack_block(r0, r1, I, dense, nz, idx, val, row_nnz);
+            const int32_t b = pack_block(r0, r1, I, dense, nz, idx, val, row_nnz, group, group_len);
             if (b > w) w = b;
         }
         int32_t cur = worst.load();

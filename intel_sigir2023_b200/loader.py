@@ -20,16 +20,29 @@ from . import _lib, synthetic
 
 # dense float64 [B,H,I] inputs of the reference's collate_batch that have a compact (index, value) device form
 _PACKABLE = ("his_intents", "his_item_int")
+# per-session number of real history rows of those tensors (collate_batch pads the rest with zeros and the encoders stop
+# at these lengths, GeneralSeq.py:58-106)
+_LENGTH_KEY = {"his_intents": "history_len", "his_item_int": "history_item_len"}
 
 
-def pack_rows(dense: torch.Tensor, nz: int, idx: torch.Tensor, val: torch.Tensor, threads: int = 0) -> int:
+def pack_rows(dense: torch.Tensor, nz: int, idx: torch.Tensor, val: torch.Tensor, threads: int = 0,
+              lengths: torch.Tensor = None) -> int:
     """Host-side packing of a dense float64 [..., I] CPU tensor into idx int32 / val float32 [..., nz] (pre-allocated,
-    ideally pinned).  Returns the largest non-zero count of any row; > nz means the rows were truncated."""
+    ideally pinned).  Returns the largest non-zero count of any row; > nz means the rows were truncated.
+    lengths (int64 [B], for a [B,H,I] tensor): only the first lengths[b] rows of session b are real; the padding rows
+    behind them are not scanned."""
     if dense.is_cuda or dense.dtype != torch.float64 or not dense.is_contiguous():
         raise ValueError("pack_rows expects a contiguous float64 CPU tensor")
     I = dense.shape[-1]
     rows = dense.numel() // I
-    got = _lib.load().intel_host_pack_rows(rows, I, dense.data_ptr(), int(nz), idx.data_ptr(), val.data_ptr(), None, int(threads))
+    group, lens_ptr = 0, None
+    if lengths is not None:
+        if dense.dim() != 3 or lengths.is_cuda or lengths.dtype != torch.int64 or lengths.numel() != dense.shape[0]:
+            raise ValueError("lengths must be an int64 CPU tensor with one entry per session of a [B,H,I] tensor")
+        lengths = lengths.contiguous()
+        group, lens_ptr = dense.shape[1], lengths.data_ptr()
+    got = _lib.load().intel_host_pack_rows(rows, I, dense.data_ptr(), int(nz), idx.data_ptr(), val.data_ptr(), None, int(threads),
+                                           group, lens_ptr)
     if got < 0:
         _lib.check(1)
     return int(got)
@@ -70,7 +83,7 @@ class DevicePrefetcher:
         self.host = [dict() for _ in range(self.depth)]     # pinned staging of the packed tensors, per slot
         self.copied_ev = [None] * self.depth                # copy-stream event: the slot's pinned staging may be rewritten
 
-    def _pack(self, key: str, v: torch.Tensor, slot: int):
+    def _pack(self, key: str, v: torch.Tensor, slot: int, lengths=None):
         """dense [B,H,I] float64 on the host -> pinned (idx, val) [B,H,nz], or None to keep the tensor dense"""
         I = v.shape[-1]
         while True:
@@ -82,7 +95,7 @@ class DevicePrefetcher:
             if st is None or st[0].shape != shape:
                 st = (torch.empty(shape, dtype=torch.int32).pin_memory(), torch.empty(shape, dtype=torch.float32).pin_memory())
                 self.host[slot][key] = st
-            got = pack_rows(v, nz, st[0], st[1], self.threads)
+            got = pack_rows(v, nz, st[0], st[1], self.threads, lengths)
             if got <= nz:
                 return st
             self.nz[key] = max(got, 2 * nz)
@@ -96,7 +109,10 @@ class DevicePrefetcher:
             for key in _PACKABLE:
                 v = items.get(key)
                 if torch.is_tensor(v) and not v.is_cuda and v.dtype == torch.float64 and v.dim() == 3:
-                    packed = self._pack(key, v.contiguous(), slot)
+                    lens = items.get(_LENGTH_KEY[key])
+                    if not (torch.is_tensor(lens) and not lens.is_cuda and lens.dtype == torch.int64 and lens.numel() == v.shape[0]):
+                        lens = None
+                    packed = self._pack(key, v.contiguous(), slot, lens)
                     if packed is not None:
                         del items[key]
                         items[key + "_idx"], items[key + "_val"] = packed

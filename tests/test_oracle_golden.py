@@ -125,3 +125,22 @@ def test_oracle_awelv_matches_reference():
     for k, v in sd.items():
         ref = z["grad.list." + k]
         assert np.abs(v.grad.numpy() - ref).max() <= 1e-5 * max(1e-6, np.abs(ref).max()) + 1e-8, k
+
+
+def test_host_pack_rows_skips_padding_rows_of_ragged_groups():
+    """with per-session lengths only the real history rows are scanned: padding rows come out empty (whatever they
+    hold - the model never reads them), real rows are packed as before"""
+    import torch
+    from intel_sigir2023_b200 import loader
+    g = torch.Generator().manual_seed(9)
+    B, H, I = 19, 6, 300
+    lens = torch.randint(1, H + 1, (B,), generator=g)
+    dense = torch.zeros(B, H, I, dtype=torch.float64)
+    hot = torch.randint(0, I, (B, H, 3), generator=g)
+    dense.scatter_(2, hot, torch.rand(B, H, 3, generator=g, dtype=torch.float64) + 0.1)   # also in the padding rows
+    idx, val = torch.empty(B, H, 4, dtype=torch.int32), torch.empty(B, H, 4, dtype=torch.float32)
+    got = loader.pack_rows(dense, 4, idx, val, threads=2, lengths=lens)
+    assert 1 <= got <= 3
+    live = (torch.arange(H)[None, :] < lens[:, None])
+    back = torch.zeros(B, H, I).scatter_add_(2, idx.long(), val)
+    assert torch.equal(back, (dense * live[:, :, None]).float())
