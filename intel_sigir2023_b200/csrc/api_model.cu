@@ -559,7 +559,7 @@ int intel_intent_fwd(const intel_dims_t* d, const intel_tensors_t* P, const inte
     } else {
         INTEL_REQUIRE(bt->his_intents, INTEL_ERR_ARG, "his_intents is null");
         INTEL_TRY(dense_rows_linear_fwd(B * d->H1, I, dint, bt->his_intents, w.Wt, P->intent_b, w.e1.seq + dctx, d1,
-                                        w.e1.nz_idx, w.e1.nz_val, w.e1.nz_cnt, NZ_CAP, s));
+                                        w.e1.nz_idx, w.e1.nz_val, w.e1.nz_cnt, NZ_CAP, s, d->H1, bt->history_len));
     }
     // item history tokens: [item id embedding | intent embedding of the one-hot item intents]
     INTEL_TRY(gather_rows(B * d->H2, diid, P->iid_emb, bt->his_item_id, w.e2.seq, d2, 0, s));
@@ -569,7 +569,7 @@ int intel_intent_fwd(const intel_dims_t* d, const intel_tensors_t* P, const inte
     } else {
         INTEL_REQUIRE(bt->his_item_int, INTEL_ERR_ARG, "his_item_int is null");
         INTEL_TRY(dense_rows_linear_fwd(B * d->H2, I, dint, bt->his_item_int, w.Wt, P->intent_b, w.e2.seq + diid, d2,
-                                        w.e2.nz_idx, w.e2.nz_val, w.e2.nz_cnt, NZ_CAP, s));
+                                        w.e2.nz_idx, w.e2.nz_val, w.e2.nz_cnt, NZ_CAP, s, d->H2, bt->history_item_len));
     }
     if (d->encoder == INTEL_ENCODER_BERT4REC) {
         INTEL_TRY(bert_fwd(d, P->enc, w.e1, bt->history_len, w.feat + off_v1, Dp, s));

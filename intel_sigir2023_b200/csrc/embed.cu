@@ -104,7 +104,8 @@ __device__ __forceinline__ void dense_row_accumulate(const double* __restrict__ 
 __global__ void __launch_bounds__(256) dense_rows_fwd_kernel(int64_t R, int64_t I, int d, const double* __restrict__ X,
                                                              const float* __restrict__ Wt, const float* __restrict__ bias,
                                                              float* __restrict__ Y, int64_t ldy, int32_t* nz_idx,
-                                                             float* nz_val, int32_t* nz_cnt, int cap) {
+                                                             float* nz_val, int32_t* nz_cnt, int cap, int64_t group,
+                                                             const int64_t* __restrict__ lens) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -112,8 +113,12 @@ __global__ void __launch_bounds__(256) dense_rows_fwd_kernel(int64_t R, int64_t 
         float acc0 = (bias && lane < d) ? bias[lane] : 0.f;
         float acc1 = (bias && lane + 32 < d) ? bias[lane + 32] : 0.f;
         int cnt = 0;
-        dense_row_accumulate(X + r * I, I, d, lane, Wt, acc0, acc1, nz_idx ? nz_idx + r * cap : nullptr,
-                             nz_val ? nz_val + r * cap : nullptr, cap, cnt);
+        // padding rows behind a session's history length are zeros by construction (collate_batch) and never read by the
+        // encoders: their output is the bias, without streaming 8 I bytes of zeros
+        const bool pad = lens != nullptr && (r % group) >= lens[r / group];
+        if (!pad)
+            dense_row_accumulate(X + r * I, I, d, lane, Wt, acc0, acc1, nz_idx ? nz_idx + r * cap : nullptr,
+                                 nz_val ? nz_val + r * cap : nullptr, cap, cnt);
         if (lane < d) Y[r * ldy + lane] = acc0;
         if (lane + 32 < d) Y[r * ldy + lane + 32] = acc1;
         if (nz_cnt && lane == 0) nz_cnt[r] = cnt;
@@ -121,12 +126,17 @@ __global__ void __launch_bounds__(256) dense_rows_fwd_kernel(int64_t R, int64_t 
 }
 
 int dense_rows_linear_fwd(int64_t R, int64_t I, int d, const double* X, const float* Wt, const float* bias, float* Y,
-                          int64_t ldy, int32_t* nz_idx, float* nz_val, int32_t* nz_cnt, int cap, cudaStream_t s) {
+                          int64_t ldy, int32_t* nz_idx, float* nz_val, int32_t* nz_cnt, int cap, cudaStream_t s, int64_t group,
+                          const int64_t* lens) {
     if (R <= 0) return INTEL_OK;
     INTEL_REQUIRE(d <= 64, INTEL_ERR_UNSUPPORTED, "intent_emb_size %d > 64 not supported", d);
     INTEL_REQUIRE(X && Wt && Y, INTEL_ERR_ARG, "dense_rows_linear_fwd: null pointer");
     unsigned grid = stream_grid(ceil_div(R, 8), 8);
-    LAUNCH(dense_rows_fwd_kernel, dim3(grid), dim3(256), 0, s, R, I, d, X, Wt, bias, Y, ldy, nz_idx, nz_val, nz_cnt, cap);
+    if (group <= 0) lens = nullptr;
+    // ragged input: one warp per row and no grid-stride loop, so that the block scheduler balances live and padding rows
+    if (lens) grid = (unsigned)ceil_div(R, 8);
+    LAUNCH(dense_rows_fwd_kernel, dim3(grid), dim3(256), 0, s, R, I, d, X, Wt, bias, Y, ldy, nz_idx, nz_val, nz_cnt, cap,
+           group > 0 ? group : 1, lens);
     return check_launch("dense_rows_fwd", (double)R * (8.0 * I + 4.0 * d), 0.0);
 }
 

@@ -46,7 +46,8 @@ int scatter_add_rows(int64_t rows, int d, const float* d_out, int64_t ld, const 
 // to stream the dense rows again; rows with more than `cap` non-zeros are re-streamed.
 int dense_rows_linear_fwd(int64_t R, int64_t I, int d, const double* X, const float* Wt, const float* bias,
                           float* Y, int64_t ldy, int32_t* nz_idx, float* nz_val, int32_t* nz_cnt, int cap,
-                          cudaStream_t s);
+                          cudaStream_t s, int64_t group = 0,
+                          const int64_t* lens = nullptr);
 // dWt[i, :] += float(X[r,i]) * dY[r, :]
 int dense_rows_linear_bwd(int64_t R, int64_t I, int d, const double* X, const float* dY, int64_t lddy,
                           const int32_t* nz_idx, const float* nz_val, const int32_t* nz_cnt, int cap,
