@@ -100,8 +100,9 @@ Reading:
   parallelism), a dedicated MMA-issuer warp with mbarrier hand-offs (long-K shapes 20-50 % slower: the chunk drain
   serialises harder), pointer-advancing address arithmetic with a full-tile fast path (slower despite fewer
   instructions).  ncu source-level sampling shows no hot spot: stall samples are spread over the whole k-tile body.
-* `dense_rows_fwd` streams the float64 [B,H,I] history intents at 5.9 TB/s algorithmic = 0.90 of the measured HBM peak
-  (707 MB DRAM read per launch for 702 MB of input).
+* `dense_rows_fwd` streams the live rows of the float64 [B,H,I] history intents (the padding rows behind history_len
+  are skipped, one warp per row so that the block scheduler balances live and padding rows): ~370 MB of DRAM reads per
+  launch instead of 707 MB; when every row is live it runs at 5.9 TB/s = 0.90 of the measured HBM peak.
 
 r01_traffic.json holds the per-launch DRAM bytes of these captures; `bench.py` copies the entry of the dominant kernel
 into `roofline.traffic`.
