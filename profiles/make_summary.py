@@ -1,6 +1,7 @@
 """Rebuilds profiles/r01_final_summary.md and profiles/r01_traffic.json from the artifacts next to it:
 r01_final_launches_ncu.csv (ncu launch list of bench.py --profile_mode), r01_final_ncu_full.jsonl (metrics extracted
-from the ncu --set full captures by scratch-side `ncu -i ... --page raw --csv`), r01_bench_final.json (bench.py)."""
+from the ncu --set full captures: `ncu --set full --clock-control none -k regex:<kernel> -c 2 -o rep python
+profiles/tools/prof_step.py; ncu -i rep.ncu-rep --page raw --csv | python profiles/tools/ncu_extract.py`), r01_bench_final.json (bench.py)."""
 import collections, csv, json, os, re
 H = os.path.dirname(os.path.abspath(__file__))
 P = lambda n: os.path.join(H, n)
