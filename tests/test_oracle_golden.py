@@ -144,3 +144,16 @@ def test_host_pack_rows_skips_padding_rows_of_ragged_groups():
     live = (torch.arange(H)[None, :] < lens[:, None])
     back = torch.zeros(B, H, I).scatter_add_(2, idx.long(), val)
     assert torch.equal(back, (dense * live[:, :, None]).float())
+
+
+def test_bench_issues_no_train_step_after_the_non_zero_ranks_left():
+    """bench.py: ranks != 0 leave the process group before rank 0 assembles the JSON line; anything after that point
+    that runs a train step (gradient all-reduce) or another collective would hang every multi-GPU run."""
+    import os
+    import re
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py")).read()
+    body = src[src.index("def run_b200"):]
+    tail = body[body.index("if rank != 0:\n        if world > 1:\n            dist.destroy_process_group()\n        return"):]
+    tail = tail[:tail.index('if __name__ == "__main__"')]
+    code = "\n".join(l.split("#")[0] for l in tail.splitlines())
+    assert not re.search(r"\btrain_step\(|\bbarrier\(|\btimed\(|dist\.(all_reduce|barrier|broadcast|all_gather)", code)
