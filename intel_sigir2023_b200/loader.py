@@ -77,7 +77,11 @@ class DevicePrefetcher:
         self.slots = [dict() for _ in range(self.depth)]
         self.free_ev = [None] * self.depth          # consumer-stream event: the slot's previous batch is no longer in use
         if threads <= 0:        # share the host cores between the ranks of a node (torchrun exports LOCAL_WORLD_SIZE)
-            threads = max(1, (os.cpu_count() or 1) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1"))))
+            try:
+                cores = len(os.sched_getaffinity(0))          # the cores this process may run on (what `nproc` reports)
+            except (AttributeError, OSError):
+                cores = os.cpu_count() or 1
+            threads = max(1, cores // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1"))))
         self.pack_history, self.threads = bool(pack_history), int(threads)
         self.nz = {k: max(1, int(pack_nz)) for k in _PACKABLE}
         self.host = [dict() for _ in range(self.depth)]     # pinned staging of the packed tensors, per slot
