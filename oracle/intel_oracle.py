@@ -415,6 +415,16 @@ def awelv(sd: State, batch: Dict[str, object]) -> Dict[str, Tensor]:
     return {"weights": w, "ens_score": (w * scores).sum(dim=2)}
 
 
+def awelv_int(sd: State, cfg: IntelConfig, batch: Dict[str, object]) -> Dict[str, Tensor]:
+    """models/supervise/aWELv_Int.py:97-113: the intent predictor of IntEL (same predict_intent, :66-95), then
+    per-session softmax over <[h_u || intent_embeddings(intent)], h_m>, broadcast over the list."""
+    scores = batch["scores"].float()
+    intent = predict_intent(sd, cfg, batch)
+    h = torch.cat([sd["uid_embeddings.weight"][batch["u_id_c"]], _lin(sd, "intent_embeddings", intent)], dim=1)
+    w = (h @ sd["model_embeddings.weight"].t()).softmax(dim=1).unsqueeze(1).repeat(1, scores.size(1), 1)
+    return {"weights": w, "ens_score": (w * scores).sum(dim=2), "intents": intent}
+
+
 def random_fusion(batch: Dict[str, object], raw_weights: Tensor) -> Dict[str, Tensor]:
     """GeneralSeq.py:23-32 with the uniform draw passed in."""
     x = batch["scores"].float()

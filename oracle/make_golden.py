@@ -10,6 +10,7 @@ reference tree with three py3.12/numpy-2 import shims and calling
     BaseRunner.evaluate_method         (helpers/BaseRunner.py:57-131)
     BaseRunner.evaluate_intents        (helpers/BaseRunner.py:133-150)
     SingleSort/Borda.forward           (models/unsupervise/*.py)
+    aWELv / aWELv_Int.forward          (models/supervise/*.py)
 
 on seeded synthetic batches from intel_sigir2023_b200.synthetic.  BPR's torch.rand_like
 is monkey-patched to return a saved noise tensor so its negative choice is replayable.
@@ -47,10 +48,10 @@ def import_reference():
     sys.path.insert(0, REF_SRC)
     from models.IntEL import IntEL as ref_intel
     from models.unsupervise import SingleSort as ref_single, Borda as ref_borda
-    from models.supervise import aWELv as ref_awelv
+    from models.supervise import aWELv as ref_awelv, aWELv_Int as ref_awelv_int
     from loss import IntListloss, IntBPRloss, IntMSEloss, Listloss
     from helpers import BaseRunner
-    return dict(aWELv=ref_awelv.aWELv, Listloss=Listloss.Listloss, IntEL=ref_intel.IntEL, SingleSort=ref_single.SingleSort, Borda=ref_borda.Borda,
+    return dict(aWELv=ref_awelv.aWELv, aWELv_Int=ref_awelv_int.aWELv_Int, Listloss=Listloss.Listloss, IntEL=ref_intel.IntEL, SingleSort=ref_single.SingleSort, Borda=ref_borda.Borda,
                 list=IntListloss.IntListloss, bpr=IntBPRloss.IntBPRloss, mse=IntMSEloss.IntMSEloss,
                 BaseRunner=BaseRunner.BaseRunner)
 
@@ -231,13 +232,63 @@ def make_awelv(ref):
     print(f"awelv: {os.path.getsize(path) / 1024:.0f} KiB  loss(list)=", out["loss.list"][0])
 
 
+AWELV_INT_CASES = {
+    # the script's flags (script/baselines.sh:40: GRU4Rec, context 32, intent 32, user 16) and the bare defaults (BERT4Rec)
+    "gru": (dict(encoder="GRU4Rec", context_emb_size=32, intent_emb_size=32, u_emb_size=16),
+            dict(n_item=70, n_class=7, n_user=19, n_ctx=11, model_num=3, intent_num=27, history_max=6),
+            dict(batch_size=9, max_len=14, min_len=2), 6),
+    "bert": (dict(encoder="BERT4Rec", u_emb_size=16),
+             dict(n_item=50, n_class=5, n_user=12, n_ctx=9, model_num=4, intent_num=20, history_max=8),
+             dict(batch_size=7, max_len=11, min_len=1), 7),
+}
+
+
+def make_awelv_int(ref):
+    """aWELv_Int.forward (models/supervise/aWELv_Int.py:66-113) + IntListloss (script/baselines.sh:40)."""
+    for name, (over, csz, bsz, seed) in AWELV_INT_CASES.items():
+        corpus = synthetic.CorpusSpec(**csz)
+        cfg = IntelConfig(item_rows=corpus.item_rows, class_rows=corpus.n_class, user_rows=corpus.user_rows,
+                          ctx_rows=corpus.n_ctx, intent_num=corpus.intent_num, model_num=corpus.model_num,
+                          history_max=corpus.history_max, **over)
+        batch = synthetic.make_batch(corpus, synthetic.BatchSpec(**bsz), seed=seed)
+        args = _args(cfg, user_emb_size=cfg.u_emb_size)
+        torch.manual_seed(200 + seed)
+        model = ref["aWELv_Int"](args, _Corpus(cfg))
+        with torch.no_grad():
+            for n, p in model.named_parameters():
+                if "layer_norm" in n:
+                    p.add_(0.1 * torch.randn_like(p))
+        model.eval()
+        out = {"cfg": np.frombuffer(json.dumps(cfg.to_dict()).encode(), dtype=np.uint8)}
+        for k, v in batch.items():
+            if torch.is_tensor(v):
+                out["batch." + k] = v.numpy()
+        for k, v in model.state_dict().items():
+            out["state." + k] = v.detach().numpy().copy()
+        res = model(dict(batch))
+        loss, ens_l, int_l = ref["list"](args)(res, batch)
+        loss.backward()
+        for k in ("weights", "ens_score", "intents"):
+            out["out." + k] = res[k].detach().numpy().copy()
+        out["loss.list"] = np.array([loss.item(), ens_l.item(), int_l.item()], dtype=np.float64)
+        for n, p in model.named_parameters():
+            out["grad.list." + n] = (p.grad if p.grad is not None else torch.zeros_like(p)).numpy().copy()
+        path = os.path.join(ROOT, "tests", "golden", f"awelv_int_{name}.npz")
+        np.savez_compressed(path, **out)
+        print(f"awelv_int_{name}: {os.path.getsize(path) / 1024:.0f} KiB  loss(list)=", out["loss.list"])
+
+
 if __name__ == "__main__":
     ref = import_reference()
     torch.set_num_threads(4)
     if "--awelv-only" in sys.argv:
         make_awelv(ref)
         sys.exit(0)
+    if "--awelv-int-only" in sys.argv:
+        make_awelv_int(ref)
+        sys.exit(0)
     for name in CASES:
         make_case(ref, name)
     make_eval(ref)
     make_awelv(ref)
+    make_awelv_int(ref)

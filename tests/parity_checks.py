@@ -486,8 +486,47 @@ def check_awelv(device):
                                               kl_weight=0.5, kl_temp=2.0))
     loss = crit(out, batch)
     loss = loss[0] if isinstance(loss, (tuple, list)) else loss
-    assert abs(float(loss) - float(z["loss.list"][0])) <= TOL * abs(float(z["loss.list"][0]))
+    assert abs(float(loss.detach()) - float(z["loss.list"][0])) <= TOL * abs(float(z["loss.list"][0]))
     loss.backward()
     gmax = max(float(np.abs(z["grad.list." + n]).max()) for n, _ in model.named_parameters())
     for n, p in model.named_parameters():
         assert_grad_close(p.grad.cpu().numpy(), z["grad.list." + n], gmax, n, rtol=1e-4, afrac=2e-6)
+
+
+def load_awelv_int_case(name, device="cpu"):
+    """-> (cfg, batch, state, npz) from tests/golden/awelv_int_<name>.npz (oracle/make_golden.py:make_awelv_int)"""
+    import json
+    from intel_sigir2023_b200.config import IntelConfig
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"awelv_int_{name}.npz"))
+    cfg = IntelConfig(**json.loads(bytes(z["cfg"]).decode()))
+    batch = {k[6:]: torch.from_numpy(z[k]).to(device) for k in z.files if k.startswith("batch.")}
+    batch["batch_size"] = int(batch["i_id_s"].shape[0])
+    batch["phase"] = "train"
+    state = {k[6:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("state.")}
+    return cfg, batch, state, z
+
+
+def check_awelv_int(device, name):
+    """baselines.aWELv_Int (intent predictor + per-session softmax fusion) + IntListloss against arrays produced by the
+    unmodified reference model (models/supervise/aWELv_Int.py, script/baselines.sh:40)"""
+    import argparse
+    from intel_sigir2023_b200 import baselines, losses
+    cfg, batch, state, z = load_awelv_int_case(name, device)
+    model = baselines.aWELv_Int(argparse.Namespace(device=device, model_path="", buffer=1), cfg=cfg)
+    assert [n for n, _ in model.named_parameters()] == list(state.keys())       # the reference's registration order
+    model.load_state_dict(state)
+    model = model.to(device)
+    out = model(batch)
+    for k in ("intents", "weights", "ens_score"):
+        assert rel_err(out[k].detach().cpu().numpy(), z["out." + k]) < TOL, k
+    crit = losses.IntListloss(argparse.Namespace(**LOSS_KW))
+    loss, ens_l, int_l = crit(out, batch)
+    for got, ref in zip((loss, ens_l, int_l), z["loss.list"]):
+        assert abs(float(got.detach()) - float(ref)) <= TOL * abs(float(ref)), (float(got.detach()), float(ref))
+    loss.backward()
+    gmax = max(float(np.abs(z["grad.list." + n]).max()) for n, _ in model.named_parameters())
+    for n, p in model.named_parameters():
+        if n == "item_embeddings.weight":           # declared, never read: no gradient on either side
+            assert p.grad is None and not np.any(z["grad.list." + n])
+            continue
+        assert_grad_close(p.grad.cpu().numpy(), z["grad.list." + n], gmax, n)

@@ -92,6 +92,11 @@ def test_awelv_matches_reference_golden():
     P.check_awelv("cpu")
 
 
+@pytest.mark.parametrize("name", ["gru", "bert"])
+def test_awelv_int_matches_reference_golden(name):
+    P.check_awelv_int("cpu", name)
+
+
 def test_fused_adam_matches_torch():
     P.check_adam("cpu")
 

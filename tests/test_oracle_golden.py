@@ -127,6 +127,29 @@ def test_oracle_awelv_matches_reference():
         assert np.abs(v.grad.numpy() - ref).max() <= 1e-5 * max(1e-6, np.abs(ref).max()) + 1e-8, k
 
 
+@pytest.mark.parametrize("name", ["gru", "bert"])
+def test_oracle_awelv_int_matches_reference(name):
+    """oracle.awelv_int + IntListloss against the unmodified reference aWELv_Int model (tests/golden/awelv_int_*.npz)"""
+    import torch
+    import parity_checks as P
+    from conftest import LOSS_KW
+    from oracle import intel_oracle as O
+    cfg, batch, state, z = P.load_awelv_int_case(name)
+    sd = {k: v.clone().requires_grad_(True) for k, v in state.items()}
+    out = O.awelv_int(sd, cfg, batch)
+    for k in ("intents", "weights", "ens_score"):
+        assert np.abs(out[k].detach().numpy() - z["out." + k]).max() < 2e-6, k
+    loss, ens_l, int_l = O.total_loss("list", out, batch, **LOSS_KW)
+    for got, ref in zip((loss, ens_l, int_l), z["loss.list"]):
+        assert abs(got.item() - float(ref)) < 2e-6 * max(1.0, abs(float(ref)))
+    loss.backward()
+    gmax = max(float(np.abs(z["grad.list." + k]).max()) for k in sd)
+    for k, v in sd.items():
+        ref = z["grad.list." + k]
+        got = v.grad.numpy() if v.grad is not None else np.zeros_like(ref)
+        assert np.abs(got - ref).max() <= 2e-5 * np.abs(ref).max() + 1e-6 * gmax, k
+
+
 def test_host_pack_rows_skips_padding_rows_of_ragged_groups():
     """with per-session lengths only the real history rows are scanned: padding rows come out empty (whatever they
     hold - the model never reads them), real rows are packed as before"""
