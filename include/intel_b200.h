@@ -209,6 +209,15 @@ int intel_awelv_bwd(int64_t B, int64_t L, int K, int h, const float* user_table,
                     const double* scores, const float* w_user, const float* d_weights, const float* d_ens, float* g_user_table,
                     float* g_model_table, intel_stream_t stream);
 
+/* ---- LambdaRank lambdas (helpers/LambdaRankRunner.py:315-344 compute_lambda_new, called at :246) ----------
+ * lambdas[b,i] = sum_{j: t_i>t_j} Delta_ij Rho_ij - sum_{j: t_i<t_j} Delta_ji Rho_ji over the valid slots of session b, with
+ * t = clamp(ranking, 0), Delta_ij = |g_i d_j + g_j d_i - g_i d_i - g_j d_j| / IDCG (g = 2^t - 1, d_j = 1/log2(j+2) of the list
+ * SLOT j), Rho_ij = 1/(1+exp(s_i - s_j)).  ranking int64 [B,L] (raw or already clamped), scores float32 [B,L] (the
+ * detached ens_score), session_len int64 [B] -> lambdas float32 [B,L]; pad slots get 0; a session without a positive
+ * item gets NaN in all L slots, like the reference's 0/0. */
+int intel_lambdarank_lambdas(int64_t B, int64_t L, const int64_t* ranking, const float* scores, const int64_t* session_len,
+                             float* lambdas, intel_stream_t stream);
+
 /* ---- optimizer step ------------------------------------------------------------------------------
  * torch.optim.Adam (BaseRunner._build_optimizer, BaseRunner.py:182-188) over `count` parameter tensors in one launch
  * per 48 tensors.  params / grads / exp_avg / exp_avg_sq / numel / weight_decay are HOST arrays of `count` entries

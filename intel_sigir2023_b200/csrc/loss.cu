@@ -369,6 +369,85 @@ __global__ void __launch_bounds__(256) scale_kernel(int64_t n, const float* __re
         y[e] = x[e] * f;
 }
 
+// ------------------------------------------------------------------------------------------------
+// LambdaRank lambdas (helpers/LambdaRankRunner.py:315-344, compute_lambda_new): for t = clamp(ranking, 0), list slot
+// discounts d_j = 1/log2(j+2) (the SLOT of the item in the list, not its current rank - kept as the reference has it),
+// gains g = 2^t - 1 and IDCG over the valid slots of the label-sorted list,
+//   Delta_ij = |g_i d_j + g_j d_i - g_i d_i - g_j d_j| / IDCG,   Rho_ij = 1 / (1 + exp(s_i - s_j)),
+//   Lambda_i = sum_{j: t_i > t_j} Delta_ij Rho_ij  -  sum_{j: t_i < t_j} Delta_ji Rho_ji      (valid i, j only).
+// A session without a positive item has IDCG = 0 and the reference's 0/0 turns its whole row into NaN: kept.
+// One warp per session; s and g of the session plus the block's discount table live in shared memory.
+static const int LR_WARPS = 4;
+
+__global__ void __launch_bounds__(LR_WARPS * 32) lambdarank_kernel(int64_t B, int64_t L, const int64_t* __restrict__ ranking,
+                                                                   const float* __restrict__ scores,
+                                                                   const int64_t* __restrict__ lens, float* __restrict__ lambdas) {
+    DYN_SMEM(float, sm);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t b = (int64_t)blockIdx.x * LR_WARPS + w;
+    float* disc = sm;                                   // [L], shared by the block's warps
+    float* s = sm + L + (size_t)w * 2 * L;              // [L] scores of this warp's session
+    float* g = s + L;                                   // [L] gains 2^t - 1 (0 on pad slots)
+    for (int64_t j = threadIdx.x; j < L; j += LR_WARPS * 32) disc[j] = 1.0f / log2f((float)j + 2.0f);
+    int64_t n = 0;
+    if (b < B) {
+        n = lens[b];
+        if (n > L) n = L;
+        for (int64_t j = lane; j < L; j += 32) {
+            int64_t t = ranking[b * L + j];
+            t = t > 0 ? (t < 62 ? t : 62) : 0;
+            s[j] = scores[b * L + j];
+            g[j] = (float)(((int64_t)1 << t) - 1);
+        }
+    }
+    __syncthreads();
+    if (b >= B) return;
+    // IDCG: slot of item i in the label-sorted list = #{t_j > t_i} + #{j < i, t_j == t_i}; slots >= n are masked
+    double idcg_part = 0.0;
+    for (int64_t i = lane; i < L; i += 32) {
+        const float gi = g[i];
+        if (gi <= 0.f) continue;
+        int64_t pos = 0;
+        for (int64_t j = 0; j < L; ++j) pos += (g[j] > gi) || (g[j] == gi && j < i);
+        if (pos < n) idcg_part += (double)(gi * disc[pos]);
+    }
+    const float idcg = (float)warp_sum_d(idcg_part);
+    if (!(idcg > 0.f)) {
+        for (int64_t i = lane; i < L; i += 32) lambdas[b * L + i] = NAN;
+        return;
+    }
+    for (int64_t i = lane; i < L; i += 32) {
+        float up = 0.f, down = 0.f;
+        if (i < n) {
+            const float gi = g[i], si = s[i], di = disc[i];
+            const float single_i = __fmul_rn(gi, di);
+            for (int64_t j = 0; j < n; ++j) {
+                const float gj = g[j];
+                if (gj == gi) continue;
+                const float dj = disc[j];
+                // (pair_ij + pair_ji - single_i - single_j) in the reference's order of operations
+                const float delta = fabsf(__fsub_rn(__fsub_rn(__fadd_rn(__fmul_rn(gi, dj), __fmul_rn(gj, di)), single_i),
+                                                    __fmul_rn(gj, dj))) / idcg;
+                if (gi > gj) up += delta * (1.0f / (1.0f + expf(si - s[j])));
+                else down += delta * (1.0f / (1.0f + expf(s[j] - si)));
+            }
+        }
+        lambdas[b * L + i] = up - down;
+    }
+}
+
+int lambdarank_lambdas(int64_t B, int64_t L, const int64_t* ranking, const float* scores, const int64_t* lens, float* lambdas,
+                       cudaStream_t st) {
+    if (B <= 0 || L <= 0) return INTEL_OK;
+    INTEL_REQUIRE(ranking && scores && lens && lambdas, INTEL_ERR_ARG, "lambdarank: null pointer");
+    const size_t smem = (size_t)(1 + 2 * LR_WARPS) * L * 4;
+    INTEL_REQUIRE(smem <= 200 * 1024, INTEL_ERR_UNSUPPORTED, "lambdarank: list length %lld too long", (long long)L);
+    ensure_smem(lambdarank_kernel, smem);
+    LAUNCH(lambdarank_kernel, dim3((unsigned)ceil_div(B, LR_WARPS)), dim3(LR_WARPS * 32), smem, st, B, L, ranking, scores, lens,
+           lambdas);
+    return check_launch("lambdarank", (double)B * L * 16.0 + (double)B * 8.0, 0.0);
+}
+
 }  // namespace intel
 
 using namespace intel;
@@ -424,6 +503,11 @@ int intel_scale_by_device_scalar(int64_t n, const float* x, const double* a, dou
     unsigned grid = stream_grid(ceil_div(n, 256 * 4), 8);
     LAUNCH(scale_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, n, x, a, ca, b, cb, y);
     return check_launch("scale");
+}
+
+int intel_lambdarank_lambdas(int64_t B, int64_t L, const int64_t* ranking, const float* scores, const int64_t* session_len,
+                             float* lambdas, intel_stream_t stream) {
+    return lambdarank_lambdas(B, L, ranking, scores, session_len, lambdas, (cudaStream_t)stream);
 }
 
 }  // extern "C"

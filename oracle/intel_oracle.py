@@ -425,6 +425,38 @@ def awelv_int(sd: State, cfg: IntelConfig, batch: Dict[str, object]) -> Dict[str
     return {"weights": w, "ens_score": (w * scores).sum(dim=2), "intents": intent}
 
 
+def compute_lambda(true_scores: Tensor, temp_scores: Tensor, session_len: Tensor) -> Tensor:
+    """helpers/LambdaRankRunner.py:315-344 (compute_lambda_new) per session with explicit loops over the valid pairs:
+    Delta_ij = |g_i d_j + g_j d_i - g_i d_i - g_j d_j| / IDCG with g = 2^t - 1 and d_j = 1/log2(j+2) of the list slot j,
+    Rho_ij = 1/(1+exp(s_i-s_j)); Lambda_i = sum_{t_i>t_j} Delta Rho_ij - sum_{t_i<t_j} Delta Rho_ji.  IDCG = 0 -> NaN row."""
+    B, L = true_scores.shape
+    t = true_scores.clamp(min=0).numpy()
+    s = temp_scores.detach().numpy().astype(np.float32)
+    d = (1.0 / np.log2(np.arange(L, dtype=np.float32) + np.float32(2.0))).astype(np.float32)
+    out = np.zeros((B, L), dtype=np.float32)
+    for b in range(B):
+        n = min(int(session_len[b]), L)
+        g = (2.0 ** t[b] - 1).astype(np.float32)
+        ideal = np.sort(g)[::-1]
+        idcg = np.float32((ideal[:n].astype(np.float64) * d[:n]).sum())
+        if not idcg > 0:
+            out[b] = np.nan
+            continue
+        for i in range(n):
+            acc = 0.0
+            for j in range(n):
+                if t[b, i] == t[b, j]:
+                    continue
+                delta = np.float32(abs(np.float32(np.float32(np.float32(g[i] * d[j]) + np.float32(g[j] * d[i]))
+                                                  - np.float32(g[i] * d[i])) - np.float32(g[j] * d[j]))) / idcg
+                if t[b, i] > t[b, j]:
+                    acc += float(delta) / (1.0 + np.exp(np.float64(s[b, i]) - np.float64(s[b, j])))
+                else:
+                    acc -= float(delta) / (1.0 + np.exp(np.float64(s[b, j]) - np.float64(s[b, i])))
+            out[b, i] = acc
+    return torch.from_numpy(out)
+
+
 def random_fusion(batch: Dict[str, object], raw_weights: Tensor) -> Dict[str, Tensor]:
     """GeneralSeq.py:23-32 with the uniform draw passed in."""
     x = batch["scores"].float()

@@ -11,6 +11,7 @@ reference tree with three py3.12/numpy-2 import shims and calling
     BaseRunner.evaluate_intents        (helpers/BaseRunner.py:133-150)
     SingleSort/Borda.forward           (models/unsupervise/*.py)
     aWELv / aWELv_Int.forward          (models/supervise/*.py)
+    LambdaRankRunner.compute_lambda_new (helpers/LambdaRankRunner.py:315-344)
 
 on seeded synthetic batches from intel_sigir2023_b200.synthetic.  BPR's torch.rand_like
 is monkey-patched to return a saved noise tensor so its negative choice is replayable.
@@ -278,11 +279,40 @@ def make_awelv_int(ref):
         print(f"awelv_int_{name}: {os.path.getsize(path) / 1024:.0f} KiB  loss(list)=", out["loss.list"])
 
 
+def make_lambdarank(ref):
+    """LambdaRankRunner.compute_lambda_new (helpers/LambdaRankRunner.py:315-344) on ragged label sets: softmaxed scores
+    as LambdaRank.forward emits them (set S), wide raw scores (set W), and a set with sessions without positives (set Z:
+    IDCG = 0 -> NaN rows in the reference)."""
+    from helpers import LambdaRankRunner
+    fn = LambdaRankRunner.LambdaRankRunner.compute_lambda_new
+    out = {}
+    for tag, n, L, lo, seed in (("S", 24, 19, 2, 0), ("W", 16, 50, 50, 1), ("Z", 12, 9, 1, 2), ("L", 6, 130, 40, 3)):
+        pred, ranking, pos, slen = synthetic.eval_set(n, L, lo, seed=seed)
+        scores = pred.float()
+        if tag == "S":
+            scores = scores.softmax(dim=-1)
+        if tag == "W":
+            scores = scores * 6
+        if tag == "Z":
+            ranking[::3] = torch.where(ranking[::3] > 0, torch.zeros_like(ranking[::3]), ranking[::3])
+        true_scores = torch.clamp(ranking, min=0)
+        lam = fn(None, true_scores, scores, slen)
+        out[f"{tag}.ranking"], out[f"{tag}.scores"], out[f"{tag}.session_len"] = ranking.numpy(), scores.numpy(), slen.numpy()
+        out[f"{tag}.lambdas"] = lam.numpy()
+    path = os.path.join(ROOT, "tests", "golden", "lambdarank.npz")
+    np.savez_compressed(path, **out)
+    print("lambdarank:", os.path.getsize(path) // 1024, "KiB", {k: float(np.nanmax(np.abs(v))) for k, v in out.items() if k.endswith("lambdas")},
+          "nan rows in Z:", int(np.isnan(out["Z.lambdas"]).all(axis=1).sum()))
+
+
 if __name__ == "__main__":
     ref = import_reference()
     torch.set_num_threads(4)
     if "--awelv-only" in sys.argv:
         make_awelv(ref)
+        sys.exit(0)
+    if "--lambdarank-only" in sys.argv:
+        make_lambdarank(ref)
         sys.exit(0)
     if "--awelv-int-only" in sys.argv:
         make_awelv_int(ref)
@@ -292,3 +322,4 @@ if __name__ == "__main__":
     make_eval(ref)
     make_awelv(ref)
     make_awelv_int(ref)
+    make_lambdarank(ref)

@@ -329,6 +329,7 @@ static inline float __frcp_rn(float x) { return 1.0f / x; }
 static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
 static inline float __fmul_rn(float a, float b) { return a * b; }
 static inline float __fadd_rn(float a, float b) { return a + b; }
+static inline float __fsub_rn(float a, float b) { return a - b; }
 static inline float __fdiv_rn(float a, float b) { return a / b; }
 static inline float __fsqrt_rn(float a) { return sqrtf(a); }
 static inline float __saturatef(float x) { return x < 0 ? 0 : (x > 1 ? 1 : x); }

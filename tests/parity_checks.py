@@ -530,3 +530,37 @@ def check_awelv_int(device, name):
             assert p.grad is None and not np.any(z["grad.list." + n])
             continue
         assert_grad_close(p.grad.cpu().numpy(), z["grad.list." + n], gmax, n)
+
+
+def load_lambdarank_case(tag, device="cpu"):
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "lambdarank.npz"))
+    return tuple(torch.from_numpy(z[f"{tag}.{k}"]).to(device) for k in ("ranking", "scores", "session_len")) + (z[f"{tag}.lambdas"],)
+
+
+def assert_lambdas_close(got, ref):
+    """NaN rows (sessions without a positive item: 0/0 in the reference) must coincide; the rest within TOL of the inf-norm"""
+    got, ref = np.asarray(got), np.asarray(ref)
+    assert got.shape == ref.shape
+    assert np.array_equal(np.isnan(got), np.isnan(ref))
+    ok = ~np.isnan(ref)
+    assert rel_err(got[ok], ref[ok]) < TOL, rel_err(got[ok], ref[ok])
+
+
+def check_lambdarank(device):
+    """lambdarank.compute_lambda_new (one kernel) against arrays produced by the unmodified reference method
+    (helpers/LambdaRankRunner.py:315-344; oracle/make_golden.py:make_lambdarank), then against the oracle on a larger set"""
+    from intel_sigir2023_b200 import lambdarank, synthetic
+    for tag in ("S", "W", "Z", "L"):
+        ranking, scores, slen, ref = load_lambdarank_case(tag, device)
+        got = lambdarank.compute_lambda_new(ranking, scores, slen)                         # raw ranking: clamped by the kernel
+        assert_lambdas_close(got.cpu().numpy(), ref)
+        got2 = lambdarank.compute_lambda_new(torch.clamp(ranking, min=0), scores, slen)    # the reference's own call (:241-246)
+        assert np.array_equal(got.cpu().numpy(), got2.cpu().numpy(), equal_nan=True)
+        pad = torch.arange(ranking.shape[1], device=device)[None, :] >= slen[:, None]
+        assert not np.any(got.cpu().numpy()[(pad & ~torch.isnan(got)).cpu().numpy()])      # pad slots of live sessions: 0
+    pred, ranking, _, slen = synthetic.eval_set(37, 70, 5, seed=11)
+    scores = pred.float().softmax(dim=-1)
+    got = lambdarank.compute_lambda_new(ranking.to(device), scores.to(device), slen.to(device))
+    assert_lambdas_close(got.cpu().numpy(), O.compute_lambda(ranking, scores, slen).numpy())
+    empty = lambdarank.compute_lambda_new(ranking[:0].to(device), scores[:0].to(device), slen[:0].to(device))
+    assert tuple(empty.shape) == (0, 70)

@@ -97,6 +97,10 @@ def test_awelv_int_matches_reference_golden(name):
     P.check_awelv_int("cpu", name)
 
 
+def test_lambdarank_matches_reference_golden():
+    P.check_lambdarank("cpu")
+
+
 def test_fused_adam_matches_torch():
     P.check_adam("cpu")
 

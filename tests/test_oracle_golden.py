@@ -150,6 +150,14 @@ def test_oracle_awelv_int_matches_reference(name):
         assert np.abs(got - ref).max() <= 2e-5 * np.abs(ref).max() + 1e-6 * gmax, k
 
 
+@pytest.mark.parametrize("tag", ["S", "W", "Z", "L"])
+def test_oracle_lambdarank_matches_reference(tag):
+    """oracle.compute_lambda against the unmodified LambdaRankRunner.compute_lambda_new (tests/golden/lambdarank.npz)"""
+    import parity_checks as P
+    ranking, scores, slen, ref = P.load_lambdarank_case(tag)
+    P.assert_lambdas_close(O.compute_lambda(ranking, scores, slen).numpy(), ref)
+
+
 def test_host_pack_rows_skips_padding_rows_of_ragged_groups():
     """with per-session lengths only the real history rows are scanned: padding rows come out empty (whatever they
     hold - the model never reads them), real rows are packed as before"""
