@@ -209,6 +209,18 @@ int intel_awelv_bwd(int64_t B, int64_t L, int K, int h, const float* user_table,
                     const double* scores, const float* w_user, const float* d_weights, const float* d_ens, float* g_user_table,
                     float* g_model_table, intel_stream_t stream);
 
+/* ---- aWELv_IntEL head (models/supervise/aWELv_IntEL.py:190-201) ------------------------------------------
+ * The reference feeds the weight head the mean over all L list slots of the gated item / score streams; the head is
+ * affine, so that equals the mean over the slots of the per-slot head output of the cross_attention = 0 path
+ * (slot_weights [B,L,K] = the `weights` output of intel_ensemble_fwd with dims.cross_attention = 0):
+ * p = softmax_k(mean_l slot_weights), w = softmax_k(p) (softmax twice, :197-198), weights[b,l,:] = w, ens = sum_k w_k scores.
+ * p_sess, w_sess [B,K] are kept for the backward call, which writes d_slot_weights[b,l,k] = dlogits_k / L (every slot);
+ * d_weights / d_ens nullable.  K <= 16. */
+int intel_pool_head_fwd(int64_t B, int64_t L, int K, const float* slot_weights, const double* scores, float* weights,
+                        float* ens_score, float* p_sess, float* w_sess, intel_stream_t stream);
+int intel_pool_head_bwd(int64_t B, int64_t L, int K, const double* scores, const float* p_sess, const float* w_sess,
+                        const float* d_weights, const float* d_ens, float* d_slot_weights, intel_stream_t stream);
+
 /* ---- LambdaRank lambdas (helpers/LambdaRankRunner.py:315-344 compute_lambda_new, called at :246) ----------
  * lambdas[b,i] = sum_{j: t_i>t_j} Delta_ij Rho_ij - sum_{j: t_i<t_j} Delta_ji Rho_ji over the valid slots of session b, with
  * t = clamp(ranking, 0), Delta_ij = |g_i d_j + g_j d_i - g_i d_i - g_j d_j| / IDCG (g = 2^t - 1, d_j = 1/log2(j+2) of the list

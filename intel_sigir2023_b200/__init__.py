@@ -2,7 +2,7 @@
 from .config import IntelConfig  # noqa: F401
 
 __all__ = ["IntelConfig", "IntEL", "IntListloss", "IntBPRloss", "IntMSEloss", "Listloss", "BPRloss", "MSEloss",
-           "evaluate_method", "evaluate_intents", "SingleSort", "Borda", "RandomFusion", "aWELv", "aWELv_Int"]
+           "evaluate_method", "evaluate_intents", "SingleSort", "Borda", "RandomFusion", "aWELv", "aWELv_Int", "aWELv_IntEL"]
 
 
 def __getattr__(name):
@@ -16,7 +16,7 @@ def __getattr__(name):
     if name in ("evaluate_method", "evaluate_intents"):
         from . import evaluate
         return getattr(evaluate, name)
-    if name in ("SingleSort", "Borda", "RandomFusion", "aWELv", "aWELv_Int"):
+    if name in ("SingleSort", "Borda", "RandomFusion", "aWELv", "aWELv_Int", "aWELv_IntEL"):
         from . import baselines
         return getattr(baselines, name)
     raise AttributeError(name)

@@ -293,3 +293,60 @@ class aWELv_Int(nn.Module):
         params = [p for _, p in self.named_parameters()]
         w, ens, intents = _AWELvIntFn.apply(self, data, *params)
         return {"weights": w, "ens_score": ens, "intents": intents}
+
+
+class _PoolHeadFn(torch.autograd.Function):
+    """(per-slot head output [B,L,K] of the cross_attention = 0 path, scores) -> (weights [B,L,K], ens_score [B,L]) through
+    intel_pool_head_fwd / intel_pool_head_bwd: mean over the list slots, softmax twice, fusion."""
+
+    @staticmethod
+    def forward(ctx, slot_weights, scores):
+        lib = _lib.load()
+        B, L, K = scores.shape
+        dev = scores.device
+        weights = torch.empty(B, L, K, dtype=torch.float32, device=dev)
+        ens = torch.empty(B, L, dtype=torch.float32, device=dev)
+        p_sess = torch.empty(B, K, dtype=torch.float32, device=dev)
+        w_sess = torch.empty(B, K, dtype=torch.float32, device=dev)
+        _lib.check(lib.intel_pool_head_fwd(B, L, K, _lib.ptr(slot_weights.contiguous(), torch.float32),
+                                           _lib.ptr(scores, torch.float64), _lib.ptr(weights), _lib.ptr(ens), _lib.ptr(p_sess),
+                                           _lib.ptr(w_sess), _lib.stream_ptr(dev)))
+        ctx.save_for_backward(scores, p_sess, w_sess)
+        return weights, ens
+
+    @staticmethod
+    def backward(ctx, d_weights, d_ens):
+        lib = _lib.load()
+        scores, p_sess, w_sess = ctx.saved_tensors
+        B, L, K = scores.shape
+        d_slot = torch.empty(B, L, K, dtype=torch.float32, device=scores.device)
+        dw = d_weights.contiguous() if d_weights is not None else None
+        de = d_ens.contiguous() if d_ens is not None else None
+        _lib.check(lib.intel_pool_head_bwd(B, L, K, _lib.ptr(scores, torch.float64), _lib.ptr(p_sess), _lib.ptr(w_sess),
+                                           _lib.ptr(dw), _lib.ptr(de), _lib.ptr(d_slot), _lib.stream_ptr(scores.device)))
+        return d_slot, None
+
+
+def _intel_base():
+    from .IntEL import IntEL
+    return IntEL
+
+
+class aWELv_IntEL(_intel_base()):
+    """aWELv with IntEL's networks (models/supervise/aWELv_IntEL.py; script/baselines.sh:47): the intent predictor, the two
+    self-attention stacks and the gate form of the intent conditioning are IntEL's `cross_attention = 0` path unchanged
+    (same parameters, same registration order); the weight head then sees the unmasked mean over the list slots and its
+    output goes through softmax twice (aWELv_IntEL.py:190-201).  The head is affine, so the mean of its per-slot output is
+    its output on the mean: `intel_ensemble_fwd` + `intel_pool_head_fwd`, and the reverse for the gradients."""
+    extra_log_args = ['cross_attn_qsize', 'num_heads', 'num_layers', 'encoder', 'intent_emb_size']
+
+    def __init__(self, args, corpus=None, cfg=None):
+        import dataclasses
+        from .config import IntelConfig
+        cfg = cfg if cfg is not None else IntelConfig.from_args(args, corpus)
+        super().__init__(args, corpus, cfg=dataclasses.replace(cfg, cross_attention=0))
+
+    def forward(self, data: Dict[str, object]) -> Dict[str, torch.Tensor]:
+        out = super().forward(data)
+        w, ens = _PoolHeadFn.apply(out["weights"], data["scores"])
+        return {"weights": w, "ens_score": ens, "intents": out["intents"]}

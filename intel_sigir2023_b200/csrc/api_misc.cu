@@ -142,6 +142,16 @@ int intel_awelv_bwd(int64_t B, int64_t L, int K, int h, const float* user_table,
                      (cudaStream_t)stream);
 }
 
+int intel_pool_head_fwd(int64_t B, int64_t L, int K, const float* slot_weights, const double* scores, float* weights,
+                        float* ens_score, float* p_sess, float* w_sess, intel_stream_t stream) {
+    return pool_head_fwd(B, L, K, slot_weights, scores, weights, ens_score, p_sess, w_sess, (cudaStream_t)stream);
+}
+
+int intel_pool_head_bwd(int64_t B, int64_t L, int K, const double* scores, const float* p_sess, const float* w_sess,
+                        const float* d_weights, const float* d_ens, float* d_slot_weights, intel_stream_t stream) {
+    return pool_head_bwd(B, L, K, scores, p_sess, w_sess, d_weights, d_ens, d_slot_weights, (cudaStream_t)stream);
+}
+
 int intel_gather_fwd(int64_t rows, int d, const float* table, const int64_t* idx, float* out, int ld_out, int relu,
                      intel_stream_t stream) {
     return gather_rows(rows, d, table, idx, out, ld_out, relu, (cudaStream_t)stream);

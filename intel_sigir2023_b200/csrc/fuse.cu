@@ -367,4 +367,115 @@ int awelv_bwd(int64_t B, int64_t L, int K, int h, const float* U, const float* M
     return check_launch("awelv_bwd", (double)B * L * K * 12.0 + (double)B * L * 4.0, 4.0 * B * L * K);
 }
 
+// ------------------------------------------------------------------------------------------------
+// aWELv_IntEL head (models/supervise/aWELv_IntEL.py:190-201): the weight head reads the MEAN over all L list slots (pads
+// included) of the gated streams.  The head is affine, so its output equals the mean over the slots of the per-slot
+// head output of the cross_attention = 0 path (Wl [B,L,K], intel_ensemble_fwd): logits = mean_l Wl[b,l,:],
+// p = softmax(logits), w = softmax(p) (the reference applies softmax twice, :197-198), weights[b,l,:] = w,
+// ens[b,l] = sum_k w_k score_k.  One warp per session; p and w [B,K] are kept for the backward pass, which returns
+// dWl[b,l,k] = dlogits_k / L.
+__global__ void __launch_bounds__(256) pool_head_fwd_kernel(int64_t B, int64_t L, int K, const float* __restrict__ Wl,
+                                                            const double* __restrict__ scores, float* __restrict__ weights,
+                                                            float* __restrict__ ens, float* __restrict__ p_out,
+                                                            float* __restrict__ w_out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (b >= B) return;
+    float w[AW_MAX_K];
+#pragma unroll
+    for (int k = 0; k < AW_MAX_K; ++k) w[k] = 0.f;
+    for (int64_t l = lane; l < L; l += 32)
+#pragma unroll
+        for (int k = 0; k < AW_MAX_K; ++k)
+            if (k < K) w[k] += Wl[(b * L + l) * K + k];
+    const float inv_l = 1.0f / (float)L;
+    for (int pass = 0; pass < 2; ++pass) {          // pass 0: p = softmax(mean), pass 1: w = softmax(p)
+        float mx = -INFINITY, sum = 0.f;
+#pragma unroll
+        for (int k = 0; k < AW_MAX_K; ++k)
+            if (k < K) {
+                if (pass == 0) w[k] = warp_sum(w[k]) * inv_l;
+                mx = fmaxf(mx, w[k]);
+            }
+#pragma unroll
+        for (int k = 0; k < AW_MAX_K; ++k)
+            if (k < K) { w[k] = expf(w[k] - mx); sum += w[k]; }
+        const float inv = 1.0f / sum;
+#pragma unroll
+        for (int k = 0; k < AW_MAX_K; ++k)
+            if (k < K) {
+                w[k] *= inv;
+                if (lane == 0) (pass == 0 ? p_out : w_out)[b * K + k] = w[k];
+            }
+    }
+    for (int64_t l = lane; l < L; l += 32) {
+        float e = 0.f;
+#pragma unroll
+        for (int k = 0; k < AW_MAX_K; ++k)
+            if (k < K) {
+                weights[(b * L + l) * K + k] = w[k];
+                e = __fadd_rn(e, __fmul_rn(w[k], (float)scores[(b * L + l) * K + k]));
+            }
+        ens[b * L + l] = e;
+    }
+}
+
+__global__ void __launch_bounds__(256) pool_head_bwd_kernel(int64_t B, int64_t L, int K, const double* __restrict__ scores,
+                                                            const float* __restrict__ p_in, const float* __restrict__ w_in,
+                                                            const float* __restrict__ d_weights, const float* __restrict__ d_ens,
+                                                            float* __restrict__ dWl) {
+    const int lane = threadIdx.x & 31;
+    const int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (b >= B) return;
+    float g[AW_MAX_K];
+#pragma unroll
+    for (int k = 0; k < AW_MAX_K; ++k) g[k] = 0.f;
+    for (int64_t l = lane; l < L; l += 32) {
+        const float de = d_ens ? d_ens[b * L + l] : 0.f;
+#pragma unroll
+        for (int k = 0; k < AW_MAX_K; ++k)
+            if (k < K) {
+                float t = de * (float)scores[(b * L + l) * K + k];
+                if (d_weights) t += d_weights[(b * L + l) * K + k];
+                g[k] += t;
+            }
+    }
+#pragma unroll
+    for (int k = 0; k < AW_MAX_K; ++k)
+        if (k < K) g[k] = warp_sum(g[k]);
+    for (int pass = 0; pass < 2; ++pass) {          // back through w = softmax(p), then p = softmax(logits)
+        const float* y = pass == 0 ? w_in : p_in;
+        float dot = 0.f;
+#pragma unroll
+        for (int k = 0; k < AW_MAX_K; ++k)
+            if (k < K) dot = fmaf(g[k], y[b * K + k], dot);
+#pragma unroll
+        for (int k = 0; k < AW_MAX_K; ++k)
+            if (k < K) g[k] = y[b * K + k] * (g[k] - dot);
+    }
+    const float inv_l = 1.0f / (float)L;
+    for (int64_t l = lane; l < L; l += 32)
+#pragma unroll
+        for (int k = 0; k < AW_MAX_K; ++k)
+            if (k < K) dWl[(b * L + l) * K + k] = g[k] * inv_l;
+}
+
+int pool_head_fwd(int64_t B, int64_t L, int K, const float* Wl, const double* scores, float* weights, float* ens, float* p,
+                  float* w, cudaStream_t s) {
+    if (B <= 0 || L <= 0) return INTEL_OK;
+    INTEL_REQUIRE(K >= 1 && K <= AW_MAX_K, INTEL_ERR_UNSUPPORTED, "aWELv_IntEL: model_num %d > %d", K, AW_MAX_K);
+    INTEL_REQUIRE(Wl && scores && weights && ens && p && w, INTEL_ERR_ARG, "pool_head_fwd: null pointer");
+    LAUNCH(pool_head_fwd_kernel, dim3((unsigned)ceil_div(B, 8)), dim3(256), 0, s, B, L, K, Wl, scores, weights, ens, p, w);
+    return check_launch("pool_head_fwd", (double)B * L * K * 16.0 + (double)B * L * 4.0, 2.0 * B * L * K);
+}
+
+int pool_head_bwd(int64_t B, int64_t L, int K, const double* scores, const float* p, const float* w, const float* d_weights,
+                  const float* d_ens, float* dWl, cudaStream_t s) {
+    if (B <= 0 || L <= 0) return INTEL_OK;
+    INTEL_REQUIRE(K >= 1 && K <= AW_MAX_K, INTEL_ERR_UNSUPPORTED, "aWELv_IntEL: model_num %d > %d", K, AW_MAX_K);
+    INTEL_REQUIRE(scores && p && w && dWl, INTEL_ERR_ARG, "pool_head_bwd: null pointer");
+    LAUNCH(pool_head_bwd_kernel, dim3((unsigned)ceil_div(B, 8)), dim3(256), 0, s, B, L, K, scores, p, w, d_weights, d_ens, dWl);
+    return check_launch("pool_head_bwd", (double)B * L * K * 16.0 + (double)B * L * 4.0, 4.0 * B * L * K);
+}
+
 }  // namespace intel

@@ -125,6 +125,10 @@ struct StackSaved { float* const* QKV; float* const* A; float* const* U; float* 
 int adam_step(int count, float* const* params, const float* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
               const int64_t* numel, const float* weight_decay, double lr, double beta1, double beta2, double eps, int64_t step,
               cudaStream_t s);
+int pool_head_fwd(int64_t B, int64_t L, int K, const float* Wl, const double* scores, float* weights, float* ens, float* p,
+                  float* w, cudaStream_t s);
+int pool_head_bwd(int64_t B, int64_t L, int K, const double* scores, const float* p, const float* w, const float* d_weights,
+                  const float* d_ens, float* dWl, cudaStream_t s);
 int awelv_fwd(int64_t B, int64_t L, int K, int h, const float* U, const float* M, const int64_t* uid, const double* scores,
               float* weights, float* ens, float* wsmall, cudaStream_t s);
 int awelv_bwd(int64_t B, int64_t L, int K, int h, const float* U, const float* M, const int64_t* uid, const double* scores,

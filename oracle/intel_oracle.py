@@ -425,6 +425,31 @@ def awelv_int(sd: State, cfg: IntelConfig, batch: Dict[str, object]) -> Dict[str
     return {"weights": w, "ens_score": (w * scores).sum(dim=2), "intents": intent}
 
 
+def awelv_intel(sd: State, cfg: IntelConfig, batch: Dict[str, object]) -> Dict[str, Tensor]:
+    """models/supervise/aWELv_IntEL.py:113-201: IntEL's intent predictor and self-attention stacks, the gate form of the
+    intent conditioning (h * MLP(intent)), then ONE weight vector per session from the unmasked mean over the list slots
+    of the gated streams, softmax applied twice (:197-198)."""
+    dt = sd["pred_layer.weight"].dtype
+    intent = predict_intent(sd, cfg, batch)
+    items, scores = batch["i_id_s"], batch["scores"].to(dt)
+    h_i = sd["iid_embeddings.weight"][items]
+    if "item_embeddings.weight" in sd:
+        h_i = torch.cat([h_i, sd["item_embeddings.weight"][batch["i_class_c"]]], dim=2)
+    h_u = torch.relu(sd["uid_embeddings.weight"][batch["u_id_c"]])
+    h_i = _self_att_stack(sd, "i", h_i, cfg)
+    h_s = _self_att_stack(sd, "s", _lin(sd, "score_embeddings", scores), cfg)
+
+    def mlp(name):
+        t = torch.relu(intent @ sd[f"{name}.0.weight"].t() + sd[f"{name}.0.bias"])
+        return (t @ sd[f"{name}.2.weight"].t())[:, None, :]
+    x_i = (h_i * mlp("intent_item_embeddings")).mean(dim=1)
+    x_s = (h_s * mlp("intent_score_embeddings")).mean(dim=1)
+    h_int = torch.relu(_lin(sd, "intent_embeddings", intent))
+    w = _lin(sd, "weight_embeddings", torch.cat([x_i, x_s, h_u, h_int], dim=-1)).softmax(dim=-1)
+    w = w.unsqueeze(1).repeat(1, items.size(1), 1).softmax(dim=-1)
+    return {"weights": w, "ens_score": (w * scores).sum(dim=2), "intents": intent}
+
+
 def compute_lambda(true_scores: Tensor, temp_scores: Tensor, session_len: Tensor) -> Tensor:
     """helpers/LambdaRankRunner.py:315-344 (compute_lambda_new) per session with explicit loops over the valid pairs:
     Delta_ij = |g_i d_j + g_j d_i - g_i d_i - g_j d_j| / IDCG with g = 2^t - 1 and d_j = 1/log2(j+2) of the list slot j,

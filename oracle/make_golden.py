@@ -10,7 +10,7 @@ reference tree with three py3.12/numpy-2 import shims and calling
     BaseRunner.evaluate_method         (helpers/BaseRunner.py:57-131)
     BaseRunner.evaluate_intents        (helpers/BaseRunner.py:133-150)
     SingleSort/Borda.forward           (models/unsupervise/*.py)
-    aWELv / aWELv_Int.forward          (models/supervise/*.py)
+    aWELv / aWELv_Int / aWELv_IntEL.forward (models/supervise/*.py)
     LambdaRankRunner.compute_lambda_new (helpers/LambdaRankRunner.py:315-344)
 
 on seeded synthetic batches from intel_sigir2023_b200.synthetic.  BPR's torch.rand_like
@@ -49,10 +49,10 @@ def import_reference():
     sys.path.insert(0, REF_SRC)
     from models.IntEL import IntEL as ref_intel
     from models.unsupervise import SingleSort as ref_single, Borda as ref_borda
-    from models.supervise import aWELv as ref_awelv, aWELv_Int as ref_awelv_int
+    from models.supervise import aWELv as ref_awelv, aWELv_Int as ref_awelv_int, aWELv_IntEL as ref_awelv_intel
     from loss import IntListloss, IntBPRloss, IntMSEloss, Listloss
     from helpers import BaseRunner
-    return dict(aWELv=ref_awelv.aWELv, aWELv_Int=ref_awelv_int.aWELv_Int, Listloss=Listloss.Listloss, IntEL=ref_intel.IntEL, SingleSort=ref_single.SingleSort, Borda=ref_borda.Borda,
+    return dict(aWELv=ref_awelv.aWELv, aWELv_Int=ref_awelv_int.aWELv_Int, aWELv_IntEL=ref_awelv_intel.aWELv_IntEL, Listloss=Listloss.Listloss, IntEL=ref_intel.IntEL, SingleSort=ref_single.SingleSort, Borda=ref_borda.Borda,
                 list=IntListloss.IntListloss, bpr=IntBPRloss.IntBPRloss, mse=IntMSEloss.IntMSEloss,
                 BaseRunner=BaseRunner.BaseRunner)
 
@@ -244,9 +244,26 @@ AWELV_INT_CASES = {
 }
 
 
-def make_awelv_int(ref):
+AWELV_INTEL_CASES = {
+    # the script's flags (script/baselines.sh:47: GRU4Rec, u_emb 16, 2 heads, 2 layers) and the bare defaults (BERT4Rec, 1/1)
+    "gru": (dict(encoder="GRU4Rec", context_emb_size=32, intent_emb_size=32, cross_attn_qsize=64, num_heads=2, num_layers=2,
+                 u_emb_size=16, cross_attention=0),
+            dict(n_item=70, n_class=7, n_user=19, n_ctx=11, model_num=3, intent_num=27, history_max=6),
+            dict(batch_size=7, max_len=15, min_len=2), 8),
+    "bert": (dict(encoder="BERT4Rec", cross_attention=0),
+             dict(n_item=50, n_class=5, n_user=12, n_ctx=9, model_num=4, intent_num=20, history_max=8),
+             dict(batch_size=6, max_len=11, min_len=1), 9),
+}
+
+
+def make_awelv_intel(ref):
+    """aWELv_IntEL.forward (models/supervise/aWELv_IntEL.py:113-201) + IntListloss."""
+    make_awelv_int(ref, model_key="aWELv_IntEL", cases=AWELV_INTEL_CASES, prefix="awelv_intel")
+
+
+def make_awelv_int(ref, model_key="aWELv_Int", cases=None, prefix="awelv_int"):
     """aWELv_Int.forward (models/supervise/aWELv_Int.py:66-113) + IntListloss (script/baselines.sh:40)."""
-    for name, (over, csz, bsz, seed) in AWELV_INT_CASES.items():
+    for name, (over, csz, bsz, seed) in (cases or AWELV_INT_CASES).items():
         corpus = synthetic.CorpusSpec(**csz)
         cfg = IntelConfig(item_rows=corpus.item_rows, class_rows=corpus.n_class, user_rows=corpus.user_rows,
                           ctx_rows=corpus.n_ctx, intent_num=corpus.intent_num, model_num=corpus.model_num,
@@ -254,7 +271,7 @@ def make_awelv_int(ref):
         batch = synthetic.make_batch(corpus, synthetic.BatchSpec(**bsz), seed=seed)
         args = _args(cfg, user_emb_size=cfg.u_emb_size)
         torch.manual_seed(200 + seed)
-        model = ref["aWELv_Int"](args, _Corpus(cfg))
+        model = ref[model_key](args, _Corpus(cfg))
         with torch.no_grad():
             for n, p in model.named_parameters():
                 if "layer_norm" in n:
@@ -274,9 +291,9 @@ def make_awelv_int(ref):
         out["loss.list"] = np.array([loss.item(), ens_l.item(), int_l.item()], dtype=np.float64)
         for n, p in model.named_parameters():
             out["grad.list." + n] = (p.grad if p.grad is not None else torch.zeros_like(p)).numpy().copy()
-        path = os.path.join(ROOT, "tests", "golden", f"awelv_int_{name}.npz")
+        path = os.path.join(ROOT, "tests", "golden", f"{prefix}_{name}.npz")
         np.savez_compressed(path, **out)
-        print(f"awelv_int_{name}: {os.path.getsize(path) / 1024:.0f} KiB  loss(list)=", out["loss.list"])
+        print(f"{prefix}_{name}: {os.path.getsize(path) / 1024:.0f} KiB  loss(list)=", out["loss.list"])
 
 
 def make_lambdarank(ref):
@@ -314,6 +331,9 @@ if __name__ == "__main__":
     if "--lambdarank-only" in sys.argv:
         make_lambdarank(ref)
         sys.exit(0)
+    if "--awelv-intel-only" in sys.argv:
+        make_awelv_intel(ref)
+        sys.exit(0)
     if "--awelv-int-only" in sys.argv:
         make_awelv_int(ref)
         sys.exit(0)
@@ -322,4 +342,5 @@ if __name__ == "__main__":
     make_eval(ref)
     make_awelv(ref)
     make_awelv_int(ref)
+    make_awelv_intel(ref)
     make_lambdarank(ref)

@@ -493,11 +493,11 @@ def check_awelv(device):
         assert_grad_close(p.grad.cpu().numpy(), z["grad.list." + n], gmax, n, rtol=1e-4, afrac=2e-6)
 
 
-def load_awelv_int_case(name, device="cpu"):
+def load_awelv_int_case(name, device="cpu", prefix="awelv_int"):
     """-> (cfg, batch, state, npz) from tests/golden/awelv_int_<name>.npz (oracle/make_golden.py:make_awelv_int)"""
     import json
     from intel_sigir2023_b200.config import IntelConfig
-    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"awelv_int_{name}.npz"))
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"{prefix}_{name}.npz"))
     cfg = IntelConfig(**json.loads(bytes(z["cfg"]).decode()))
     batch = {k[6:]: torch.from_numpy(z[k]).to(device) for k in z.files if k.startswith("batch.")}
     batch["batch_size"] = int(batch["i_id_s"].shape[0])
@@ -564,3 +564,26 @@ def check_lambdarank(device):
     assert_lambdas_close(got.cpu().numpy(), O.compute_lambda(ranking, scores, slen).numpy())
     empty = lambdarank.compute_lambda_new(ranking[:0].to(device), scores[:0].to(device), slen[:0].to(device))
     assert tuple(empty.shape) == (0, 70)
+
+
+def check_awelv_intel(device, name):
+    """baselines.aWELv_IntEL (IntEL's gate path + the pooled, twice-softmaxed head) + IntListloss against arrays produced by
+    the unmodified reference model (models/supervise/aWELv_IntEL.py, script/baselines.sh:47)"""
+    import argparse
+    from intel_sigir2023_b200 import baselines, losses
+    cfg, batch, state, z = load_awelv_int_case(name, device, prefix="awelv_intel")
+    model = baselines.aWELv_IntEL(argparse.Namespace(device=device, model_path="", buffer=1), cfg=cfg)
+    assert [n for n, _ in model.named_parameters()] == list(state.keys())       # the reference's registration order
+    model.load_state_dict(state)
+    model = model.to(device)
+    out = model(batch)
+    for k in ("intents", "weights", "ens_score"):
+        assert rel_err(out[k].detach().cpu().numpy(), z["out." + k]) < TOL, k
+    crit = losses.IntListloss(argparse.Namespace(**LOSS_KW))
+    loss, ens_l, int_l = crit(out, batch)
+    for got, ref in zip((loss, ens_l, int_l), z["loss.list"]):
+        assert abs(float(got.detach()) - float(ref)) <= TOL * abs(float(ref)), (float(got.detach()), float(ref))
+    loss.backward()
+    gmax = max(float(np.abs(z["grad.list." + n]).max()) for n, _ in model.named_parameters())
+    for n, p in model.named_parameters():
+        assert_grad_close(p.grad.cpu().numpy(), z["grad.list." + n], gmax, n)

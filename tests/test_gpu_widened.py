@@ -24,6 +24,11 @@ def test_awelv_int_matches_reference_golden(name):
     P.check_awelv_int(DEV, name)
 
 
+@pytest.mark.parametrize("name", ["gru", "bert"])
+def test_awelv_intel_matches_reference_golden(name):
+    P.check_awelv_intel(DEV, name)
+
+
 def test_lambdarank_matches_reference_golden():
     P.check_lambdarank(DEV)
 

@@ -150,6 +150,25 @@ def test_oracle_awelv_int_matches_reference(name):
         assert np.abs(got - ref).max() <= 2e-5 * np.abs(ref).max() + 1e-6 * gmax, k
 
 
+@pytest.mark.parametrize("name", ["gru", "bert"])
+def test_oracle_awelv_intel_matches_reference(name):
+    """oracle.awelv_intel + IntListloss against the unmodified reference aWELv_IntEL model (tests/golden/awelv_intel_*.npz)"""
+    import parity_checks as P
+    cfg, batch, state, z = P.load_awelv_int_case(name, prefix="awelv_intel")
+    sd = {k: v.clone().requires_grad_(True) for k, v in state.items()}
+    out = O.awelv_intel(sd, cfg, batch)
+    for k in ("intents", "weights", "ens_score"):
+        assert np.abs(out[k].detach().numpy() - z["out." + k]).max() < 2e-6, k
+    loss, ens_l, int_l = O.total_loss("list", out, batch, **LOSS_KW)
+    for got, ref in zip((loss, ens_l, int_l), z["loss.list"]):
+        assert abs(got.item() - float(ref)) < 2e-6 * max(1.0, abs(float(ref)))
+    loss.backward()
+    gmax = max(float(np.abs(z["grad.list." + k]).max()) for k in sd)
+    for k, v in sd.items():
+        ref = z["grad.list." + k]
+        assert np.abs(v.grad.numpy() - ref).max() <= 2e-5 * np.abs(ref).max() + 1e-6 * gmax, k
+
+
 @pytest.mark.parametrize("tag", ["S", "W", "Z", "L"])
 def test_oracle_lambdarank_matches_reference(tag):
     """oracle.compute_lambda against the unmodified LambdaRankRunner.compute_lambda_new (tests/golden/lambdarank.npz)"""
