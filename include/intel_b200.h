@@ -275,6 +275,18 @@ int intel_linear_dx(int64_t M, int64_t N, int64_t K, const float* dY, const floa
                     intel_stream_t stream);
 int intel_linear_dw(int64_t M, int64_t N, int64_t K, const float* dY, const float* X, float* dW, float* db,
                     intel_stream_t stream);
+/* the same three passes with leading dimensions and the ReLU of an MLP folded in (nn.Sequential(Linear, ReLU, ...), e.g.
+ * models/supervise/LambdaRank.py:30-37): relu_a applies max(.,0) to A on load, relu_mask [M,K] (pre-activations, leading
+ * dimension ldmask) gates dX, relu_x applies max(.,0) to X on load.  W is [N,K] dense, dY is [M,N] dense. */
+int intel_linear_fwd_ex(int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* W, const float* bias,
+                        float* C, int64_t ldc, int relu_a, intel_stream_t stream);
+int intel_linear_dx_ex(int64_t M, int64_t N, int64_t K, const float* dY, const float* W, float* dX, int64_t lddx,
+                       const float* relu_mask, int64_t ldmask, intel_stream_t stream);
+int intel_linear_dw_ex(int64_t M, int64_t N, int64_t K, const float* dY, const float* X, int64_t ldx, float* dW, float* db,
+                       int relu_x, intel_stream_t stream);
+/* P = softmax over each row of Z [R,N] (Tensor.softmax(dim=-1)); dZ = P * (dP - sum(P dP)) */
+int intel_softmax_rows_fwd(int64_t R, int64_t N, const float* Z, float* P, intel_stream_t stream);
+int intel_softmax_rows_bwd(int64_t R, int64_t N, const float* P, const float* dP, float* dZ, intel_stream_t stream);
 /* layers.py MultiHeadAttention core on packed qkv [B,T,3d] -> out [B,T,d]; lens nullable (key mask) */
 int intel_mha_fwd(int64_t B, int64_t T, int d, int heads, const float* qkv, const int64_t* lens, float* out,
                   intel_stream_t stream);

@@ -93,6 +93,11 @@ def _declare(lib: C.CDLL) -> None:
         "intel_linear_fwd": (i32, [i64, i64, i64, _p, _p, _p, _p, _p]),
         "intel_linear_dx": (i32, [i64, i64, i64, _p, _p, _p, _p, _p]),
         "intel_linear_dw": (i32, [i64, i64, i64, _p, _p, _p, _p, _p]),
+        "intel_linear_fwd_ex": (i32, [i64, i64, i64, _p, i64, _p, _p, _p, i64, i32, _p]),
+        "intel_linear_dx_ex": (i32, [i64, i64, i64, _p, _p, _p, i64, _p, i64, _p]),
+        "intel_linear_dw_ex": (i32, [i64, i64, i64, _p, _p, i64, _p, _p, i32, _p]),
+        "intel_softmax_rows_fwd": (i32, [i64, i64, _p, _p, _p]),
+        "intel_softmax_rows_bwd": (i32, [i64, i64, _p, _p, _p, _p]),
         "intel_mha_fwd": (i32, [i64, i64, i32, i32, _p, _p, _p, _p]),
         "intel_mha_bwd": (i32, [i64, i64, i32, i32, _p, _p, _p, _p, _p]),
         "intel_debug_use_fused_stack": (i32, [i32]),
@@ -122,7 +127,8 @@ EXPORTED = ["intel_last_error", "intel_abi_version", "intel_intent_workspace_byt
             "intel_rank_lists", "intel_gather_fwd", "intel_scatter_add_bwd", "intel_linear_fwd",
             "intel_profile_enable", "intel_profile_report", "intel_linear_dx", "intel_linear_dw", "intel_mha_fwd",
             "intel_mha_bwd", "intel_debug_use_fused_stack", "intel_debug_stack_sessions_per_cta", "intel_debug_use_tcgen05_gemm", "intel_host_pack_rows", "intel_adam_step", "intel_awelv_fwd", "intel_awelv_bwd",
-            "intel_lambdarank_lambdas", "intel_pool_head_fwd", "intel_pool_head_bwd"]
+            "intel_lambdarank_lambdas", "intel_pool_head_fwd", "intel_pool_head_bwd",
+            "intel_linear_fwd_ex", "intel_linear_dx_ex", "intel_linear_dw_ex", "intel_softmax_rows_fwd", "intel_softmax_rows_bwd"]
 
 
 def load(path: Optional[str] = None) -> C.CDLL:

@@ -177,6 +177,29 @@ int intel_linear_dw(int64_t M, int64_t N, int64_t K, const float* dY, const floa
     return linear_dw(M, N, K, dY, N, X, K, dW, K, db, (cudaStream_t)stream, false);
 }
 
+int intel_linear_fwd_ex(int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* W, const float* bias,
+                        float* C, int64_t ldc, int relu_a, intel_stream_t stream) {
+    return linear(M, N, K, A, lda, W, K, bias, C, ldc, (cudaStream_t)stream, relu_a != 0, false);
+}
+
+int intel_linear_dx_ex(int64_t M, int64_t N, int64_t K, const float* dY, const float* W, float* dX, int64_t lddx,
+                       const float* relu_mask, int64_t ldmask, intel_stream_t stream) {
+    return linear_dx(M, N, K, dY, N, W, K, dX, lddx, (cudaStream_t)stream, 0, relu_mask, ldmask);
+}
+
+int intel_linear_dw_ex(int64_t M, int64_t N, int64_t K, const float* dY, const float* X, int64_t ldx, float* dW, float* db,
+                       int relu_x, intel_stream_t stream) {
+    return linear_dw(M, N, K, dY, N, X, ldx, dW, K, db, (cudaStream_t)stream, relu_x != 0);
+}
+
+int intel_softmax_rows_fwd(int64_t R, int64_t N, const float* Z, float* P, intel_stream_t stream) {
+    return softmax_rows(R, N, Z, P, (cudaStream_t)stream);
+}
+
+int intel_softmax_rows_bwd(int64_t R, int64_t N, const float* P, const float* dP, float* dZ, intel_stream_t stream) {
+    return softmax_rows_bwd(R, N, P, dP, nullptr, dZ, (cudaStream_t)stream);
+}
+
 int intel_mha_fwd(int64_t B, int64_t T, int d, int heads, const float* qkv, const int64_t* lens, float* out,
                   intel_stream_t stream) {
     return mha_fwd(B, T, d, heads, qkv, lens, out, (cudaStream_t)stream);

@@ -450,6 +450,18 @@ def awelv_intel(sd: State, cfg: IntelConfig, batch: Dict[str, object]) -> Dict[s
     return {"weights": w, "ens_score": (w * scores).sum(dim=2), "intents": intent}
 
 
+def lambdarank_scorer(sd: State, batch: Dict[str, object]) -> Dict[str, Tensor]:
+    """models/supervise/LambdaRank.py:39-47: MLP over [E_iid || category id || scores] per slot, softmax over the padded list."""
+    scores = batch["scores"].float()
+    h = torch.cat([sd["iid_embeddings.weight"][batch["i_id_s"]], batch["i_class_c"].unsqueeze(2).float(), scores], dim=2)
+    n_lin = sum(1 for k in sd if k.startswith("mlp.Linear-") and k.endswith(".weight"))
+    for i in range(n_lin):
+        h = h @ sd[f"mlp.Linear-{i}.weight"].t() + sd[f"mlp.Linear-{i}.bias"]
+        if i < n_lin - 1:
+            h = torch.relu(h)
+    return {"weights": torch.zeros_like(scores), "ens_score": h.squeeze(-1).softmax(dim=-1)}
+
+
 def compute_lambda(true_scores: Tensor, temp_scores: Tensor, session_len: Tensor) -> Tensor:
     """helpers/LambdaRankRunner.py:315-344 (compute_lambda_new) per session with explicit loops over the valid pairs:
     Delta_ij = |g_i d_j + g_j d_i - g_i d_i - g_j d_j| / IDCG with g = 2^t - 1 and d_j = 1/log2(j+2) of the list slot j,

@@ -296,6 +296,42 @@ def make_awelv_int(ref, model_key="aWELv_Int", cases=None, prefix="awelv_int"):
         print(f"{prefix}_{name}: {os.path.getsize(path) / 1024:.0f} KiB  loss(list)=", out["loss.list"])
 
 
+def make_lambdarank_model(ref):
+    """LambdaRank.forward (models/supervise/LambdaRank.py:39-47) and one training signal of LambdaRankRunner.fit (:240-259):
+    lambdas = compute_lambda_new(clamp(ranking, 0), ens.detach(), session_len); ens.backward(lambdas)."""
+    from models.supervise import LambdaRank as ref_lr
+    from helpers import LambdaRankRunner
+    for name, hidden, K, seed in (("h32", "32", 3, 12), ("h24_8", "24,8", 4, 13)):
+        corpus = synthetic.CorpusSpec(n_item=60, n_class=9, n_user=7, n_ctx=5, model_num=K, intent_num=6, history_max=2)
+        cfg = IntelConfig(item_rows=corpus.item_rows, class_rows=corpus.n_class, user_rows=corpus.user_rows,
+                          ctx_rows=corpus.n_ctx, intent_num=corpus.intent_num, model_num=K, history_max=2)
+        batch = synthetic.make_batch(corpus, synthetic.BatchSpec(batch_size=8, max_len=13, min_len=2), seed=seed)
+        args = _args(cfg, hidden_size=hidden, i_emb_size=32)
+        torch.manual_seed(300 + seed)
+        model = ref_lr.LambdaRank(args, _Corpus(cfg))
+        model.eval()
+        out = {"hidden_size": np.frombuffer(hidden.encode(), dtype=np.uint8), "model_num": np.array([K]),
+               "item_rows": np.array([cfg.item_rows])}
+        for k, v in batch.items():
+            if torch.is_tensor(v):
+                out["batch." + k] = v.numpy()
+        for k, v in model.state_dict().items():
+            out["state." + k] = v.detach().numpy().copy()
+        res = model(dict(batch))
+        ens = res["ens_score"]
+        lam = LambdaRankRunner.LambdaRankRunner.compute_lambda_new(None, torch.clamp(batch["ranking"], min=0), ens.detach(),
+                                                                   batch["session_len"])
+        lam = torch.nan_to_num(lam, nan=0.0)        # sessions without positives: the reference stops on NaN (:247-255)
+        model.zero_grad()
+        ens.backward(lam)
+        out["out.ens_score"], out["out.weights"], out["lambdas"] = ens.detach().numpy().copy(), res["weights"].numpy().copy(), lam.numpy()
+        for n, p in model.named_parameters():
+            out["grad." + n] = p.grad.numpy().copy()
+        path = os.path.join(ROOT, "tests", "golden", f"lambdarank_model_{name}.npz")
+        np.savez_compressed(path, **out)
+        print(f"lambdarank_model_{name}: {os.path.getsize(path) // 1024} KiB", float(np.abs(out["grad.iid_embeddings.weight"]).max()))
+
+
 def make_lambdarank(ref):
     """LambdaRankRunner.compute_lambda_new (helpers/LambdaRankRunner.py:315-344) on ragged label sets: softmaxed scores
     as LambdaRank.forward emits them (set S), wide raw scores (set W), and a set with sessions without positives (set Z:
@@ -330,6 +366,7 @@ if __name__ == "__main__":
         sys.exit(0)
     if "--lambdarank-only" in sys.argv:
         make_lambdarank(ref)
+        make_lambdarank_model(ref)
         sys.exit(0)
     if "--awelv-intel-only" in sys.argv:
         make_awelv_intel(ref)
@@ -344,3 +381,4 @@ if __name__ == "__main__":
     make_awelv_int(ref)
     make_awelv_intel(ref)
     make_lambdarank(ref)
+    make_lambdarank_model(ref)

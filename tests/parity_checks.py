@@ -587,3 +587,34 @@ def check_awelv_intel(device, name):
     gmax = max(float(np.abs(z["grad.list." + n]).max()) for n, _ in model.named_parameters())
     for n, p in model.named_parameters():
         assert_grad_close(p.grad.cpu().numpy(), z["grad.list." + n], gmax, n)
+
+
+def load_lambdarank_model_case(name, device="cpu"):
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"lambdarank_model_{name}.npz"))
+    batch = {k[6:]: torch.from_numpy(z[k]).to(device) for k in z.files if k.startswith("batch.")}
+    state = {k[6:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("state.")}
+    return z, batch, state
+
+
+def check_lambdarank_model(device, name):
+    """lambdarank.LambdaRank (gather + MLP + list softmax) and one training signal of LambdaRankRunner.fit (lambdas, then
+    ens_score.backward(lambdas)) against arrays produced by the unmodified reference model and runner method"""
+    import argparse
+    from intel_sigir2023_b200 import lambdarank
+    z, batch, state = load_lambdarank_model_case(name, device)
+    args = argparse.Namespace(hidden_size=bytes(z["hidden_size"]).decode(), i_emb_size=32, model_num=int(z["model_num"][0]),
+                              device=device)
+    model = lambdarank.LambdaRank(args, item_num=int(z["item_rows"][0]))
+    assert [n for n, _ in model.named_parameters()] == list(state.keys())
+    model.load_state_dict(state)
+    model = model.to(device)
+    out = model(batch)
+    assert rel_err(out["ens_score"].detach().cpu().numpy(), z["out.ens_score"]) < TOL
+    assert out["weights"].shape == z["out.weights"].shape and not out["weights"].any()
+    lam = lambdarank.compute_lambda_new(torch.clamp(batch["ranking"], min=0), out["ens_score"].detach(), batch["session_len"])
+    lam = torch.nan_to_num(lam, nan=0.0)
+    assert rel_err(lam.cpu().numpy(), z["lambdas"]) < 5 * TOL
+    out["ens_score"].backward(torch.from_numpy(z["lambdas"]).to(device))
+    gmax = max(float(np.abs(z["grad." + n]).max()) for n, _ in model.named_parameters())
+    for n, p in model.named_parameters():
+        assert_grad_close(p.grad.cpu().numpy(), z["grad." + n], gmax, n)

@@ -102,6 +102,11 @@ def test_awelv_intel_matches_reference_golden(name):
     P.check_awelv_intel("cpu", name)
 
 
+@pytest.mark.parametrize("name", ["h32", "h24_8"])
+def test_lambdarank_scorer_matches_reference_golden(name):
+    P.check_lambdarank_model("cpu", name)
+
+
 def test_lambdarank_matches_reference_golden():
     P.check_lambdarank("cpu")
 

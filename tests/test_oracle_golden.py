@@ -169,6 +169,20 @@ def test_oracle_awelv_intel_matches_reference(name):
         assert np.abs(v.grad.numpy() - ref).max() <= 2e-5 * np.abs(ref).max() + 1e-6 * gmax, k
 
 
+@pytest.mark.parametrize("name", ["h32", "h24_8"])
+def test_oracle_lambdarank_scorer_matches_reference(name):
+    """oracle.lambdarank_scorer + backward(lambdas) against the unmodified reference LambdaRank model"""
+    import parity_checks as P
+    z, batch, state = P.load_lambdarank_model_case(name)
+    sd = {k: v.clone().requires_grad_(True) for k, v in state.items()}
+    out = O.lambdarank_scorer(sd, batch)
+    assert np.abs(out["ens_score"].detach().numpy() - z["out.ens_score"]).max() < 1e-6
+    out["ens_score"].backward(torch.from_numpy(z["lambdas"]))
+    for k, v in sd.items():
+        ref = z["grad." + k]
+        assert np.abs(v.grad.numpy() - ref).max() <= 2e-5 * np.abs(ref).max() + 1e-9, k
+
+
 @pytest.mark.parametrize("tag", ["S", "W", "Z", "L"])
 def test_oracle_lambdarank_matches_reference(tag):
     """oracle.compute_lambda against the unmodified LambdaRankRunner.compute_lambda_new (tests/golden/lambdarank.npz)"""
