@@ -104,6 +104,13 @@ def evaluate_intents(true_intents, predict_intents, topk=(1, 5, 10, 30), device=
     pi = predict_intents if torch.is_tensor(predict_intents) else torch.from_numpy(np.asarray(predict_intents, dtype=np.float32))
     ti, pi = ti.to(device).double().contiguous(), pi.to(device).float().contiguous()
     N, I = pi.shape
+    for k in topk:
+        # the reference multiplies true_sort[:, :k] ([N, min(k, I)]) by discounts[:k] ([min(k, 40)]) (BaseRunner.py:142-144):
+        # a cut-off beyond the number of intent classes is a numpy broadcast error there, so it is an error here too
+        a, b = min(int(k), I), min(int(k), 40)
+        if a != b and a != 1 and b != 1:
+            raise ValueError(f"operands could not be broadcast together with shapes ({N},{a}) ({b},) "
+                             f"(Int-NDCG@{k} needs k <= intent_num = {I} and k <= 40, as in BaseRunner.evaluate_intents)")
     sums = torch.zeros(len(topk) * 2, dtype=torch.float64, device=pi.device)
     ws = torch.empty(lib.intel_intent_topk_workspace_bytes(N, len(topk)), dtype=torch.uint8, device=pi.device)
     _lib.check(lib.intel_intent_topk(N, I, _lib.ptr(ti), _lib.ptr(pi), _topk_array(topk), len(topk), _lib.ptr(sums),

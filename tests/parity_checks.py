@@ -272,6 +272,19 @@ def check_evaluate_intents(device):
     res = evaluate.evaluate_intents(z["I.true"], z["I.pred"], topk=[1, 3, 5, 10, 30], device=device)
     for k, v in res.items():
         assert abs(v - float(z[f"I.metric.{k}"])) < 1e-6, (k, v)
+    # config-3 shape (12 intent classes): the reference's default cut-offs [1,5,10,30] fail on a numpy broadcast
+    # (BaseRunner.py:142-144, verified against the unmodified method); cut-offs <= I work and match the oracle
+    import pytest
+    t12 = z["I.true"][:, :12] + 1e-3
+    t12 = t12 / t12.sum(axis=1, keepdims=True)
+    p12 = z["I.pred"][:, :12] / z["I.pred"][:, :12].sum(axis=1, keepdims=True)
+    with pytest.raises(ValueError):
+        evaluate.evaluate_intents(t12, p12, topk=[1, 5, 10, 30], device=device)
+    with pytest.raises(ValueError):
+        O.evaluate_intents(t12, p12, [1, 5, 10, 30])
+    got, ref = evaluate.evaluate_intents(t12, p12, topk=[1, 3, 5, 10], device=device), O.evaluate_intents(t12, p12, [1, 3, 5, 10])
+    for k, v in ref.items():
+        assert abs(got[k] - v) < 1e-6, (k, got[k], v)
 
 
 def check_baselines(device):
@@ -322,6 +335,18 @@ def check_against_oracle(device, seed=0, B=70, L=21, min_len=3, kind="list", cor
     for k, p in model.named_parameters():
         ref_g = sd[k].grad.numpy() if sd[k].grad is not None else np.zeros(tuple(p.shape), np.float32)
         assert_grad_close(p.grad.cpu().numpy(), ref_g, gmax, f"{k} {cfg_kw}", rtol=1e-3, afrac=5e-6)
+
+
+C3_MODEL = dict(encoder="GRU4Rec", num_heads=2, num_layers=2, context_emb_size=32, intent_emb_size=32, cross_attn_qsize=64)
+
+
+def check_config3_shapes(device, intent_num, B=6, kind="list"):
+    """BASELINE.json configs[2] (LifeData-shaped): K = 2 basic lists, four context features with
+    cardinalities (24,7,16,8) -> 21 504 context rows, I = 12 (the code hint) or 2048 (the stress size), L = 50, the
+    script's GRU4Rec sizes: forward, loss and every parameter gradient against the oracle"""
+    check_against_oracle(device, seed=3, B=B, L=50, min_len=20, kind=kind,
+                         corpus_kw=dict(model_num=2, intent_num=intent_num, n_ctx=24 * 7 * 16 * 8, history_max=20, n_item=500,
+                                        n_user=60), **C3_MODEL)
 
 
 def check_compact_layout(device):

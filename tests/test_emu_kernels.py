@@ -80,6 +80,11 @@ def test_against_oracle_multi_tile():
                            corpus_kw=dict(history_max=4, intent_num=24))
 
 
+@pytest.mark.parametrize("intent_num", [12, 2048])
+def test_config3_shapes_against_the_oracle(intent_num):
+    P.check_config3_shapes("cpu", intent_num)
+
+
 def test_compact_layout_matches_dense():
     P.check_compact_layout("cpu")
 

@@ -55,3 +55,8 @@ def test_lambdarank_properties_at_full_batch():
     flat = lambdarank.compute_lambda_new(ranking, torch.zeros_like(scores), slen)
     tot = flat[live].sum(dim=1).abs().max().item()
     assert tot < 1e-4, tot
+
+
+@pytest.mark.parametrize("intent_num,kind", [(12, "list"), (2048, "list"), (12, "bpr")])
+def test_config3_shapes_against_the_oracle(intent_num, kind):
+    P.check_config3_shapes(DEV, intent_num, B=40, kind=kind)
