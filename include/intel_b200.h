@@ -111,6 +111,20 @@ typedef struct {
 const char* intel_last_error(void);
 int intel_abi_version(void);
 
+/* ---- input validation ------------------------------------------------------------------- */
+/* The reference's nn.Embedding raises IndexError on an id outside its table (IntEL.py:135-178) and its encoders need
+ * 1 <= history_len <= H (GeneralSeq.py:64-78, 95-106).  This pass ORs one bit per offending field class into flags[0]
+ * (device int32, zeroed by the caller); the model entry points themselves stay memory-safe on such input (a bad id reads
+ * a zero row and is skipped by the gradient scatter) but their results are then meaningless. */
+#define INTEL_BAD_USER_ID 1
+#define INTEL_BAD_ITEM_ID 2
+#define INTEL_BAD_CLASS_ID 4
+#define INTEL_BAD_CONTEXT_ID 8
+#define INTEL_BAD_SESSION_LEN 16
+#define INTEL_BAD_HISTORY_LEN 32
+#define INTEL_BAD_INTENT_IDX 64
+int intel_batch_validate(const intel_dims_t* d, const intel_batch_t* batch, int32_t* flags, intel_stream_t stream);
+
 /* ---- model forward / backward -------------------------------------------------------- */
 /* IntEL.predict_intent (IntEL.py:126-155): intents_out f32 [B,I] = softmax(pred_layer(...)). */
 size_t intel_intent_workspace_bytes(const intel_dims_t* d);
@@ -255,6 +269,8 @@ int64_t intel_host_pack_rows(int64_t rows, int64_t I, const double* dense, int32
 int intel_debug_use_fused_stack(int on);
 /* test hook: 0 keeps large GEMMs on the mma.sync kernels instead of the tcgen05 / TMEM kernel. Default 1. */
 int intel_debug_use_tcgen05_gemm(int on);
+/* test hook: 0 keeps the fused stack forward pass on the mma.sync kernel instead of the tcgen05 / TMEM kernel. Default 1. */
+int intel_debug_use_tcgen05_stack(int on);
 /* tuning / test hook: sessions that share one CTA (and one staged copy of the weights) in the fused stack
  * kernels, 1..4. */
 int intel_debug_stack_sessions_per_cta(int n);

@@ -79,7 +79,7 @@ class _IntelFn(torch.autograd.Function):
     """(parameters...) -> (weights, ens_score, intents); backward = ensemble_bwd then intent_bwd."""
 
     @staticmethod
-    def forward(ctx, model: "IntEL", batch: Dict[str, object], *params: torch.Tensor):
+    def forward(ctx, model: "IntEL", batch: Dict[str, object], grad_mode: bool, *params: torch.Tensor):
         lib = _lib.load()
         cfg = model.cfg
         dev = params[0].device
@@ -96,13 +96,17 @@ class _IntelFn(torch.autograd.Function):
         stream = _lib.stream_ptr(dev)
         ws_int = _take_ws(model, lib.intel_intent_workspace_bytes(dims), dev)
         ws_ens = _take_ws(model, lib.intel_ensemble_workspace_bytes(dims), dev)
+        if model.validate_inputs:
+            model._queue_input_check(lib, dims, bt, dev, stream)
         intents = torch.empty(B, cfg.intent_num, dtype=torch.float32, device=dev)
         weights = torch.empty(B, L, cfg.model_num, dtype=torch.float32, device=dev)
         ens = torch.empty(B, L, dtype=torch.float32, device=dev)
         _lib.check(lib.intel_intent_fwd(dims, P, bt, _lib.ptr(intents), _lib.ptr(ws_int), ws_int.numel(), stream))
         _lib.check(lib.intel_ensemble_fwd(dims, P, bt, _lib.ptr(intents), _lib.ptr(weights), _lib.ptr(ens),
                                           _lib.ptr(ws_ens), ws_ens.numel(), stream))
-        if any(ctx.needs_input_grad):
+        # needs_input_grad stays True under torch.no_grad() (BaseRunner.predict) and the grad mode is always off inside
+        # Function.forward: the caller's grad mode arrives as an argument
+        if grad_mode and any(ctx.needs_input_grad):
             ctx.model, ctx.batch, ctx.dims = model, batch, dims
             ctx.ws_int, ctx.ws_ens = ws_int, ws_ens
             ctx.params = params
@@ -117,6 +121,9 @@ class _IntelFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d_weights, d_ens, d_intents):
         lib = _lib.load()
+        if getattr(ctx, "ws_int", None) is None or ctx.ws_ens is None:
+            raise RuntimeError("IntEL backward ran twice on one forward pass: the activations live in a pooled workspace "
+                               "that the first backward handed back (retain_graph is not supported)")
         model, cfg, batch, dims = ctx.model, ctx.model.cfg, ctx.batch, ctx.dims
         params = ctx.params
         (intents,) = ctx.saved_tensors
@@ -150,7 +157,7 @@ class _IntelFn(torch.autograd.Function):
         _give_ws(model, ctx.ws_int)
         _give_ws(model, ctx.ws_ens)
         ctx.ws_int = ctx.ws_ens = None
-        return (None, None) + tuple(grads)
+        return (None, None, None) + tuple(grads)
 
 
 class IntEL(nn.Module):
@@ -189,6 +196,10 @@ class IntEL(nn.Module):
         self.optimizer, self.scheduler = None, None
         self.check_list = list()
         self._ws_pool = {}
+        # index range check of every batch (nn.Embedding raises IndexError in the reference): the check kernel runs with
+        # the forward pass, its verdict is read without a sync at the next forward / by check_inputs()
+        self.validate_inputs = True
+        self._check_flag = self._check_host = self._check_event = None
         self._drop_seed, self._drop_step = int(torch.initial_seed()) & 0x7FFFFFFF, 0
         self.intent_num, self.model_num = c.intent_num, c.model_num
         self.user_num, self.item_num = c.user_rows, c.item_rows
@@ -225,10 +236,37 @@ class IntEL(nn.Module):
         for n, p in self.named_parameters():
             assert tuple(p.shape) == shapes[n], (n, tuple(p.shape), shapes[n])
 
+    def _queue_input_check(self, lib, dims, bt, dev, stream) -> None:
+        self.check_inputs(wait=False)
+        if self._check_flag is None or self._check_flag.device != dev:
+            self._check_flag = torch.zeros(1, dtype=torch.int32, device=dev)
+            self._check_host = torch.zeros(1, dtype=torch.int32).pin_memory() if dev.type == "cuda" else torch.zeros(1, dtype=torch.int32)
+            self._check_event = torch.cuda.Event() if dev.type == "cuda" else None
+        _lib.check(lib.intel_batch_validate(dims, bt, _lib.ptr(self._check_flag), stream))
+        self._check_host.copy_(self._check_flag, non_blocking=True)
+        if self._check_event is not None:
+            self._check_event.record(torch.cuda.current_stream(dev))
+
+    def check_inputs(self, wait: bool = True) -> None:
+        """Raise IndexError if a batch fed so far carried an id outside its embedding table (or a history length
+        outside [1, H]).  wait=False only looks at verdicts that have already arrived (no device sync)."""
+        if self._check_host is None:
+            return
+        if self._check_event is not None:
+            if wait:
+                self._check_event.synchronize()
+            elif not self._check_event.query():
+                return
+        flags = int(self._check_host.item())
+        if flags:
+            self._check_flag.zero_()
+            self._check_host.zero_()
+            raise IndexError("IntEL batch out of range: " + _lib.describe_bad_input(flags))
+
     # ---- the hot path ----
     def forward(self, data: Dict[str, object]) -> Dict[str, torch.Tensor]:
         params = [p for _, p in self.named_parameters()]
-        weights, ens, intents = _IntelFn.apply(self, data, *params)
+        weights, ens, intents = _IntelFn.apply(self, data, torch.is_grad_enabled(), *params)
         return {"weights": weights, "ens_score": ens, "intents": intents}
 
     # ---- auxiliary methods kept from BaseModel (BaseModel.py:53-78) ----

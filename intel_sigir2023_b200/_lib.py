@@ -88,6 +88,7 @@ def _declare(lib: C.CDLL) -> None:
         "intel_fuse_fwd": (i32, [i64, i64, i64, _p, _p, _p, _p]),
         "intel_select_list": (i32, [i64, i64, i64, _p, i32, _p, _p]),
         "intel_rank_lists": (i32, [i64, i64, i64, _p, _p, _p]),
+        "intel_batch_validate": (i32, [PD, PB, _p, _p]),
         "intel_gather_fwd": (i32, [i64, i32, _p, _p, _p, i32, i32, _p]),
         "intel_scatter_add_bwd": (i32, [i64, i32, _p, i32, _p, _p, _p]),
         "intel_linear_fwd": (i32, [i64, i64, i64, _p, _p, _p, _p, _p]),
@@ -103,6 +104,7 @@ def _declare(lib: C.CDLL) -> None:
         "intel_debug_use_fused_stack": (i32, [i32]),
         "intel_debug_stack_sessions_per_cta": (i32, [i32]),
         "intel_debug_use_tcgen05_gemm": (i32, [i32]),
+        "intel_debug_use_tcgen05_stack": (i32, [i32]),
         "intel_host_pack_rows": (i64, [i64, i64, _p, i32, _p, _p, _p, i32, i64, _p]),
         "intel_awelv_fwd": (i32, [i64, i64, i32, i32, _p, _p, _p, _p, _p, _p, _p, _p]),
         "intel_awelv_bwd": (i32, [i64, i64, i32, i32, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
@@ -128,7 +130,8 @@ EXPORTED = ["intel_last_error", "intel_abi_version", "intel_intent_workspace_byt
             "intel_profile_enable", "intel_profile_report", "intel_linear_dx", "intel_linear_dw", "intel_mha_fwd",
             "intel_mha_bwd", "intel_debug_use_fused_stack", "intel_debug_stack_sessions_per_cta", "intel_debug_use_tcgen05_gemm", "intel_host_pack_rows", "intel_adam_step", "intel_awelv_fwd", "intel_awelv_bwd",
             "intel_lambdarank_lambdas", "intel_pool_head_fwd", "intel_pool_head_bwd",
-            "intel_linear_fwd_ex", "intel_linear_dx_ex", "intel_linear_dw_ex", "intel_softmax_rows_fwd", "intel_softmax_rows_bwd"]
+            "intel_linear_fwd_ex", "intel_linear_dx_ex", "intel_linear_dw_ex", "intel_softmax_rows_fwd", "intel_softmax_rows_bwd",
+            "intel_batch_validate", "intel_debug_use_tcgen05_stack"]
 
 
 def load(path: Optional[str] = None) -> C.CDLL:
@@ -262,6 +265,16 @@ def make_batch(batch: Dict[str, object], cfg: IntelConfig) -> Batch:
         b.his_item_int = ptr(batch["his_item_int"], f64)
     b.history_item_len = ptr(batch["history_item_len"], i64)
     return b
+
+
+BAD_INPUT_BITS = {1: "u_id_c outside uid_embeddings", 2: "i_id_s / his_item_id outside iid_embeddings",
+                  4: "i_class_c outside item_embeddings", 8: "context_mh / his_context_mh outside context_embeddings",
+                  16: "session_len outside [0, L]", 32: "history_len / history_item_len outside [1, H]",
+                  64: "compact history intent index outside [0, intent_num)"}
+
+
+def describe_bad_input(flags: int) -> str:
+    return "; ".join(msg for bit, msg in BAD_INPUT_BITS.items() if flags & bit)
 
 
 def profile(on) -> None:

@@ -152,6 +152,18 @@ int intel_pool_head_bwd(int64_t B, int64_t L, int K, const double* scores, const
     return pool_head_bwd(B, L, K, scores, p_sess, w_sess, d_weights, d_ens, d_slot_weights, (cudaStream_t)stream);
 }
 
+int intel_batch_validate(const intel_dims_t* d, const intel_batch_t* bt, int32_t* flags, intel_stream_t stream) {
+    INTEL_REQUIRE(d && bt, INTEL_ERR_ARG, "intel_batch_validate: null argument");
+    ValidateArgs a;
+    a.B = d->B; a.L = d->L; a.H1 = d->H1; a.H2 = d->H2; a.I = d->I;
+    a.item_rows = d->item_rows; a.class_rows = d->class_rows; a.user_rows = d->user_rows; a.ctx_rows = d->ctx_rows;
+    a.u_id = bt->u_id; a.i_id = bt->i_id; a.i_class = bt->i_class; a.session_len = bt->session_len;
+    a.context_mh = bt->context_mh; a.his_context = bt->his_context; a.history_len = bt->history_len;
+    a.his_item_id = bt->his_item_id; a.history_item_len = bt->history_item_len;
+    a.idx1 = bt->his_intents_idx; a.idx2 = bt->his_item_int_idx; a.nz1 = bt->nz1; a.nz2 = bt->nz2;
+    return batch_validate(a, flags, (cudaStream_t)stream);
+}
+
 int intel_gather_fwd(int64_t rows, int d, const float* table, const int64_t* idx, float* out, int ld_out, int relu,
                      intel_stream_t stream) {
     return gather_rows(rows, d, table, idx, out, ld_out, relu, (cudaStream_t)stream);

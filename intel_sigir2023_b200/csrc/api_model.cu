@@ -54,7 +54,9 @@ int g_use_fused_stack = 1;
 int stack_fwd(int64_t B, int64_t L, int d, int heads, int layers, const intel_selfatt_t& p, StackWs& w, float drop_p,
               uint64_t drop_seed, int stream_id, cudaStream_t s) {
     const int64_t R = B * L;
-    if (g_use_fused_stack && trunk_supported(L, d, heads, layers)) {     // whole stack of a session on chip (trunk.cu)
+    // whole stack of a session on chip: tcgen05 kernel (trunk_tc.cu, L <= 128) or the mma.sync kernel (trunk.cu, L <= 64);
+    // both leave the same activations behind, which the fused and the staged backward passes read alike
+    if (g_use_fused_stack && d == TD && trunk_fwd_supported(L, heads, layers)) {
         const StackParams sp{p.wq, p.wk, p.wv, p.w1, p.b1, p.w2, p.b2, p.lnw, p.lnb};
         const StackSaved sv{w.QKV, w.A, w.U, w.Z, w.st};
         return trunk_fwd(B, L, heads, layers, sp, w.X, sv, drop_p, drop_seed, stream_id, s);
@@ -352,6 +354,11 @@ int intel_debug_use_tcgen05_gemm(int on) {
     return INTEL_OK;
 }
 
+int intel_debug_use_tcgen05_stack(int on) {
+    trunk_debug_use_tcgen05(on);
+    return INTEL_OK;
+}
+
 int intel_debug_stack_sessions_per_cta(int n) {
     trunk_debug_sessions_per_cta(n);
     return INTEL_OK;
@@ -383,8 +390,8 @@ int intel_ensemble_fwd(const intel_dims_t* d, const intel_tensors_t* P, const in
     const int D = di + ds + du + dint, off_u = di + ds, off_h = di + ds + du;
 
     // embedding gathers straight into the concatenated item-stream rows (IntEL.py:170-175)
-    INTEL_TRY(gather_rows(R, d->d_iid, P->iid_emb, bt->i_id, w.item.X[0], di, 0, s));
-    if (d->d_im > 0) INTEL_TRY(gather_rows(R, d->d_im, P->item_emb, bt->i_class, w.item.X[0] + d->d_iid, di, 0, s));
+    INTEL_TRY(gather_rows(R, d->d_iid, P->iid_emb, bt->i_id, w.item.X[0], di, 0, s, d->item_rows));
+    if (d->d_im > 0) INTEL_TRY(gather_rows(R, d->d_im, P->item_emb, bt->i_class, w.item.X[0] + d->d_iid, di, 0, s, d->class_rows));
     INTEL_TRY(score_embed_fwd(R, K, ds, bt->scores, P->score_w, P->score_b, w.score.X[0], w.xs, s));
     INTEL_TRY(stack_fwd(B, L, di, d->heads, d->layers, P->item, w.item, d->dropout_p, d->dropout_seed, 0, s));
     INTEL_TRY(stack_fwd(B, L, ds, d->heads, d->layers, P->score, w.score, d->dropout_p, d->dropout_seed, 1, s));
@@ -404,7 +411,7 @@ int intel_ensemble_fwd(const intel_dims_t* d, const intel_tensors_t* P, const in
         INTEL_TRY(cross_pool_fwd(B, L, ds, Xs, w.qk_s, bt->session_len, scale, w.p_s, w.xbar_s, s));
         INTEL_TRY(linear(B, ds, ds, w.xbar_s, ds, P->xv_score, ds, nullptr, w.all + di, D, s));
         // user + intent parts of the head input
-        INTEL_TRY(gather_rows(B, du, P->uid_emb, bt->u_id, w.all + off_u, D, 1, s));
+        INTEL_TRY(gather_rows(B, du, P->uid_emb, bt->u_id, w.all + off_u, D, 1, s, d->user_rows));
         INTEL_TRY(linear(B, dint, I, intents, I, P->intent_w, I, P->intent_b, w.all + off_h, D, s, false, true));
         // weights of the valid rows and of the pad rows (whose pooled inputs are zero)
         INTEL_TRY(linear(B, K, D, w.all, D, P->head_w, D, P->head_b, w.w_valid, K, s));
@@ -418,7 +425,7 @@ int intel_ensemble_fwd(const intel_dims_t* d, const intel_tensors_t* P, const in
         INTEL_TRY(linear(B, ds, q, w.t_s, q, P->gate_score_w2, q, nullptr, w.m_s, ds, s));
         INTEL_TRY(gate_fwd(B, L, di, Xi, w.m_i, w.all_item, D, s));
         INTEL_TRY(gate_fwd(B, L, ds, Xs, w.m_s, w.all_item + di, D, s));
-        INTEL_TRY(gather_rows(B, du, P->uid_emb, bt->u_id, w.hu, du, 1, s));
+        INTEL_TRY(gather_rows(B, du, P->uid_emb, bt->u_id, w.hu, du, 1, s, d->user_rows));
         INTEL_TRY(bcast_rows(B, L, du, w.hu, du, w.all_item + off_u, D, s));
         INTEL_TRY(linear(B, dint, I, intents, I, P->intent_w, I, P->intent_b, w.hint, dint, s, false, true));
         INTEL_TRY(bcast_rows(B, L, dint, w.hint, dint, w.all_item + off_h, D, s));
@@ -456,7 +463,7 @@ int intel_ensemble_bwd(const intel_dims_t* d, const intel_tensors_t* P, const in
         INTEL_TRY(linear_dw(B, dint, I, w.dall + off_h, D, intents, I, G->intent_w, I, G->intent_b, s));
         INTEL_TRY(linear_dx(B, dint, I, w.dall + off_h, D, P->intent_w, I, d_intents_out, I, s, 0));
         // h_u = relu(uid_embeddings[u])
-        INTEL_TRY(scatter_add_rows(B, du, w.dall + off_u, D, bt->u_id, G->uid_emb, P->uid_emb, s));
+        INTEL_TRY(scatter_add_rows(B, du, w.dall + off_u, D, bt->u_id, G->uid_emb, P->uid_emb, s, d->user_rows));
         // the two pooled cross attentions, then the self-attention stacks
         for (int st = 0; st < 2; ++st) {
             const int dd = st == 0 ? di : ds;
@@ -478,8 +485,8 @@ int intel_ensemble_bwd(const intel_dims_t* d, const intel_tensors_t* P, const in
             if (st == 0) {
                 INTEL_TRY(stack_bwd(B, L, di, d->heads, d->layers, P->item, G->item, w.item, w.dXa, w.t1, w.t2, w.dqkv, d->dropout_p,
                                     d->dropout_seed, 0, s));
-                INTEL_TRY(scatter_add_rows(R, d->d_iid, w.dXa, di, bt->i_id, G->iid_emb, nullptr, s));
-                if (d->d_im > 0) INTEL_TRY(scatter_add_rows(R, d->d_im, w.dXa + d->d_iid, di, bt->i_class, G->item_emb, nullptr, s));
+                INTEL_TRY(scatter_add_rows(R, d->d_iid, w.dXa, di, bt->i_id, G->iid_emb, nullptr, s, d->item_rows));
+                if (d->d_im > 0) INTEL_TRY(scatter_add_rows(R, d->d_im, w.dXa + d->d_iid, di, bt->i_class, G->item_emb, nullptr, s, d->class_rows));
             } else {
                 INTEL_TRY(stack_bwd(B, L, ds, d->heads, d->layers, P->score, G->score, w.score, w.dXa, w.t1, w.t2, w.dqkv, d->dropout_p,
                                     d->dropout_seed, 1, s));
@@ -497,7 +504,7 @@ int intel_ensemble_bwd(const intel_dims_t* d, const intel_tensors_t* P, const in
         INTEL_TRY(linear_dw(B, dint, I, w.dvec, dint, intents, I, G->intent_w, I, G->intent_b, s));
         INTEL_TRY(linear_dx(B, dint, I, w.dvec, dint, P->intent_w, I, d_intents_out, I, s, 0));
         INTEL_TRY(bcast_rows_bwd(B, L, du, w.dall_item + off_u, D, w.dvec, du, 0, s));
-        INTEL_TRY(scatter_add_rows(B, du, w.dvec, du, bt->u_id, G->uid_emb, P->uid_emb, s));
+        INTEL_TRY(scatter_add_rows(B, du, w.dvec, du, bt->u_id, G->uid_emb, P->uid_emb, s, d->user_rows));
         for (int st = 0; st < 2; ++st) {
             const int dd = st == 0 ? di : ds;
             const int off = st == 0 ? 0 : di;
@@ -514,8 +521,8 @@ int intel_ensemble_bwd(const intel_dims_t* d, const intel_tensors_t* P, const in
             if (st == 0) {
                 INTEL_TRY(stack_bwd(B, L, di, d->heads, d->layers, P->item, G->item, w.item, w.dXa, w.t1, w.t2, w.dqkv, d->dropout_p,
                                     d->dropout_seed, 0, s));
-                INTEL_TRY(scatter_add_rows(R, d->d_iid, w.dXa, di, bt->i_id, G->iid_emb, nullptr, s));
-                if (d->d_im > 0) INTEL_TRY(scatter_add_rows(R, d->d_im, w.dXa + d->d_iid, di, bt->i_class, G->item_emb, nullptr, s));
+                INTEL_TRY(scatter_add_rows(R, d->d_iid, w.dXa, di, bt->i_id, G->iid_emb, nullptr, s, d->item_rows));
+                if (d->d_im > 0) INTEL_TRY(scatter_add_rows(R, d->d_im, w.dXa + d->d_iid, di, bt->i_class, G->item_emb, nullptr, s, d->class_rows));
             } else {
                 INTEL_TRY(stack_bwd(B, L, ds, d->heads, d->layers, P->score, G->score, w.score, w.dXa, w.t1, w.t2, w.dqkv, d->dropout_p,
                                     d->dropout_seed, 1, s));
@@ -552,7 +559,7 @@ int intel_intent_fwd(const intel_dims_t* d, const intel_tensors_t* P, const inte
 
     INTEL_TRY(transpose(dint, I, P->intent_w, w.Wt, 0, s));
     // session history tokens: [context embedding | intent embedding of the dense history intents]
-    INTEL_TRY(gather_rows(B * d->H1, dctx, P->ctx_emb, bt->his_context, w.e1.seq, d1, 0, s));
+    INTEL_TRY(gather_rows(B * d->H1, dctx, P->ctx_emb, bt->his_context, w.e1.seq, d1, 0, s, d->ctx_rows));
     if (bt->his_intents_idx) {
         INTEL_TRY(sparse_rows_linear_fwd(B * d->H1, bt->nz1, dint, bt->his_intents_idx, bt->his_intents_val, w.Wt,
                                          P->intent_b, w.e1.seq + dctx, d1, s));
@@ -562,7 +569,7 @@ int intel_intent_fwd(const intel_dims_t* d, const intel_tensors_t* P, const inte
                                         w.e1.nz_idx, w.e1.nz_val, w.e1.nz_cnt, NZ_CAP, s, d->H1, bt->history_len));
     }
     // item history tokens: [item id embedding | intent embedding of the one-hot item intents]
-    INTEL_TRY(gather_rows(B * d->H2, diid, P->iid_emb, bt->his_item_id, w.e2.seq, d2, 0, s));
+    INTEL_TRY(gather_rows(B * d->H2, diid, P->iid_emb, bt->his_item_id, w.e2.seq, d2, 0, s, d->item_rows));
     if (bt->his_item_int_idx) {
         INTEL_TRY(sparse_rows_linear_fwd(B * d->H2, bt->nz2, dint, bt->his_item_int_idx, bt->his_item_int_val, w.Wt,
                                          P->intent_b, w.e2.seq + diid, d2, s));
@@ -578,8 +585,8 @@ int intel_intent_fwd(const intel_dims_t* d, const intel_tensors_t* P, const inte
         INTEL_TRY(gru_fwd(d, P->enc, w.e1, bt->history_len, w.feat + off_v1, Dp, s));
         INTEL_TRY(gru_fwd(d, P->item_enc, w.e2, bt->history_item_len, w.feat + off_v2, Dp, s));
     }
-    INTEL_TRY(gather_rows(B, dctx, P->ctx_emb, bt->context_mh, w.feat, Dp, 0, s));
-    INTEL_TRY(gather_rows(B, du, P->uid_emb, bt->u_id, w.feat + dctx, Dp, 0, s));
+    INTEL_TRY(gather_rows(B, dctx, P->ctx_emb, bt->context_mh, w.feat, Dp, 0, s, d->ctx_rows));
+    INTEL_TRY(gather_rows(B, du, P->uid_emb, bt->u_id, w.feat + dctx, Dp, 0, s, d->user_rows));
     INTEL_TRY(linear(B, I, Dp, w.feat, Dp, P->pred_w, Dp, P->pred_b, w.logits, I, s));
     return softmax_rows(B, I, w.logits, intents_out, s);
 }
@@ -602,8 +609,8 @@ int intel_intent_bwd(const intel_dims_t* d, const intel_tensors_t* P, const inte
     INTEL_TRY(softmax_rows_bwd(B, I, intents, d_intents, d_intents_extra, w.dlogits, s));
     INTEL_TRY(linear_dw(B, I, Dp, w.dlogits, I, w.feat, Dp, G->pred_w, Dp, G->pred_b, s));
     INTEL_TRY(linear_dx(B, I, Dp, w.dlogits, I, P->pred_w, Dp, w.dfeat, Dp, s));
-    INTEL_TRY(scatter_add_rows(B, dctx, w.dfeat, Dp, bt->context_mh, G->ctx_emb, nullptr, s));
-    INTEL_TRY(scatter_add_rows(B, du, w.dfeat + dctx, Dp, bt->u_id, G->uid_emb, nullptr, s));
+    INTEL_TRY(scatter_add_rows(B, dctx, w.dfeat, Dp, bt->context_mh, G->ctx_emb, nullptr, s, d->ctx_rows));
+    INTEL_TRY(scatter_add_rows(B, du, w.dfeat + dctx, Dp, bt->u_id, G->uid_emb, nullptr, s, d->user_rows));
     if (d->encoder == INTEL_ENCODER_BERT4REC) {
         INTEL_TRY(bert_bwd(d, P->enc, G->enc, w.e1, bt->history_len, w.dfeat + off_v1, Dp, w.t1, w.t2, w.dqkv, s));
         INTEL_TRY(bert_bwd(d, P->item_enc, G->item_enc, w.e2, bt->history_item_len, w.dfeat + off_v2, Dp, w.t1, w.t2, w.dqkv, s));
@@ -612,7 +619,7 @@ int intel_intent_bwd(const intel_dims_t* d, const intel_tensors_t* P, const inte
         INTEL_TRY(gru_bwd(d, P->item_enc, G->item_enc, w.e2, bt->history_item_len, w.dfeat + off_v2, Dp, s));
     }
     INTEL_TRY(fill_zero(w.dWt, (size_t)I * dint * 4, s));
-    INTEL_TRY(scatter_add_rows(B * d->H1, dctx, w.e1.dseq, d1, bt->his_context, G->ctx_emb, nullptr, s));
+    INTEL_TRY(scatter_add_rows(B * d->H1, dctx, w.e1.dseq, d1, bt->his_context, G->ctx_emb, nullptr, s, d->ctx_rows));
     if (bt->his_intents_idx) {
         INTEL_TRY(dense_rows_linear_bwd(B * d->H1, I, dint, nullptr, w.e1.dseq + dctx, d1, bt->his_intents_idx,
                                         bt->his_intents_val, nullptr, bt->nz1, w.dWt, s));
@@ -621,7 +628,7 @@ int intel_intent_bwd(const intel_dims_t* d, const intel_tensors_t* P, const inte
                                         w.e1.nz_cnt, NZ_CAP, w.dWt, s));
     }
     INTEL_TRY(colsum(B * d->H1, dint, w.e1.dseq + dctx, d1, G->intent_b, s));
-    INTEL_TRY(scatter_add_rows(B * d->H2, diid, w.e2.dseq, d2, bt->his_item_id, G->iid_emb, nullptr, s));
+    INTEL_TRY(scatter_add_rows(B * d->H2, diid, w.e2.dseq, d2, bt->his_item_id, G->iid_emb, nullptr, s, d->item_rows));
     if (bt->his_item_int_idx) {
         INTEL_TRY(dense_rows_linear_bwd(B * d->H2, I, dint, nullptr, w.e2.dseq + diid, d2, bt->his_item_int_idx,
                                         bt->his_item_int_val, nullptr, bt->nz2, w.dWt, s));

@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(XP_WARPS * 32) cross_pool_fwd_kernel(int64_t B
             a *= scale;
             if (j < L) {
                 if (sub == 0) pb[j] = a;
-                mx = fmaxf(mx, a);         // row max over ALL slots, pads included (attention.py:57)
+                if (j < n) mx = fmaxf(mx, a);
             }
         }
         __syncwarp();
@@ -204,9 +204,12 @@ __global__ void __launch_bounds__(XP_WARPS * 32) cross_pool_fwd_kernel(int64_t B
             for (int c = 0; c < d; ++c) a = fmaf(x[j * d + c], q[c], a);
             a *= scale;
             pb[j] = a;
-            mx = fmaxf(mx, a);             // row max over ALL slots, pads included (attention.py:57)
+            if (j < n) mx = fmaxf(mx, a);
         }
     }
+    // attention.py:57-60 subtracts the max over ALL slots, masks the pads to -inf and calls softmax, which shifts by the
+    // largest VALID logit once more: that second shift is the one that decides the result, so it is the one used here
+    // (a pad logit far above every valid one must not underflow the whole row to zero)
     mx = warp_max(mx);
     float sum = 0.f;
     for (int64_t j = lane; j < L; j += 32) {

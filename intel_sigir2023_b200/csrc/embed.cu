@@ -10,33 +10,35 @@ namespace intel {
 template <int VEC>
 __global__ void __launch_bounds__(256) gather_kernel(int64_t rows, int d, const float* __restrict__ table,
                                                      const int64_t* __restrict__ idx, float* __restrict__ out,
-                                                     int64_t ld_out, int relu) {
+                                                     int64_t ld_out, int relu, int64_t table_rows) {
     const int per_row = d / VEC;
     const int64_t total = rows * per_row;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r = e / per_row;
         const int c = (int)(e % per_row) * VEC;
         const int64_t id = idx[r];
+        // an id outside the table (nn.Embedding raises IndexError; intel_batch_validate reports it) reads as a zero row
+        const bool ok = table_rows <= 0 || (id >= 0 && id < table_rows);
         if (VEC == 4) {
-            float4 v = *reinterpret_cast<const float4*>(table + id * d + c);
+            float4 v = ok ? *reinterpret_cast<const float4*>(table + id * d + c) : make_float4(0.f, 0.f, 0.f, 0.f);
             if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
             *reinterpret_cast<float4*>(out + r * ld_out + c) = v;
         } else {
-            float v = table[id * d + c];
+            float v = ok ? table[id * d + c] : 0.f;
             out[r * ld_out + c] = relu ? fmaxf(v, 0.f) : v;
         }
     }
 }
 
 int gather_rows(int64_t rows, int d, const float* table, const int64_t* idx, float* out, int64_t ld_out, int relu,
-                cudaStream_t s) {
+                cudaStream_t s, int64_t table_rows) {
     if (rows <= 0 || d <= 0) return INTEL_OK;
     INTEL_REQUIRE(table && idx && out, INTEL_ERR_ARG, "gather: null pointer");
     const bool vec = (d % 4 == 0) && (ld_out % 4 == 0) && (((uintptr_t)table | (uintptr_t)out) % 16 == 0);
     const int64_t total = rows * (vec ? d / 4 : d);
     unsigned grid = stream_grid(ceil_div(total, 256), 8);
-    if (vec) { auto k = gather_kernel<4>; LAUNCH(k, dim3(grid), dim3(256), 0, s, rows, d, table, idx, out, ld_out, relu); }
-    else { auto k = gather_kernel<1>; LAUNCH(k, dim3(grid), dim3(256), 0, s, rows, d, table, idx, out, ld_out, relu); }
+    if (vec) { auto k = gather_kernel<4>; LAUNCH(k, dim3(grid), dim3(256), 0, s, rows, d, table, idx, out, ld_out, relu, table_rows); }
+    else { auto k = gather_kernel<1>; LAUNCH(k, dim3(grid), dim3(256), 0, s, rows, d, table, idx, out, ld_out, relu, table_rows); }
     return check_launch("gather", (double)rows * (8.0 * d + 8.0), 0.0);
 }
 
@@ -44,12 +46,14 @@ int gather_rows(int64_t rows, int d, const float* table, const int64_t* idx, flo
 // DENSE so torch.optim.Adam(weight_decay) is a drop-in).  fp32 atomics.
 __global__ void __launch_bounds__(256) scatter_add_kernel(int64_t rows, int d, const float* __restrict__ d_out,
                                                           int64_t ld, const int64_t* __restrict__ idx,
-                                                          float* grad_table, const float* __restrict__ relu_table) {
+                                                          float* grad_table, const float* __restrict__ relu_table,
+                                                          int64_t table_rows) {
     const int64_t total = rows * d;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r = e / d;
         const int c = (int)(e % d);
         const int64_t id = idx[r];
+        if (table_rows > 0 && (id < 0 || id >= table_rows)) continue;      // would land in another parameter's gradient
         float g = d_out[r * ld + c];
         if (relu_table && !(relu_table[id * d + c] > 0.f)) g = 0.f;
         if (g != 0.f) atomicAdd(grad_table + id * d + c, g);
@@ -57,12 +61,50 @@ __global__ void __launch_bounds__(256) scatter_add_kernel(int64_t rows, int d, c
 }
 
 int scatter_add_rows(int64_t rows, int d, const float* d_out, int64_t ld, const int64_t* idx, float* grad_table,
-                     const float* relu_table, cudaStream_t s) {
+                     const float* relu_table, cudaStream_t s, int64_t table_rows) {
     if (rows <= 0 || d <= 0) return INTEL_OK;
     INTEL_REQUIRE(d_out && idx && grad_table, INTEL_ERR_ARG, "scatter_add: null pointer");
     unsigned grid = stream_grid(ceil_div(rows * d, 256), 8);
-    LAUNCH(scatter_add_kernel, dim3(grid), dim3(256), 0, s, rows, d, d_out, ld, idx, grad_table, relu_table);
+    LAUNCH(scatter_add_kernel, dim3(grid), dim3(256), 0, s, rows, d, d_out, ld, idx, grad_table, relu_table, table_rows);
     return check_launch("scatter_add", (double)rows * (12.0 * d + 8.0), (double)rows * d);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Range check of every index a batch feeds to the tables (nn.Embedding raises IndexError on these, IntEL.py:135-178)
+// and of the history lengths the encoders index with (pack_padded_sequence / the last-state gather need 1..H).
+// One pass over the int64 fields, a few KB per session; bits are ORed into flags[0].
+__device__ __forceinline__ void check_ids(const int64_t* v, int64_t n, int64_t lo, int64_t hi, int bit, int& bad) {
+    if (!v) return;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t x = v[e];
+        if (x < lo || x >= hi) bad |= bit;
+    }
+}
+__global__ void __launch_bounds__(256) batch_validate_kernel(ValidateArgs a, int32_t* flags) {
+    int bad = 0;
+    check_ids(a.u_id, a.B, 0, a.user_rows, 1, bad);
+    check_ids(a.i_id, a.B * a.L, 0, a.item_rows, 2, bad);
+    if (a.class_rows > 0) check_ids(a.i_class, a.B * a.L, 0, a.class_rows, 4, bad);
+    check_ids(a.context_mh, a.B, 0, a.ctx_rows, 8, bad);
+    check_ids(a.his_context, a.B * a.H1, 0, a.ctx_rows, 8, bad);
+    check_ids(a.his_item_id, a.B * a.H2, 0, a.item_rows, 2, bad);
+    check_ids(a.session_len, a.B, 0, a.L + 1, 16, bad);
+    check_ids(a.history_len, a.B, 1, a.H1 + 1, 32, bad);
+    check_ids(a.history_item_len, a.B, 1, a.H2 + 1, 32, bad);
+    if (a.idx1)
+        for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < a.B * a.H1 * a.nz1; e += (int64_t)gridDim.x * blockDim.x)
+            if (a.idx1[e] < 0 || a.idx1[e] >= a.I) bad |= 64;
+    if (a.idx2)
+        for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < a.B * a.H2 * a.nz2; e += (int64_t)gridDim.x * blockDim.x)
+            if (a.idx2[e] < 0 || a.idx2[e] >= a.I) bad |= 64;
+    if (bad) atomicOr(flags, bad);
+}
+int batch_validate(const ValidateArgs& a, int32_t* flags, cudaStream_t s) {
+    INTEL_REQUIRE(flags, INTEL_ERR_ARG, "batch_validate: null flag pointer");
+    if (a.B <= 0) return INTEL_OK;
+    const unsigned grid = stream_grid(ceil_div(a.B * (a.L > a.H1 ? a.L : a.H1), 256), 4);
+    LAUNCH(batch_validate_kernel, dim3(grid), dim3(256), 0, s, a, flags);
+    return check_launch("batch_validate", 8.0 * (double)a.B * (2.0 * a.L + a.H1 + a.H2 + 6.0), 0.0);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -33,11 +33,21 @@ int linear_dw(int64_t M, int64_t N, int64_t K, const float* dY, int64_t lddy, co
 int colsum(int64_t M, int64_t N, const float* X, int64_t ld, float* out, cudaStream_t s);
 
 // ---- embed.cu ---------------------------------------------------------------------------------
+// table_rows > 0: ids outside [0, table_rows) read as a zero row / are skipped by the scatter (memory safety; the
+// error itself is reported by batch_validate)
 int gather_rows(int64_t rows, int d, const float* table, const int64_t* idx, float* out, int64_t ld_out,
-                int relu, cudaStream_t s);
+                int relu, cudaStream_t s, int64_t table_rows = 0);
 // grad_table[idx[r]] += d_out[r] (* (table[idx[r]] > 0) when relu_table != null)
 int scatter_add_rows(int64_t rows, int d, const float* d_out, int64_t ld, const int64_t* idx, float* grad_table,
-                     const float* relu_table, cudaStream_t s);
+                     const float* relu_table, cudaStream_t s, int64_t table_rows = 0);
+// ORs a bit into flags[0] for every class of out-of-range input (bit values: INTEL_BAD_* of intel_b200.h)
+struct ValidateArgs {
+    int64_t B, L, H1, H2, I, item_rows, class_rows, user_rows, ctx_rows;
+    const int64_t *u_id, *i_id, *i_class, *session_len, *context_mh, *his_context, *history_len, *his_item_id, *history_item_len;
+    const int32_t *idx1, *idx2;
+    int nz1, nz2;
+};
+int batch_validate(const ValidateArgs& a, int32_t* flags, cudaStream_t s);
 // out[b, l, :] += table[idx[b]]-style broadcast helpers are not needed: per-session rows are gathered once.
 
 // Dense float64 rows X[R, I] times the intent_embeddings weight, exploiting that the rows are (nearly)
@@ -133,9 +143,28 @@ int awelv_fwd(int64_t B, int64_t L, int K, int h, const float* U, const float* M
               float* weights, float* ens, float* wsmall, cudaStream_t s);
 int awelv_bwd(int64_t B, int64_t L, int K, int h, const float* U, const float* M, const int64_t* uid, const double* scores,
               const float* wsmall, const float* d_weights, const float* d_ens, float* gU, float* gM, cudaStream_t s);
+static const int TD = 32;            // stream width of the fused stack kernels
+struct TrunkArgs {
+    int64_t B;
+    int L, heads, layers;
+    const float *wq, *wk, *wv, *w1, *b1, *w2, *b2, *lnw, *lnb;
+    float* X[9];                     // X[0] input, X[l+1] output of layer l, each [B*L, 32]
+    // activations of layer l kept for the backward pass (written by the forward kernel when save != 0):
+    float *QKV[8], *A[8], *U[8], *Z[8], *ST[8];   // [B*L,96] q|k|v, [B*L,32] x3, [B*L,2] LN mean / rstd
+    int save;
+    Dropout drop[8];                 // per layer (p = 0: off)
+    // backward only
+    float* dX;                       // [B*L,32]: d loss / d X[layers] on entry, d loss / d X[0] on return
+    float *gwq, *gwk, *gwv, *gw1, *gb1, *gw2, *gb2, *glnw, *glnb;
+};
+// tcgen05 / tensor-memory forward pass of the same stack (trunk_tc.cu): L <= 128, same saved activations
+bool trunk_tc_supported(const TrunkArgs& a);
+int trunk_tc_fwd(const TrunkArgs& a, cudaStream_t s);
+void trunk_debug_use_tcgen05(int on);
 void trunk_debug_sessions_per_cta(int n);
 void gemm_debug_use_umma(int on);
-bool trunk_supported(int64_t L, int d, int heads, int layers);
+bool trunk_supported(int64_t L, int d, int heads, int layers);      // mma.sync kernels, forward and backward
+bool trunk_fwd_supported(int64_t L, int heads, int layers);         // any fused forward kernel (d = 32)
 // X[0] = stack input [B*L,32]; X[l+1] receives the output of layer l
 int trunk_fwd(int64_t B, int64_t L, int heads, int layers, const StackParams& p, float* const* X, const StackSaved& sv,
               float drop_p, uint64_t drop_seed, int stream_id, cudaStream_t s);

@@ -13,21 +13,7 @@
 
 namespace intel {
 
-static const int TD = 32;            // stream width
 
-struct TrunkArgs {
-    int64_t B;
-    int L, heads, layers;
-    const float *wq, *wk, *wv, *w1, *b1, *w2, *b2, *lnw, *lnb;
-    float* X[9];                     // X[0] input, X[l+1] output of layer l, each [B*L, 32]
-    // activations of layer l kept for the backward pass (written by the forward kernel when save != 0):
-    float *QKV[8], *A[8], *U[8], *Z[8], *ST[8];   // [B*L,96] q|k|v, [B*L,32] x3, [B*L,2] LN mean / rstd
-    int save;
-    Dropout drop[8];                 // per layer (p = 0: off)
-    // backward only
-    float* dX;                       // [B*L,32]: d loss / d X[layers] on entry, d loss / d X[0] on return
-    float *gwq, *gwk, *gwv, *gw1, *gb1, *gw2, *gb2, *glnw, *glnb;
-};
 
 // ================================================================================================
 // Register-resident forward pass.  A warp owns 16 tokens of a session for the whole stack: its rows of X, Q,
@@ -952,8 +938,16 @@ static int trunk_launch(const TrunkArgs& a, bool bwd, cudaStream_t s) {
     return check_launch("trunk_bwd", bytes, flops);
 }
 
+bool trunk_fwd_supported(int64_t L, int heads, int layers) {
+    TrunkArgs a;
+    memset(&a, 0, sizeof(a));
+    a.L = (int)(L > 1 << 20 ? 1 << 20 : L); a.heads = heads; a.layers = layers;
+    return trunk_tc_supported(a) || trunk_supported(L, TD, heads, layers);
+}
+
 int trunk_run(const TrunkArgs& a, bool bwd, cudaStream_t s) {
     if (a.B <= 0) return INTEL_OK;
+    if (!bwd && trunk_tc_supported(a)) return trunk_tc_fwd(a, s);
     INTEL_REQUIRE(trunk_supported(a.L, TD, a.heads, a.layers), INTEL_ERR_UNSUPPORTED, "fused stack: unsupported shape");
     const int tp = (a.L + 15) / 16 * 16;
 #define INTEL_TRUNK(TPV)                                                            \

@@ -1,0 +1,400 @@
+// Fused self-attention stack of IntEL.predict_ensemble (IntEL.py:182-197, layers.py:31-60) on the 5th-generation
+// tensor cores: tcgen05.mma with accumulators AND the A operands in tensor memory (TMEM).  Forward pass, stream
+// width 32, list length L <= 128; writes exactly the activations trunk_bwd_kernel (trunk.cu) reads back.
+//
+// Mapping.  A tile is 128 token rows = the 128 TMEM lanes: 4 sessions of <= 32 slots, 2 sessions of <= 64 or one of
+// <= 128.  A warpgroup (4 warps) owns a tile and thread t owns token row t for the whole stack: tcgen05.ld / st give
+// it its own lane, so softmax, bias, ReLU, residual and LayerNorm are thread-local (no shuffles).  Every product is
+// 3xTF32 (a_lo b_hi + a_hi b_lo + a_hi b_hi, fp32 accumulation) like the rest of the library:
+//   q|k|v = X [Wq;Wk;Wv]^T   A = X hi/lo planes in TMEM (tcgen05.st by the row owners), B = weight planes in smem, N = 96
+//   S_h   = Q_h K_h^T         A = Q hi/lo in TMEM, B = the session's K rows in smem (K-major), N = padded keys;
+//                             the sessions of a tile write the SAME accumulator columns under a disable-output-lane mask
+//   O_h   = P_h V_h           A = exp(S - max) hi/lo written over S in TMEM, B = the session's V^T (transposing scalar
+//                             stores, chunk stride 528 B keeps them conflict-free), rows scaled by 1/sum afterwards
+//   U = A W1^T + b1, Z = relu(U) W2^T + b2 (+ dropout, + X), LayerNorm
+// Only K and V^T (and the weights) live in shared memory: 65 KB per tile, so two warpgroups = two tiles share an SM and
+// one computes while the other waits for its MMAs (tcgen05.commit -> mbarrier).  Lists of 65..128 slots need all 512
+// TMEM columns for one tile (scores + probabilities of both heads) and run one warpgroup per CTA.
+#include "kernels.h"
+#include "mma.cuh"
+#ifndef INTEL_EMU
+#include "tc05.cuh"
+
+namespace intel {
+
+namespace {
+
+constexpr int TC_WQKV_HI = 0, TC_WQKV_LO = 12288, TC_W1_HI = 24576, TC_W1_LO = 28672, TC_W2_HI = 32768, TC_W2_LO = 36864;
+constexpr int TC_VEC = 40960, TC_BAR = 41472, TC_TMEM = 41488, TC_WG = 41600;
+constexpr int TC_K_HI = 0, TC_K_LO = 16384, TC_VT_HI = 32768, TC_VT_LO = 49664, TC_WG_BYTES = 66560;
+constexpr int TC_K_LBO = 2048;       // K planes [k-chunk][128 rows][4]
+constexpr int TC_VT_LBO = 528;       // V^T planes [key-chunk][32 channels][4] + 16 B: transposing stores hit 32 banks
+
+__device__ __forceinline__ void split32(const float (&v)[32], uint32_t (&h)[32], uint32_t (&l)[32]) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) split_tf32(v[j], h[j], l[j]);
+}
+
+// thread's row of a [*, ld] fp32 tensor -> 32 registers (dead rows read as zero)
+__device__ __forceinline__ void load_row(float (&v)[32], const float* __restrict__ src, bool live) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float4 x = live ? *reinterpret_cast<const float4*>(src + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[4 * j] = x.x; v[4 * j + 1] = x.y; v[4 * j + 2] = x.z; v[4 * j + 3] = x.w;
+    }
+}
+__device__ __forceinline__ void store_row(float* dst, const float (&v)[32], bool live) {
+    if (!live) return;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(dst + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+}
+
+// weight W [rows_w][32] (nn.Linear: [out][in]) -> K-major hi / lo planes, plane row = row0 + out of `rows` rows
+__device__ __forceinline__ void stage_weight(uint8_t* hi, uint8_t* lo, const float* __restrict__ W, int rows, int row0) {
+    for (int e = threadIdx.x; e < TD * TD; e += blockDim.x) {
+        const int n = e >> 5, k = e & 31;
+        uint32_t h, l;
+        split_tf32(W[e], h, l);
+        const int off = ((k >> 2) * rows + row0 + n) * 16 + (k & 3) * 4;
+        *reinterpret_cast<uint32_t*>(hi + off) = h;
+        *reinterpret_cast<uint32_t*>(lo + off) = l;
+    }
+}
+
+// three MMAs of one 8-wide k-slice: D (+)= A B with A in tensor memory
+__device__ __forceinline__ void mma3_ts(uint32_t d, uint32_t a_hi, uint32_t a_lo, uint64_t b_hi, uint64_t b_lo, uint32_t idesc, bool first) {
+    tc05::mma_ts(d, a_lo, b_hi, idesc, first ? 0u : 1u);
+    tc05::mma_ts(d, a_hi, b_lo, idesc, 1u);
+    tc05::mma_ts(d, a_hi, b_hi, idesc, 1u);
+}
+__device__ __forceinline__ void mma3_ts(uint32_t d, uint32_t a_hi, uint32_t a_lo, uint64_t b_hi, uint64_t b_lo, uint32_t idesc, bool first,
+                                        const tc05::LaneMask& m) {
+    tc05::mma_ts(d, a_lo, b_hi, idesc, first ? 0u : 1u, m);
+    tc05::mma_ts(d, a_hi, b_lo, idesc, 1u, m);
+    tc05::mma_ts(d, a_hi, b_hi, idesc, 1u, m);
+}
+
+}  // namespace
+
+// SR: slots of a tile reserved per session (32 / 64 / 128), KP: padded key count (multiple of 32, >= L),
+// COLS: tensor-memory columns of one warpgroup
+template <int HEADS>
+__global__ void __launch_bounds__(256, 1) trunk_tc_fwd_kernel(TrunkArgs a, int SR, int KP, int COLS) {
+    constexpr int DK = TD / HEADS;
+    extern __shared__ __align__(1024) uint8_t tc_smem[];
+    uint8_t* sm = tc_smem;
+    const int tid = threadIdx.x, g = tid >> 7, t = tid & 127, warp = t >> 5;
+    const int WGS = blockDim.x >> 7;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + TC_BAR);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + TC_TMEM);
+    const float* vec = reinterpret_cast<const float*>(sm + TC_VEC);
+
+    // ---- one-time set-up: weight planes, vectors, barriers, tensor memory ----
+    stage_weight(sm + TC_WQKV_HI, sm + TC_WQKV_LO, a.wq, 96, 0);
+    stage_weight(sm + TC_WQKV_HI, sm + TC_WQKV_LO, a.wk, 96, 32);
+    stage_weight(sm + TC_WQKV_HI, sm + TC_WQKV_LO, a.wv, 96, 64);
+    stage_weight(sm + TC_W1_HI, sm + TC_W1_LO, a.w1, 32, 0);
+    stage_weight(sm + TC_W2_HI, sm + TC_W2_LO, a.w2, 32, 0);
+    if (tid < TD) {
+        float* v = reinterpret_cast<float*>(sm + TC_VEC);
+        v[tid] = a.b1[tid]; v[TD + tid] = a.b2[tid]; v[2 * TD + tid] = a.lnw[tid]; v[3 * TD + tid] = a.lnb[tid];
+    }
+    if (tid == 0) {
+        tc05::mbar_init(&bars[0], 1);
+        tc05::mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (tid < 32) tc05::tmem_alloc(tmem_slot, 512);
+    tc05::fence_smem_to_mma();
+    tc05::fence_before();
+    __syncthreads();
+    tc05::fence_after();
+
+    const uint32_t tm = *tmem_slot + (uint32_t)(g * COLS);         // this warpgroup's columns, lane 0
+    const uint32_t tl = tm + ((uint32_t)(warp * 32) << 16);         // ... this warp's 32 lanes
+    const uint32_t cA = 0, cS = 64, cPlo = 64 + HEADS * KP, cO = 0;
+    uint64_t* bar = &bars[g];
+    uint32_t phase = 0;
+    uint8_t* wg = sm + TC_WG + g * TC_WG_BYTES;
+    const uint32_t s_wqkv_hi = tc05::smem_u32(sm + TC_WQKV_HI), s_wqkv_lo = tc05::smem_u32(sm + TC_WQKV_LO);
+    const uint32_t s_w1_hi = tc05::smem_u32(sm + TC_W1_HI), s_w1_lo = tc05::smem_u32(sm + TC_W1_LO);
+    const uint32_t s_w2_hi = tc05::smem_u32(sm + TC_W2_HI), s_w2_lo = tc05::smem_u32(sm + TC_W2_LO);
+    const uint32_t s_k_hi = tc05::smem_u32(wg + TC_K_HI), s_k_lo = tc05::smem_u32(wg + TC_K_LO);
+    const uint32_t s_vt_hi = tc05::smem_u32(wg + TC_VT_HI), s_vt_lo = tc05::smem_u32(wg + TC_VT_LO);
+
+    const int L = a.L, NS = 128 / SR;
+    const int slot = t / SR, r = t - slot * SR;                     // session slot of the tile, row inside the session
+    const int vt_sess = (SR >> 2) * TC_VT_LBO;                      // bytes of one session's V^T plane
+    const float scale = 1.0f / sqrtf((float)DK);
+    const int64_t tiles = (a.B + NS - 1) / NS;
+    const int bar_id = 1 + g;
+
+    // all row owners are done writing operands -> the elected thread may issue
+#define TC_PUBLISH()              \
+    do {                          \
+        tc05::wait_st();          \
+        tc05::fence_smem_to_mma(); \
+        tc05::fence_before();     \
+        bar_sync(bar_id, 128);    \
+    } while (0)
+#define TC_WAIT()                     \
+    do {                              \
+        tc05::mbar_wait(bar, phase);  \
+        phase ^= 1u;                  \
+        tc05::fence_after();          \
+    } while (0)
+
+    for (int64_t tile = (int64_t)blockIdx.x * WGS + g; tile < tiles; tile += (int64_t)gridDim.x * WGS) {
+        const int64_t b = tile * NS + slot;
+        const bool live = b < a.B && r < L;
+        const int64_t grow = b * L + r;                              // token row in the [B*L, *] tensors
+        float x[32];
+        load_row(x, a.X[0] + grow * TD, live);
+
+        for (int l = 0; l < a.layers; ++l) {
+            // ---- q|k|v ----
+            {
+                uint32_t h[32], lo[32];
+                split32(x, h, lo);
+                tc05::st32(tl + cA, h);
+                tc05::st32(tl + cA + 32, lo);
+            }
+            TC_PUBLISH();
+            if (t == 0) {
+                tc05::fence_after();
+                const uint32_t id = tc05::make_idesc(128, 96);
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+                    mma3_ts(tm + cS, tm + cA + 8 * ks, tm + cA + 32 + 8 * ks, tc05::make_desc(s_wqkv_hi + ks * 2 * 1536, 1536, 128),
+                            tc05::make_desc(s_wqkv_lo + ks * 2 * 1536, 1536, 128), id, ks == 0);
+                tc05::commit(bar);
+            }
+            TC_WAIT();
+            {
+                float v[32];
+                uint32_t u[32], h[32], lo[32];
+                // Q -> A operand of the score products
+                tc05::ld32(tl + cS, u);
+                tc05::wait_ld();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(u[j]);
+                if (a.save) store_row(a.QKV[l] + grow * 3 * TD, v, live);
+                split32(v, h, lo);
+                tc05::st32(tl + cA, h);
+                tc05::st32(tl + cA + 32, lo);
+                // K -> the tile's key planes (row = tile row; dead rows hold zeros)
+                tc05::ld32(tl + cS + 32, u);
+                tc05::wait_ld();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(u[j]);
+                if (a.save) store_row(a.QKV[l] + grow * 3 * TD + TD, v, live);
+                split32(v, h, lo);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    *reinterpret_cast<uint4*>(wg + TC_K_HI + c * TC_K_LBO + t * 16) = make_uint4(h[4 * c], h[4 * c + 1], h[4 * c + 2], h[4 * c + 3]);
+                    *reinterpret_cast<uint4*>(wg + TC_K_LO + c * TC_K_LBO + t * 16) = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
+                }
+                // V -> the session's V^T planes
+                tc05::ld32(tl + cS + 64, u);
+                tc05::wait_ld();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(u[j]);
+                if (a.save) store_row(a.QKV[l] + grow * 3 * TD + 2 * TD, v, live);
+                split32(v, h, lo);
+                const int vo = slot * vt_sess + (r >> 2) * TC_VT_LBO + (r & 3) * 4;
+#pragma unroll
+                for (int ch = 0; ch < 32; ++ch) {
+                    *reinterpret_cast<uint32_t*>(wg + TC_VT_HI + vo + ch * 16) = h[ch];
+                    *reinterpret_cast<uint32_t*>(wg + TC_VT_LO + vo + ch * 16) = lo[ch];
+                }
+            }
+            // ---- scores of every head and session ----
+            TC_PUBLISH();
+            if (t == 0) {
+                tc05::fence_after();
+                const uint32_t id = tc05::make_idesc(128, KP);
+#pragma unroll
+                for (int hd = 0; hd < HEADS; ++hd)
+                    for (int ss = 0; ss < NS; ++ss) {
+                        const tc05::LaneMask m = tc05::mask_rows(ss * SR, SR);
+#pragma unroll
+                        for (int ks = 0; ks < DK / 8; ++ks) {
+                            const uint32_t koff = (uint32_t)((hd * (DK / 4) + 2 * ks) * TC_K_LBO + ss * SR * 16);
+                            mma3_ts(tm + cS + hd * KP, tm + cA + hd * DK + 8 * ks, tm + cA + 32 + hd * DK + 8 * ks,
+                                    tc05::make_desc(s_k_hi + koff, TC_K_LBO, 128), tc05::make_desc(s_k_lo + koff, TC_K_LBO, 128), id, ks == 0, m);
+                        }
+                    }
+                tc05::commit(bar);
+            }
+            TC_WAIT();
+            // ---- softmax numerators over S (in place) and the attention output, head by head ----
+            float inv[HEADS];
+#pragma unroll
+            for (int hd = 0; hd < HEADS; ++hd) {
+                const uint32_t cs = cS + hd * KP;
+                float mx = -INFINITY;
+                for (int c = 0; c < KP; c += 32) {
+                    uint32_t u[32];
+                    tc05::ld32(tl + cs + c, u);
+                    tc05::wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (c + j < L) mx = fmaxf(mx, __uint_as_float(u[j]) * scale);
+                }
+                if (hd > 0) TC_WAIT();                  // the previous head's P V product is done with the shared lo plane
+                float sum = 0.f;
+                for (int c = 0; c < KP; c += 32) {
+                    uint32_t u[32], h[32], lo[32];
+                    tc05::ld32(tl + cs + c, u);
+                    tc05::wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float e = (c + j < L) ? expf(__uint_as_float(u[j]) * scale - mx) : 0.f;
+                        sum += e;
+                        split_tf32(e, h[j], lo[j]);
+                    }
+                    tc05::st32(tl + cs + c, h);
+                    tc05::st32(tl + cPlo + c, lo);
+                }
+                inv[hd] = 1.0f / sum;
+                TC_PUBLISH();
+                if (t == 0) {
+                    tc05::fence_after();
+                    const uint32_t id = tc05::make_idesc(128, DK);
+                    for (int ss = 0; ss < NS; ++ss) {
+                        const tc05::LaneMask m = tc05::mask_rows(ss * SR, SR);
+                        for (int ks = 0; ks < KP / 8; ++ks) {
+                            const uint32_t voff = (uint32_t)(ss * vt_sess + hd * DK * 16 + ks * 2 * TC_VT_LBO);
+                            mma3_ts(tm + cO + hd * DK, tm + cs + 8 * ks, tm + cPlo + 8 * ks, tc05::make_desc(s_vt_hi + voff, TC_VT_LBO, 128),
+                                    tc05::make_desc(s_vt_lo + voff, TC_VT_LBO, 128), id, ks == 0, m);
+                        }
+                    }
+                    tc05::commit(bar);
+                }
+            }
+            TC_WAIT();
+            // ---- FFN ----
+            float att[32];
+            {
+                uint32_t u[32], h[32], lo[32];
+                tc05::ld32(tl + cO, u);
+                tc05::wait_ld();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) att[j] = __uint_as_float(u[j]) * inv[j / DK];
+                if (a.save) store_row(a.A[l] + grow * TD, att, live);
+                split32(att, h, lo);
+                tc05::st32(tl + cA, h);
+                tc05::st32(tl + cA + 32, lo);
+            }
+            TC_PUBLISH();
+            if (t == 0) {
+                tc05::fence_after();
+                const uint32_t id = tc05::make_idesc(128, 32);
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+                    mma3_ts(tm + cS, tm + cA + 8 * ks, tm + cA + 32 + 8 * ks, tc05::make_desc(s_w1_hi + ks * 2 * 512, 512, 128),
+                            tc05::make_desc(s_w1_lo + ks * 2 * 512, 512, 128), id, ks == 0);
+                tc05::commit(bar);
+            }
+            TC_WAIT();
+            {
+                uint32_t u[32], h[32], lo[32];
+                float uu[32];
+                tc05::ld32(tl + cS, u);
+                tc05::wait_ld();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) uu[j] = __uint_as_float(u[j]) + vec[j];
+                if (a.save) store_row(a.U[l] + grow * TD, uu, live);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) split_tf32(fmaxf(uu[j], 0.f), h[j], lo[j]);
+                tc05::st32(tl + cA, h);
+                tc05::st32(tl + cA + 32, lo);
+            }
+            TC_PUBLISH();
+            if (t == 0) {
+                tc05::fence_after();
+                const uint32_t id = tc05::make_idesc(128, 32);
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+                    mma3_ts(tm + cS + 32, tm + cA + 8 * ks, tm + cA + 32 + 8 * ks, tc05::make_desc(s_w2_hi + ks * 2 * 512, 512, 128),
+                            tc05::make_desc(s_w2_lo + ks * 2 * 512, 512, 128), id, ks == 0);
+                tc05::commit(bar);
+            }
+            TC_WAIT();
+            // ---- Z = dropout(F) + X, LayerNorm (the row is in this thread's registers) ----
+            {
+                uint32_t u[32];
+                float z[32];
+                tc05::ld32(tl + cS + 32, u);
+                tc05::wait_ld();
+                const Dropout& dr = a.drop[l];
+                float sum = 0.f;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    z[j] = (__uint_as_float(u[j]) + vec[TD + j]) * dropout_scale(dr, grow, j, TD) + x[j];
+                    sum += z[j];
+                }
+                const float mean = sum * (1.0f / TD);
+                float var = 0.f;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float d0 = z[j] - mean;
+                    var = fmaf(d0, d0, var);
+                }
+                const float rstd = rsqrtf(var * (1.0f / TD) + 1e-5f);
+                if (a.save) {
+                    store_row(a.Z[l] + grow * TD, z, live);
+                    if (live) *reinterpret_cast<float2*>(a.ST[l] + grow * 2) = make_float2(mean, rstd);
+                }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) x[j] = live ? (z[j] - mean) * rstd * vec[2 * TD + j] + vec[3 * TD + j] : 0.f;
+                if (a.save || l == a.layers - 1) store_row(a.X[l + 1] + grow * TD, x, live);
+            }
+        }
+    }
+#undef TC_PUBLISH
+#undef TC_WAIT
+    tc05::fence_before();
+    __syncthreads();
+    if (tid < 32) tc05::tmem_free(*tmem_slot, 512);
+}
+
+static int g_use_tc = 1;
+void trunk_debug_use_tcgen05(int on) { g_use_tc = on ? 1 : 0; }
+
+bool trunk_tc_supported(const TrunkArgs& a) {
+    return g_use_tc && a.L >= 1 && a.L <= 128 && (a.heads == 1 || a.heads == 2) && a.layers >= 1 && a.layers <= 8;
+}
+
+int trunk_tc_fwd(const TrunkArgs& a, cudaStream_t s) {
+    const int SR = a.L <= 32 ? 32 : (a.L <= 64 ? 64 : 128);
+    const int KP = (a.L + 31) / 32 * 32;
+    const int need = 64 + (a.heads + 1) * KP;                      // A planes | S (P hi) per head | P lo
+    const int WGS = need <= 256 ? 2 : 1;
+    const int COLS = 512 / WGS;
+    const size_t smem = (size_t)TC_WG + (size_t)WGS * TC_WG_BYTES;
+    const int64_t tiles = ceil_div(a.B, 128 / SR);
+    const unsigned grid = stream_grid(ceil_div(tiles, WGS), 1);
+    if (a.heads == 1) {
+        auto k = trunk_tc_fwd_kernel<1>;
+        ensure_smem(k, smem);
+        LAUNCH(k, dim3(grid), dim3(128 * WGS), smem, s, a, SR, KP, COLS);
+    } else {
+        auto k = trunk_tc_fwd_kernel<2>;
+        ensure_smem(k, smem);
+        LAUNCH(k, dim3(grid), dim3(128 * WGS), smem, s, a, SR, KP, COLS);
+    }
+    const double tok = (double)a.B * a.L;
+    const double flops = tok * a.layers * (2.0 * 5 * TD * TD + 4.0 * a.L * TD);
+    const double bytes = tok * (4.0 * TD + (a.save ? 4.0 * (3 * TD + 4 * TD + 2) * a.layers : 4.0 * TD));
+    return check_launch("trunk_fwd", bytes, flops);
+}
+
+}  // namespace intel
+#else   // INTEL_EMU: the emulator has no tensor memory; the mma.sync kernels of trunk.cu cover the same math there
+namespace intel {
+void trunk_debug_use_tcgen05(int) {}
+bool trunk_tc_supported(const TrunkArgs&) { return false; }
+int trunk_tc_fwd(const TrunkArgs&, cudaStream_t) { return INTEL_ERR_UNSUPPORTED; }
+}  // namespace intel
+#endif

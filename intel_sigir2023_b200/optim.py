@@ -50,12 +50,16 @@ class Adam(torch.optim.Optimizer):
             step_t = cache["step"]
             step_t += 1                                   # one shared tensor: every parameter's state["step"] aliases it
             n = len(ps)
-            grads = cache["grads"]
+            grads, params, ms, vs = cache["grads"], cache["params"], cache["m"], cache["v"]
             for i, p in enumerate(ps):
                 g = p.grad
                 if g.dtype != torch.float32 or not g.is_contiguous() or g.device != p.device:
                     raise ValueError("intel_adam_step needs contiguous float32 gradients on the parameter's device")
                 grads[i] = g.data_ptr()
+                # the Parameter object can outlive its storage (model.to(), p.data = ..., a replaced state tensor):
+                # re-read the pointers every step like torch.optim.Adam re-reads the tensors
+                st = self.state[p]
+                params[i], ms[i], vs[i] = p.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr()
             b1, b2 = group["betas"]
             wd = float(group["weight_decay"])
             if wd != cache["wd_value"]:

@@ -18,6 +18,17 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+def pytest_collection_modifyitems(config, items):
+    """Without a CUDA device the gpu-marked tests are skipped (a CPU CI run stays readable); INTEL_REQUIRE_GPU=1 turns
+    the skip back into a hard failure on the box that is supposed to have one."""
+    if torch.cuda.is_available() or os.environ.get("INTEL_REQUIRE_GPU") == "1":
+        return
+    skip = pytest.mark.skip(reason="no CUDA device (set INTEL_REQUIRE_GPU=1 to fail instead)")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
 def load_model_case(name, device="cpu"):
     """-> (cfg, batch, state, golden dict) from tests/golden/model_<name>.npz"""
     from intel_sigir2023_b200.config import IntelConfig
@@ -43,9 +54,10 @@ LOSS_KW = dict(cal_diversity=1, diversity_alpha=0.05, intent_weight=0.1, ensembl
                kl_weight=0.5, kl_temp=2.0)
 
 
-def assert_grad_close(g, ref, gmax, name, rtol=5e-4, afrac=2e-6):
+def assert_grad_close(g, ref, gmax, name, rtol=1e-5, afrac=2e-6):
     """|g-ref| <= rtol*max|ref| + afrac*gmax, gmax = largest gradient entry of the whole model
-    (gradients that are analytically zero, e.g. softmax key biases, are pure rounding noise)."""
+    (gradients that are analytically zero, e.g. softmax key biases, are pure rounding noise).
+    BASELINE.md section 3: parameter gradients within 1e-5 of the tensor's inf-norm."""
     g = np.asarray(g, dtype=np.float64)
     ref = np.asarray(ref, dtype=np.float64)
     assert g.shape == ref.shape, (name, g.shape, ref.shape)

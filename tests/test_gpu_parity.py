@@ -109,5 +109,9 @@ def test_fused_stack_shapes():
     P.check_fused_shapes(DEV)
 
 
+def test_tcgen05_stack_matches_mma_sync_stack():
+    P.check_tc_stack(DEV)
+
+
 def test_dropout():
     P.check_dropout(DEV)
