@@ -53,6 +53,9 @@ typedef struct {
      * Masks come from a counter-based hash of (seed, stream, layer, row, channel); pass a new seed per step. */
     float dropout_p;
     uint64_t dropout_seed;
+    /* 1: forward only (BaseRunner.predict runs under torch.no_grad()): the fused stack kernels skip the activations they
+     * would otherwise leave in the workspace for intel_ensemble_bwd, which must then not be called on this workspace. */
+    int32_t inference;
 } intel_dims_t;
 
 typedef struct {             /* layers.py TransformerLayer, one block of BERT4RecEncoder */
@@ -205,6 +208,44 @@ int intel_select_list(int64_t B, int64_t L, int64_t K, const double* scores, int
 /* Borda.forward (Borda.py:23-30): mean over lists of the ascending rank inside the padded list. */
 int intel_rank_lists(int64_t B, int64_t L, int64_t K, const double* scores, float* ens_out,
                      intel_stream_t stream);
+
+/* ---- device-side batch construction ----------------------------------------------------------
+ * A columnar corpus resident in device memory replaces the per-session `_get_feed_dict` + `collate_batch` of the reference
+ * (models/BaseModel.py:121-197, models/GeneralSeq.py:35-54, models/IntEL/IntEL.py:220-239).  All arrays are device pointers
+ * owned by the caller.  Per-row columns have N entries (one per session of the phase, reference row order); the item lists
+ * are CSR (item_off [N+1]) with precomputed in-session rankings (BaseModel.py:177-185) and min-max normalised float64
+ * scores [nnz, K] (BaseModel.py:173); uhis_* / uitem_* are the per-user session / item histories of SeqReader
+ * (helpers/SeqReader.py:18-60), CSR by user id; int_* is the CSR of the intent vectors, row 0 = the all-zero vector. */
+typedef struct {
+    int64_t N, K, I, max_his;     /* sessions, basic lists, intents, --history_max (0: unlimited) */
+    int32_t nz1;                  /* entries per history row in the compact his_intents output (>= longest intent row) */
+    const int64_t *u_id, *c_id, *context_mh, *user_mh, *pay, *fav, *click, *session_len, *position, *item_position, *intent_row;
+    const int64_t *item_off, *item_id, *item_class, *ranking;
+    const double  *scores;
+    const int64_t *uhis_off, *uhis_row, *uhis_ctx;       /* [users+1], intent-row and context_mh of each history session */
+    const int64_t *uitem_off, *uitem_id;                 /* [users+1], item ids of the user's positive items */
+    const int32_t *uitem_int;                            /* behaviour * I / K + class of each of them (IntEL.py:226) */
+    const int64_t *int_off;                              /* [rows+1] */
+    const int32_t *int_idx;
+    const double  *int_val;
+} intel_corpus_t;
+/* the batch in the layout intel_batch_t reads (compact history intents) + the fields the losses / evaluation need */
+typedef struct {
+    int64_t *u_id, *c_id, *context_mh, *user_mh, *pay, *fav, *click, *session_len, *position, *history_len, *history_item_len; /* [B] */
+    int64_t *i_id, *i_class, *ranking;    /* [B,L], right-padded with 0 */
+    double  *scores;                      /* [B,L,K] */
+    double  *intents;                     /* [B,I] dense */
+    int64_t *his_context;                 /* [B,H1] */
+    int32_t *his_intents_idx;             /* [B,H1,nz1] */
+    float   *his_intents_val;
+    int64_t *his_item_id;                 /* [B,H2] */
+    int32_t *his_item_int_idx;            /* [B,H2,1] */
+    float   *his_item_int_val;
+} intel_built_batch_t;
+/* rows: device int64 [B] indices into the phase; perm: device int32 [B,L] or NULL - slot l of session b takes slot
+ * perm[b,l] of its stored list (the per-fetch shuffle of BaseModel.py:194-196); L, H1, H2: padded widths of this batch. */
+int intel_batch_build(const intel_corpus_t* corpus, int64_t B, const int64_t* rows, const int32_t* perm, int64_t L,
+                      int64_t H1, int64_t H2, const intel_built_batch_t* out, intel_stream_t stream);
 
 /* ---- optional per-kernel device timing (used by bench.py for the live roofline numbers) ------ */
 /* While enabled every kernel launch is bracketed by CUDA events on its stream. */

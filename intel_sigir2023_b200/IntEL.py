@@ -90,7 +90,8 @@ class _IntelFn(torch.autograd.Function):
         p_drop = float(cfg.dropout) if model.training else 0.0
         if p_drop > 0.0:
             model._drop_step += 1
-        dims = _lib.make_dims(cfg, B, L, H1, H2, p_drop, model._drop_seed * 1000003 + model._drop_step)
+        keep = grad_mode and any(ctx.needs_input_grad)
+        dims = _lib.make_dims(cfg, B, L, H1, H2, p_drop, model._drop_seed * 1000003 + model._drop_step, inference=not keep)
         P = _lib.make_tensors(cfg, tensors)
         bt = _lib.make_batch(batch, cfg)
         stream = _lib.stream_ptr(dev)
@@ -106,7 +107,7 @@ class _IntelFn(torch.autograd.Function):
                                           _lib.ptr(ws_ens), ws_ens.numel(), stream))
         # needs_input_grad stays True under torch.no_grad() (BaseRunner.predict) and the grad mode is always off inside
         # Function.forward: the caller's grad mode arrives as an argument
-        if grad_mode and any(ctx.needs_input_grad):
+        if keep:
             ctx.model, ctx.batch, ctx.dims = model, batch, dims
             ctx.ws_int, ctx.ws_ens = ws_int, ws_ens
             ctx.params = params

@@ -26,7 +26,7 @@ class Dims(C.Structure):
                [(n, C.c_int32) for n in ("d_iid", "d_im", "d_u", "d_s", "d_int", "d_ctx", "qsize", "heads", "layers",
                                          "cross_attention", "encoder", "gru_hidden", "bert_layers", "bert_heads",
                                          "history_max")] + \
-               [("dropout_p", C.c_float), ("dropout_seed", C.c_uint64)]
+               [("dropout_p", C.c_float), ("dropout_seed", C.c_uint64), ("inference", C.c_int32)]
 
 
 class BertLayer(C.Structure):
@@ -89,6 +89,7 @@ def _declare(lib: C.CDLL) -> None:
         "intel_select_list": (i32, [i64, i64, i64, _p, i32, _p, _p]),
         "intel_rank_lists": (i32, [i64, i64, i64, _p, _p, _p]),
         "intel_batch_validate": (i32, [PD, PB, _p, _p]),
+        "intel_batch_build": (i32, [_p, i64, _p, _p, i64, i64, i64, _p, _p]),
         "intel_gather_fwd": (i32, [i64, i32, _p, _p, _p, i32, i32, _p]),
         "intel_scatter_add_bwd": (i32, [i64, i32, _p, i32, _p, _p, _p]),
         "intel_linear_fwd": (i32, [i64, i64, i64, _p, _p, _p, _p, _p]),
@@ -131,7 +132,7 @@ EXPORTED = ["intel_last_error", "intel_abi_version", "intel_intent_workspace_byt
             "intel_mha_bwd", "intel_debug_use_fused_stack", "intel_debug_stack_sessions_per_cta", "intel_debug_use_tcgen05_gemm", "intel_host_pack_rows", "intel_adam_step", "intel_awelv_fwd", "intel_awelv_bwd",
             "intel_lambdarank_lambdas", "intel_pool_head_fwd", "intel_pool_head_bwd",
             "intel_linear_fwd_ex", "intel_linear_dx_ex", "intel_linear_dw_ex", "intel_softmax_rows_fwd", "intel_softmax_rows_bwd",
-            "intel_batch_validate", "intel_debug_use_tcgen05_stack"]
+            "intel_batch_validate", "intel_debug_use_tcgen05_stack", "intel_batch_build"]
 
 
 def load(path: Optional[str] = None) -> C.CDLL:
@@ -180,8 +181,10 @@ def stream_ptr(device: torch.device) -> Optional[int]:
     return torch.cuda.current_stream(device).cuda_stream
 
 
-def make_dims(cfg: IntelConfig, B: int, L: int, H1: int, H2: int, dropout_p: float = 0.0, seed: int = 0) -> Dims:
+def make_dims(cfg: IntelConfig, B: int, L: int, H1: int, H2: int, dropout_p: float = 0.0, seed: int = 0,
+              inference: bool = False) -> Dims:
     d = Dims()
+    d.inference = 1 if inference else 0
     d.dropout_p, d.dropout_seed = float(dropout_p), int(seed) & 0xFFFFFFFFFFFFFFFF
     d.B, d.L, d.K, d.I, d.H1, d.H2 = B, L, cfg.model_num, cfg.intent_num, H1, H2
     d.item_rows, d.class_rows, d.user_rows, d.ctx_rows = cfg.item_rows, cfg.class_rows, cfg.user_rows, cfg.ctx_rows

@@ -52,14 +52,14 @@ void stack_layout(Arena& a, int64_t R, int d, int layers, StackWs& w) {
 int g_use_fused_stack = 1;
 
 int stack_fwd(int64_t B, int64_t L, int d, int heads, int layers, const intel_selfatt_t& p, StackWs& w, float drop_p,
-              uint64_t drop_seed, int stream_id, cudaStream_t s) {
+              uint64_t drop_seed, int stream_id, cudaStream_t s, bool save = true) {
     const int64_t R = B * L;
     // whole stack of a session on chip: tcgen05 kernel (trunk_tc.cu, L <= 128) or the mma.sync kernel (trunk.cu, L <= 64);
     // both leave the same activations behind, which the fused and the staged backward passes read alike
     if (g_use_fused_stack && d == TD && trunk_fwd_supported(L, heads, layers)) {
         const StackParams sp{p.wq, p.wk, p.wv, p.w1, p.b1, p.w2, p.b2, p.lnw, p.lnb};
         const StackSaved sv{w.QKV, w.A, w.U, w.Z, w.st};
-        return trunk_fwd(B, L, heads, layers, sp, w.X, sv, drop_p, drop_seed, stream_id, s);
+        return trunk_fwd(B, L, heads, layers, sp, w.X, sv, drop_p, drop_seed, stream_id, s, save);
     }
     for (int l = 0; l < layers; ++l) {
         INTEL_TRY(linear(R, d, d, w.X[l], d, p.wq, d, nullptr, w.QKV[l], 3 * d, s));
@@ -393,8 +393,8 @@ int intel_ensemble_fwd(const intel_dims_t* d, const intel_tensors_t* P, const in
     INTEL_TRY(gather_rows(R, d->d_iid, P->iid_emb, bt->i_id, w.item.X[0], di, 0, s, d->item_rows));
     if (d->d_im > 0) INTEL_TRY(gather_rows(R, d->d_im, P->item_emb, bt->i_class, w.item.X[0] + d->d_iid, di, 0, s, d->class_rows));
     INTEL_TRY(score_embed_fwd(R, K, ds, bt->scores, P->score_w, P->score_b, w.score.X[0], w.xs, s));
-    INTEL_TRY(stack_fwd(B, L, di, d->heads, d->layers, P->item, w.item, d->dropout_p, d->dropout_seed, 0, s));
-    INTEL_TRY(stack_fwd(B, L, ds, d->heads, d->layers, P->score, w.score, d->dropout_p, d->dropout_seed, 1, s));
+    INTEL_TRY(stack_fwd(B, L, di, d->heads, d->layers, P->item, w.item, d->dropout_p, d->dropout_seed, 0, s, d->inference == 0));
+    INTEL_TRY(stack_fwd(B, L, ds, d->heads, d->layers, P->score, w.score, d->dropout_p, d->dropout_seed, 1, s, d->inference == 0));
     float* Xi = w.item.X[d->layers];
     float* Xs = w.score.X[d->layers];
 

@@ -167,7 +167,7 @@ bool trunk_supported(int64_t L, int d, int heads, int layers);      // mma.sync 
 bool trunk_fwd_supported(int64_t L, int heads, int layers);         // any fused forward kernel (d = 32)
 // X[0] = stack input [B*L,32]; X[l+1] receives the output of layer l
 int trunk_fwd(int64_t B, int64_t L, int heads, int layers, const StackParams& p, float* const* X, const StackSaved& sv,
-              float drop_p, uint64_t drop_seed, int stream_id, cudaStream_t s);
+              float drop_p, uint64_t drop_seed, int stream_id, cudaStream_t s, bool save = true);
 // dX: d loss / d X[layers] on entry, d loss / d X[0] on return; weight gradients are accumulated into g
 int trunk_bwd(int64_t B, int64_t L, int heads, int layers, const StackParams& p, const StackGrads& g, float* const* X,
               const StackSaved& sv, float* dX, float drop_p, uint64_t drop_seed, int stream_id, cudaStream_t s);

@@ -977,8 +977,9 @@ static TrunkArgs trunk_args(int64_t B, int64_t L, int heads, int layers, const S
 }
 
 int trunk_fwd(int64_t B, int64_t L, int heads, int layers, const StackParams& p, float* const* X, const StackSaved& sv,
-              float drop_p, uint64_t drop_seed, int stream_id, cudaStream_t s) {
+              float drop_p, uint64_t drop_seed, int stream_id, cudaStream_t s, bool save) {
     TrunkArgs a = trunk_args(B, L, heads, layers, p, X, sv, drop_p, drop_seed, stream_id);
+    a.save = save ? 1 : 0;
     return trunk_run(a, false, s);
 }
 

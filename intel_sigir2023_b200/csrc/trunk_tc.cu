@@ -76,11 +76,28 @@ __device__ __forceinline__ void mma3_ts(uint32_t d, uint32_t a_hi, uint32_t a_lo
 
 }  // namespace
 
-// SR: slots of a tile reserved per session (32 / 64 / 128), KP: padded key count (multiple of 32, >= L),
+// one lane of a converged warp (the MMA operands then stay in uniform registers instead of going through R2UR per MMA)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t p;
+    asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}" : "=r"(p));
+    return p != 0;
+}
+// descriptor of the same layout `bytes` further into shared memory
+__device__ __forceinline__ uint64_t desc_at(uint64_t base, uint32_t bytes) { return base + (uint64_t)(bytes >> 4); }
+
+// exp(x) for x <= 0 as one FFMA + MUFU.EX2 (relative error 2^-22, far inside the 1e-5 budget of the softmax)
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// SR: slots of a tile reserved per session (32 / 64 / 128), NCH * 32 = KP: padded key count (>= L),
 // COLS: tensor-memory columns of one warpgroup
-template <int HEADS>
-__global__ void __launch_bounds__(256, 1) trunk_tc_fwd_kernel(TrunkArgs a, int SR, int KP, int COLS) {
-    constexpr int DK = TD / HEADS;
+template <int HEADS, int NCH>
+__global__ void __launch_bounds__(256, 1) trunk_tc_fwd_kernel(TrunkArgs a, int COLS) {
+    constexpr int DK = TD / HEADS, KP = 32 * NCH;
+    constexpr int SR = NCH == 1 ? 32 : (NCH == 2 ? 64 : 128), NS = 128 / SR;
     extern __shared__ __align__(1024) uint8_t tc_smem[];
     uint8_t* sm = tc_smem;
     const int tid = threadIdx.x, g = tid >> 7, t = tid & 127, warp = t >> 5;
@@ -121,11 +138,19 @@ __global__ void __launch_bounds__(256, 1) trunk_tc_fwd_kernel(TrunkArgs a, int S
     const uint32_t s_w2_hi = tc05::smem_u32(sm + TC_W2_HI), s_w2_lo = tc05::smem_u32(sm + TC_W2_LO);
     const uint32_t s_k_hi = tc05::smem_u32(wg + TC_K_HI), s_k_lo = tc05::smem_u32(wg + TC_K_LO);
     const uint32_t s_vt_hi = tc05::smem_u32(wg + TC_VT_HI), s_vt_lo = tc05::smem_u32(wg + TC_VT_LO);
+    const uint64_t d_wqkv_hi = tc05::make_desc(s_wqkv_hi, 1536, 128), d_wqkv_lo = tc05::make_desc(s_wqkv_lo, 1536, 128);
+    const uint64_t d_w1_hi = tc05::make_desc(s_w1_hi, 512, 128), d_w1_lo = tc05::make_desc(s_w1_lo, 512, 128);
+    const uint64_t d_w2_hi = tc05::make_desc(s_w2_hi, 512, 128), d_w2_lo = tc05::make_desc(s_w2_lo, 512, 128);
+    const uint64_t d_k_hi = tc05::make_desc(s_k_hi, TC_K_LBO, 128), d_k_lo = tc05::make_desc(s_k_lo, TC_K_LBO, 128);
+    const uint64_t d_vt_hi = tc05::make_desc(s_vt_hi, TC_VT_LBO, 128), d_vt_lo = tc05::make_desc(s_vt_lo, TC_VT_LBO, 128);
+    const uint32_t id_qkv = tc05::make_idesc(128, 96), id_s = tc05::make_idesc(128, KP), id_pv = tc05::make_idesc(128, DK),
+                   id_ffn = tc05::make_idesc(128, 32);
+    const int pv_steps = (a.L + 7) >> 3;                             // key slices of 8 that hold a live key
 
-    const int L = a.L, NS = 128 / SR;
+    const int L = a.L;
     const int slot = t / SR, r = t - slot * SR;                     // session slot of the tile, row inside the session
-    const int vt_sess = (SR >> 2) * TC_VT_LBO;                      // bytes of one session's V^T plane
-    const float scale = 1.0f / sqrtf((float)DK);
+    constexpr int vt_sess = (SR >> 2) * TC_VT_LBO;                  // bytes of one session's V^T plane
+    const float sl2 = 1.4426950408889634f / sqrtf((float)DK);       // softmax scale folded into the base-2 exponent
     const int64_t tiles = (a.B + NS - 1) / NS;
     const int bar_id = 1 + g;
 
@@ -160,71 +185,78 @@ __global__ void __launch_bounds__(256, 1) trunk_tc_fwd_kernel(TrunkArgs a, int S
                 tc05::st32(tl + cA + 32, lo);
             }
             TC_PUBLISH();
-            if (t == 0) {
+            if (warp == 0) {
                 tc05::fence_after();
-                const uint32_t id = tc05::make_idesc(128, 96);
+                if (elect_one()) {
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks)
-                    mma3_ts(tm + cS, tm + cA + 8 * ks, tm + cA + 32 + 8 * ks, tc05::make_desc(s_wqkv_hi + ks * 2 * 1536, 1536, 128),
-                            tc05::make_desc(s_wqkv_lo + ks * 2 * 1536, 1536, 128), id, ks == 0);
-                tc05::commit(bar);
+                    for (int ks = 0; ks < 4; ++ks)
+                        mma3_ts(tm + cS, tm + cA + 8 * ks, tm + cA + 32 + 8 * ks, desc_at(d_wqkv_hi, ks * 2 * 1536),
+                                desc_at(d_wqkv_lo, ks * 2 * 1536), id_qkv, ks == 0);
+                    tc05::commit(bar);
+                }
+                __syncwarp();
             }
+            // the layer input goes to HBM while the product runs (layer 0's input is the caller's X[0])
+            if (l > 0 && a.save) store_row(a.X[l] + grow * TD, x, live);
             TC_WAIT();
             {
-                float v[32];
-                uint32_t u[32], h[32], lo[32];
-                // Q -> A operand of the score products
-                tc05::ld32(tl + cS, u);
+                uint32_t uq[32], uk[32], uv[32], h[32], lo[32];
+                tc05::ld32(tl + cS, uq);
+                tc05::ld32(tl + cS + 32, uk);
+                tc05::ld32(tl + cS + 64, uv);
                 tc05::wait_ld();
+                // Q -> A operand of the score products
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(u[j]);
-                if (a.save) store_row(a.QKV[l] + grow * 3 * TD, v, live);
-                split32(v, h, lo);
+                for (int j = 0; j < 32; ++j) split_tf32(__uint_as_float(uq[j]), h[j], lo[j]);
                 tc05::st32(tl + cA, h);
                 tc05::st32(tl + cA + 32, lo);
                 // K -> the tile's key planes (row = tile row; dead rows hold zeros)
-                tc05::ld32(tl + cS + 32, u);
-                tc05::wait_ld();
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(u[j]);
-                if (a.save) store_row(a.QKV[l] + grow * 3 * TD + TD, v, live);
-                split32(v, h, lo);
+                for (int j = 0; j < 32; ++j) split_tf32(__uint_as_float(uk[j]), h[j], lo[j]);
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
                     *reinterpret_cast<uint4*>(wg + TC_K_HI + c * TC_K_LBO + t * 16) = make_uint4(h[4 * c], h[4 * c + 1], h[4 * c + 2], h[4 * c + 3]);
                     *reinterpret_cast<uint4*>(wg + TC_K_LO + c * TC_K_LBO + t * 16) = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
                 }
                 // V -> the session's V^T planes
-                tc05::ld32(tl + cS + 64, u);
-                tc05::wait_ld();
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(u[j]);
-                if (a.save) store_row(a.QKV[l] + grow * 3 * TD + 2 * TD, v, live);
-                split32(v, h, lo);
+                for (int j = 0; j < 32; ++j) split_tf32(__uint_as_float(uv[j]), h[j], lo[j]);
                 const int vo = slot * vt_sess + (r >> 2) * TC_VT_LBO + (r & 3) * 4;
 #pragma unroll
                 for (int ch = 0; ch < 32; ++ch) {
                     *reinterpret_cast<uint32_t*>(wg + TC_VT_HI + vo + ch * 16) = h[ch];
                     *reinterpret_cast<uint32_t*>(wg + TC_VT_LO + vo + ch * 16) = lo[ch];
                 }
-            }
-            // ---- scores of every head and session ----
-            TC_PUBLISH();
-            if (t == 0) {
-                tc05::fence_after();
-                const uint32_t id = tc05::make_idesc(128, KP);
+                // ---- scores of every head and session ----
+                TC_PUBLISH();
+                if (warp == 0) {
+                    tc05::fence_after();
+                    if (elect_one()) {
 #pragma unroll
-                for (int hd = 0; hd < HEADS; ++hd)
-                    for (int ss = 0; ss < NS; ++ss) {
-                        const tc05::LaneMask m = tc05::mask_rows(ss * SR, SR);
+                        for (int hd = 0; hd < HEADS; ++hd)
 #pragma unroll
-                        for (int ks = 0; ks < DK / 8; ++ks) {
-                            const uint32_t koff = (uint32_t)((hd * (DK / 4) + 2 * ks) * TC_K_LBO + ss * SR * 16);
-                            mma3_ts(tm + cS + hd * KP, tm + cA + hd * DK + 8 * ks, tm + cA + 32 + hd * DK + 8 * ks,
-                                    tc05::make_desc(s_k_hi + koff, TC_K_LBO, 128), tc05::make_desc(s_k_lo + koff, TC_K_LBO, 128), id, ks == 0, m);
-                        }
+                            for (int ss = 0; ss < NS; ++ss) {
+                                const tc05::LaneMask m = tc05::mask_rows(ss * SR, SR);
+#pragma unroll
+                                for (int ks = 0; ks < DK / 8; ++ks) {
+                                    const uint32_t koff = (uint32_t)((hd * (DK / 4) + 2 * ks) * TC_K_LBO + ss * SR * 16);
+                                    mma3_ts(tm + cS + hd * KP, tm + cA + hd * DK + 8 * ks, tm + cA + 32 + hd * DK + 8 * ks,
+                                            desc_at(d_k_hi, koff), desc_at(d_k_lo, koff), id_s, ks == 0, m);
+                                }
+                            }
+                        tc05::commit(bar);
                     }
-                tc05::commit(bar);
+                    __syncwarp();
+                }
+                if (a.save && live) {            // q | k | v rows for the backward pass, behind the score products
+                    float* dst = a.QKV[l] + grow * 3 * TD;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        *reinterpret_cast<uint4*>(dst + 4 * j) = make_uint4(uq[4 * j], uq[4 * j + 1], uq[4 * j + 2], uq[4 * j + 3]);
+                        *reinterpret_cast<uint4*>(dst + TD + 4 * j) = make_uint4(uk[4 * j], uk[4 * j + 1], uk[4 * j + 2], uk[4 * j + 3]);
+                        *reinterpret_cast<uint4*>(dst + 2 * TD + 4 * j) = make_uint4(uv[4 * j], uv[4 * j + 1], uv[4 * j + 2], uv[4 * j + 3]);
+                    }
+                }
             }
             TC_WAIT();
             // ---- softmax numerators over S (in place) and the attention output, head by head ----
@@ -232,69 +264,98 @@ __global__ void __launch_bounds__(256, 1) trunk_tc_fwd_kernel(TrunkArgs a, int S
 #pragma unroll
             for (int hd = 0; hd < HEADS; ++hd) {
                 const uint32_t cs = cS + hd * KP;
-                float mx = -INFINITY;
-                for (int c = 0; c < KP; c += 32) {
-                    uint32_t u[32];
-                    tc05::ld32(tl + cs + c, u);
+                float mx = -INFINITY, sum = 0.f;
+                if (NCH <= 2) {                                  // the whole row of scores stays in registers
+                    uint32_t u[NCH][32], h[32], lo[32];
+#pragma unroll
+                    for (int c = 0; c < NCH; ++c) tc05::ld32(tl + cs + 32 * c, u[c]);
                     tc05::wait_ld();
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (c + j < L) mx = fmaxf(mx, __uint_as_float(u[j]) * scale);
-                }
-                if (hd > 0) TC_WAIT();                  // the previous head's P V product is done with the shared lo plane
-                float sum = 0.f;
-                for (int c = 0; c < KP; c += 32) {
-                    uint32_t u[32], h[32], lo[32];
-                    tc05::ld32(tl + cs + c, u);
-                    tc05::wait_ld();
+                    for (int c = 0; c < NCH; ++c)
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float e = (c + j < L) ? expf(__uint_as_float(u[j]) * scale - mx) : 0.f;
-                        sum += e;
-                        split_tf32(e, h[j], lo[j]);
+                        for (int j = 0; j < 32; ++j) mx = fmaxf(mx, (32 * c + j < L) ? __uint_as_float(u[c][j]) : -INFINITY);
+                    const float sh = -mx * sl2;
+                    if (hd > 0) TC_WAIT();                       // the previous head's P V product is done with the shared lo plane
+#pragma unroll
+                    for (int c = 0; c < NCH; ++c) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float e = (32 * c + j < L) ? ex2_approx(fmaf(__uint_as_float(u[c][j]), sl2, sh)) : 0.f;
+                            sum += e;
+                            split_tf32(e, h[j], lo[j]);
+                        }
+                        tc05::st32(tl + cs + 32 * c, h);
+                        tc05::st32(tl + cPlo + 32 * c, lo);
                     }
-                    tc05::st32(tl + cs + c, h);
-                    tc05::st32(tl + cPlo + c, lo);
+                } else {
+                    for (int c = 0; c < KP; c += 32) {
+                        uint32_t u[32];
+                        tc05::ld32(tl + cs + c, u);
+                        tc05::wait_ld();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) mx = fmaxf(mx, (c + j < L) ? __uint_as_float(u[j]) : -INFINITY);
+                    }
+                    const float sh = -mx * sl2;
+                    if (hd > 0) TC_WAIT();
+                    for (int c = 0; c < KP; c += 32) {
+                        uint32_t u[32], h[32], lo[32];
+                        tc05::ld32(tl + cs + c, u);
+                        tc05::wait_ld();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float e = (c + j < L) ? ex2_approx(fmaf(__uint_as_float(u[j]), sl2, sh)) : 0.f;
+                            sum += e;
+                            split_tf32(e, h[j], lo[j]);
+                        }
+                        tc05::st32(tl + cs + c, h);
+                        tc05::st32(tl + cPlo + c, lo);
+                    }
                 }
                 inv[hd] = 1.0f / sum;
                 TC_PUBLISH();
-                if (t == 0) {
+                if (warp == 0) {
                     tc05::fence_after();
-                    const uint32_t id = tc05::make_idesc(128, DK);
-                    for (int ss = 0; ss < NS; ++ss) {
-                        const tc05::LaneMask m = tc05::mask_rows(ss * SR, SR);
-                        for (int ks = 0; ks < KP / 8; ++ks) {
-                            const uint32_t voff = (uint32_t)(ss * vt_sess + hd * DK * 16 + ks * 2 * TC_VT_LBO);
-                            mma3_ts(tm + cO + hd * DK, tm + cs + 8 * ks, tm + cPlo + 8 * ks, tc05::make_desc(s_vt_hi + voff, TC_VT_LBO, 128),
-                                    tc05::make_desc(s_vt_lo + voff, TC_VT_LBO, 128), id, ks == 0, m);
+                    if (elect_one()) {
+#pragma unroll
+                        for (int ss = 0; ss < NS; ++ss) {
+                            const tc05::LaneMask m = tc05::mask_rows(ss * SR, SR);
+#pragma unroll 2
+                            for (int ks = 0; ks < pv_steps; ++ks) {
+                                const uint32_t voff = (uint32_t)(ss * vt_sess + hd * DK * 16 + ks * 2 * TC_VT_LBO);
+                                mma3_ts(tm + cO + hd * DK, tm + cs + 8 * ks, tm + cPlo + 8 * ks, desc_at(d_vt_hi, voff), desc_at(d_vt_lo, voff),
+                                        id_pv, ks == 0, m);
+                            }
                         }
+                        tc05::commit(bar);
                     }
-                    tc05::commit(bar);
+                    __syncwarp();
                 }
             }
             TC_WAIT();
             // ---- FFN ----
-            float att[32];
             {
                 uint32_t u[32], h[32], lo[32];
+                float att[32];
                 tc05::ld32(tl + cO, u);
                 tc05::wait_ld();
 #pragma unroll
                 for (int j = 0; j < 32; ++j) att[j] = __uint_as_float(u[j]) * inv[j / DK];
-                if (a.save) store_row(a.A[l] + grow * TD, att, live);
                 split32(att, h, lo);
                 tc05::st32(tl + cA, h);
                 tc05::st32(tl + cA + 32, lo);
-            }
-            TC_PUBLISH();
-            if (t == 0) {
-                tc05::fence_after();
-                const uint32_t id = tc05::make_idesc(128, 32);
+                TC_PUBLISH();
+                if (warp == 0) {
+                    tc05::fence_after();
+                    if (elect_one()) {
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks)
-                    mma3_ts(tm + cS, tm + cA + 8 * ks, tm + cA + 32 + 8 * ks, tc05::make_desc(s_w1_hi + ks * 2 * 512, 512, 128),
-                            tc05::make_desc(s_w1_lo + ks * 2 * 512, 512, 128), id, ks == 0);
-                tc05::commit(bar);
+                        for (int ks = 0; ks < 4; ++ks)
+                            mma3_ts(tm + cS, tm + cA + 8 * ks, tm + cA + 32 + 8 * ks, desc_at(d_w1_hi, ks * 2 * 512), desc_at(d_w1_lo, ks * 2 * 512),
+                                    id_ffn, ks == 0);
+                        tc05::commit(bar);
+                    }
+                    __syncwarp();
+                }
+                if (a.save) store_row(a.A[l] + grow * TD, att, live);
             }
             TC_WAIT();
             {
@@ -303,22 +364,25 @@ __global__ void __launch_bounds__(256, 1) trunk_tc_fwd_kernel(TrunkArgs a, int S
                 tc05::ld32(tl + cS, u);
                 tc05::wait_ld();
 #pragma unroll
-                for (int j = 0; j < 32; ++j) uu[j] = __uint_as_float(u[j]) + vec[j];
-                if (a.save) store_row(a.U[l] + grow * TD, uu, live);
-#pragma unroll
-                for (int j = 0; j < 32; ++j) split_tf32(fmaxf(uu[j], 0.f), h[j], lo[j]);
+                for (int j = 0; j < 32; ++j) {
+                    uu[j] = __uint_as_float(u[j]) + vec[j];
+                    split_tf32(fmaxf(uu[j], 0.f), h[j], lo[j]);
+                }
                 tc05::st32(tl + cA, h);
                 tc05::st32(tl + cA + 32, lo);
-            }
-            TC_PUBLISH();
-            if (t == 0) {
-                tc05::fence_after();
-                const uint32_t id = tc05::make_idesc(128, 32);
+                TC_PUBLISH();
+                if (warp == 0) {
+                    tc05::fence_after();
+                    if (elect_one()) {
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks)
-                    mma3_ts(tm + cS + 32, tm + cA + 8 * ks, tm + cA + 32 + 8 * ks, tc05::make_desc(s_w2_hi + ks * 2 * 512, 512, 128),
-                            tc05::make_desc(s_w2_lo + ks * 2 * 512, 512, 128), id, ks == 0);
-                tc05::commit(bar);
+                        for (int ks = 0; ks < 4; ++ks)
+                            mma3_ts(tm + cS + 32, tm + cA + 8 * ks, tm + cA + 32 + 8 * ks, desc_at(d_w2_hi, ks * 2 * 512),
+                                    desc_at(d_w2_lo, ks * 2 * 512), id_ffn, ks == 0);
+                        tc05::commit(bar);
+                    }
+                    __syncwarp();
+                }
+                if (a.save) store_row(a.U[l] + grow * TD, uu, live);
             }
             TC_WAIT();
             // ---- Z = dropout(F) + X, LayerNorm (the row is in this thread's registers) ----
@@ -342,15 +406,15 @@ __global__ void __launch_bounds__(256, 1) trunk_tc_fwd_kernel(TrunkArgs a, int S
                     var = fmaf(d0, d0, var);
                 }
                 const float rstd = rsqrtf(var * (1.0f / TD) + 1e-5f);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) x[j] = live ? (z[j] - mean) * rstd * vec[2 * TD + j] + vec[3 * TD + j] : 0.f;
                 if (a.save) {
                     store_row(a.Z[l] + grow * TD, z, live);
                     if (live) *reinterpret_cast<float2*>(a.ST[l] + grow * 2) = make_float2(mean, rstd);
                 }
-#pragma unroll
-                for (int j = 0; j < 32; ++j) x[j] = live ? (z[j] - mean) * rstd * vec[2 * TD + j] + vec[3 * TD + j] : 0.f;
-                if (a.save || l == a.layers - 1) store_row(a.X[l + 1] + grow * TD, x, live);
             }
         }
+        store_row(a.X[a.layers] + grow * TD, x, live);
     }
 #undef TC_PUBLISH
 #undef TC_WAIT
@@ -366,24 +430,25 @@ bool trunk_tc_supported(const TrunkArgs& a) {
     return g_use_tc && a.L >= 1 && a.L <= 128 && (a.heads == 1 || a.heads == 2) && a.layers >= 1 && a.layers <= 8;
 }
 
+template <int HEADS, int NCH>
+static void trunk_tc_launch(const TrunkArgs& a, int WGS, unsigned grid, size_t smem, cudaStream_t s) {
+    auto k = trunk_tc_fwd_kernel<HEADS, NCH>;
+    ensure_smem(k, smem);
+    LAUNCH(k, dim3(grid), dim3(128 * WGS), smem, s, a, 512 / WGS);
+}
+
 int trunk_tc_fwd(const TrunkArgs& a, cudaStream_t s) {
-    const int SR = a.L <= 32 ? 32 : (a.L <= 64 ? 64 : 128);
-    const int KP = (a.L + 31) / 32 * 32;
-    const int need = 64 + (a.heads + 1) * KP;                      // A planes | S (P hi) per head | P lo
+    const int NCH = (a.L + 31) / 32;
+    const int SR = NCH == 1 ? 32 : (NCH == 2 ? 64 : 128);
+    const int need = 64 + (a.heads + 1) * 32 * NCH;                // A planes | S (P hi) per head | P lo
     const int WGS = need <= 256 ? 2 : 1;
-    const int COLS = 512 / WGS;
     const size_t smem = (size_t)TC_WG + (size_t)WGS * TC_WG_BYTES;
     const int64_t tiles = ceil_div(a.B, 128 / SR);
     const unsigned grid = stream_grid(ceil_div(tiles, WGS), 1);
-    if (a.heads == 1) {
-        auto k = trunk_tc_fwd_kernel<1>;
-        ensure_smem(k, smem);
-        LAUNCH(k, dim3(grid), dim3(128 * WGS), smem, s, a, SR, KP, COLS);
-    } else {
-        auto k = trunk_tc_fwd_kernel<2>;
-        ensure_smem(k, smem);
-        LAUNCH(k, dim3(grid), dim3(128 * WGS), smem, s, a, SR, KP, COLS);
-    }
+#define TC_CASE(H, N) if (a.heads == H && NCH == N) trunk_tc_launch<H, N>(a, WGS, grid, smem, s)
+    TC_CASE(1, 1); TC_CASE(1, 2); TC_CASE(1, 3); TC_CASE(1, 4);
+    TC_CASE(2, 1); TC_CASE(2, 2); TC_CASE(2, 3); TC_CASE(2, 4);
+#undef TC_CASE
     const double tok = (double)a.B * a.L;
     const double flops = tok * a.layers * (2.0 * 5 * TD * TD + 4.0 * a.L * TD);
     const double bytes = tok * (4.0 * TD + (a.save ? 4.0 * (3 * TD + 4 * TD + 2) * a.layers : 4.0 * TD));

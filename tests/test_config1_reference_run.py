@@ -1,0 +1,89 @@
+"""BASELINE.json configs[0]: the reference's own `main.py --model_name IntEL` wiring on the bundled Tmall toy sample
+(script/IntEL.sh flags), once with the UNMODIFIED reference classes on the CPU and once with the reference-side stubs of
+INTEGRATION.md (`IntEL_b200`, `IntListloss_b200`, `BaseRunner_b200`) on the GPU: same reader, same Dataset / collate_batch,
+same runner loop, same seeds.  The reference copy comes from oracle/_ref (oracle/make_ref.py); without it the tests skip.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from conftest import rel_err  # noqa: E402
+from oracle import ref_run  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+needs_ref = pytest.mark.skipif(not ref_run.available(), reason="oracle/_ref missing: run oracle/make_ref.py in the build container")
+
+
+def _pair(variant, tmp_path, extra=()):
+    """(reference on cpu, stubs on cuda) sharing one corpus and one set of initial weights"""
+    flags = ref_run.SCRIPT_FLAGS[variant] + ["--epoch", "1"] + list(extra)
+    loss = ref_run.LOSS_NAME[variant]
+    ref = ref_run.wire("IntEL", loss, "BaseRunner", flags, torch.device("cpu"), str(tmp_path / "ref"))
+    b2 = ref_run.wire("IntEL_b200", loss + "_b200", "BaseRunner_b200", flags, torch.device("cuda"), str(tmp_path / "b200"),
+                      corpus=ref.corpus)
+    assert [k for k, _ in b2.model.state_dict().items()] == [k for k, _ in ref.model.state_dict().items()]
+    b2.model.load_state_dict(ref.model.state_dict())
+    return ref, b2
+
+
+@needs_ref
+@pytest.mark.parametrize("variant", ["pl", "mse"])
+def test_first_batch_of_the_reference_dataset(variant, tmp_path):
+    """a dict straight out of BaseModel.Dataset.collate_batch (BaseModel.py:121-142) through both models and criteria"""
+    ref, b2 = _pair(variant, tmp_path)
+    cfg = b2.model.cfg                                   # IntelConfig.from_args(args, SeqReader corpus)
+    assert (cfg.item_rows, cfg.user_rows, cfg.class_rows, cfg.intent_num, cfg.model_num) == \
+        (ref.corpus.max_iid + 1, ref.corpus.max_uid + 1, ref.corpus.itemfnum[0], len(ref.corpus.zero_int), 3)
+    ref.model.eval(); b2.model.eval()                    # IntEL-MSE runs dropout 0.5: compare without the masks
+    batch = ref_run.first_batch(ref, "train", 512)
+    assert batch["scores"].dtype == torch.float64 and batch["i_id_s"].shape[1] > 64          # toy lists: 52..90 slots
+    dev_batch = ref_run.to_device(batch, torch.device("cuda"))
+    out_ref = ref.model(batch)
+    out = b2.model(dev_batch)
+    for k in ("intents", "weights", "ens_score"):
+        assert rel_err(out[k].detach().cpu().numpy(), out_ref[k].detach().numpy()) < 1e-5, k
+    if variant == "pl":                                  # BPR draws its negatives from torch's generator; MSE is covered below
+        l_ref = ref.criterion(out_ref, batch)
+        l = b2.criterion(out, dev_batch)
+        for a, b in zip(l, l_ref):
+            assert abs(float(a) - float(b)) <= 1e-5 * abs(float(b)) + 1e-7, (float(a), float(b))
+        l_ref[0].backward()
+        l[0].backward()
+        gref = {k: p.grad for k, p in ref.model.named_parameters() if p.grad is not None}
+        gmax = max(float(g.abs().max()) for g in gref.values())
+        for k, p in b2.model.named_parameters():
+            g = p.grad.cpu().numpy()
+            r = gref[k].numpy() if k in gref else np.zeros_like(g)
+            assert np.abs(g - r).max() <= 1e-5 * np.abs(r).max() + 2e-6 * gmax, k
+    b2.model.check_inputs()
+
+
+@needs_ref
+def test_one_epoch_of_basrunner_fit_and_final_evaluation(tmp_path):
+    """BaseRunner.fit (BaseRunner.py:268-291) for one epoch, then BaseRunner.evaluate with all cut-offs (main.py:113):
+    shared shuffles (numpy + torch seeded alike before each run)"""
+    ref, b2 = _pair("pl", tmp_path)
+    losses, results = [], []
+    for w in (ref, b2):
+        np.random.seed(7)
+        torch.manual_seed(7)
+        losses.append(w.runner.fit(w.data["train"], epoch=1, criterion=w.criterion))
+        np.random.seed(8)
+        torch.manual_seed(8)
+        results.append(w.runner.evaluate(w.data["dev"], w.runner.topk, w.runner.metrics, w.criterion, phase=""))
+    assert abs(losses[0] - losses[1]) <= 1e-5 * abs(losses[0]), losses
+    (dl_ref, m_ref), (dl, m) = results
+    assert abs(dl_ref - dl) <= 1e-4 * abs(dl_ref), (dl_ref, dl)
+    assert set(m) == set(m_ref)
+    assert abs(m["NDCG@3"] - m_ref["NDCG@3"]) <= 1e-6, (m["NDCG@3"], m_ref["NDCG@3"])
+    for k in m_ref:
+        assert abs(m[k] - m_ref[k]) <= 1e-6 + 1e-5 * abs(m_ref[k]), (k, m[k], m_ref[k])
+    # three Adam steps later the weights still agree
+    sd = b2.model.state_dict()
+    for k, v in ref.model.state_dict().items():
+        assert rel_err(sd[k].cpu().numpy(), v.numpy()) < 2e-4, k
