@@ -1,27 +1,34 @@
 #!/usr/bin/env python
-"""IntEL hot-path benchmark (BASELINE.json metric: sessions/sec, train fwd+bwd; eval reported beside it).
+"""IntEL hot-path benchmark (BASELINE.json metric: sessions/sec, train fwd+bwd and eval; one JSON line on stdout, rank 0).
 
-    python bench.py --gpus N --steps K --warmup W            # B200 path (one rank per GPU under torchrun)
-    python bench.py --impl reference --steps K --warmup W     # the reference's CPU PyTorch path (oracle port)
+    python bench.py --gpus N --steps K --warmup W [--config c2|c3|c4|c5]     # B200 path (one rank per GPU under torchrun)
+    python bench.py --impl reference --steps K --warmup W [--config ...]      # the reference's own CPU PyTorch path
 
-A "step" is one pass of the hot path over one batch of synthetic Tmall-schema sessions:
-model forward (intent predictor + ensemble) + criterion + backward; the optimizer is excluded, as in
-SURVEY.md 8(d).  Workload = BASELINE.json configs[1] ("IntEL synthetic Tmall-schema, 1M sessions x 50
-candidates x K=4 basic lists, 1 B200"), streamed as batches of 4096 sessions per GPU with the IntEL-PL
-flags of the reference's own script (IntEL/script/IntEL.sh:21).  `value` has its inputs resident in HBM;
-`e2e` goes through the same public API with HOST (pinned) buffers, H2D copies and the loss read-back inside
-the timed region.  One JSON line on stdout (rank 0).
+Workloads (BASELINE.json `configs`; synthetic Tmall-schema data, random-init weights):
+  c2 (default, the configuration the metric is quoted on): configs[1], 50 candidates x K = 4 lists, I = 1071, IntEL-PL flags
+      of IntEL/script/IntEL.sh:21, batches of 4096 sessions per GPU; step = model forward + criterion + backward (optimizer
+      excluded).  The eval rate (forward under no_grad + evaluate_method) rides along with its own roofline.
+  c3: configs[2], LifeData-shaped: K = 2 lists, 21 504 context rows, I = 2048, same step.
+  c4: configs[3], eval only: 200 candidates, default BERT4Rec sizes, step = forward + NDCG/HR@{3,1,5,10}.
+  c5: configs[4], the fixed-weight ensembles of script/baselines.sh (SingleSort x K, Borda, random-softmax fusion) + NDCG.
+`value`: inputs resident in HBM (three batches larger than L2, cycled).  `e2e`: the same step fed from the HOST through the
+public API: the step's session indices (pinned host memory, what a sampler yields) are copied to the device, the batch is
+built there from the device-resident columnar corpus (corpus.DeviceCorpus), the result is read back; every step.
+`--impl reference`: the UNMODIFIED reference modules from oracle/_ref (oracle/make_ref.py) on the host cores, on a bounded
+sample of the same workload; the oracle port only if that copy is absent.
 """
 from __future__ import annotations
 
 import argparse
 import json
 import os
+import statistics
 import subprocess
 import sys
 import tempfile
 import time
 
+import numpy as np
 import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -40,6 +47,18 @@ VARIANTS = {
     "default": dict(loss="list", encoder="BERT4Rec", intent_weight=0.1, diversity_alpha=1e-4),
 }
 MODEL_KEYS = ("encoder", "context_emb_size", "intent_emb_size", "cross_attn_qsize", "num_heads", "num_layers")
+CONFIGS = {
+    "c2": dict(mode="train", list_len=50, model_num=4, intent_num=1071, n_ctx=931, variant="pl", batch=4096,
+               name="BASELINE.json configs[1]: IntEL synthetic Tmall-schema, 1M sessions x 50 candidates x K=4 basic lists"),
+    "c3": dict(mode="train", list_len=50, model_num=2, intent_num=2048, n_ctx=21504, variant="pl", batch=4096,
+               name="BASELINE.json configs[2]: IntEL synthetic LifeData-shaped (K=2 lists, 21 504 context rows, I=2048)"),
+    "c4": dict(mode="eval", list_len=200, model_num=4, intent_num=1071, n_ctx=931, variant="default", batch=2048,
+               name="BASELINE.json configs[3]: eval-only scoring + NDCG@3 sweep, 10M sessions x 200 candidates"),
+    "c5": dict(mode="baselines", list_len=50, model_num=4, intent_num=1071, n_ctx=931, variant="default", batch=4096,
+               name="BASELINE.json configs[4]: fixed-weight ensembles of script/baselines.sh (SingleSort x K, Borda, random fusion) + NDCG"),
+}
+TOPK, METRICS = [3, 1, 5, 10], ["NDCG", "HR"]
+TENSOR_KERNELS = {"trunk_fwd", "trunk_bwd", "gru_seq_fwd", "gru_seq_bwd", "gemm_fwd", "gemm_dgrad", "gemm_wgrad", "mha_fwd", "mha_bwd"}
 
 
 def parse():
@@ -48,25 +67,35 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--variant", default="pl", choices=sorted(VARIANTS))
-    ap.add_argument("--batch", type=int, default=4096, help="sessions per step per GPU")
-    ap.add_argument("--list_len", type=int, default=50)
-    ap.add_argument("--model_num", type=int, default=4)
-    ap.add_argument("--intent_num", type=int, default=1071)
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--variant", default=None, choices=sorted(VARIANTS))
+    ap.add_argument("--batch", type=int, default=None, help="sessions per step per GPU")
+    ap.add_argument("--list_len", type=int, default=None)
+    ap.add_argument("--model_num", type=int, default=None)
+    ap.add_argument("--intent_num", type=int, default=None)
     ap.add_argument("--n_item", type=int, default=1_000_000)
     ap.add_argument("--n_user", type=int, default=100_000)
     ap.add_argument("--resident_batches", type=int, default=3, help="distinct batches kept in HBM and cycled")
-    ap.add_argument("--cpu_batch", type=int, default=512, help="sessions per CPU-baseline step")
+    ap.add_argument("--cpu_batch", type=int, default=512, help="sessions per step of the CPU reference sample")
+    ap.add_argument("--corpus_batches", type=int, default=16, help="device-resident corpus of the e2e leg, in batches")
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--no_e2e", action="store_true")
+    ap.add_argument("--e2e_dense_api", action="store_true", help="also time the host-packed dense-API input path of round 1")
     ap.add_argument("--eval_steps", type=int, default=10)
     ap.add_argument("--profile_mode", action="store_true", help="under ncu: only warm-up + timed steps, nothing else")
-    return ap.parse_args()
+    a = ap.parse_args()
+    c = CONFIGS[a.config]
+    for k in ("variant", "batch", "list_len", "model_num", "intent_num"):
+        if getattr(a, k) is None:
+            setattr(a, k, c[k])
+    a.mode, a.n_ctx = c["mode"], c["n_ctx"]
+    return a
 
 
 def make_cfg(a) -> tuple:
     v = VARIANTS[a.variant]
-    corpus = synthetic.CorpusSpec(n_item=a.n_item, n_class=357, n_user=a.n_user, n_ctx=931, model_num=a.model_num,
+    n_ctx = getattr(a, "n_ctx", 931)
+    corpus = synthetic.CorpusSpec(n_item=a.n_item, n_class=357, n_user=a.n_user, n_ctx=n_ctx, model_num=a.model_num,
                                   intent_num=a.intent_num, history_max=20)
     cfg = IntelConfig(item_rows=corpus.item_rows, class_rows=corpus.n_class, user_rows=corpus.user_rows,
                       ctx_rows=corpus.n_ctx, intent_num=corpus.intent_num, model_num=corpus.model_num,
@@ -80,34 +109,82 @@ def batch_bytes(batch) -> int:
     return sum(t.numel() * t.element_size() for t in batch.values() if torch.is_tensor(t))
 
 
+def metric_name(mode: str) -> str:
+    return {"train": "sessions/sec (train fwd+bwd)", "eval": "sessions/sec (eval: forward + NDCG/HR@k)",
+            "baselines": "sessions/sec (fixed-weight ensembles + NDCG/HR@k)"}[mode]
+
+
+def workload_config(a, cfg, loss_kind, batch):
+    return {"workload": f"{CONFIGS[a.config]['name']}; streamed in batches of {batch} sessions"
+                        + (f" (1M sessions = {1_000_000 // max(batch, 1)} such steps)" if a.config == "c2" else ""),
+            "config_id": a.config, "step": a.mode, "list_len": a.list_len, "model_num": a.model_num, "intent_num": a.intent_num,
+            "context_rows": cfg.ctx_rows, "variant": f"IntEL-{a.variant} (IntEL/script/IntEL.sh flags)", "loss": loss_kind,
+            "cal_diversity": 1, "encoder": cfg.encoder, "num_heads": cfg.num_heads, "num_layers": cfg.num_layers,
+            "batch_per_gpu": batch, "history_max": 20, "n_item": cfg.item_rows - 1,
+            "input_layout": "dense reference API (float64 [B,H,I] history intents) for `value`; device-built compact batches for `e2e`",
+            "l2_policy": "inputs larger than L2 (resident batches of 0.1-1.5 GB, cycled)"}
+
+
 # ------------------------------------------------------------------------------------------------
 def cpu_reference_rate(a, corpus, cfg, loss_kind, loss_args, steps: int, warmup: int):
-    """The reference's CPU PyTorch path, restated by oracle/intel_oracle.py (the unmodified reference
-    cannot travel to the GPU box), timed on this host's cores on a bounded sample."""
+    """The reference's CPU PyTorch path on this host's cores on a bounded sample (B = --cpu_batch sessions per step):
+    the UNMODIFIED reference modules when oracle/_ref is present (kind "reference"), else the oracle port (kind "port")."""
     from oracle import intel_oracle as O
+    from oracle import ref_run
     ncores = os.cpu_count() or 1
     torch.set_num_threads(ncores)
-    B = a.cpu_batch
-    batch = synthetic.make_batch(corpus, synthetic.BatchSpec(batch_size=B, max_len=a.list_len, min_len=a.list_len), seed=11)
-    sd = {k: v.requires_grad_(True) for k, v in O.init_state(cfg, seed=0).items()}
-    noise = torch.rand(B, a.list_len, a.list_len) if loss_kind == "bpr" else None
+    B, L = a.cpu_batch, a.list_len
+    batch = synthetic.make_batch(corpus, synthetic.BatchSpec(batch_size=B, max_len=L, min_len=L), seed=11)
+    kind = "reference" if ref_run.available() else "port"
     kw = dict(cal_diversity=1, diversity_alpha=loss_args.diversity_alpha, intent_weight=loss_args.intent_weight,
-              ensemble_weight=1.0, kl_weight=0.5, kl_temp=2.0, noise=noise)
+              ensemble_weight=1.0, kl_weight=0.5, kl_temp=2.0)
+    pos = {k: batch[k].numpy() for k in ("c_paynum_i", "c_favnum_i", "c_clicknum_i")}
+    if a.mode == "baselines":
+        kind = "port"
 
-    def step():
-        for p in sd.values():
-            p.grad = None
-        out = O.forward(sd, cfg, batch)
-        loss, _, _ = O.total_loss(loss_kind, out, batch, **kw)
-        loss.backward()
-        return float(loss)
+        def step():
+            for fn in [lambda b, k=k: O.single_sort(b, k) for k in range(3)] + [O.borda, lambda b: O.random_fusion(b, torch.rand(b["scores"].shape))]:
+                ens = fn(batch)["ens_score"].numpy()
+                O.evaluate_method(list(ens), list(batch["ranking"].numpy()), pos, TOPK, METRICS, batch["session_len"].numpy())
+    elif kind == "reference":
+        model, crit = ref_run.reference_on_synthetic(cfg, loss_kind, dict(diversity_alpha=loss_args.diversity_alpha,
+                                                                          intent_weight=loss_args.intent_weight))
+        runner_cls = ref_run._cls("helpers", "BaseRunner")
+        if a.mode == "train":
+            def step():
+                model.zero_grad()
+                loss, _, _ = crit(model(batch), batch)
+                loss.backward()
+        else:
+            model.eval()
+
+            def step():
+                with torch.no_grad():
+                    ens = model(batch)["ens_score"].numpy()
+                runner_cls.evaluate_method(list(ens), list(batch["ranking"].numpy()), pos, TOPK, METRICS, batch["session_len"].numpy())
+    else:
+        sd = {k: v.requires_grad_(a.mode == "train") for k, v in O.init_state(cfg, seed=0).items()}
+        noise = torch.rand(B, L, L) if loss_kind == "bpr" else None
+
+        def step():
+            if a.mode == "train":
+                for p in sd.values():
+                    p.grad = None
+                loss, _, _ = O.total_loss(loss_kind, O.forward(sd, cfg, batch), batch, noise=noise, **kw)
+                loss.backward()
+            else:
+                with torch.no_grad():
+                    ens = O.forward(sd, cfg, batch)["ens_score"].numpy()
+                O.evaluate_method(list(ens), list(batch["ranking"].numpy()), pos, TOPK, METRICS, batch["session_len"].numpy())
     for _ in range(warmup):
         step()
     t0 = time.perf_counter()
     for _ in range(steps):
         step()
     dt = time.perf_counter() - t0
-    return B * steps / dt, dt / steps * 1e3, ncores, f"{steps} steps x {B} sessions (L={a.list_len}, K={a.model_num}, I={a.intent_num}), fwd+loss+bwd"
+    what = {"train": "fwd+loss+bwd", "eval": "forward + evaluate_method", "baselines": "3 SingleSort + Borda + random fusion, each + evaluate_method"}[a.mode]
+    return (B * steps / dt, dt / steps * 1e3, ncores, kind,
+            f"{steps} steps x {B} sessions (L={L}, K={a.model_num}, I={a.intent_num}), {what}, torch {torch.__version__} on {ncores} threads")
 
 
 def run_reference(a):
@@ -115,29 +192,20 @@ def run_reference(a):
     if rank != 0:
         return
     corpus, cfg, loss_kind, loss_args = make_cfg(a)
-    # a step of this arm is a 512-session sample of the same workload (~0.13 s on 16 cores): K <= 100 keeps the run short
+    # a step of this arm is a --cpu_batch sample of the same workload (~0.1-0.3 s on 16 cores): K <= 100 keeps the run short
     steps, warmup = max(1, min(a.steps, 100)), max(1, min(a.warmup, 5))
-    rate, ms, ncores, sample = cpu_reference_rate(a, corpus, cfg, loss_kind, loss_args, steps, warmup)
+    rate, ms, ncores, kind, sample = cpu_reference_rate(a, corpus, cfg, loss_kind, loss_args, steps, warmup)
+    conf = workload_config(a, cfg, loss_kind, a.cpu_batch)
+    conf["batch_note"] = f"this arm runs {a.cpu_batch}-session steps of the workload (the B200 arm: {a.batch}); rates are per session"
     line = {
-        "impl": "reference", "metric": "sessions/sec (train fwd+bwd)", "value": rate, "unit": "sessions/s",
+        "impl": "reference", "metric": metric_name(a.mode), "value": rate, "unit": "sessions/s",
         "n_gpus": a.gpus, "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(a, cfg, loss_kind, a.batch),
-        "cpu_baseline": {"value": rate, "unit": "sessions/s", "cores": ncores, "kind": "port", "sample": sample},
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": conf,
+        "cpu_baseline": {"value": rate, "unit": "sessions/s", "cores": ncores, "kind": kind, "sample": sample},
         "e2e": {"value": rate, "unit": "sessions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
-
-
-def workload_config(a, cfg, loss_kind, batch):
-    return {"workload": f"BASELINE.json configs[1]: IntEL synthetic Tmall-schema, {a.list_len} candidates x K={a.model_num}, "
-                        f"I={a.intent_num}, streamed in batches (1M sessions = {1_000_000 // max(batch, 1)} such steps)",
-            "variant": f"IntEL-{a.variant} (IntEL/script/IntEL.sh flags)", "loss": loss_kind, "cal_diversity": 1,
-            "encoder": cfg.encoder, "num_heads": cfg.num_heads, "num_layers": cfg.num_layers,
-            "batch_per_gpu": batch, "history_max": 20, "n_item": cfg.item_rows - 1,
-            "input_layout": "dense reference API (float64 [B,H,I] history intents)",
-            "l2_policy": "inputs larger than L2 (each resident batch > 1 GB), batches cycled"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -180,9 +248,51 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(rows)}
 
 
+def load_peaks():
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    hbm_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    tc = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0)))
+    tc_src = ("measured (MEASURED_PEAKS.json bf16_tflops_sustained; the TF32 rate is half of it)" if peaks
+              else "fallback 1590 TFLOP/s dense bf16 (B200_PROFILING.md)")
+    return hbm, hbm_src, tc, tc_src
+
+
+def roofline_of(prof, prof_steps, traffic, pick=None):
+    """roofline object of the kernel with the largest share (or of `pick`) from a live per-kernel profile"""
+    hbm_peak, hbm_src, tc_peak, tc_src = load_peaks()
+    total_ms = sum(v["ms"] for v in prof.values())
+    name, rec = max(prof.items(), key=lambda kv: kv[1]["ms"]) if pick is None else (pick, prof[pick])
+    sec = rec["ms"] * 1e-3
+    gbs = rec["bytes"] / sec / 1e9 if sec > 0 else 0.0
+    if name in TENSOR_KERNELS:
+        achieved = 3.0 * rec["flops"] / sec / 1e12 if sec > 0 else 0.0
+        roof = {"kernel": name, "bound": "tensor", "achieved": achieved, "peak": tc_peak, "unit": "TFLOP/s", "frac": achieved / tc_peak,
+                "peak_source": tc_src, "flops_counted": "TF32 MMA flops issued = 3 x the fp32 product's flops (3xTF32 split for 1e-5 parity)",
+                "hbm_gbs_algorithmic": gbs}
+    else:
+        roof = {"kernel": name, "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "peak_source": hbm_src}
+    tr = traffic.get(name)
+    roof.update({
+        "traffic": tr.get("dram_bytes_per_launch") if isinstance(tr, dict) else None,
+        "algorithmic_bytes_per_launch": rec["bytes"] / rec["launches"],
+        "share_of_step": rec["ms"] / total_ms if total_ms else None,
+        "avg_launch_us": rec["ms"] * 1e3 / rec["launches"],
+        "per_kernel": {k: {"share": v["ms"] / total_ms, "ms_per_step": v["ms"] / prof_steps,
+                           "gbs": (v["bytes"] / (v["ms"] * 1e-3) / 1e9) if v["ms"] > 0 else 0.0,
+                           "tflops_3xtf32": (3.0 * v["flops"] / (v["ms"] * 1e-3) / 1e12) if (v["ms"] > 0 and k in TENSOR_KERNELS) else None,
+                           "launches_per_step": v["launches"] / prof_steps}
+                       for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}})
+    return roof
+
+
 def run_b200(a):
     import torch.distributed as dist
-    from intel_sigir2023_b200 import _lib, losses, evaluate, dp, loader
+    from intel_sigir2023_b200 import _lib, baselines, corpus as corpus_mod, dp, evaluate, loader, losses
     from intel_sigir2023_b200.IntEL import IntEL
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -194,16 +304,17 @@ def run_b200(a):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
-    corpus, cfg, loss_kind, loss_args = make_cfg(a)
+    spec_corpus, cfg, loss_kind, loss_args = make_cfg(a)
     torch.manual_seed(0)
     model = IntEL(argparse.Namespace(device=dev, model_path="", buffer=1), cfg=cfg).to(dev)
     crit = {"list": losses.IntListloss, "bpr": losses.IntBPRloss, "mse": losses.IntMSEloss}[loss_kind](loss_args)
-    reducer = dp.GradReducer(model, world) if world > 1 else None
+    reducer = dp.GradReducer(model, world) if (world > 1 and a.mode == "train") else None
     B, L = a.batch, a.list_len
     spec = synthetic.BatchSpec(batch_size=B, max_len=L, min_len=L)
     # weak scaling: every rank owns its own shard of the session stream (different seeds)
-    resident = [synthetic.make_batch(corpus, spec, seed=1000 * rank + i, device=dev) for i in range(a.resident_batches)]
-    launches = {"n": 0}
+    resident = [synthetic.make_batch(spec_corpus, spec, seed=1000 * rank + i, device=dev) for i in range(a.resident_batches)]
+    single = [baselines.SingleSort(choose_list=n) for n in ("pCTR", "pCVR", "pFVR")]      # script/baselines.sh:1-20
+    borda, fusion = baselines.Borda(), baselines.RandomFusion()
 
     def train_step(batch):
         for p in model.parameters():
@@ -214,6 +325,24 @@ def run_b200(a):
         if reducer is not None:
             reducer.allreduce()
         return loss
+
+    def ndcg(ens, b):
+        return evaluate.ndcg_sums(ens, b["ranking"], b["session_len"], b["c_paynum_i"], b["c_favnum_i"], b["c_clicknum_i"],
+                                  max(L, max(TOPK)), TOPK)[0]
+
+    def eval_step(b):
+        with torch.no_grad():
+            out = model(b)
+        return ndcg(out["ens_score"], b)
+
+    def baselines_step(b):
+        s = None
+        for m in single + [borda, fusion]:
+            r = ndcg(m(b)["ens_score"], b)
+            s = r if s is None else s + r
+        return s
+
+    step_fn = {"train": train_step, "eval": eval_step, "baselines": baselines_step}[a.mode]
 
     def barrier():
         if world > 1:
@@ -238,11 +367,13 @@ def run_b200(a):
     import gc
     gc.collect()
     gc.freeze()
+    if a.mode != "train":
+        model.eval()
     # ---- warm-up, then the timed region (inputs resident in HBM) ----
     for i in range(a.warmup if a.profile_mode else max(a.warmup, 3)):
-        train_step(resident[i % len(resident)])
+        step_fn(resident[i % len(resident)])
     sampler = ClockSampler(local) if rank == 0 else None
-    ms_total = timed(lambda i: train_step(resident[i % len(resident)]), a.steps)
+    ms_total = timed(lambda i: step_fn(resident[i % len(resident)]), a.steps)
     clocks = sampler.stop() if sampler else None
     ms_step = ms_total / a.steps
     value = world * B / (ms_step * 1e-3)
@@ -252,166 +383,108 @@ def run_b200(a):
         return
 
     # ---- launch count + live per-kernel timing (CUDA events around every launch; separate pass) ----
-    _lib.profile(True)
+    def profile(fn, n=3):
+        _lib.profile(True)
+        for i in range(n):
+            fn(resident[i % len(resident)])
+        prof = _lib.profile_report()
+        _lib.profile(False)
+        if "dense_rows_fwd" in prof:
+            # the library books every history row of the dense float64 inputs; the kernel skips the padding rows behind
+            # history_len / history_item_len, so only the live share of those bytes is actually streamed
+            live = [float(b[k].double().mean()) / b[t].shape[1] for b in resident[:n]
+                    for k, t in (("history_len", "his_intents"), ("history_item_len", "his_item_int"))]
+            prof["dense_rows_fwd"]["bytes"] *= sum(live) / len(live)
+        return prof
     prof_steps = 3
-    for i in range(prof_steps):
-        train_step(resident[i % len(resident)])
-    prof = _lib.profile_report()
-    _lib.profile(False)
-    if "dense_rows_fwd" in prof:
-        # the library books every history row of the dense float64 inputs; the kernel skips the padding rows behind
-        # history_len / history_item_len, so only the live share of those bytes is actually streamed
-        live = [float(b[k].double().mean()) / b[t].shape[1] for b in resident[:prof_steps]
-                for k, t in (("history_len", "his_intents"), ("history_item_len", "his_item_int"))]
-        prof["dense_rows_fwd"]["bytes"] *= sum(live) / len(live)
+    prof = profile(step_fn, prof_steps)
     gpu_launches = int(sum(v["launches"] for v in prof.values()) / prof_steps * a.steps)
-    total_ms = sum(v["ms"] for v in prof.values())
-    top = max(prof.items(), key=lambda kv: kv[1]["ms"])
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    # kernels whose inner loop is tensor-core MMA work (3xTF32: three TF32 MMAs per fp32 product);
-    # everything else streams HBM
-    tensor_kernels = {"trunk_fwd", "trunk_bwd", "gru_seq_fwd", "gru_seq_bwd", "gemm_fwd", "gemm_dgrad", "gemm_wgrad",
-                      "mha_fwd", "mha_bwd"}
-    tc_peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 2250.0)))
-    tc_src = ("measured (MEASURED_PEAKS.json bf16_tflops_sustained; the TF32 rate is half of it)" if peaks
-              else "fallback 2250 TFLOP/s nominal dense bf16 (B200_PROFILING.md)")
     traffic = {}
-    try:        # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-    except Exception:
-        pass
-    name, rec = top
-    sec = rec["ms"] * 1e-3
-    gbs = rec["bytes"] / sec / 1e9 if sec > 0 else 0.0
-    if name in tensor_kernels:
-        achieved = 3.0 * rec["flops"] / sec / 1e12 if sec > 0 else 0.0
-        roofline = {"kernel": name, "bound": "tensor", "achieved": achieved, "peak": tc_peak, "unit": "TFLOP/s",
-                    "frac": achieved / tc_peak, "peak_source": tc_src,
-                    "flops_counted": "TF32 MMA flops issued = 3 x the fp32 product's flops (3xTF32 split for 1e-5 parity)",
-                    "hbm_gbs_algorithmic": gbs}
-    else:
-        roofline = {"kernel": name, "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": gbs / hbm_peak, "peak_source": peak_src}
-    tr = traffic.get(name)
-    roofline.update({
-        "traffic": tr.get("dram_bytes_per_launch") if isinstance(tr, dict) else None,
-        "algorithmic_bytes_per_launch": rec["bytes"] / rec["launches"],
-        "share_of_step": rec["ms"] / total_ms if total_ms else None,
-        "avg_launch_us": rec["ms"] * 1e3 / rec["launches"],
-        "per_kernel": {k: {"share": v["ms"] / total_ms,
-                           "gbs": (v["bytes"] / (v["ms"] * 1e-3) / 1e9) if v["ms"] > 0 else 0.0,
-                           "tflops_3xtf32": (3.0 * v["flops"] / (v["ms"] * 1e-3) / 1e12) if (v["ms"] > 0 and k in tensor_kernels) else None,
-                           "launches_per_step": v["launches"] / prof_steps}
-                       for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}})
+    for f in ("r02_traffic.json", "r01_traffic.json"):     # dram bytes per launch from the committed ncu --set full captures
+        try:
+            for k, v in json.load(open(os.path.join(ROOT, "profiles", f))).items():
+                traffic.setdefault(k, v)
+        except Exception:
+            pass
+    roofline = roofline_of(prof, prof_steps, traffic)
 
-    # ---- end to end: host (pinned) batch -> H2D -> step -> loss D2H, every step ----
-    def run_e2e(dev_batches, pack=False):
-        host = [{k: (v.cpu().pin_memory() if torch.is_tensor(v) else v) for k, v in b.items()} for b in dev_batches]
-        h2d = batch_bytes(host[0])
-        if pack:        # bytes that actually cross PCIe: the packed form of the two dense history tensors
+    # ---- eval rate of the train configs (BASELINE metric: "train fwd+bwd and eval"), with the roofline of its own kernels ----
+    eval_rate = roofline_eval = None
+    if a.mode == "train":
+        model.eval()
+        for i in range(2):
+            eval_step(resident[i % len(resident)])
+        ms_eval = timed(lambda i: eval_step(resident[i % len(resident)]), a.eval_steps) / a.eval_steps
+        eval_rate = world * B / (ms_eval * 1e-3)
+        eprof = profile(eval_step, prof_steps)
+        roofline_eval = {"step": "forward (no_grad) + intel_ndcg_topk", "ms_per_step": ms_eval,
+                         "dominant": {k: v for k, v in roofline_of(eprof, prof_steps, traffic).items() if k != "per_kernel"}}
+        if "ndcg" in eprof:
+            roofline_eval["ndcg_kernel"] = {k: v for k, v in roofline_of(eprof, prof_steps, traffic, pick="ndcg").items() if k != "per_kernel"}
+        model.train()
+
+    # ---- end to end: host indices -> H2D -> device batch builder -> step -> result D2H, every step ----
+    e2e = e2e_dense = None
+    if not a.no_e2e:
+        n_corpus = a.corpus_batches * B
+        cols, shared, nz = corpus_mod.synthetic_columns(n_corpus, L, a.n_item, 357, a.n_user, a.n_ctx, a.model_num, a.intent_num,
+                                                        max_his=20, seed=77 + rank)
+        dc = corpus_mod.DeviceCorpus(cols, shared, a.model_num, a.intent_num, 20, nz, dev)
+        del cols, shared
+        order = np.random.default_rng(5 + rank).permutation(n_corpus)
+        result_host = torch.zeros(len(TOPK) * 7 if a.mode != "train" else 1, dtype=torch.float64).pin_memory()
+
+        def e2e_step(i):
+            rows = order[(i % a.corpus_batches) * B:(i % a.corpus_batches + 1) * B]       # what a sampler hands to the loader
+            r = step_fn(dc.batch(rows))
+            result_host.copy_(r.detach().reshape(-1)[:result_host.numel()], non_blocking=True)
+        for i in range(3):
+            e2e_step(i)
+        n_e2e = max(5, min(a.steps, 10))
+        passes = sorted(timed(e2e_step, n_e2e) / n_e2e for _ in range(3))
+        ms = passes[1]
+        e2e = {"value": world * B / (ms * 1e-3), "unit": "sessions/s", "h2d_bytes_per_step": B * 8, "d2h_bytes_per_step": result_host.numel() * 8,
+               "ms_per_step": ms, "passes_ms": passes, "reported": "median of 3 passes",
+               "input_path": "host session indices (pinned) -> H2D -> intel_batch_build from the device-resident columnar corpus "
+                             f"({n_corpus} sessions) -> step -> result D2H"}
+        del dc
+        if a.e2e_dense_api and a.mode == "train":
+            host = [{k: (v.cpu().pin_memory() if torch.is_tensor(v) else v) for k, v in b.items()} for b in resident[:2]]
             pf = loader.DevicePrefetcher(iter(host[:1]), dev, pack_history=True)
             h2d = batch_bytes(next(iter(pf)))
             torch.cuda.synchronize()
-        loss_host = torch.zeros(1, dtype=torch.float64).pin_memory()
+            loss_host = torch.zeros(1, dtype=torch.float64).pin_memory()
 
-        # every step copies its own inputs host -> device inside the timed region; the copy of step i + 1 runs on the
-        # loader's side stream while step i computes (loader.DevicePrefetcher), the loss is read back every step
-        def e2e_pass(n):
-            def run(_):
-                for b in loader.DevicePrefetcher((host[i % len(host)] for i in range(n)), dev, pack_history=pack):
-                    loss = train_step(b)
-                    loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
-            return run
-        timed(e2e_pass(3), 1)
-        n_e2e = max(5, min(a.steps, 10))
-        ms = min(timed(e2e_pass(n_e2e), 1) / n_e2e for _ in range(2))      # best of two passes: PCIe is shared on the box
-        return {"value": world * B / (ms * 1e-3), "unit": "sessions/s", "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": 8, "ms_per_step": ms, "overlap": "H2D of step i+1 on a copy stream"}
-
-    e2e = e2e_compact = None
-    if not a.no_e2e:
-        e2e_copy = run_e2e(resident[:2])
-        e2e_copy["input_layout"] = "dense reference API, dense tensors copied as they are"
-        # same host batches, but the two dense float64 history tensors are scanned on the host cores and only their
-        # non-zeros cross PCIe (loader.DevicePrefetcher(pack_history=True) -> intel_host_pack_rows)
-        e2e_packed = run_e2e(resident[:2], pack=True)
-        e2e_packed["input_layout"] = "dense reference API, history tensors packed on the host before the copy"
-        e2e = dict(e2e_packed if e2e_packed["value"] > e2e_copy["value"] else e2e_copy)
-        e2e["modes"] = {"dense_copy": e2e_copy, "host_packed": e2e_packed}
-        # the opt-in index form of his_intents / his_item_int (what a device-side batch builder would emit,
-        # SURVEY.md 8f-2): same sessions, same math, 70x fewer bytes over PCIe
-        compact = [synthetic.make_batch(corpus, spec, seed=1000 * rank + i, device=dev, layout="compact") for i in range(2)]
-        for i in range(2):
-            train_step(compact[i])
-        ms_c = timed(lambda i: train_step(compact[i % 2]), a.steps) / a.steps
-        e2e_compact = run_e2e(compact)
-        e2e_compact["input_layout"] = "compact (index/value) history intents, opt-in extension"
-        e2e_compact["value_resident"] = world * B / (ms_c * 1e-3)
-        del compact
-
-    # ---- eval throughput: forward (no_grad) + evaluate_method on device ----
-    topk, metrics = [3, 1, 5, 10], ["NDCG", "HR"]
-
-    def eval_step(i):
-        b = resident[i % len(resident)]
-        with torch.no_grad():
-            out = model(b)
-        evaluate.ndcg_sums(out["ens_score"], b["ranking"], b["session_len"], b["c_paynum_i"], b["c_favnum_i"],
-                           b["c_clicknum_i"], max(L, max(topk)), topk)
-    model.eval()
-    for i in range(2):
-        eval_step(i)
-    ms_eval = timed(eval_step, a.eval_steps) / a.eval_steps
-    model.train()
+            def dense_pass(_):
+                for b in loader.DevicePrefetcher((host[i % len(host)] for i in range(n_e2e)), dev, pack_history=True):
+                    loss_host.copy_(train_step(b).detach().reshape(1), non_blocking=True)
+            timed(dense_pass, 1)
+            ms_d = statistics.median(timed(dense_pass, 1) / n_e2e for _ in range(3))
+            e2e_dense = {"value": world * B / (ms_d * 1e-3), "unit": "sessions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
+                         "ms_per_step": ms_d, "input_path": "pinned host batches in the reference's dense float64 layout, history tensors "
+                                                            "packed by host threads, H2D of step i+1 on a copy stream (round-1 e2e)"}
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ---- optimizer step (not part of `value`): fused Adam + L2 vs torch.optim.Adam on the same gradients ----
-    # Single-process runs only, and on the gradients the last train step left behind: by now the other ranks of a
-    # multi-GPU run have left the process group, so nothing here may issue a collective (train_step would all-reduce).
-    def time_opt(make):
-        opt = make()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        for _ in range(2):
-            opt.step()
-        e0.record()
-        for _ in range(5):
-            opt.step()
-        e1.record()
-        torch.cuda.synchronize()
-        return e0.elapsed_time(e1) / 5
-    optimizer = None
-    if world == 1 and all(p.grad is not None for p in model.parameters()):
-        try:
-            from intel_sigir2023_b200 import optim
-            groups = lambda: optim.customize_parameters(model)
-            optimizer = {"fused_adam_ms": time_opt(lambda: optim.Adam(groups(), lr=1e-3, weight_decay=1e-6)),
-                         "torch_adam_ms": time_opt(lambda: torch.optim.Adam(groups(), lr=1e-3, weight_decay=1e-6)),
-                         "parameters": int(sum(p.numel() for p in model.parameters()))}
-        except Exception as exc:       # never let the extra measurement take the bench line down
-            optimizer = {"error": repr(exc)[:200]}
     line = {
-        "metric": "sessions/sec (train fwd+bwd)", "value": value, "unit": "sessions/s", "n_gpus": world,
+        "metric": metric_name(a.mode), "value": value, "unit": "sessions/s", "n_gpus": world,
         "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(a, cfg, loss_kind, B), "clocks": clocks, "gpu_launches": gpu_launches,
-        "roofline": roofline, "eval_sessions_per_s": world * B / (ms_eval * 1e-3), "optimizer": optimizer,
+        "config": workload_config(a, cfg, loss_kind, B), "clocks": clocks, "gpu_launches": gpu_launches, "roofline": roofline,
     }
+    if eval_rate is not None:
+        line["eval_sessions_per_s"] = eval_rate
+        line["roofline_eval"] = roofline_eval
     if e2e is not None:
         line["e2e"] = e2e
-        line["e2e_compact"] = e2e_compact
+    if e2e_dense is not None:
+        line["e2e_dense_api"] = e2e_dense
     if not a.no_cpu_baseline and world == 1:
-        rate, ms, ncores, sample = cpu_reference_rate(a, corpus, cfg, loss_kind, loss_args, 60, 2)     # ~10 s of CPU work
-        line["cpu_baseline"] = {"value": rate, "unit": "sessions/s", "cores": ncores, "kind": "port", "sample": sample}
+        rate, ms, ncores, kind, sample = cpu_reference_rate(a, spec_corpus, cfg, loss_kind, loss_args, 40, 2)     # ~10 s of CPU work
+        line["cpu_baseline"] = {"value": rate, "unit": "sessions/s", "cores": ncores, "kind": kind, "sample": sample}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

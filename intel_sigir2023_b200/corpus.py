@@ -305,7 +305,7 @@ def synthetic_columns(n_sessions: int, list_len: int, n_item: int, n_class: int,
     position = np.empty(N, dtype=np.int64)
     position[order] = np.arange(N) - uhis_off[u_id[order]]
     first_cls = item_class[order, 0]
-    beh = np.where(pay[order] > 0, 2, np.where(fav[order] > 0, 1, 0))
+    beh = np.minimum(np.where(pay[order] > 0, 2, np.where(fav[order] > 0, 1, 0)), K - 1)      # behaviour block of IntEL.py:226
     columns = {
         "u_id_c": u_id, "c_id_c": np.arange(1, N + 1, dtype=np.int64), "context_mh": ctx,
         "user_mh": np.zeros(N, dtype=np.int64), "c_paynum_i": pay.astype(np.int64), "c_favnum_i": fav.astype(np.int64),

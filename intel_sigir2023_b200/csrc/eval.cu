@@ -22,12 +22,30 @@ __device__ __forceinline__ double disc_at(int p) { return 1.0 / log2((double)p +
 
 // Deterministic block reduction of per-warp partial sums: warp w of block blk wrote part[w][c];
 // thread c sums the EV_WARPS rows in fixed order and stores the block partial.
-__global__ void __launch_bounds__(256) reduce_partials_kernel(int64_t nblocks, int stride, int ncols,
-                                                              const double* __restrict__ part, double* __restrict__ out) {
-    for (int c = threadIdx.x; c < ncols; c += blockDim.x) {
+// Deterministic reduction of the per-block partial rows [nblocks][stride]: 32 row groups run in parallel (group g sums
+// rows g, g + 32, ... in order, coalesced 8-byte loads), then the 32 group sums of a column are added in a fixed order.
+// Columns [0, ncols) go to `out`, columns [ncols, ncols + ncols2) to `out2` (nullable): one launch for sums and counts.
+static const int RP_GROUPS = 32;
+__global__ void __launch_bounds__(1024) reduce_partials_kernel(int64_t nblocks, int stride, int ncols, const double* __restrict__ part,
+                                                               double* __restrict__ out, int ncols2, double* __restrict__ out2) {
+    __shared__ double grp[RP_GROUPS][33];
+    const int g = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int total = ncols + (out2 ? ncols2 : 0);
+    for (int c0 = 0; c0 < total; c0 += 32) {
+        const int c = c0 + lane;
         double acc = 0.0;
-        for (int64_t i = 0; i < nblocks; ++i) acc += part[i * stride + c];
-        out[c] = acc;
+        if (c < total)
+            for (int64_t i = g; i < nblocks; i += RP_GROUPS) acc += part[i * stride + c];
+        grp[g][lane] = acc;
+        __syncthreads();
+        if (g == 0 && c < total) {
+            double t = 0.0;
+#pragma unroll 4
+            for (int k = 0; k < RP_GROUPS; ++k) t += grp[k][lane];
+            if (c < ncols) out[c] = t;
+            else out2[c - ncols] = t;
+        }
+        __syncthreads();
     }
 }
 
@@ -334,10 +352,8 @@ int intel_ndcg_topk(int64_t N, int64_t ld, const float* pred, const int64_t* ran
            max_len, tk, partial);
     INTEL_TRY(check_launch("ndcg", (double)N * ld * 12.0, 0.0));
     // fixed-order (deterministic) reduction of the per-block partial rows
-    LAUNCH(reduce_partials_kernel, dim3(1), dim3(256), 0, s, (int64_t)grid, ncols, n_topk * EV_OUT, partial, sums);
-    INTEL_TRY(check_launch("ndcg_reduce"));
-    LAUNCH(reduce_partials_kernel, dim3(1), dim3(256), 0, s, (int64_t)grid, ncols, 4, partial + n_topk * EV_OUT, counts);
-    return check_launch("ndcg_reduce_counts");
+    LAUNCH(reduce_partials_kernel, dim3(1), dim3(1024), 0, s, (int64_t)grid, ncols, n_topk * EV_OUT, partial, sums, 4, counts);
+    return check_launch("ndcg_reduce", (double)grid * ncols * 8.0, 0.0);
 }
 
 size_t intel_intent_topk_workspace_bytes(int64_t N, int n_topk) {
@@ -360,7 +376,8 @@ int intel_intent_topk(int64_t N, int64_t I, const double* true_intents, const fl
     double* partial = reinterpret_cast<double*>(workspace);
     LAUNCH(intent_topk_kernel, dim3(grid), dim3(EV_WARPS * 32), smem, s, N, I, true_intents, pred_intents, tk, partial);
     INTEL_TRY(check_launch("intent_topk"));
-    LAUNCH(reduce_partials_kernel, dim3(1), dim3(256), 0, s, (int64_t)grid, n_topk * 2, n_topk * 2, partial, sums);
+    LAUNCH(reduce_partials_kernel, dim3(1), dim3(1024), 0, s, (int64_t)grid, n_topk * 2, n_topk * 2, partial, sums, 0,
+           (double*)nullptr);
     return check_launch("intent_topk_reduce");
 }
 

@@ -44,23 +44,23 @@ __device__ __forceinline__ void stage_session(const LossArgs& a, int64_t b, int 
 }
 
 // ------------------------------------------------------------------------------------------------
-// Plackett-Luce style list loss (Listloss.py:12-43):
+// Plackett-Luce style list loss (Listloss.py:12-43), O(L K) per session instead of the reference's [L, L, K] pair tensors:
 //   E_i = sum_{j valid, r_j < r_i} exp(s_j - s_i),  l_i = log(1 + E_i) for r_i > 0
-//   F_ik = sum_j exp(s_j - s_i) ((x_ik - x_jk) - (s_i - s_j)),  div_i = sum_k w_ik F_ik^2 / (2 (1+E_i)^2)
+//   F_ik = sum_j exp(s_j - s_i) (u_ik - u_jk),  u = x - s,   div_i = sum_k w_ik F_ik^2 / (2 (1+E_i)^2)
 //   loss = mean_b( sum_i l_i / #pos ) - alpha * mean_b( sum_i div_i / #pos )
-__global__ void __launch_bounds__(LOSS_WARPS * 32) loss_pl_kernel(LossArgs a) {
-    DYN_SMEM(float, sm);
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int64_t b = (int64_t)blockIdx.x * LOSS_WARPS + w;
-    if (b >= a.B) return;
+// The clamped rankings take four values, so every "sum over the items ranked below i" is a prefix over three bucket sums
+// (SURVEY.md 8a-7):  A_rho = sum_{r_j = rho} e^{s_j - m},  C_rho,k = sum_{r_j = rho} e^{s_j - m} u_jk  (m = max s, the
+// shift the reference does not apply: same value, no overflow until s differs by ~88 inside one session)
+//   E_i = e^{m - s_i} A_{<r_i},   F_ik = u_ik E_i - e^{m - s_i} C_{<r_i,k}
+// and the gradient that item j receives from all positives ranked above it is a suffix over the buckets of
+//   a_i = e^{m - s_i} (c1_i + sum_k q_ik (u_ik + 1)),  b_ik = e^{m - s_i} q_ik,   c1_i = cl/(1+E_i) - cd G_i/(1+E_i)^3,
+//   q_ik = cd w_ik F_ik / (1+E_i)^2:   d s_j += e^{s_j - m} (a_{>r_j} - sum_k u_jk b_{>r_j,k}).
+// pair form (one pass over the lower-ranked items per positive): exact for any number of rank levels; the bucket kernel
+// below falls back to it for a session whose clamped rankings exceed the three levels the reference's datasets emit
+__device__ __noinline__ void pl_pairs_session(const LossArgs& a, int64_t b, int lane, const float* s, const int* r, float* ds, int64_t n,
+                                             int npos) {
     const int64_t L = a.L;
     const int K = a.K;
-    float* s = sm + (size_t)w * 3 * L;
-    int* r = reinterpret_cast<int*>(s + L);
-    float* ds = s + 2 * L;
-    int64_t n;
-    int npos;
-    stage_session(a, b, lane, s, r, ds, n, npos);
     const float inv_pos = 1.0f / (float)npos;      // 0 positives -> inf -> NaN loss, as the reference
     const float cl = inv_pos / (float)a.B;
     const float cd = -a.alpha * cl;
@@ -140,6 +140,191 @@ __global__ void __launch_bounds__(LOSS_WARPS * 32) loss_pl_kernel(LossArgs a) {
     }
     __syncwarp();
     for (int64_t j = lane; j < L; j += 32) a.d_ens[b * L + j] = ds[j];
+    if (npos == 0) loss_acc = (double)NAN;      // 0 / 0 positives, as the reference
+    if (lane == 0) atomicAdd(a.out, loss_acc / (double)a.B);
+}
+
+static const int PL_LEVELS = 3;         // rank levels that can sit below a positive: 0, 1, 2
+
+__global__ void __launch_bounds__(LOSS_WARPS * 32) loss_pl_kernel(LossArgs a) {
+    DYN_SMEM(float, sm);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t b = (int64_t)blockIdx.x * LOSS_WARPS + w;
+    if (b >= a.B) return;
+    const int64_t L = a.L;
+    const int K = a.K;
+    float* s = sm + (size_t)w * 3 * L;
+    int* r = reinterpret_cast<int*>(s + L);
+    float* ds = s + 2 * L;
+    int64_t n;
+    int npos;
+    stage_session(a, b, lane, s, r, ds, n, npos);
+    {
+        int mr = 0;
+        for (int64_t j = lane; j < n; j += 32) mr = r[j] > mr ? r[j] : mr;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { const int t = __shfl_xor_sync(0xffffffffu, mr, o); mr = t > mr ? t : mr; }
+        if (mr > PL_LEVELS) {                      // more rank levels than pay / fav / click: pair form
+            pl_pairs_session(a, b, lane, s, r, ds, n, npos);
+            return;
+        }
+    }
+    const float inv_pos = 1.0f / (float)npos;      // 0 positives -> inf -> NaN loss, as the reference
+    const float cl = inv_pos / (float)a.B;
+    const float cd = -a.alpha * cl;
+    const double* xb = a.scores + b * L * K;
+    const float* wb = a.weights ? a.weights + b * L * K : nullptr;
+    float* dwb = a.d_weights ? a.d_weights + b * L * K : nullptr;
+    const bool div = a.cal_div != 0;
+    // ---- pass A: bucket sums over the valid items ----
+    float m = -INFINITY;
+    for (int64_t j = lane; j < n; j += 32) m = fmaxf(m, s[j]);
+    m = warp_max(m);
+    float A[PL_LEVELS], C[PL_LEVELS][LOSS_MAX_K];
+#pragma unroll
+    for (int q = 0; q < PL_LEVELS; ++q) {
+        A[q] = 0.f;
+#pragma unroll
+        for (int k = 0; k < LOSS_MAX_K; ++k) C[q][k] = 0.f;
+    }
+    for (int64_t j = lane; j < n; j += 32) {
+        const int rj = r[j];
+        if (rj >= PL_LEVELS) continue;
+        const float e = expf(s[j] - m);
+#pragma unroll
+        for (int q = 0; q < PL_LEVELS; ++q) A[q] += (rj == q) ? e : 0.f;
+        if (div) {
+#pragma unroll
+            for (int k = 0; k < LOSS_MAX_K; ++k) {
+                if (k < K) {
+                    const float eu = e * ((float)xb[j * K + k] - s[j]);
+#pragma unroll
+                    for (int q = 0; q < PL_LEVELS; ++q) C[q][k] += (rj == q) ? eu : 0.f;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < PL_LEVELS; ++q) {
+        A[q] = warp_sum(A[q]);
+        if (div) {
+#pragma unroll
+            for (int k = 0; k < LOSS_MAX_K; ++k)
+                if (k < K) C[q][k] = warp_sum(C[q][k]);
+        }
+    }
+    // prefixes: slot q holds the sum over the levels < q + 1, i.e. what a positive of rank q + 1 sees below it
+#pragma unroll
+    for (int q = 1; q < PL_LEVELS; ++q) {
+        A[q] += A[q - 1];
+#pragma unroll
+        for (int k = 0; k < LOSS_MAX_K; ++k) C[q][k] += C[q - 1][k];
+    }
+    // ---- pass B: the positives (lanes over items), bucket sums of their gradient coefficients by rank ----
+    float Ga[PL_LEVELS], Gb[PL_LEVELS][LOSS_MAX_K];      // level q: positives of rank q + 1
+#pragma unroll
+    for (int q = 0; q < PL_LEVELS; ++q) {
+        Ga[q] = 0.f;
+#pragma unroll
+        for (int k = 0; k < LOSS_MAX_K; ++k) Gb[q][k] = 0.f;
+    }
+    double loss_acc = 0.0;
+    for (int64_t i = lane; i < L; i += 32) {
+        const int ri = r[i];
+        const bool pos = ri > 0 && i < n;
+        if (dwb && !pos)
+            for (int k = 0; k < K; ++k) dwb[i * K + k] = 0.f;
+        if (!pos) continue;
+        const int lv = ri - 1;
+        float Alo = 0.f;
+#pragma unroll
+        for (int q = 0; q < PL_LEVELS; ++q) Alo = (lv == q) ? A[q] : Alo;
+        const float si = s[i], ei = expf(m - si);
+        const float E = ei * Alo, opE = 1.f + E;
+        const float inv1 = 1.f / opE, inv2 = inv1 * inv1, inv3 = inv2 * inv1;
+        loss_acc += (double)(logf(opE) * inv_pos);
+        float dsi = cl * (-E * inv1);
+        float alpha_i = cl * inv1;
+        if (div) {
+            float G = 0.f, H = 0.f, t1 = 0.f;
+            float F[LOSS_MAX_K], wi[LOSS_MAX_K], ui[LOSS_MAX_K];
+#pragma unroll
+            for (int k = 0; k < LOSS_MAX_K; ++k) {
+                F[k] = 0.f; wi[k] = 0.f; ui[k] = 0.f;
+                if (k < K) {
+                    float Clo = 0.f;
+#pragma unroll
+                    for (int q = 0; q < PL_LEVELS; ++q) Clo = (lv == q) ? C[q][k] : Clo;
+                    ui[k] = (float)xb[i * K + k] - si;
+                    wi[k] = wb[i * K + k];
+                    F[k] = ui[k] * E - ei * Clo;
+                    G = fmaf(wi[k] * F[k], F[k], G);
+                    H = fmaf(wi[k] * F[k], -F[k] - E, H);
+                }
+            }
+            loss_acc += (double)(-a.alpha * inv_pos * G * 0.5f * inv2);
+            dsi += cd * (H * inv2 + G * E * inv3);
+            alpha_i -= cd * G * inv3;
+#pragma unroll
+            for (int k = 0; k < LOSS_MAX_K; ++k) {
+                if (k < K) {
+                    const float q_ik = cd * inv2 * wi[k] * F[k];
+                    t1 = fmaf(q_ik, ui[k] + 1.f, t1);
+                    const float bik = ei * q_ik;
+#pragma unroll
+                    for (int q = 0; q < PL_LEVELS; ++q) Gb[q][k] += (lv == q) ? bik : 0.f;
+                    if (dwb) dwb[i * K + k] = cd * F[k] * F[k] * 0.5f * inv2;
+                }
+            }
+            alpha_i += t1;
+        }
+        alpha_i *= ei;
+#pragma unroll
+        for (int q = 0; q < PL_LEVELS; ++q) Ga[q] += (lv == q) ? alpha_i : 0.f;
+        ds[i] = dsi;                                    // each slot is owned by one lane
+    }
+#pragma unroll
+    for (int q = 0; q < PL_LEVELS; ++q) {
+        Ga[q] = warp_sum(Ga[q]);
+        if (div) {
+#pragma unroll
+            for (int k = 0; k < LOSS_MAX_K; ++k)
+                if (k < K) Gb[q][k] = warp_sum(Gb[q][k]);
+        }
+    }
+    // suffixes: slot q = sum over the positives of rank > q, i.e. what an item of level q receives
+#pragma unroll
+    for (int q = PL_LEVELS - 2; q >= 0; --q) {
+        Ga[q] += Ga[q + 1];
+#pragma unroll
+        for (int k = 0; k < LOSS_MAX_K; ++k) Gb[q][k] += Gb[q + 1][k];
+    }
+    __syncwarp();
+    // ---- pass C: what every valid item receives from the positives ranked above it ----
+    for (int64_t j = lane; j < L; j += 32) {
+        float g = ds[j];
+        const int rj = r[j];
+        if (j < n && rj < PL_LEVELS) {
+            float ga = 0.f;
+#pragma unroll
+            for (int q = 0; q < PL_LEVELS; ++q) ga = (rj == q) ? Ga[q] : ga;
+            float acc = ga;
+            if (div) {
+#pragma unroll
+                for (int k = 0; k < LOSS_MAX_K; ++k) {
+                    if (k < K) {
+                        float gb = 0.f;
+#pragma unroll
+                        for (int q = 0; q < PL_LEVELS; ++q) gb = (rj == q) ? Gb[q][k] : gb;
+                        acc = fmaf(-((float)xb[j * K + k] - s[j]), gb, acc);
+                    }
+                }
+            }
+            g = fmaf(expf(s[j] - m), acc, g);
+        }
+        a.d_ens[b * L + j] = g;
+    }
+    loss_acc = warp_sum_d(loss_acc);
     if (npos == 0) loss_acc = (double)NAN;      // 0 / 0 positives, as the reference
     if (lane == 0) atomicAdd(a.out, loss_acc / (double)a.B);
 }

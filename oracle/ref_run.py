@@ -66,7 +66,10 @@ class Wired:
 
 
 def wire(model_name: str, loss_name: str, runner_name: str, flags: List[str], device: torch.device, work_dir: str,
-         corpus=None, seed: int = 0, phases=("train", "dev", "test")) -> Wired:
+         share_from: Optional["Wired"] = None, seed: int = 0, phases=("train", "dev", "test")) -> Wired:
+    """share_from: a previous wiring whose corpus (and buffered dev / test feed dicts) this one re-uses: Dataset.prepare()
+    pops the list columns out of the corpus once the feed dicts are buffered (BaseModel.py:112-119), so a corpus can be
+    prepared only once."""
     root = ref_shims.ref_root()
     assert root is not None, "no reference tree (run oracle/make_ref.py in the build container)"
     ref_shims.install(os.path.join(root, "src"))
@@ -88,15 +91,17 @@ def wire(model_name: str, loss_name: str, runner_name: str, flags: List[str], de
     args.device = device
     np.random.seed(args.random_seed)                   # main.py:51-54
     torch.manual_seed(args.random_seed)
-    if corpus is None:
-        corpus = reader_cls(args)
+    corpus = share_from.corpus if share_from is not None else reader_cls(args)
     model = model_cls(args, corpus).to(device)
     criterion = loss_cls(args)
     runner = runner_cls(args)
     data_dict: Dict[str, object] = {}
     for phase in phases:
         data_dict[phase] = model_cls.Dataset(model, corpus, phase)
-        data_dict[phase].prepare()
+        if share_from is not None and phase != "train" and model.buffer:
+            data_dict[phase].buffer_dict = share_from.data[phase].buffer_dict
+        else:
+            data_dict[phase].prepare()
     return Wired(args=args, corpus=corpus, model=model, criterion=criterion, runner=runner, data=data_dict)
 
 
@@ -110,3 +115,31 @@ def first_batch(w: Wired, phase: str = "train", n: int = 512, seed: int = 0) -> 
 
 def to_device(batch: Dict[str, object], device) -> Dict[str, object]:
     return {k: (v.to(device) if torch.is_tensor(v) else v) for k, v in batch.items()}
+
+
+# ---- the reference classes on a synthetic corpus (bench.py's reference arm, BASELINE.json configs[1..]) ----
+class _SyntheticCorpus:
+    """the attributes IntEL.__init__ reads from a reader (IntEL.py:36-49, BaseModel.py:152-156)"""
+
+    def __init__(self, cfg):
+        self.itemfnum = [cfg.class_rows]
+        self.contextfnum = [cfg.ctx_rows]
+        self.zero_int = np.zeros(cfg.intent_num)
+        self.max_uid = cfg.user_rows - 1
+        self.max_iid = cfg.item_rows - 1
+
+
+def reference_on_synthetic(cfg, loss_kind: str, loss_kw: Dict[str, float], device=torch.device("cpu")):
+    """(model, criterion) = the UNMODIFIED reference IntEL + Int{List,BPR,MSE}loss for an IntelConfig"""
+    root = ref_shims.ref_root()
+    assert root is not None
+    ref_shims.install(os.path.join(root, "src"))
+    model_cls = _cls("models.IntEL", "IntEL")
+    loss_cls = _cls("loss", {"list": "IntListloss", "bpr": "IntBPRloss", "mse": "IntMSEloss"}[loss_kind])
+    a = argparse.Namespace(**cfg.to_dict())
+    a.device, a.model_path, a.buffer = device, "/tmp/intel_ref/model.pt", 1
+    a.cal_diversity, a.ensemble_weight, a.kl_temp, a.kl_weight = 1, 1.0, 2.0, 0.5
+    for k, v in loss_kw.items():
+        setattr(a, k, v)
+    model = model_cls(a, _SyntheticCorpus(cfg)).to(device)
+    return model, loss_cls(a)

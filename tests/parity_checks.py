@@ -234,6 +234,35 @@ def check_loss_edge_cases(device):
     assert np.allclose(il.detach().cpu().numpy(), [ref.item(), ce.item(), kl.item()], rtol=TOL), (il, ref, ce, kl)
 
 
+def check_list_loss_forms(device, B=37, L=41, K=4, seed=5):
+    """the rank-bucket (O(L K)) Plackett-Luce kernel on ragged sessions with ties, empty levels, unlabeled (-1) slots and pad
+    positives, and the pair form it falls back to when a session has more than three rank levels: both against the oracle's
+    literal [B,L,L,K] restatement of Listloss.py:12-43 (loss, d ens_score, d weights)"""
+    from intel_sigir2023_b200 import losses
+    g = torch.Generator().manual_seed(seed)
+    for levels in (3, 5):
+        n = torch.randint(1, L + 1, (B,), generator=g)
+        n[0], n[1] = L, 1
+        ranking = torch.randint(-1, levels + 1, (B, L), generator=g)
+        ranking[2] = torch.where(ranking[2] > 0, 2, 0)                    # a single positive level
+        ranking[3, : int(n[3])] = 1                                       # only positives: nothing ranked below them
+        ranking[:, 0] = torch.maximum(ranking[:, 0], torch.ones(B, dtype=torch.long))      # every session has a positive
+        valid = torch.arange(L)[None, :] < n[:, None]
+        batch = {"ranking": ranking, "session_len": n, "scores": torch.rand(B, L, K, generator=g, dtype=torch.float64) * valid[:, :, None],
+                 "batch_size": B}
+        out = {"ens_score": (torch.randn(B, L, generator=g) * 1.5 * valid).requires_grad_(True),
+               "weights": torch.randn(B, L, K, generator=g).requires_grad_(True)}
+        ref = O.list_loss(out, batch, 1, 0.07)
+        ref.backward()
+        dev_out = {k: v.detach().to(device).requires_grad_(True) for k, v in out.items()}
+        dev_batch = {k: (v.to(device) if torch.is_tensor(v) else v) for k, v in batch.items()}
+        l, _, _ = losses.Listloss(loss_args(cal_diversity=1, diversity_alpha=0.07))(dev_out, dev_batch)
+        l.backward()
+        assert abs(l.item() - ref.item()) <= TOL * abs(ref.item()) + 1e-7, (levels, l.item(), ref.item())
+        for k in ("ens_score", "weights"):
+            assert rel_err(dev_out[k].grad.cpu().numpy(), out[k].grad.numpy()) < 2e-5, (levels, k)
+
+
 def check_evaluate(tag, device):
     from intel_sigir2023_b200 import evaluate
     z = np.load(f"{GOLDEN}/eval.npz")

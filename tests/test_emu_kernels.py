@@ -58,6 +58,10 @@ def test_loss_edge_cases():
     P.check_loss_edge_cases("cpu")
 
 
+def test_list_loss_bucket_and_pair_forms():
+    P.check_list_loss_forms("cpu")
+
+
 @pytest.mark.parametrize("tag", ["A", "B", "C"])
 def test_evaluate(tag):
     P.check_evaluate(tag, "cpu")
