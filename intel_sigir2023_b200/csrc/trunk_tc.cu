@@ -423,11 +423,351 @@ __global__ void __launch_bounds__(256, 1) trunk_tc_fwd_kernel(TrunkArgs a, int C
     if (tid < 32) tc05::tmem_free(*tmem_slot, 512);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Lists of 129..208 slots (BASELINE.json configs[3]: 200 candidates): a session spans two 128-row tiles.  One warpgroup
+// per CTA; thread t owns rows t and 128 + t.  Per layer: q|k|v of both tiles first (K rows and V^T columns of all keys go
+// to shared memory, the Q rows to an fp32 stash), then per tile and head S = Q_h K_h^T over all keys (N = padded key
+// count, no lane mask), softmax in 32-column passes over tensor memory, O_h = P V_h, and the FFN + LayerNorm of the tile.
+// Tensor memory: A planes 64 | O 32 | S / P hi KP | P lo KP  (KP <= 208 -> 512 columns).
+namespace {
+constexpr int TL_K_LBO = 4096;                                  // K planes [k-chunk][256 rows][4]
+constexpr int TL_K_HI = 0, TL_K_LO = 32768, TL_VT_HI = 65536, TL_VT_LO = 65536 + 28672, TL_Q = 65536 + 2 * 28672;
+constexpr int TL_BYTES = TL_Q + 256 * 128;                       // + Q stash [256 rows][32 floats], 16-byte chunks rotated by row
+}  // namespace
+
+template <int HEADS>
+__global__ void __launch_bounds__(128, 1) trunk_tc_long_fwd_kernel(TrunkArgs a, int KP) {
+    constexpr int DK = TD / HEADS;
+    extern __shared__ __align__(1024) uint8_t tc_smem[];
+    uint8_t* sm = tc_smem;
+    const int t = threadIdx.x, warp = t >> 5;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sm + TC_BAR);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + TC_TMEM);
+    const float* vec = reinterpret_cast<const float*>(sm + TC_VEC);
+    stage_weight(sm + TC_WQKV_HI, sm + TC_WQKV_LO, a.wq, 96, 0);
+    stage_weight(sm + TC_WQKV_HI, sm + TC_WQKV_LO, a.wk, 96, 32);
+    stage_weight(sm + TC_WQKV_HI, sm + TC_WQKV_LO, a.wv, 96, 64);
+    stage_weight(sm + TC_W1_HI, sm + TC_W1_LO, a.w1, 32, 0);
+    stage_weight(sm + TC_W2_HI, sm + TC_W2_LO, a.w2, 32, 0);
+    if (t < TD) {
+        float* v = reinterpret_cast<float*>(sm + TC_VEC);
+        v[t] = a.b1[t]; v[TD + t] = a.b2[t]; v[2 * TD + t] = a.lnw[t]; v[3 * TD + t] = a.lnb[t];
+    }
+    if (t == 0) {
+        tc05::mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (t < 32) tc05::tmem_alloc(tmem_slot, 512);
+    tc05::fence_smem_to_mma();
+    tc05::fence_before();
+    __syncthreads();
+    tc05::fence_after();
+    const uint32_t tm = *tmem_slot;
+    const uint32_t tl = tm + ((uint32_t)(warp * 32) << 16);
+    const uint32_t cA = 0, cO = 64, cS = 96, cPlo = 96 + KP;
+    uint32_t phase = 0;
+    uint8_t* wg = sm + TC_WG;
+    const uint64_t d_wqkv_hi = tc05::make_desc(tc05::smem_u32(sm + TC_WQKV_HI), 1536, 128), d_wqkv_lo = tc05::make_desc(tc05::smem_u32(sm + TC_WQKV_LO), 1536, 128);
+    const uint64_t d_w1_hi = tc05::make_desc(tc05::smem_u32(sm + TC_W1_HI), 512, 128), d_w1_lo = tc05::make_desc(tc05::smem_u32(sm + TC_W1_LO), 512, 128);
+    const uint64_t d_w2_hi = tc05::make_desc(tc05::smem_u32(sm + TC_W2_HI), 512, 128), d_w2_lo = tc05::make_desc(tc05::smem_u32(sm + TC_W2_LO), 512, 128);
+    const uint64_t d_k_hi = tc05::make_desc(tc05::smem_u32(wg + TL_K_HI), TL_K_LBO, 128), d_k_lo = tc05::make_desc(tc05::smem_u32(wg + TL_K_LO), TL_K_LBO, 128);
+    const uint64_t d_vt_hi = tc05::make_desc(tc05::smem_u32(wg + TL_VT_HI), TC_VT_LBO, 128), d_vt_lo = tc05::make_desc(tc05::smem_u32(wg + TL_VT_LO), TC_VT_LBO, 128);
+    const uint32_t id_qkv = tc05::make_idesc(128, 96), id_s = tc05::make_idesc(128, KP), id_pv = tc05::make_idesc(128, DK),
+                   id_ffn = tc05::make_idesc(128, 32);
+    const int L = a.L, pv_steps = (L + 7) >> 3;
+    const float sl2 = 1.4426950408889634f / sqrtf((float)DK);
+    float* qs = reinterpret_cast<float*>(wg + TL_Q);
+
+#define TL_PUBLISH()               \
+    do {                           \
+        tc05::wait_st();           \
+        tc05::fence_smem_to_mma(); \
+        tc05::fence_before();      \
+        __syncthreads();           \
+    } while (0)
+#define TL_WAIT()                    \
+    do {                             \
+        tc05::mbar_wait(bar, phase); \
+        phase ^= 1u;                 \
+        tc05::fence_after();         \
+    } while (0)
+
+    for (int64_t b = blockIdx.x; b < a.B; b += gridDim.x) {
+        float x[2][32];
+        bool live[2];
+        int64_t grow[2];
+#pragma unroll
+        for (int tt = 0; tt < 2; ++tt) {
+            const int r = tt * 128 + t;
+            live[tt] = r < L;
+            grow[tt] = b * L + r;
+            load_row(x[tt], a.X[0] + grow[tt] * TD, live[tt]);
+        }
+        for (int l = 0; l < a.layers; ++l) {
+            // ---- q|k|v of both tiles ----
+#pragma unroll
+            for (int tt = 0; tt < 2; ++tt) {
+                const int r = tt * 128 + t;
+                {
+                    uint32_t h[32], lo[32];
+                    split32(x[tt], h, lo);
+                    tc05::st32(tl + cA, h);
+                    tc05::st32(tl + cA + 32, lo);
+                }
+                TL_PUBLISH();
+                if (warp == 0) {
+                    tc05::fence_after();
+                    if (elect_one()) {
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks)
+                            mma3_ts(tm + cS, tm + cA + 8 * ks, tm + cA + 32 + 8 * ks, desc_at(d_wqkv_hi, ks * 2 * 1536),
+                                    desc_at(d_wqkv_lo, ks * 2 * 1536), id_qkv, ks == 0);
+                        tc05::commit(bar);
+                    }
+                    __syncwarp();
+                }
+                if (l > 0 && a.save) store_row(a.X[l] + grow[tt] * TD, x[tt], live[tt]);
+                TL_WAIT();
+                uint32_t uq[32], uk[32], uv[32], h[32], lo[32];
+                tc05::ld32(tl + cS, uq);
+                tc05::ld32(tl + cS + 32, uk);
+                tc05::ld32(tl + cS + 64, uv);
+                tc05::wait_ld();
+#pragma unroll
+                for (int c = 0; c < 8; ++c)          // Q stash: this thread's own row, chunk order rotated against bank conflicts
+                    *reinterpret_cast<uint4*>(qs + r * 32 + ((c + t) & 7) * 4) = make_uint4(uq[4 * c], uq[4 * c + 1], uq[4 * c + 2], uq[4 * c + 3]);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) split_tf32(__uint_as_float(uk[j]), h[j], lo[j]);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    *reinterpret_cast<uint4*>(wg + TL_K_HI + c * TL_K_LBO + r * 16) = make_uint4(h[4 * c], h[4 * c + 1], h[4 * c + 2], h[4 * c + 3]);
+                    *reinterpret_cast<uint4*>(wg + TL_K_LO + c * TL_K_LBO + r * 16) = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
+                }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) split_tf32(__uint_as_float(uv[j]), h[j], lo[j]);
+                if (r < KP) {                          // key slots beyond the padded count are never read
+                    const int vo = (r >> 2) * TC_VT_LBO + (r & 3) * 4;
+#pragma unroll
+                    for (int ch = 0; ch < 32; ++ch) {
+                        *reinterpret_cast<uint32_t*>(wg + TL_VT_HI + vo + ch * 16) = h[ch];
+                        *reinterpret_cast<uint32_t*>(wg + TL_VT_LO + vo + ch * 16) = lo[ch];
+                    }
+                }
+                if (a.save && live[tt]) {
+                    float* dst = a.QKV[l] + grow[tt] * 3 * TD;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        *reinterpret_cast<uint4*>(dst + 4 * j) = make_uint4(uq[4 * j], uq[4 * j + 1], uq[4 * j + 2], uq[4 * j + 3]);
+                        *reinterpret_cast<uint4*>(dst + TD + 4 * j) = make_uint4(uk[4 * j], uk[4 * j + 1], uk[4 * j + 2], uk[4 * j + 3]);
+                        *reinterpret_cast<uint4*>(dst + 2 * TD + 4 * j) = make_uint4(uv[4 * j], uv[4 * j + 1], uv[4 * j + 2], uv[4 * j + 3]);
+                    }
+                }
+            }
+            // ---- attention + FFN, tile by tile ----
+#pragma unroll 1
+            for (int tt = 0; tt < 2; ++tt) {
+                const int r = tt * 128 + t;
+                const bool lv = r < L;
+                const int64_t gr = b * L + r;
+                float inv[HEADS];
+#pragma unroll
+                for (int hd = 0; hd < HEADS; ++hd) {
+                    {
+                        uint32_t h[32], lo[32];
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            const uint4 q4 = *reinterpret_cast<const uint4*>(qs + r * 32 + ((c + t) & 7) * 4);
+                            split_tf32(__uint_as_float(q4.x), h[4 * c], lo[4 * c]);
+                            split_tf32(__uint_as_float(q4.y), h[4 * c + 1], lo[4 * c + 1]);
+                            split_tf32(__uint_as_float(q4.z), h[4 * c + 2], lo[4 * c + 2]);
+                            split_tf32(__uint_as_float(q4.w), h[4 * c + 3], lo[4 * c + 3]);
+                        }
+                        if (hd == 0) {
+                            tc05::st32(tl + cA, h);
+                            tc05::st32(tl + cA + 32, lo);
+                        }
+                    }
+                    TL_PUBLISH();
+                    if (warp == 0) {
+                        tc05::fence_after();
+                        if (elect_one()) {
+#pragma unroll
+                            for (int ks = 0; ks < DK / 8; ++ks) {
+                                const uint32_t koff = (uint32_t)((hd * (DK / 4) + 2 * ks) * TL_K_LBO);
+                                mma3_ts(tm + cS, tm + cA + hd * DK + 8 * ks, tm + cA + 32 + hd * DK + 8 * ks, desc_at(d_k_hi, koff),
+                                        desc_at(d_k_lo, koff), id_s, ks == 0);
+                            }
+                            tc05::commit(bar);
+                        }
+                        __syncwarp();
+                    }
+                    TL_WAIT();
+                    float mx = -INFINITY, sum = 0.f;
+                    for (int c = 0; c < KP; c += 32) {
+                        if (c + 32 <= KP) {
+                            uint32_t u[32];
+                            tc05::ld32(tl + cS + c, u);
+                            tc05::wait_ld();
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) mx = fmaxf(mx, (c + j < L) ? __uint_as_float(u[j]) : -INFINITY);
+                        } else {
+                            uint32_t u[16];
+                            tc05::ld16(tl + cS + c, u);
+                            tc05::wait_ld();
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) mx = fmaxf(mx, (c + j < L) ? __uint_as_float(u[j]) : -INFINITY);
+                        }
+                    }
+                    const float sh = -mx * sl2;
+                    for (int c = 0; c < KP; c += 32) {
+                        if (c + 32 <= KP) {
+                            uint32_t u[32], h[32], lo[32];
+                            tc05::ld32(tl + cS + c, u);
+                            tc05::wait_ld();
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                const float e = (c + j < L) ? ex2_approx(fmaf(__uint_as_float(u[j]), sl2, sh)) : 0.f;
+                                sum += e;
+                                split_tf32(e, h[j], lo[j]);
+                            }
+                            tc05::st32(tl + cS + c, h);
+                            tc05::st32(tl + cPlo + c, lo);
+                        } else {
+                            uint32_t u[16], h[16], lo[16];
+                            tc05::ld16(tl + cS + c, u);
+                            tc05::wait_ld();
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                const float e = (c + j < L) ? ex2_approx(fmaf(__uint_as_float(u[j]), sl2, sh)) : 0.f;
+                                sum += e;
+                                split_tf32(e, h[j], lo[j]);
+                            }
+                            tc05::st16(tl + cS + c, h);
+                            tc05::st16(tl + cPlo + c, lo);
+                        }
+                    }
+                    inv[hd] = 1.0f / sum;
+                    TL_PUBLISH();
+                    if (warp == 0) {
+                        tc05::fence_after();
+                        if (elect_one()) {
+#pragma unroll 2
+                            for (int ks = 0; ks < pv_steps; ++ks) {
+                                const uint32_t voff = (uint32_t)(hd * DK * 16 + ks * 2 * TC_VT_LBO);
+                                mma3_ts(tm + cO + hd * DK, tm + cS + 8 * ks, tm + cPlo + 8 * ks, desc_at(d_vt_hi, voff), desc_at(d_vt_lo, voff),
+                                        id_pv, ks == 0);
+                            }
+                            tc05::commit(bar);
+                        }
+                        __syncwarp();
+                    }
+                    TL_WAIT();
+                }
+                // FFN
+                {
+                    uint32_t u[32], h[32], lo[32];
+                    float att[32];
+                    tc05::ld32(tl + cO, u);
+                    tc05::wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) att[j] = __uint_as_float(u[j]) * inv[j / DK];
+                    split32(att, h, lo);
+                    tc05::st32(tl + cA, h);
+                    tc05::st32(tl + cA + 32, lo);
+                    TL_PUBLISH();
+                    if (warp == 0) {
+                        tc05::fence_after();
+                        if (elect_one()) {
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks)
+                                mma3_ts(tm + cS, tm + cA + 8 * ks, tm + cA + 32 + 8 * ks, desc_at(d_w1_hi, ks * 2 * 512), desc_at(d_w1_lo, ks * 2 * 512),
+                                        id_ffn, ks == 0);
+                            tc05::commit(bar);
+                        }
+                        __syncwarp();
+                    }
+                    if (a.save) store_row(a.A[l] + gr * TD, att, lv);
+                }
+                TL_WAIT();
+                {
+                    uint32_t u[32], h[32], lo[32];
+                    float uu[32];
+                    tc05::ld32(tl + cS, u);
+                    tc05::wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        uu[j] = __uint_as_float(u[j]) + vec[j];
+                        split_tf32(fmaxf(uu[j], 0.f), h[j], lo[j]);
+                    }
+                    tc05::st32(tl + cA, h);
+                    tc05::st32(tl + cA + 32, lo);
+                    TL_PUBLISH();
+                    if (warp == 0) {
+                        tc05::fence_after();
+                        if (elect_one()) {
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks)
+                                mma3_ts(tm + cS + 32, tm + cA + 8 * ks, tm + cA + 32 + 8 * ks, desc_at(d_w2_hi, ks * 2 * 512),
+                                        desc_at(d_w2_lo, ks * 2 * 512), id_ffn, ks == 0);
+                            tc05::commit(bar);
+                        }
+                        __syncwarp();
+                    }
+                    if (a.save) store_row(a.U[l] + gr * TD, uu, lv);
+                }
+                TL_WAIT();
+                {
+                    uint32_t u[32];
+                    float z[32];
+                    tc05::ld32(tl + cS + 32, u);
+                    tc05::wait_ld();
+                    const Dropout& dr = a.drop[l];
+                    float sum = 0.f;
+                    // x[tt] with a run-time tt: both copies are updated under a predicate, so the array stays in registers
+                    float xin[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) xin[j] = tt == 0 ? x[0][j] : x[1][j];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        z[j] = (__uint_as_float(u[j]) + vec[TD + j]) * dropout_scale(dr, gr, j, TD) + xin[j];
+                        sum += z[j];
+                    }
+                    const float mean = sum * (1.0f / TD);
+                    float var = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float d0 = z[j] - mean;
+                        var = fmaf(d0, d0, var);
+                    }
+                    const float rstd = rsqrtf(var * (1.0f / TD) + 1e-5f);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float y = lv ? (z[j] - mean) * rstd * vec[2 * TD + j] + vec[3 * TD + j] : 0.f;
+                        if (tt == 0) x[0][j] = y;
+                        else x[1][j] = y;
+                    }
+                    if (a.save) {
+                        store_row(a.Z[l] + gr * TD, z, lv);
+                        if (lv) *reinterpret_cast<float2*>(a.ST[l] + gr * 2) = make_float2(mean, rstd);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int tt = 0; tt < 2; ++tt) store_row(a.X[a.layers] + grow[tt] * TD, x[tt], live[tt]);
+    }
+#undef TL_PUBLISH
+#undef TL_WAIT
+    tc05::fence_before();
+    __syncthreads();
+    if (t < 32) tc05::tmem_free(*tmem_slot, 512);
+}
+
 static int g_use_tc = 1;
 void trunk_debug_use_tcgen05(int on) { g_use_tc = on ? 1 : 0; }
 
 bool trunk_tc_supported(const TrunkArgs& a) {
-    return g_use_tc && a.L >= 1 && a.L <= 128 && (a.heads == 1 || a.heads == 2) && a.layers >= 1 && a.layers <= 8;
+    return g_use_tc && a.L >= 1 && a.L <= 208 && (a.heads == 1 || a.heads == 2) && a.layers >= 1 && a.layers <= 8;
 }
 
 template <int HEADS, int NCH>
@@ -438,6 +778,23 @@ static void trunk_tc_launch(const TrunkArgs& a, int WGS, unsigned grid, size_t s
 }
 
 int trunk_tc_fwd(const TrunkArgs& a, cudaStream_t s) {
+    if (a.L > 128) {                                               // two row tiles per session
+        const int KP = (a.L + 15) / 16 * 16;
+        const size_t smem = (size_t)TC_WG + TL_BYTES;
+        const unsigned grid = stream_grid(a.B, 1);
+        if (a.heads == 1) {
+            auto k = trunk_tc_long_fwd_kernel<1>;
+            ensure_smem(k, smem);
+            LAUNCH(k, dim3(grid), dim3(128), smem, s, a, KP);
+        } else {
+            auto k = trunk_tc_long_fwd_kernel<2>;
+            ensure_smem(k, smem);
+            LAUNCH(k, dim3(grid), dim3(128), smem, s, a, KP);
+        }
+        const double tok = (double)a.B * a.L;
+        return check_launch("trunk_fwd", tok * (4.0 * TD + (a.save ? 4.0 * (3 * TD + 4 * TD + 2) * a.layers : 4.0 * TD)),
+                            tok * a.layers * (2.0 * 5 * TD * TD + 4.0 * a.L * TD));
+    }
     const int NCH = (a.L + 31) / 32;
     const int SR = NCH == 1 ? 32 : (NCH == 2 ? 64 : 128);
     const int need = 64 + (a.heads + 1) * 32 * NCH;                // A planes | S (P hi) per head | P lo

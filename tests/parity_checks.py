@@ -467,7 +467,8 @@ def check_tc_stack(device, cases=((10, 30, 2, 2), (7, 50, 2, 2), (5, 64, 1, 1), 
 
 
 def check_fused_shapes(device, cases=((5, 7, 2, 1, 1), (9, 16, 1, 2, 2), (7, 40, 2, 1, 4), (6, 50, 2, 2, 3), (5, 64, 1, 1, 2),
-                                      (4, 70, 2, 2, 4), (3, 100, 1, 1, 4), (3, 128, 2, 1, 4), (10, 30, 2, 2, 4))):
+                                      (4, 70, 2, 2, 4), (3, 100, 1, 1, 4), (3, 128, 2, 1, 4), (10, 30, 2, 2, 4),
+                                      (3, 200, 1, 1, 4), (2, 150, 2, 2, 4), (3, 208, 2, 1, 4), (2, 129, 1, 2, 4))):
     """every padded-length / head-count instantiation of the fused stack kernels, and every sessions-per-CTA
     setting, against the staged kernels: cases are (B, L, heads, layers, sessions per CTA)"""
     for (B, L, heads, layers, ns) in cases:
