@@ -312,6 +312,8 @@ int intel_debug_use_fused_stack(int on);
 int intel_debug_use_tcgen05_gemm(int on);
 /* test hook: 0 keeps the fused stack forward pass on the mma.sync kernel instead of the tcgen05 / TMEM kernel. Default 1. */
 int intel_debug_use_tcgen05_stack(int on);
+/* test hook: 0 keeps the GRU forward recurrence on the mma.sync kernel instead of the tcgen05 cluster kernel. Default 1. */
+int intel_debug_use_tcgen05_gru(int on);
 /* tuning / test hook: sessions that share one CTA (and one staged copy of the weights) in the fused stack
  * kernels, 1..4. */
 int intel_debug_stack_sessions_per_cta(int n);

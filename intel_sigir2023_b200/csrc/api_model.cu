@@ -308,7 +308,7 @@ int gru_fwd(const intel_dims_t* d, const intel_encoder_t& p, EncWs& e, const int
     INTEL_TRY(linear(R, 3 * h, dd, e.seq, dd, p.w_ih, dd, p.b_ih, w.gi, 3 * h, s));
     INTEL_TRY(fill_zero(w.h_all, (size_t)B * (T + 1) * h * 4, s));
     if (h == 128) {
-        INTEL_TRY(gru_seq_fwd(B, T, h, lens, w.gi, p.w_hh, p.b_hh, w.h_all, w.gates, s));
+        INTEL_TRY(gru_seq_fwd(B, T, h, lens, w.gi, p.w_hh, p.b_hh, w.h_all, w.gates, s, d->inference == 0));
     } else {
         for (int64_t t = 0; t < T; ++t) {
             INTEL_TRY(linear(B, 3 * h, h, w.h_all + t * h, (T + 1) * h, p.w_hh, h, p.b_hh, w.gh, 3 * h, s));
@@ -351,6 +351,11 @@ int intel_debug_use_fused_stack(int on) {
 
 int intel_debug_use_tcgen05_gemm(int on) {
     gemm_debug_use_umma(on);
+    return INTEL_OK;
+}
+
+int intel_debug_use_tcgen05_gru(int on) {
+    gru_debug_use_tcgen05(on);
     return INTEL_OK;
 }
 

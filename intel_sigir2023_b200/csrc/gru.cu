@@ -239,9 +239,10 @@ __global__ void __launch_bounds__(256, 1) gru_seq_fwd_kernel(int64_t B, int64_t 
 
 // h_all[:, 0] must be zero (the caller clears it); h_all [B, T+1, 128], gates [B, T, 512]
 int gru_seq_fwd(int64_t B, int64_t T, int h, const int64_t* lens, const float* gi, const float* w_hh,
-                const float* b_hh, float* h_all, float* gates, cudaStream_t s) {
+                const float* b_hh, float* h_all, float* gates, cudaStream_t s, bool save_gates) {
     if (B <= 0 || T <= 0) return INTEL_OK;
     INTEL_REQUIRE(h == GH, INTEL_ERR_UNSUPPORTED, "fused GRU needs hidden size 128");
+    if (gru_tc_supported(h)) return gru_tc_fwd(B, T, lens, gi, w_hh, b_hh, h_all, gates, s, save_gates);
     const size_t smem = (size_t)(3 * GH * GW + GF_SB * GW) * 4;
     ensure_smem(gru_seq_fwd_kernel, smem);
     LAUNCH(gru_seq_fwd_kernel, dim3((unsigned)ceil_div(B, GF_SB)), dim3(256), smem, s, B, T, lens, gi, w_hh, b_hh, h_all,

@@ -122,7 +122,12 @@ int gru_step_bwd(int64_t B, int64_t T, int h, int t, const int64_t* lens, const 
 // resident in shared memory (see gru.cu).  h_all [B,T+1,h] (slot 0 pre-zeroed), gates [B,T,4h],
 // dgi [B,T,3h], dgh_all [B,T+1,3h] (pre-zeroed), dh_in [B,h] = d loss / d h_T.
 int gru_seq_fwd(int64_t B, int64_t T, int h, const int64_t* lens, const float* gi, const float* w_hh,
-                const float* b_hh, float* h_all, float* gates, cudaStream_t s);
+                const float* b_hh, float* h_all, float* gates, cudaStream_t s, bool save_gates = true);
+// tcgen05 forward recurrence (gru_tc.cu): clusters of four CTAs, W_hh slices resident as UMMA B operands; same outputs
+bool gru_tc_supported(int h);
+int gru_tc_fwd(int64_t B, int64_t T, const int64_t* lens, const float* gi, const float* w_hh, const float* b_hh, float* h_all,
+               float* gates, cudaStream_t s, bool save_gates = true);
+void gru_debug_use_tcgen05(int on);
 int gru_seq_bwd(int64_t B, int64_t T, int h, const int64_t* lens, const float* w_hh, const float* h_all,
                 const float* gates, const float* dh_in, float* dgi, float* dgh_all, float* db_ih, float* db_hh, cudaStream_t s);
 

@@ -466,6 +466,31 @@ def check_tc_stack(device, cases=((10, 30, 2, 2), (7, 50, 2, 2), (5, 64, 1, 1), 
             assert_grad_close(a[2][k].cpu().numpy(), g.cpu().numpy(), gmax, f"{k} {(B, L, heads, layers)}", rtol=2e-4, afrac=3e-6)
 
 
+def check_gru_tc(device, B=300, L=9):
+    """the tcgen05 cluster kernel of the GRU recurrence (gru_tc.cu) against the mma.sync kernel (gru.cu): several session
+    tiles with a ragged tail, history lengths 1..H, outputs and every parameter gradient"""
+    from intel_sigir2023_b200 import _lib, synthetic
+    from intel_sigir2023_b200.config import IntelConfig
+    corpus = synthetic.CorpusSpec(n_item=200, n_class=9, n_user=30, n_ctx=19, model_num=3, intent_num=40, history_max=11)
+    cfg = IntelConfig(item_rows=corpus.item_rows, class_rows=corpus.n_class, user_rows=corpus.user_rows, ctx_rows=corpus.n_ctx,
+                      intent_num=corpus.intent_num, model_num=3, history_max=11, encoder="GRU4Rec", num_heads=2, num_layers=1,
+                      context_emb_size=32, intent_emb_size=32)
+    batch = synthetic.make_batch(corpus, synthetic.BatchSpec(batch_size=B, max_len=L, min_len=2), seed=21)
+    batch = {k: (v.to(device) if torch.is_tensor(v) else v) for k, v in batch.items()}
+    state = O.init_state(cfg, seed=9)
+    a = _fresh(cfg, state, device, batch)
+    _lib.check(_lib.load().intel_debug_use_tcgen05_gru(0))
+    try:
+        b = _fresh(cfg, state, device, batch)
+    finally:
+        _lib.check(_lib.load().intel_debug_use_tcgen05_gru(1))
+    for k in ("intents", "weights", "ens_score"):
+        assert rel_err(a[0][k].detach().cpu().numpy(), b[0][k].detach().cpu().numpy()) < 5e-6, k
+    gmax = max(float(g.abs().max()) for g in b[2].values())
+    for k, g in b[2].items():
+        assert_grad_close(a[2][k].cpu().numpy(), g.cpu().numpy(), gmax, k, rtol=2e-5, afrac=3e-6)
+
+
 def check_fused_shapes(device, cases=((5, 7, 2, 1, 1), (9, 16, 1, 2, 2), (7, 40, 2, 1, 4), (6, 50, 2, 2, 3), (5, 64, 1, 1, 2),
                                       (4, 70, 2, 2, 4), (3, 100, 1, 1, 4), (3, 128, 2, 1, 4), (10, 30, 2, 2, 4),
                                       (3, 200, 1, 1, 4), (2, 150, 2, 2, 4), (3, 208, 2, 1, 4), (2, 129, 1, 2, 4))):

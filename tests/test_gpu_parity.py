@@ -117,5 +117,9 @@ def test_tcgen05_stack_matches_mma_sync_stack():
     P.check_tc_stack(DEV)
 
 
+def test_tcgen05_gru_matches_mma_sync_gru():
+    P.check_gru_tc(DEV)
+
+
 def test_dropout():
     P.check_dropout(DEV)
