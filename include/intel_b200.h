@@ -314,6 +314,8 @@ int intel_debug_use_tcgen05_gemm(int on);
 int intel_debug_use_tcgen05_stack(int on);
 /* test hook: 0 keeps the GRU forward recurrence on the mma.sync kernel instead of the tcgen05 cluster kernel. Default 1. */
 int intel_debug_use_tcgen05_gru(int on);
+/* test hook: 0 keeps the tall resident-weight products on the generic tcgen05 GEMM instead of the persistent kernel. Default 1. */
+int intel_debug_use_rows_gemm(int on);
 /* tuning / test hook: sessions that share one CTA (and one staged copy of the weights) in the fused stack
  * kernels, 1..4. */
 int intel_debug_stack_sessions_per_cta(int n);

@@ -354,6 +354,11 @@ int intel_debug_use_tcgen05_gemm(int on) {
     return INTEL_OK;
 }
 
+int intel_debug_use_rows_gemm(int on) {
+    gemm_debug_use_rows_tc(on);
+    return INTEL_OK;
+}
+
 int intel_debug_use_tcgen05_gru(int on) {
     gru_debug_use_tcgen05(on);
     return INTEL_OK;

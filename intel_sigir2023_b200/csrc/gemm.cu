@@ -758,6 +758,10 @@ int gemm(const Gemm& g, cudaStream_t s) {
     const char* what = wgrad ? "gemm_wgrad" : (g.b_t ? "gemm_dgrad" : "gemm_fwd");
     const double bytes = 4.0 * ((double)d.M * d.K + (double)d.N * d.K +
                                 (double)d.M * d.N * (1 + (d.add != nullptr) + (d.mask != nullptr)));
+    {   // tall products with a small resident weight operand: persistent warp-specialised tcgen05 kernel (gemm_rows_tc.cu)
+        int st = 0;
+        if (g_use_umma && !prezero && gemm_rows_tc_try(g, s, what, &st)) return st;
+    }
 #ifndef INTEL_EMU
     // large products with 16-byte aligned operands: tcgen05 path (gemm_umma.cuh), 128 x bn tiles, TMEM accumulators
     // (tall outputs with few columns and a long inner dimension fill too few 128-row tiles: the skinny kernel below)

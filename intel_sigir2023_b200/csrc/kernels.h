@@ -19,6 +19,9 @@ struct Gemm {
     int splits = 1;       // split of the inner dimension (0 = pick automatically for accumulate == 2)
 };
 int gemm(const Gemm& g, cudaStream_t s);
+// gemm_rows_tc.cu: persistent tcgen05 kernel for tall products with a resident weight operand; false = shape not taken
+bool gemm_rows_tc_try(const Gemm& g, cudaStream_t s, const char* what, int* status);
+void gemm_debug_use_rows_tc(int on);
 // C[M,N] = A[M,K] W[N,K]^T (+bias)
 int linear(int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* W, int64_t ldw,
            const float* bias, float* C, int64_t ldc, cudaStream_t s, bool relu_a = false, bool relu_out = false,

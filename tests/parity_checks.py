@@ -102,6 +102,38 @@ def check_linear_large(device):
             assert rel_err(a.cpu().numpy(), c.cpu().numpy()) < 4e-6
 
 
+def check_rows_gemm(device):
+    """the persistent warp-specialised tcgen05 kernel for tall products with a resident weight (gemm_rows_tc.cu): forward
+    (several N blocks per row tile) and input gradient (several K chunks per block), ragged row / column tails, against
+    float64 and against the generic kernel"""
+    from intel_sigir2023_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(11)
+    st = _lib.stream_ptr(torch.device(device))
+    for (M, N, K) in [(20000, 384, 64), (16500, 384, 48), (33001, 96, 40), (81920, 384, 64)]:
+        X = torch.randn(M, K, generator=g).to(device)
+        W = torch.randn(N, K, generator=g).to(device)
+        b = torch.randn(N, generator=g).to(device)
+        dY = torch.randn(M, N, generator=g).to(device)
+        ref_y = (X.double() @ W.double().t() + b.double()).cpu().numpy()
+        ref_dx = (dY.double() @ W.double()).cpu().numpy()
+        outs = []
+        for on in (1, 0):
+            _lib.check(lib.intel_debug_use_rows_gemm(on))
+            try:
+                Y = torch.full((M, N), float("nan"), device=device)
+                _lib.check(lib.intel_linear_fwd(M, N, K, _lib.ptr(X), _lib.ptr(W), _lib.ptr(b), _lib.ptr(Y), st))
+                dX = torch.full((M, K), float("nan"), device=device)
+                _lib.check(lib.intel_linear_dx(M, N, K, _lib.ptr(dY), _lib.ptr(W), _lib.ptr(dX), None, st))
+            finally:
+                _lib.check(lib.intel_debug_use_rows_gemm(1))
+            assert rel_err(Y.cpu().numpy(), ref_y) < 3e-6, ("fwd", M, N, K, on, rel_err(Y.cpu().numpy(), ref_y))
+            assert rel_err(dX.cpu().numpy(), ref_dx) < 3e-6, ("dx", M, N, K, on, rel_err(dX.cpu().numpy(), ref_dx))
+            outs.append((Y, dX))
+        for a, c in zip(*outs):
+            assert rel_err(a.cpu().numpy(), c.cpu().numpy()) < 4e-6
+
+
 def check_mha(device, shapes=((3, 12, 32, 2), (2, 50, 32, 2), (2, 100, 32, 1), (1, 130, 48, 2))):
     """attention core vs torch on list lengths that span several 64-row query blocks, with and without key masks."""
     from intel_sigir2023_b200 import _lib

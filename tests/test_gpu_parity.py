@@ -97,6 +97,10 @@ def test_linear_large_tcgen05_vs_mma_sync():
     P.check_linear_large(DEV)
 
 
+def test_rows_gemm_persistent_tcgen05():
+    P.check_rows_gemm(DEV)
+
+
 def test_fused_stack_matches_staged():
     P.check_fused_vs_staged(DEV)
 
