@@ -314,7 +314,8 @@ int intel_debug_use_tcgen05_gemm(int on);
 int intel_debug_use_tcgen05_stack(int on);
 /* test hook: 0 keeps the GRU forward recurrence on the mma.sync kernel instead of the tcgen05 cluster kernel. Default 1. */
 int intel_debug_use_tcgen05_gru(int on);
-/* test hook: 0 keeps the tall resident-weight products on the generic tcgen05 GEMM instead of the persistent kernel. Default 1. */
+/* test hook: 0 keeps the tall resident-weight products and the tall weight gradients on the generic tcgen05 GEMM instead of the
+ * persistent kernels (gemm_rows_tc.cu, gemm_wgrad_tc.cu). Default 1. */
 int intel_debug_use_rows_gemm(int on);
 /* tuning / test hook: sessions that share one CTA (and one staged copy of the weights) in the fused stack
  * kernels, 1..4. */

@@ -356,6 +356,7 @@ int intel_debug_use_tcgen05_gemm(int on) {
 
 int intel_debug_use_rows_gemm(int on) {
     gemm_debug_use_rows_tc(on);
+    gemm_debug_use_wgrad_tc(on);
     return INTEL_OK;
 }
 

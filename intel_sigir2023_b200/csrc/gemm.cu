@@ -761,6 +761,7 @@ int gemm(const Gemm& g, cudaStream_t s) {
     {   // tall products with a small resident weight operand: persistent warp-specialised tcgen05 kernel (gemm_rows_tc.cu)
         int st = 0;
         if (g_use_umma && !prezero && gemm_rows_tc_try(g, s, what, &st)) return st;
+        if (g_use_umma && !prezero && gemm_wgrad_tc_try(g, s, what, &st)) return st;       // gemm_wgrad_tc.cu
     }
 #ifndef INTEL_EMU
     // large products with 16-byte aligned operands: tcgen05 path (gemm_umma.cuh), 128 x bn tiles, TMEM accumulators

@@ -59,15 +59,29 @@ __global__ void __launch_bounds__(RT_THREADS, 1) gemm_rows_tc_kernel(RowsArgs a)
     uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + ((Np + 31) / 32) * 32);      // a_full[2] a_empty[2] d_full[2] d_empty[2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
     // ---- weights -> resident hi / lo planes (zero padded), bias ----
-    for (int e = tid; e < Np * Kp; e += RT_THREADS) {
-        const int n = e / Kp, k = e - n * Kp;
-        float v = 0.f;
-        if (n < a.N && k < a.K) v = a.w_t ? a.W[(int64_t)k * a.ldw + n] : a.W[(int64_t)n * a.ldw + k];
-        uint32_t h, l;
-        split_tf32(v, h, l);
-        const int off = ((k >> 2) * Np + n) * 16 + (k & 3) * 4;
-        *reinterpret_cast<uint32_t*>(w_hi + off) = h;
-        *reinterpret_cast<uint32_t*>(w_lo + off) = l;
+    // one 16-byte plane unit (row n, 4 consecutive k) per iteration: a float4 of a [N][K] weight row, or four coalesced scalars
+    // of a [K][N] one; consecutive threads take consecutive n so the shared-memory stores of a warp are contiguous
+    {
+        const int units = Np * (Kp / 4);
+#pragma unroll 4
+        for (int e = tid; e < units; e += RT_THREADS) {
+            const int kq = e / Np, n = e - kq * Np, k = 4 * kq;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (n < a.N && k < a.K) {
+                if (!a.w_t && (a.ldw % 4 == 0) && ((uintptr_t)a.W % 16 == 0)) v = *reinterpret_cast<const float4*>(a.W + (int64_t)n * a.ldw + k);
+                else if (!a.w_t) v = make_float4(a.W[(int64_t)n * a.ldw + k], a.W[(int64_t)n * a.ldw + k + 1], a.W[(int64_t)n * a.ldw + k + 2],
+                                                 a.W[(int64_t)n * a.ldw + k + 3]);
+                else v = make_float4(a.W[(int64_t)k * a.ldw + n], a.W[(int64_t)(k + 1) * a.ldw + n], a.W[(int64_t)(k + 2) * a.ldw + n],
+                                     a.W[(int64_t)(k + 3) * a.ldw + n]);
+            }
+            uint4 h, l;
+            split_tf32(v.x, h.x, l.x);
+            split_tf32(v.y, h.y, l.y);
+            split_tf32(v.z, h.z, l.z);
+            split_tf32(v.w, h.w, l.w);
+            *reinterpret_cast<uint4*>(w_hi + (size_t)e * 16) = h;
+            *reinterpret_cast<uint4*>(w_lo + (size_t)e * 16) = l;
+        }
     }
     for (int n = tid; n < Np; n += RT_THREADS) bias_s[n] = (a.bias && n < a.N) ? a.bias[n] : 0.f;
     if (tid == 0) {
@@ -90,38 +104,46 @@ __global__ void __launch_bounds__(RT_THREADS, 1) gemm_rows_tc_kernel(RowsArgs a)
     if (warp < 4) {
         // ================= producers =================
         const uint32_t tl = tm + ((uint32_t)(warp * 32) << 16);
-        uint32_t ia = 0;
-        for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        // the loads of chunk i + 1 (next K chunk or next tile) are issued before chunk i is split and stored, so the HBM
+        // latency overlaps one chunk of work
+        const int64_t my_tiles = blockIdx.x < tiles ? (tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+        const int64_t nch = my_tiles * a.nkc;
+        float4 v[RT_KC / 4], nx[RT_KC / 4];
+        auto load_chunk = [&](int64_t i, float4 (&x)[RT_KC / 4]) {
+            const int64_t tile = blockIdx.x + (i / a.nkc) * gridDim.x;
+            const int kc = (int)(i % a.nkc);
             const int64_t row = tile * 128 + tid;
-            const bool live = row < a.M;
             const float* src = a.A + row * a.lda;
-            for (int kc = 0; kc < a.nkc; ++kc, ++ia) {
-                const uint32_t buf = ia & 1u;
-                float4 v[RT_KC / 4];
 #pragma unroll
-                for (int j = 0; j < RT_KC / 4; ++j) {
-                    const int k = kc * RT_KC + 4 * j;
-                    v[j] = (live && k < a.K) ? *reinterpret_cast<const float4*>(src + k) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-                if (ia >= 2) tc05::mbar_wait(&a_empty[buf], ((ia >> 1) - 1) & 1u);
-                tc05::fence_after();
-#pragma unroll
-                for (int q = 0; q < RT_KC / 32; ++q) {
-                    uint32_t h[32], lo[32];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        split_tf32(v[8 * q + j].x, h[4 * j], lo[4 * j]);
-                        split_tf32(v[8 * q + j].y, h[4 * j + 1], lo[4 * j + 1]);
-                        split_tf32(v[8 * q + j].z, h[4 * j + 2], lo[4 * j + 2]);
-                        split_tf32(v[8 * q + j].w, h[4 * j + 3], lo[4 * j + 3]);
-                    }
-                    tc05::st32(tl + cA + buf * 128 + 32 * q, h);
-                    tc05::st32(tl + cA + buf * 128 + 64 + 32 * q, lo);
-                }
-                tc05::wait_st();
-                tc05::fence_before();
-                mbar_arrive(&a_full[buf]);
+            for (int j = 0; j < RT_KC / 4; ++j) {
+                const int k = kc * RT_KC + 4 * j;
+                x[j] = (row < a.M && k < a.K) ? *reinterpret_cast<const float4*>(src + k) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
+        };
+        if (nch > 0) load_chunk(0, v);
+        for (int64_t i = 0; i < nch; ++i) {
+            const uint32_t ia = (uint32_t)i, buf = ia & 1u;
+            if (i + 1 < nch) load_chunk(i + 1, nx);
+            if (ia >= 2) tc05::mbar_wait(&a_empty[buf], ((ia >> 1) - 1) & 1u);
+            tc05::fence_after();
+#pragma unroll
+            for (int q = 0; q < RT_KC / 32; ++q) {
+                uint32_t h[32], lo[32];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    split_tf32(v[8 * q + j].x, h[4 * j], lo[4 * j]);
+                    split_tf32(v[8 * q + j].y, h[4 * j + 1], lo[4 * j + 1]);
+                    split_tf32(v[8 * q + j].z, h[4 * j + 2], lo[4 * j + 2]);
+                    split_tf32(v[8 * q + j].w, h[4 * j + 3], lo[4 * j + 3]);
+                }
+                tc05::st32(tl + cA + buf * 128 + 32 * q, h);
+                tc05::st32(tl + cA + buf * 128 + 64 + 32 * q, lo);
+            }
+            tc05::wait_st();
+            tc05::fence_before();
+            mbar_arrive(&a_full[buf]);
+#pragma unroll
+            for (int j = 0; j < RT_KC / 4; ++j) v[j] = nx[j];
         }
     } else if (warp == 8) {
         // ================= MMA issuer =================

@@ -74,14 +74,19 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(128, 1)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gsm + GT_TMEM);
     float* bias = reinterpret_cast<float*>(gsm + GT_BIAS);           // [3][32] of the own units
     // ---- W_hh rows of the own units -> hi / lo planes (plane row = gate * 32 + unit) ----
-    for (int e = t; e < GT_N * GT_H; e += 128) {
-        const int n = e >> 7, k = e & 127;
+    // one 16-byte plane unit (row n, 4 consecutive k) per iteration = one float4 of a W_hh row
+#pragma unroll 4
+    for (int e = t; e < GT_N * (GT_H / 4); e += 128) {
+        const int kq = e / GT_N, n = e - kq * GT_N;
         const int grow = (n >> 5) * GT_H + (int)c * GT_U + (n & 31);
-        uint32_t h, l;
-        split_tf32(w_hh[grow * GT_H + k], h, l);
-        const int off = ((k >> 2) * GT_N + n) * 16 + (k & 3) * 4;
-        *reinterpret_cast<uint32_t*>(gsm + GT_W_HI + off) = h;
-        *reinterpret_cast<uint32_t*>(gsm + GT_W_LO + off) = l;
+        const float4 v = *reinterpret_cast<const float4*>(w_hh + grow * GT_H + 4 * kq);
+        uint4 h, l;
+        split_tf32(v.x, h.x, l.x);
+        split_tf32(v.y, h.y, l.y);
+        split_tf32(v.z, h.z, l.z);
+        split_tf32(v.w, h.w, l.w);
+        *reinterpret_cast<uint4*>(gsm + GT_W_HI + (size_t)e * 16) = h;
+        *reinterpret_cast<uint4*>(gsm + GT_W_LO + (size_t)e * 16) = l;
     }
     if (t < GT_N) bias[t] = b_hh[(t >> 5) * GT_H + (int)c * GT_U + (t & 31)];
     for (int e = t; e < 128 * 32; e += 128) reinterpret_cast<uint4*>(gsm + GT_STAGE)[e] = make_uint4(0u, 0u, 0u, 0u);      // h_0 = 0

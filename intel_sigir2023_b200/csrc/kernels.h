@@ -22,6 +22,9 @@ int gemm(const Gemm& g, cudaStream_t s);
 // gemm_rows_tc.cu: persistent tcgen05 kernel for tall products with a resident weight operand; false = shape not taken
 bool gemm_rows_tc_try(const Gemm& g, cudaStream_t s, const char* what, int* status);
 void gemm_debug_use_rows_tc(int on);
+// gemm_wgrad_tc.cu: dW += dY^T X over tens of thousands of rows, both operands MN-major natural tiles
+bool gemm_wgrad_tc_try(const Gemm& g, cudaStream_t s, const char* what, int* status);
+void gemm_debug_use_wgrad_tc(int on);
 // C[M,N] = A[M,K] W[N,K]^T (+bias)
 int linear(int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* W, int64_t ldw,
            const float* bias, float* C, int64_t ldc, cudaStream_t s, bool relu_a = false, bool relu_out = false,

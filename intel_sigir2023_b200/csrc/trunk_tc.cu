@@ -49,15 +49,20 @@ __device__ __forceinline__ void store_row(float* dst, const float (&v)[32], bool
     for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(dst + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
 }
 
-// weight W [rows_w][32] (nn.Linear: [out][in]) -> K-major hi / lo planes, plane row = row0 + out of `rows` rows
+// weight W [32][32] (nn.Linear: [out][in]) -> K-major hi / lo planes, plane row = row0 + out of `rows` rows; one 16-byte
+// plane unit (4 consecutive in-channels of one out-channel) per thread: a float4 load, two 16-byte stores
 __device__ __forceinline__ void stage_weight(uint8_t* hi, uint8_t* lo, const float* __restrict__ W, int rows, int row0) {
-    for (int e = threadIdx.x; e < TD * TD; e += blockDim.x) {
-        const int n = e >> 5, k = e & 31;
-        uint32_t h, l;
-        split_tf32(W[e], h, l);
-        const int off = ((k >> 2) * rows + row0 + n) * 16 + (k & 3) * 4;
-        *reinterpret_cast<uint32_t*>(hi + off) = h;
-        *reinterpret_cast<uint32_t*>(lo + off) = l;
+    for (int e = threadIdx.x; e < TD * TD / 4; e += blockDim.x) {
+        const int kq = e >> 5, n = e & 31;
+        const float4 v = *reinterpret_cast<const float4*>(W + n * TD + 4 * kq);
+        uint4 h, l;
+        split_tf32(v.x, h.x, l.x);
+        split_tf32(v.y, h.y, l.y);
+        split_tf32(v.z, h.z, l.z);
+        split_tf32(v.w, h.w, l.w);
+        const int off = (kq * rows + row0 + n) * 16;
+        *reinterpret_cast<uint4*>(hi + off) = h;
+        *reinterpret_cast<uint4*>(lo + off) = l;
     }
 }
 

@@ -110,13 +110,14 @@ def check_rows_gemm(device):
     lib = _lib.load()
     g = torch.Generator().manual_seed(11)
     st = _lib.stream_ptr(torch.device(device))
-    for (M, N, K) in [(20000, 384, 64), (16500, 384, 48), (33001, 96, 40), (81920, 384, 64)]:
+    for (M, N, K) in [(20000, 384, 64), (16500, 384, 48), (33001, 96, 40), (81920, 384, 64), (86016, 384, 128), (17000, 128, 32)]:
         X = torch.randn(M, K, generator=g).to(device)
         W = torch.randn(N, K, generator=g).to(device)
         b = torch.randn(N, generator=g).to(device)
         dY = torch.randn(M, N, generator=g).to(device)
         ref_y = (X.double() @ W.double().t() + b.double()).cpu().numpy()
         ref_dx = (dY.double() @ W.double()).cpu().numpy()
+        ref_dw = (dY.double().t() @ X.double()).cpu().numpy()
         outs = []
         for on in (1, 0):
             _lib.check(lib.intel_debug_use_rows_gemm(on))
@@ -125,11 +126,14 @@ def check_rows_gemm(device):
                 _lib.check(lib.intel_linear_fwd(M, N, K, _lib.ptr(X), _lib.ptr(W), _lib.ptr(b), _lib.ptr(Y), st))
                 dX = torch.full((M, K), float("nan"), device=device)
                 _lib.check(lib.intel_linear_dx(M, N, K, _lib.ptr(dY), _lib.ptr(W), _lib.ptr(dX), None, st))
+                dW = torch.zeros(N, K, device=device)         # weight gradient: both operands contracted over the rows
+                _lib.check(lib.intel_linear_dw(M, N, K, _lib.ptr(dY), _lib.ptr(X), _lib.ptr(dW), None, st))
             finally:
                 _lib.check(lib.intel_debug_use_rows_gemm(1))
             assert rel_err(Y.cpu().numpy(), ref_y) < 3e-6, ("fwd", M, N, K, on, rel_err(Y.cpu().numpy(), ref_y))
             assert rel_err(dX.cpu().numpy(), ref_dx) < 3e-6, ("dx", M, N, K, on, rel_err(dX.cpu().numpy(), ref_dx))
-            outs.append((Y, dX))
+            assert rel_err(dW.cpu().numpy(), ref_dw) < 3e-6, ("dw", M, N, K, on, rel_err(dW.cpu().numpy(), ref_dw))
+            outs.append((Y, dX, dW))
         for a, c in zip(*outs):
             assert rel_err(a.cpu().numpy(), c.cpu().numpy()) < 4e-6
 
