@@ -302,6 +302,7 @@ def run_b200(a):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        dp.configure_nccl_for_overlap()      # the gradient exchange runs beside the tail of the backward pass (dp.GradReducer)
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
     spec_corpus, cfg, loss_kind, loss_args = make_cfg(a)

@@ -151,6 +151,22 @@ int intel_ensemble_bwd(const intel_dims_t* d, const intel_tensors_t* params, con
                        intel_tensors_t* grads, float* d_intents_out,
                        void* workspace, size_t workspace_bytes, intel_stream_t stream);
 
+/* The same backward pass in phases, for data-parallel callers that want to exchange gradients while the tail of the
+ * pass still runs (no counterpart in the reference, which is single process: helpers/BaseRunner.py:268-291).
+ * HEAD: weight head + both pooled cross attentions; d_intents_out is final afterwards.  ITEM / SCORE: the self-attention
+ * stack of one stream plus the gradients of its inputs (item / class embedding rows; score_embeddings).  HEAD must come
+ * first; intel_ensemble_bwd == all three in the order HEAD, ITEM, SCORE. */
+#define INTEL_ENS_BWD_HEAD 1
+#define INTEL_ENS_BWD_ITEM 2
+#define INTEL_ENS_BWD_SCORE 4
+int intel_ensemble_bwd_phase(const intel_dims_t* d, const intel_tensors_t* params, const intel_batch_t* batch,
+                             const float* intents, const float* d_weights, const float* d_ens,
+                             intel_tensors_t* grads, float* d_intents_out,
+                             void* workspace, size_t workspace_bytes, intel_stream_t stream, int phases);
+/* Number of SMs (0..64) the persistent backward kernel of the self-attention stack leaves free when the SCORE phase is
+ * called on its own, so that a collective launched on another stream finds room to run beside it.  Default 0. */
+int intel_reserve_sms(int n);
+
 /* ---- losses with fused gradients ------------------------------------------------------ */
 /* Each writes the scalar loss (batch mean, diversity term folded in like the reference's in-place
  * `loss +=`) to loss_out[0] (float64 accumulator) and the gradient of that scalar w.r.t. ens_score / weights to

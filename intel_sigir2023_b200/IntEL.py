@@ -132,29 +132,52 @@ class _IntelFn(torch.autograd.Function):
         names = model._param_names
         P = _lib.make_tensors(cfg, dict(zip(names, params)))
         # one zero-filled buffer for all dense gradients (a single fill kernel instead of one per parameter); the
-        # per-parameter gradients are 256-byte aligned views into it
-        offs, total = [], 0
-        for p in params:
-            offs.append(total)
-            total += (p.numel() + 63) // 64 * 64
+        # per-parameter gradients are 256-byte aligned views into it.  The score stream's parameters sit at the end: they
+        # are the last gradients the pass below completes, so everything before `late` can be exchanged while they are
+        # still being computed (dp.GradReducer installs model._early_reduce for that).
+        late_names = model._late_grad_names
+        order = [i for i, n in enumerate(names) if n not in late_names] + [i for i, n in enumerate(names) if n in late_names]
+        offs, total, late = [0] * len(params), 0, None
+        for i in order:
+            if late is None and names[i] in late_names:
+                late = total
+            offs[i] = total
+            total += (params[i].numel() + 63) // 64 * 64
+        late = total if late is None else late
         flat = torch.zeros(total, dtype=torch.float32, device=dev)
         grads = [flat[o:o + p.numel()].view(p.shape) for o, p in zip(offs, params)]
         model._flat_grad = flat         # dp.GradReducer all-reduces this one buffer when the .grad tensors still alias it
+        model._flat_late = late
         G = _lib.make_tensors(cfg, dict(zip(names, grads)))
         bt = _lib.make_batch(batch, cfg)
         stream = _lib.stream_ptr(dev)
+        have_ens = d_weights is not None or d_ens is not None
         d_int_ens: Optional[torch.Tensor] = None
-        if d_weights is not None or d_ens is not None:
+        dw = de = None
+
+        def ens_bwd(phases: int) -> None:
+            _lib.check(lib.intel_ensemble_bwd_phase(dims, P, bt, _lib.ptr(intents), _lib.ptr(dw), _lib.ptr(de), G,
+                                                    _lib.ptr(d_int_ens), _lib.ptr(ctx.ws_ens), ctx.ws_ens.numel(), stream, phases))
+
+        # order of the pass: head + cross attentions (the gradient w.r.t. the predicted intents is final) ->
+        # intent predictor -> item stack + embedding rows -> [every gradient but the score stream's is final] -> score stack
+        if have_ens:
             d_int_ens = torch.empty_like(intents)
             dw = d_weights.contiguous() if d_weights is not None else None
             de = d_ens.contiguous() if d_ens is not None else None
-            _lib.check(lib.intel_ensemble_bwd(dims, P, bt, _lib.ptr(intents), _lib.ptr(dw), _lib.ptr(de), G,
-                                              _lib.ptr(d_int_ens), _lib.ptr(ctx.ws_ens), ctx.ws_ens.numel(), stream))
+            ens_bwd(_lib.ENS_BWD_HEAD)
         first = d_intents.contiguous() if d_intents is not None else d_int_ens
         extra = d_int_ens if d_intents is not None else None
         if first is not None:
             _lib.check(lib.intel_intent_bwd(dims, P, bt, _lib.ptr(intents), _lib.ptr(first), _lib.ptr(extra), G,
                                             _lib.ptr(ctx.ws_int), ctx.ws_int.numel(), stream))
+        if have_ens:
+            ens_bwd(_lib.ENS_BWD_ITEM)
+        early = getattr(model, "_early_reduce", None)
+        if early is not None:
+            early(flat, late)            # asynchronous: runs beside the score stack below
+        if have_ens:
+            ens_bwd(_lib.ENS_BWD_SCORE)
         _give_ws(model, ctx.ws_int)
         _give_ws(model, ctx.ws_ens)
         ctx.ws_int = ctx.ws_ens = None
@@ -233,6 +256,10 @@ class IntEL(nn.Module):
         self.item_encoder = _encoder_container(c, c.d_his_item)
         self.pred_layer = nn.Linear(c.d_pred, I)
         self._param_names = [n for n, _ in self.named_parameters()]
+        # gradients that only the last phase of the backward pass (the score stream's stack) writes
+        self._late_grad_names = {n for n in self._param_names
+                                 if n.startswith(("s_attn_head.", "s_W1.", "s_W2.", "s_layer_norm.", "score_embeddings."))}
+        self._early_reduce = None       # set by dp.GradReducer: callable(flat_grad, late_offset)
         shapes = c.param_shapes()
         for n, p in self.named_parameters():
             assert tuple(p.shape) == shapes[n], (n, tuple(p.shape), shapes[n])

@@ -60,6 +60,8 @@ class Batch(C.Structure):
                [("nz1", C.c_int32), ("nz2", C.c_int32)]
 
 
+ENS_BWD_HEAD, ENS_BWD_ITEM, ENS_BWD_SCORE = 1, 2, 4     # INTEL_ENS_BWD_* of include/intel_b200.h
+
 _lib: Optional[C.CDLL] = None
 _allow_host_tensors = False     # flipped only by tests/emu (kernel-logic emulator), never by the package
 
@@ -76,6 +78,8 @@ def _declare(lib: C.CDLL) -> None:
         "intel_ensemble_workspace_bytes": (sz, [PD]),
         "intel_ensemble_fwd": (i32, [PD, PT, PB, _p, _p, _p, _p, sz, _p]),
         "intel_ensemble_bwd": (i32, [PD, PT, PB, _p, _p, _p, PT, _p, _p, sz, _p]),
+        "intel_ensemble_bwd_phase": (i32, [PD, PT, PB, _p, _p, _p, PT, _p, _p, sz, _p, i32]),
+        "intel_reserve_sms": (i32, [i32]),
         "intel_loss_pl_fwd_bwd": (i32, [i64, i64, i64, _p, _p, _p, _p, _p, i32, dbl, _p, _p, _p, _p]),
         "intel_loss_bpr_fwd_bwd": (i32, [i64, i64, i64, _p, _p, _p, _p, _p, _p, C.c_uint64, i32, dbl, _p, _p, _p, _p]),
         "intel_loss_mse_fwd_bwd": (i32, [i64, i64, i64, _p, _p, _p, _p, _p, i32, dbl, _p, _p, _p, _p]),
@@ -124,7 +128,7 @@ def _declare(lib: C.CDLL) -> None:
         fn.argtypes = args
 
 
-EXPORTED = ["intel_last_error", "intel_abi_version", "intel_intent_workspace_bytes", "intel_intent_fwd",
+EXPORTED = ["intel_ensemble_bwd_phase", "intel_reserve_sms", "intel_last_error", "intel_abi_version", "intel_intent_workspace_bytes", "intel_intent_fwd",
             "intel_intent_bwd", "intel_ensemble_workspace_bytes", "intel_ensemble_fwd", "intel_ensemble_bwd",
             "intel_loss_pl_fwd_bwd", "intel_loss_bpr_fwd_bwd", "intel_loss_mse_fwd_bwd", "intel_intent_loss_fwd_bwd",
             "intel_scale_by_device_scalar", "intel_ndcg_workspace_bytes", "intel_ndcg_topk",

@@ -126,7 +126,7 @@ struct EnsWs {
     float *w_valid, *w_pad;       // [B,K]
     float *t_i, *t_s, *m_i, *m_s, *hu, *hint, *all_item;            // cross_attention = 0
     // backward scratch
-    float *dall, *dwv, *dwp, *dxbar, *dqk, *dq, *dXa, *t1, *t2, *dqkv;
+    float *dall, *dwv, *dwp, *dxbar, *dqk, *dq, *dXa, *dXs, *t1, *t2, *dqkv;   // dXa / dXs: d(stack output) of the item / score stream
     float *g, *dall_item, *dm, *dt, *dvec;
 };
 
@@ -144,6 +144,7 @@ void ens_layout(const intel_dims_t* d, Arena& a, EnsWs& w) {
     w.dwv = a.take<float>(B * d->K);
     w.dwp = a.take<float>(B * d->K);
     w.dXa = a.take<float>(R * dmax);
+    w.dXs = a.take<float>(R * dmax);
     w.t1 = a.take<float>(R * dmax);
     w.t2 = a.take<float>(R * dmax);
     w.dqkv = a.take<float>(R * 3 * dmax);
@@ -370,6 +371,12 @@ int intel_debug_use_tcgen05_stack(int on) {
     return INTEL_OK;
 }
 
+int intel_reserve_sms(int n) {
+    INTEL_REQUIRE(n >= 0 && n <= 64, INTEL_ERR_ARG, "reserve_sms: n must be in [0, 64]");
+    trunk_reserve_sms(n);
+    return INTEL_OK;
+}
+
 int intel_debug_stack_sessions_per_cta(int n) {
     trunk_debug_sessions_per_cta(n);
     return INTEL_OK;
@@ -446,10 +453,16 @@ int intel_ensemble_fwd(const intel_dims_t* d, const intel_tensors_t* P, const in
     return INTEL_OK;
 }
 
-int intel_ensemble_bwd(const intel_dims_t* d, const intel_tensors_t* P, const intel_batch_t* bt, const float* intents,
-                       const float* d_weights, const float* d_ens, intel_tensors_t* G, float* d_intents_out,
-                       void* workspace, size_t workspace_bytes, intel_stream_t stream) {
+// The backward pass in three phases (INTEL_ENS_BWD_*): HEAD = weight head + both pooled cross attentions (d_intents_out is
+// final afterwards, d(stack output) of each stream is left in the workspace), ITEM / SCORE = the self-attention stack of
+// one stream and the gradients of its inputs.  A data-parallel caller runs HEAD, intel_intent_bwd, ITEM - after which every
+// gradient except the score stream's is final and can be exchanged - and hides that exchange behind SCORE.
+int intel_ensemble_bwd_phase(const intel_dims_t* d, const intel_tensors_t* P, const intel_batch_t* bt, const float* intents,
+                             const float* d_weights, const float* d_ens, intel_tensors_t* G, float* d_intents_out,
+                             void* workspace, size_t workspace_bytes, intel_stream_t stream, int phases) {
     INTEL_TRY(check_dims(d));
+    INTEL_REQUIRE(phases > 0 && phases < 8, INTEL_ERR_ARG, "ensemble_bwd: phases must be a combination of INTEL_ENS_BWD_*");
+    const bool do_head = phases & INTEL_ENS_BWD_HEAD, do_item = phases & INTEL_ENS_BWD_ITEM, do_score = phases & INTEL_ENS_BWD_SCORE;
     INTEL_REQUIRE(P && bt && intents && G && d_intents_out, INTEL_ERR_ARG, "ensemble_bwd: null argument");
     Arena a(workspace, workspace_bytes);
     EnsWs w;
@@ -462,8 +475,10 @@ int intel_ensemble_bwd(const intel_dims_t* d, const intel_tensors_t* P, const in
     float* Xi = w.item.X[d->layers];
     float* Xs = w.score.X[d->layers];
 
+    float* const dXst[2] = {w.dXa, w.dXs};
     if (d->cross_attention) {
         const float scale = 1.0f / sqrtf((float)d->qsize);
+        if (do_head) {
         INTEL_TRY(head_fuse_bwd(B, L, K, d_weights, d_ens, bt->scores, bt->session_len, w.dwv, w.dwp, s));
         INTEL_TRY(linear_dw(B, K, D, w.dwv, K, w.all, D, G->head_w, D, G->head_b, s));
         INTEL_TRY(linear_dw(B, K, du + dint, w.dwp, K, w.all + off_u, D, G->head_w + off_u, D, G->head_b, s));
@@ -475,7 +490,7 @@ int intel_ensemble_bwd(const intel_dims_t* d, const intel_tensors_t* P, const in
         INTEL_TRY(linear_dx(B, dint, I, w.dall + off_h, D, P->intent_w, I, d_intents_out, I, s, 0));
         // h_u = relu(uid_embeddings[u])
         INTEL_TRY(scatter_add_rows(B, du, w.dall + off_u, D, bt->u_id, G->uid_emb, P->uid_emb, s, d->user_rows));
-        // the two pooled cross attentions, then the self-attention stacks
+        // the two pooled cross attentions
         for (int st = 0; st < 2; ++st) {
             const int dd = st == 0 ? di : ds;
             const int off = st == 0 ? 0 : di;
@@ -488,24 +503,16 @@ int intel_ensemble_bwd(const intel_dims_t* d, const intel_tensors_t* P, const in
                   *gxv = st == 0 ? G->xv_item : G->xv_score;
             INTEL_TRY(linear_dw(B, dd, dd, w.dall + off, D, xbar, dd, gxv, dd, nullptr, s));
             INTEL_TRY(linear_dx(B, dd, dd, w.dall + off, D, xv, dd, w.dxbar, dd, s));
-            INTEL_TRY(cross_pool_bwd(B, L, dd, X, qk, bt->session_len, scale, p, w.dxbar, w.dXa, w.dqk, s));
+            INTEL_TRY(cross_pool_bwd(B, L, dd, X, qk, bt->session_len, scale, p, w.dxbar, dXst[st], w.dqk, s));
             INTEL_TRY(linear_dw(B, dd, dd, q, dd, w.dqk, dd, gxk, dd, nullptr, s));            // dW_k[a,c] = sum q_a dqk_c
             INTEL_TRY(linear(B, dd, dd, w.dqk, dd, xk, dd, nullptr, w.dq, dd, s));              // dq = W_k dqk
             INTEL_TRY(linear_dw(B, dd, I, w.dq, dd, intents, I, gxq, I, nullptr, s));
             INTEL_TRY(linear_dx(B, dd, I, w.dq, dd, xq, I, d_intents_out, I, s, 1));
-            if (st == 0) {
-                INTEL_TRY(stack_bwd(B, L, di, d->heads, d->layers, P->item, G->item, w.item, w.dXa, w.t1, w.t2, w.dqkv, d->dropout_p,
-                                    d->dropout_seed, 0, s));
-                INTEL_TRY(scatter_add_rows(R, d->d_iid, w.dXa, di, bt->i_id, G->iid_emb, nullptr, s, d->item_rows));
-                if (d->d_im > 0) INTEL_TRY(scatter_add_rows(R, d->d_im, w.dXa + d->d_iid, di, bt->i_class, G->item_emb, nullptr, s, d->class_rows));
-            } else {
-                INTEL_TRY(stack_bwd(B, L, ds, d->heads, d->layers, P->score, G->score, w.score, w.dXa, w.t1, w.t2, w.dqkv, d->dropout_p,
-                                    d->dropout_seed, 1, s));
-                INTEL_TRY(linear_dw(R, ds, K, w.dXa, ds, w.xs, K, G->score_w, K, G->score_b, s));
-            }
+        }
         }
     } else {
         const int q = d->qsize;
+        if (do_head) {
         INTEL_TRY(item_fuse_bwd(R, K, d_weights, d_ens, bt->scores, w.g, s));
         INTEL_TRY(linear_dw(R, K, D, w.g, K, w.all_item, D, G->head_w, D, G->head_b, s));
         INTEL_TRY(linear_dx(R, K, D, w.g, K, P->head_w, D, w.dall_item, D, s));
@@ -524,25 +531,40 @@ int intel_ensemble_bwd(const intel_dims_t* d, const intel_tensors_t* P, const in
             const float *w0 = st == 0 ? P->gate_item_w0 : P->gate_score_w0, *w2 = st == 0 ? P->gate_item_w2 : P->gate_score_w2;
             float *gw0 = st == 0 ? G->gate_item_w0 : G->gate_score_w0, *gb0 = st == 0 ? G->gate_item_b0 : G->gate_score_b0,
                   *gw2 = st == 0 ? G->gate_item_w2 : G->gate_score_w2;
-            INTEL_TRY(gate_bwd(B, L, dd, X, m, w.dall_item + off, D, w.dXa, w.dm, s));
+            INTEL_TRY(gate_bwd(B, L, dd, X, m, w.dall_item + off, D, dXst[st], w.dm, s));
             INTEL_TRY(linear_dw(B, dd, q, w.dm, dd, t, q, gw2, q, nullptr, s));
             INTEL_TRY(linear_dx(B, dd, q, w.dm, dd, w2, q, w.dt, q, s, 0, t, q));       // relu mask (t = relu(.) > 0)
             INTEL_TRY(linear_dw(B, q, I, w.dt, q, intents, I, gw0, I, gb0, s));
             INTEL_TRY(linear_dx(B, q, I, w.dt, q, w0, I, d_intents_out, I, s, 1));
-            if (st == 0) {
-                INTEL_TRY(stack_bwd(B, L, di, d->heads, d->layers, P->item, G->item, w.item, w.dXa, w.t1, w.t2, w.dqkv, d->dropout_p,
-                                    d->dropout_seed, 0, s));
-                INTEL_TRY(scatter_add_rows(R, d->d_iid, w.dXa, di, bt->i_id, G->iid_emb, nullptr, s, d->item_rows));
-                if (d->d_im > 0) INTEL_TRY(scatter_add_rows(R, d->d_im, w.dXa + d->d_iid, di, bt->i_class, G->item_emb, nullptr, s, d->class_rows));
-            } else {
-                INTEL_TRY(stack_bwd(B, L, ds, d->heads, d->layers, P->score, G->score, w.score, w.dXa, w.t1, w.t2, w.dqkv, d->dropout_p,
-                                    d->dropout_seed, 1, s));
-                INTEL_TRY(linear_dw(R, ds, K, w.dXa, ds, w.xs, K, G->score_w, K, G->score_b, s));
-            }
         }
+        }
+    }
+    // the self-attention stacks (IntEL.py:182-197) and what feeds them
+    if (do_item) {
+        INTEL_TRY(stack_bwd(B, L, di, d->heads, d->layers, P->item, G->item, w.item, w.dXa, w.t1, w.t2, w.dqkv, d->dropout_p,
+                            d->dropout_seed, 0, s));
+        INTEL_TRY(scatter_add_rows(R, d->d_iid, w.dXa, di, bt->i_id, G->iid_emb, nullptr, s, d->item_rows));
+        if (d->d_im > 0) INTEL_TRY(scatter_add_rows(R, d->d_im, w.dXa + d->d_iid, di, bt->i_class, G->item_emb, nullptr, s, d->class_rows));
+    }
+    if (do_score) {
+        // run on its own, this phase is the one a caller overlaps with its gradient exchange: leave the reserved SMs free
+        trunk_reserve_apply(phases == INTEL_ENS_BWD_SCORE);
+        const int st = stack_bwd(B, L, ds, d->heads, d->layers, P->score, G->score, w.score, w.dXs, w.t1, w.t2, w.dqkv, d->dropout_p,
+                                 d->dropout_seed, 1, s);
+        trunk_reserve_apply(false);
+        INTEL_TRY(st);
+        INTEL_TRY(linear_dw(R, ds, K, w.dXs, ds, w.xs, K, G->score_w, K, G->score_b, s));
     }
     return INTEL_OK;
 }
+
+int intel_ensemble_bwd(const intel_dims_t* d, const intel_tensors_t* P, const intel_batch_t* bt, const float* intents,
+                       const float* d_weights, const float* d_ens, intel_tensors_t* G, float* d_intents_out,
+                       void* workspace, size_t workspace_bytes, intel_stream_t stream) {
+    return intel_ensemble_bwd_phase(d, P, bt, intents, d_weights, d_ens, G, d_intents_out, workspace, workspace_bytes, stream,
+                                    INTEL_ENS_BWD_HEAD | INTEL_ENS_BWD_ITEM | INTEL_ENS_BWD_SCORE);
+}
+
 
 // ================================================================================================
 size_t intel_intent_workspace_bytes(const intel_dims_t* d) {

@@ -173,6 +173,8 @@ bool trunk_tc_supported(const TrunkArgs& a);
 int trunk_tc_fwd(const TrunkArgs& a, cudaStream_t s);
 void trunk_debug_use_tcgen05(int on);
 void trunk_debug_sessions_per_cta(int n);
+void trunk_reserve_sms(int n);      // SMs the persistent backward kernel leaves to a concurrent collective ...
+void trunk_reserve_apply(bool on);  // ... in the launches made while this is on
 void gemm_debug_use_umma(int on);
 bool trunk_supported(int64_t L, int d, int heads, int layers);      // mma.sync kernels, forward and backward
 bool trunk_fwd_supported(int64_t L, int heads, int layers);         // any fused forward kernel (d = 32)

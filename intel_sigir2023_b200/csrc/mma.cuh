@@ -35,8 +35,9 @@ static inline uint32_t to_tf32(float x) {
 static inline void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
     static float sa[64][32][4], sb[64][32][2];
     const int lin = emu::S().cur->lin, w = lin >> 5, lane = lin & 31;
-    for (int i = 0; i < 4; ++i) sa[w][lane][i] = emu::from_bits<float>((uint64_t)a[i]);
-    for (int i = 0; i < 2; ++i) sb[w][lane][i] = emu::from_bits<float>((uint64_t)b[i]);
+    // the tensor core reads the upper 19 bits of an operand register (tests/hw/umma_probe.cu, tests 15-17)
+    for (int i = 0; i < 4; ++i) sa[w][lane][i] = emu::from_bits<float>((uint64_t)(a[i] & 0xffffe000u));
+    for (int i = 0; i < 2; ++i) sb[w][lane][i] = emu::from_bits<float>((uint64_t)(b[i] & 0xffffe000u));
     emu::warp_barrier();
     const int g = lane >> 2, t = lane & 3;
     auto A = [&](int r, int k) { return sa[w][(r & 7) * 4 + (k & 3)][(r >> 3) + 2 * (k >> 2)]; };
@@ -54,11 +55,13 @@ static inline void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_
 // Operand split for 3xTF32.  cvt.rna.tf32.f32 expands to a ~5-instruction sequence on sm_100a and made the
 // MMA kernels issue-bound (profiles/r01_summary.md), so the split is done with integer ops on the bit pattern:
 //   hi = round-to-nearest of x to 10 mantissa bits  ((bits + 0x1000) & ~0x1fff; operands are finite)
-//   lo = x - hi (exact in fp32), low 13 bits cleared - the tensor core would ignore them anyway.
-// |x - hi - lo| <= 2^-21 |x|.
+//   lo = x - hi (exact in fp32); its low 13 bits are left in place: the tensor core reads only the upper 19 bits of an
+//        operand (mma.sync and tcgen05, shared-memory and tensor-memory operands alike: tests/hw/umma_probe.cu, tests 15-17),
+//        so clearing them would be a wasted instruction in the hottest sequence of every 3xTF32 kernel.
+// |x - hi - trunc(lo)| <= 2^-21 |x|.
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
     hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
-    lo = __float_as_uint(x - __uint_as_float(hi)) & 0xffffe000u;
+    lo = __float_as_uint(x - __uint_as_float(hi));
 }
 
 // d += a * b at ~fp32 accuracy from three TF32 MMAs; af / bf are fp32 fragment values

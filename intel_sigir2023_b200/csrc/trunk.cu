@@ -890,6 +890,9 @@ bool trunk_supported(int64_t L, int d, int heads, int layers) {
 }
 
 static int g_fwd_sessions_per_cta = 4;
+static int g_reserved_sms = 0, g_reserve_now = 0;
+void trunk_reserve_sms(int n) { g_reserved_sms = n < 0 ? 0 : (n > 64 ? 64 : n); }
+void trunk_reserve_apply(bool on) { g_reserve_now = on ? 1 : 0; }
 void trunk_debug_sessions_per_cta(int n) { g_fwd_sessions_per_cta = n < 1 ? 1 : (n > 4 ? 4 : n); }
 
 // algorithmic HBM bytes per token: the stack input (and dX in / out), and per layer the saved q|k|v (96), attention
@@ -929,7 +932,8 @@ template <int TP, int DK>
 static int trunk_launch(const TrunkArgs& a, bool bwd, cudaStream_t s) {
     if (!bwd) return trunk_fwd_sessions<TP / 16, DK>(a, s);
     const size_t smem = (size_t)bwd_plan(a.L).total * 4;
-    const unsigned grid = stream_grid((a.B + BWD_NS - 1) / BWD_NS, 1);
+    unsigned grid = stream_grid((a.B + BWD_NS - 1) / BWD_NS, 1);
+    if (g_reserve_now && grid > (unsigned)(kNumSMs - g_reserved_sms)) grid = (unsigned)(kNumSMs - g_reserved_sms);   // one CTA owns an SM
     auto k = trunk_bwd_kernel<TP / 16, DK>;
     ensure_smem(k, smem);
     LAUNCH(k, dim3(grid), dim3(32 * BWD_NS * BWD_WPS), smem, s, a);

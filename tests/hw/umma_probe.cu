@@ -9,6 +9,11 @@
 //   6  TS + MN-major B (the input-gradient form dX = dY W)
 //   7  SS MN-major A with M = 128, K-major B
 //   8  cycles of one issue -> commit -> wait round trip (M = 128, N = 64, 12 MMAs)
+//  14  K-major operands read from the SAME natural tiles (32-byte chunk XOR row & 3) that tests 9-11 read MN-major:
+//      SWIZZLE_128B_BASE32B as a K-major layout (one tile = both views: S = Q K^T and dQ = dS K from one copy of K)
+//  15  SS, quad-slab planes, operands with garbage in the low 13 mantissa bits: the tensor core truncates (ignores them)
+//  16  TS, A in tensor memory with garbage low bits
+//  17  mma.sync.m16n8k8 tf32 with garbage low bits (one warp)
 #include <cstdio>
 #include <cstdlib>
 #include <cstdint>
@@ -111,6 +116,16 @@ __device__ void stage_nat128(float* sm, const float* P, int ld, int c0, int rows
     }
 }
 
+__device__ __forceinline__ float dirty(float x, int i) {      // same tf32 value, random low 13 bits
+    return __uint_as_float(__float_as_uint(x) | ((uint32_t)(i * 2654435761u) >> 19));
+}
+__device__ void stage_plane_dirty(float* sm, const float* P, int rows, int cols) {
+    for (int e = threadIdx.x; e < rows * cols; e += blockDim.x) {
+        const int r = e / cols, c = e % cols;
+        sm[(c / 4) * rows * 4 + r * 4 + (c % 4)] = dirty(P[e], e + 7);
+    }
+}
+
 struct Args {
     int test;
     const float *A, *B, *B2;    // row-major inputs
@@ -183,6 +198,17 @@ __global__ void __launch_bounds__(128) probe(Args a) {
         stage_nat128(sA, a.A, 64, 0, 128);
         stage_nat128(sA + 128 * 32, a.A, 64, 32, 128);
         stage_nat128(sB, a.B, 32, 0, 128);
+    } else if (T == 14) {                                        // A [128][32], B [32][32]: the MN-major natural tiles, read K-major
+        stage_nat(sA, a.A, 32, 0, 128);
+        stage_nat(sB, a.B, 32, 0, 32);
+    } else if (T == 15) {
+        stage_plane_dirty(sA, a.A, 128, 32);
+        stage_plane_dirty(sB, a.B, 32, 32);
+    } else if (T == 16) {
+        uint32_t r[32];
+        for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(dirty(a.A[tid * 32 + j], tid * 32 + j + 3));
+        tmem_st32(lane_addr + 256, r);
+        stage_plane_dirty(sB, a.B, 32, 32);
     } else if (T == 11) {                                        // G [32 k][128 m] as four natural tiles, B [32 n][32 k] K-major
         for (int q = 0; q < 4; ++q) stage_nat(sA + q * 32 * 32, a.A, 128, 32 * q, 32);
         stage_plane(sB, a.B, 32, 32);
@@ -234,6 +260,17 @@ __global__ void __launch_bounds__(128) probe(Args a) {
             const uint32_t id = make_idesc(64, 32, 1, 1);
             for (int ks = 0; ks < 16; ++ks)
                 mma_ss(tm, make_desc_sw(aA + ks * 1024, 16384, 512, 1), make_desc_sw(aB + ks * 1024, 16384, 512, 1), id, ks ? 1u : 0u);
+        } else if (T == 14) {
+            const uint32_t id = make_idesc(128, 32, 0, 0);
+            for (int ks = 0; ks < 4; ++ks)
+                mma_ss(tm, make_desc_sw(aA + ks * 32, 16, 1024, 1), make_desc_sw(aB + ks * 32, 16, 1024, 1), id, ks ? 1u : 0u);
+        } else if (T == 15) {
+            const uint32_t id = make_idesc(128, 32, 0, 0);
+            for (int ks = 0; ks < 4; ++ks)
+                mma_ss(tm, make_desc(aA + ks * 2 * 2048, 2048, 128), make_desc(aB + ks * 2 * 512, 512, 128), id, ks ? 1u : 0u);
+        } else if (T == 16) {
+            const uint32_t id = make_idesc(128, 32, 0, 0);
+            for (int ks = 0; ks < 4; ++ks) mma_ts(tm, tm + 256 + ks * 8, make_desc(aB + ks * 2 * 512, 512, 128), id, ks ? 1u : 0u);
         } else if (T == 12) {
             const uint32_t id = make_idesc(128, 32, 0, 0);
             for (int ks = 0; ks < 4; ++ks)
@@ -276,6 +313,23 @@ __global__ void __launch_bounds__(128) probe(Args a) {
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tm) : "memory");
 }
 
+// test 17: D[16][8] = A[16][8] B[8][8]^T on one warp with mma.sync tf32, operands carrying garbage low bits
+__global__ void probe_mma_sync(const float* A, const float* B, float* D) {
+    const int lane = threadIdx.x, g = lane >> 2, t = lane & 3;
+    uint32_t a[4], b[2];
+    a[0] = __float_as_uint(dirty(A[g * 32 + t], lane));
+    a[1] = __float_as_uint(dirty(A[(g + 8) * 32 + t], lane + 40));
+    a[2] = __float_as_uint(dirty(A[g * 32 + t + 4], lane + 80));
+    a[3] = __float_as_uint(dirty(A[(g + 8) * 32 + t + 4], lane + 120));
+    b[0] = __float_as_uint(dirty(B[g * 32 + t], lane + 160));
+    b[1] = __float_as_uint(dirty(B[g * 32 + t + 4], lane + 200));
+    float d[4] = {0.f, 0.f, 0.f, 0.f};
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+    D[g * 8 + 2 * t] = d[0]; D[g * 8 + 2 * t + 1] = d[1]; D[(g + 8) * 8 + 2 * t] = d[2]; D[(g + 8) * 8 + 2 * t + 1] = d[3];
+}
+
 static std::vector<float> ints(int n, unsigned seed) {
     std::vector<float> v(n);
     unsigned s = seed * 2654435761u + 12345u;
@@ -299,6 +353,20 @@ int main(int argc, char** argv) {
     CK(cudaMemset(dD, 0, D.size() * 4));
     const int smem = 128 * 64 * 4 + 128 * 32 * 4 + 32 * 32 * 4;
     CK(cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    if (T == 17) {
+        probe_mma_sync<<<1, 32>>>(dA, dB, dD);
+        CK(cudaDeviceSynchronize());
+        CK(cudaMemcpy(D.data(), dD, 16 * 8 * 4, cudaMemcpyDeviceToHost));
+        int bad = 0;
+        for (int m = 0; m < 16; ++m)
+            for (int n = 0; n < 8; ++n) {
+                float e = 0;
+                for (int k = 0; k < 8; ++k) e += A[m * 32 + k] * B[n * 32 + k];
+                if (D[m * 8 + n] != e) { if (bad < 8) printf("  mismatch %d %d: got %.9g want %g\n", m, n, D[m * 8 + n], e); ++bad; }
+            }
+        printf("test 17: %s (%d mismatches)\n", bad ? "FAIL" : "PASS", bad);
+        return bad ? 1 : 0;
+    }
     Args a{T, dA, dB, dB2, dD, dC};
     probe<<<1, 128, smem>>>(a);
     CK(cudaDeviceSynchronize());
@@ -308,7 +376,7 @@ int main(int argc, char** argv) {
     // expected accumulator E[lane][col]
     std::vector<float> E(128 * 64, -777.0f);
     auto dot = [&](const float* x, int sx, const float* y, int sy, int n) { float s = 0; for (int k = 0; k < n; ++k) s += x[k * sx] * y[k * sy]; return s; };
-    if (T == 1 || T == 2 || T == 12) {
+    if (T == 1 || T == 2 || T == 12 || T == 14 || T == 15 || T == 16) {
         for (int m = 0; m < 128; ++m) for (int n = 0; n < 32; ++n) E[m * 64 + n] = dot(&A[m * 32], 1, &B[n * 32], 1, 32);
     } else if (T == 3 || T == 4) {
         for (int m = 0; m < 128; ++m) for (int n = 0; n < 32; ++n) E[m * 64 + n] = dot(&A[m * 32], 1, m < 64 ? &B[n * 32] : &B2[n * 32], 1, 32);

@@ -23,7 +23,7 @@ def _setup_emu():
     _lib._allow_host_tensors = True
 
 
-def _grads_and_metrics(rank, world, case):
+def _grads_and_metrics(rank, world, case, overlap=True):
     import parity_checks as P
     from conftest import load_model_case
     from intel_sigir2023_b200 import dp, losses, synthetic
@@ -35,33 +35,38 @@ def _grads_and_metrics(rank, world, case):
     shard = synthetic.shard_batch(batch, rank, world)
     model = P.make_model(cfg, state, "cpu").train()
     crit = losses.IntListloss(P.loss_args())
+    # overlap: the reducer hooks into the backward pass and exchanges everything but the score stream's gradients while
+    # the score stack is still being differentiated; the late reducer (old call order) takes the one-collective path
+    reducer = dp.GradReducer(model, world, overlap=overlap) if overlap else None
     out = model(shard)
     loss, _, _ = crit(out, shard)
     loss.backward()
-    dp.GradReducer(model, world).allreduce()
+    if overlap and world > 1:
+        assert reducer._pending is not None and 0 < model._flat_late < model._flat_grad.numel()
+    (reducer or dp.GradReducer(model, world, overlap=False)).allreduce()
     pos = {k: shard[k] for k in ("c_paynum_i", "c_favnum_i", "c_clicknum_i")}
     res = dp.evaluate_sharded(out["ens_score"].detach(), shard["ranking"], pos, shard["session_len"], [3, 1, 5], ["NDCG", "HR"])
     return {n: p.grad.clone() for n, p in model.named_parameters()}, res
 
 
-def _worker(rank, world, port, case, q):
+def _worker(rank, world, port, case, q, overlap=True):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     torch.set_num_threads(1)
     _setup_emu()
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    grads, res = _grads_and_metrics(rank, world, case)
+    grads, res = _grads_and_metrics(rank, world, case, overlap)
     if rank == 0:
         q.put(({k: v.numpy() for k, v in grads.items()}, res))
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("case", ["script_bpr_gru_k4", "default_bert"])
-def test_two_rank_grads_match_single_process(case):
+@pytest.mark.parametrize("case,overlap", [("script_bpr_gru_k4", True), ("default_bert", True), ("script_bpr_gru_k4", False)])
+def test_two_rank_grads_match_single_process(case, overlap):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 29500 + (os.getpid() % 2000)
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, case, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, case, q, overlap)) for r in range(2)]
     for p in procs:
         p.start()
     grads2, res2 = q.get(timeout=300)
