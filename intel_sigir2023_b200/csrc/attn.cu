@@ -311,13 +311,15 @@ int cross_pool_bwd(int64_t B, int64_t L, int d, const float* X, const float* qk,
 
 // ------------------------------------------------------------------------------------------------
 // Row softmax (pred_layer(...).softmax, IntEL.py:153) and its backward; one warp per row.
+// ldz: row stride of Z (the logits workspace pads its rows to a multiple of four floats so that the GEMM that writes it and
+// the two that read its gradient move 16-byte vectors although N = intent_num is odd); P is dense [R, N].
 __global__ void __launch_bounds__(256) softmax_rows_kernel(int64_t R, int64_t N, const float* __restrict__ Z,
-                                                           float* __restrict__ P) {
+                                                           float* __restrict__ P, int64_t ldz) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t r = warp; r < R; r += nwarps) {
-        const float* z = Z + r * N;
+        const float* z = Z + r * ldz;
         float mx = -INFINITY;
         for (int64_t c = lane; c < N; c += 32) mx = fmaxf(mx, z[c]);
         mx = warp_max(mx);
@@ -328,16 +330,17 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(int64_t R, int64_t N,
         for (int64_t c = lane; c < N; c += 32) P[r * N + c] = expf(z[c] - mx) * inv;
     }
 }
-int softmax_rows(int64_t R, int64_t N, const float* Z, float* P, cudaStream_t s) {
+int softmax_rows(int64_t R, int64_t N, const float* Z, float* P, cudaStream_t s, int64_t ldz) {
     if (R <= 0) return INTEL_OK;
+    if (ldz <= 0) ldz = N;
     unsigned grid = stream_grid(ceil_div(R, 8), 8);
-    LAUNCH(softmax_rows_kernel, dim3(grid), dim3(256), 0, s, R, N, Z, P);
+    LAUNCH(softmax_rows_kernel, dim3(grid), dim3(256), 0, s, R, N, Z, P, ldz);
     return check_launch("softmax_rows", 8.0 * R * N, 4.0 * R * N);
 }
 
 __global__ void __launch_bounds__(256) softmax_rows_bwd_kernel(int64_t R, int64_t N, const float* __restrict__ P,
                                                                const float* __restrict__ dP,
-                                                               const float* __restrict__ dP2, float* __restrict__ dZ) {
+                                                               const float* __restrict__ dP2, float* __restrict__ dZ, int64_t ldz) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -350,15 +353,16 @@ __global__ void __launch_bounds__(256) softmax_rows_bwd_kernel(int64_t R, int64_
         dot = warp_sum(dot);
         for (int64_t c = lane; c < N; c += 32) {
             const float g = dP[r * N + c] + (dP2 ? dP2[r * N + c] : 0.f);
-            dZ[r * N + c] = P[r * N + c] * (g - dot);
+            dZ[r * ldz + c] = P[r * N + c] * (g - dot);
         }
     }
 }
 int softmax_rows_bwd(int64_t R, int64_t N, const float* P, const float* dP, const float* dP2, float* dZ,
-                     cudaStream_t s) {
+                     cudaStream_t s, int64_t ldz) {
     if (R <= 0) return INTEL_OK;
+    if (ldz <= 0) ldz = N;
     unsigned grid = stream_grid(ceil_div(R, 8), 8);
-    LAUNCH(softmax_rows_bwd_kernel, dim3(grid), dim3(256), 0, s, R, N, P, dP, dP2, dZ);
+    LAUNCH(softmax_rows_bwd_kernel, dim3(grid), dim3(256), 0, s, R, N, P, dP, dP2, dZ, ldz);
     return check_launch("softmax_rows_bwd", 12.0 * R * N, 4.0 * R * N);
 }
 

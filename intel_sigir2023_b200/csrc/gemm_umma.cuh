@@ -363,14 +363,45 @@ __global__ void __launch_bounds__(UTHREADS) gemm_umma_kernel(GemmDev g, int bn, 
     const bool v4 = vec_c4 && col + 3 < g.N;
     float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
     if (lane_on && v4 && first && g.bias) bias4 = *reinterpret_cast<const float4*>(g.bias + col);
+    if (!vec_c4) {
+        // rows that are not 16-byte aligned (N = intent_num = 1071 is odd): lanes on consecutive columns, scalar but
+        // coalesced stores; everything that does not depend on the row (column guards, bias) is fetched once per lane
+        float bj[NACC / 32 > 0 ? NACC / 32 : 1];
+        bool on[NACC / 32 > 0 ? NACC / 32 : 1];
+#pragma unroll
+        for (int j = 0; j < (NACC / 32 > 0 ? NACC / 32 : 1); ++j) {
+            const int c = lane + 32 * j;
+            on[j] = c < bn && n0 + c < g.N;
+            bj[j] = (on[j] && first && g.bias) ? g.bias[n0 + c] : 0.f;
+        }
+        const bool plain = g.accumulate == 0 && !g.mask && !(first && g.add);
+        for (int r = warp; r < UM; r += UTHREADS / 32) {
+            const int64_t gm = m0 + r;
+            if (gm >= g.M) break;
+            float* crow = g.C + gm * g.ldc + n0;
+#pragma unroll
+            for (int j = 0; j < (NACC / 32 > 0 ? NACC / 32 : 1); ++j) {
+                if (!on[j]) continue;
+                const int c = lane + 32 * j;
+                float v = tile[r * ts + c] + bj[j];
+                if (plain) {
+                    crow[c] = g.relu_out ? fmaxf(v, 0.f) : v;
+                    continue;
+                }
+                if (first && g.add) v += g.add[gm * g.ldadd + n0 + c];
+                if (g.relu_out) v = fmaxf(v, 0.f);
+                if (g.mask) v = (g.mask[gm * g.ldmask + n0 + c] > 0.f) ? v : 0.f;
+                if (g.accumulate == 0) crow[c] = v;
+                else if (g.accumulate == 1) crow[c] += v;
+                else atomicAdd(crow + c, v);
+            }
+        }
+        return;
+    }
 #pragma unroll 2
     for (int r = warp; r < UM; r += UTHREADS / 32) {
         const int64_t gm = m0 + r;
         if (gm >= g.M) break;
-        if (!vec_c4) {          // unaligned rows: lanes on consecutive columns, scalar stores
-            for (int c = lane; c < bn; c += 32) gemm_store(g, gm, n0 + c, tile[r * ts + c], first);
-            continue;
-        }
         if (!lane_on) continue;
         float4 v = *reinterpret_cast<const float4*>(tile + r * ts + 4 * lane);
         if (v4) {

@@ -109,9 +109,9 @@ int cross_pool_fwd(int64_t B, int64_t L, int d, const float* X, const float* qk,
 int cross_pool_bwd(int64_t B, int64_t L, int d, const float* X, const float* qk, const int64_t* lens,
                    float scale, const float* p, const float* dxbar, float* dX, float* dqk, cudaStream_t s);
 // softmax over rows and its backward: dZ = p * (dP - sum(p dP))
-int softmax_rows(int64_t R, int64_t N, const float* Z, float* P, cudaStream_t s);
+int softmax_rows(int64_t R, int64_t N, const float* Z, float* P, cudaStream_t s, int64_t ldz = 0);   // ldz: row stride of Z (0 = N)
 int softmax_rows_bwd(int64_t R, int64_t N, const float* P, const float* dP, const float* dP2, float* dZ,
-                     cudaStream_t s);   // incoming gradient dP + dP2 (dP2 nullable)
+                     cudaStream_t s, int64_t ldz = 0);   // incoming gradient dP + dP2 (dP2 nullable)
 
 // ---- gru.cu -------------------------------------------------------------------------------------
 // One masked GRU step for all sessions (gate order r,z,n; torch.nn.GRU equations).
