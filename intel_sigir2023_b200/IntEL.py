@@ -136,13 +136,18 @@ class _IntelFn(torch.autograd.Function):
         # are the last gradients the pass below completes, so everything before `late` can be exchanged while they are
         # still being computed (dp.GradReducer installs model._early_reduce for that).
         late_names = model._late_grad_names
-        order = [i for i, n in enumerate(names) if n not in late_names] + [i for i, n in enumerate(names) if n in late_names]
+        pack = [n for n in model._packed_grad_names if n in names]
+        rest = [n for n in names if n not in late_names and n not in pack]
+        order = [names.index(n) for n in rest + pack] + [i for i, n in enumerate(names) if n in late_names]
         offs, total, late = [0] * len(params), 0, None
         for i in order:
             if late is None and names[i] in late_names:
                 late = total
             offs[i] = total
-            total += (params[i].numel() + 63) // 64 * 64
+            # the three weights multiplied by the predicted intents sit back to back (no alignment gap): the library then
+            # forms their gradients with one product (api_model.cu, intel_ensemble_bwd_phase)
+            packed_next = names[i] in pack and names[i] != pack[-1]
+            total += params[i].numel() if packed_next else (params[i].numel() + 63) // 64 * 64
         late = total if late is None else late
         flat = torch.zeros(total, dtype=torch.float32, device=dev)
         grads = [flat[o:o + p.numel()].view(p.shape) for o, p in zip(offs, params)]
@@ -260,6 +265,9 @@ class IntEL(nn.Module):
         self._late_grad_names = {n for n in self._param_names
                                  if n.startswith(("s_attn_head.", "s_W1.", "s_W2.", "s_layer_norm.", "score_embeddings."))}
         self._early_reduce = None       # set by dp.GradReducer: callable(flat_grad, late_offset)
+        # gradients kept back to back in the flat buffer, in the row order of the library's stacked weight (Wcat)
+        self._packed_grad_names = (["intent_item_attention.query_layer.weight", "intent_score_attention.query_layer.weight",
+                                    "intent_embeddings.weight"] if c.cross_attention else [])
         shapes = c.param_shapes()
         for n, p in self.named_parameters():
             assert tuple(p.shape) == shapes[n], (n, tuple(p.shape), shapes[n])

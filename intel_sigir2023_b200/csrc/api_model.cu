@@ -123,6 +123,9 @@ struct EnsWs {
     StackWs item, score;
     float* xs;                    // float copy of the scores [R,K]
     float *q_i, *q_s, *qk_i, *qk_s, *p_i, *p_s, *xbar_i, *xbar_s;   // cross attention
+    // the three products that read the predicted intents ([B, I] x {query_layer (item), query_layer (score),
+    // intent_embeddings}) run as one: Wcat [di + ds + dint, I] = the three weights stacked, qcat / dcat [B, di + ds + dint]
+    float *Wcat, *qcat, *dcat;
     float* all;                   // [B, D] head input of the valid rows
     float *w_valid, *w_pad;       // [B,K]
     float *t_i, *t_s, *m_i, *m_s, *hu, *hint, *all_item;            // cross_attention = 0
@@ -150,7 +153,11 @@ void ens_layout(const intel_dims_t* d, Arena& a, EnsWs& w) {
     w.t2 = a.take<float>(R * dmax);
     w.dqkv = a.take<float>(R * 3 * dmax);
     if (d->cross_attention) {
-        w.q_i = a.take<float>(B * di); w.q_s = a.take<float>(B * ds);
+        const int dc = di + ds + d->d_int;
+        w.Wcat = a.take<float>((int64_t)dc * d->I);
+        w.qcat = a.take<float>(B * dc);
+        w.dcat = a.take<float>(B * dc);
+        w.q_i = w.qcat; w.q_s = w.qcat + di;                    // column blocks of qcat (row stride dc)
         w.qk_i = a.take<float>(B * di); w.qk_s = a.take<float>(B * ds);
         w.p_i = a.take<float>(B * L); w.p_s = a.take<float>(B * L);
         w.xbar_i = a.take<float>(B * di); w.xbar_s = a.take<float>(B * ds);
@@ -178,7 +185,7 @@ struct BertWs {
     float *QKV[INTEL_MAX_BERT_LAYERS], *Z1[INTEL_MAX_BERT_LAYERS], *st1[INTEL_MAX_BERT_LAYERS], *C[INTEL_MAX_BERT_LAYERS],
         *F[INTEL_MAX_BERT_LAYERS], *Z2[INTEL_MAX_BERT_LAYERS], *st2[INTEL_MAX_BERT_LAYERS];
 };
-struct GruWs { float *gi, *h_all, *gates, *gh, *dh, *dgi, *dgh_all; };
+struct GruWs { float *gi, *h_all, *gates, *gh, *dh, *dgi, *dgh_all; int32_t* order; };
 struct EncWs {
     int64_t T; int d;
     float* seq;          // [B*T, d] token embeddings (BERT: positions added in place)
@@ -223,6 +230,7 @@ void enc_layout(const intel_dims_t* d, Arena& a, EncWs& e, int64_t T, int dd) {
         e.gru.dh = a.take<float>(B * h);
         e.gru.dgi = a.take<float>(R * 3 * h);
         e.gru.dgh_all = a.take<float>(B * (T + 1) * 3 * h);
+        e.gru.order = a.take<int32_t>(B + 1);
     }
 }
 
@@ -337,7 +345,12 @@ int gru_bwd(const intel_dims_t* d, const intel_encoder_t& p, intel_encoder_t& g,
         cudaError_t ce = cudaMemset2DAsync(w.dgh_all + T * 3 * h, (size_t)(T + 1) * 3 * h * 4, 0, (size_t)3 * h * 4, (size_t)B, s);
         INTEL_REQUIRE(ce == cudaSuccess, INTEL_ERR_CUDA, "cudaMemset2DAsync: %s", cudaGetErrorString(ce));
         // the fused kernel also sums the bias gradients (column sums of dgi / dgh) on its way
-        INTEL_TRY(gru_seq_bwd(B, T, h, lens, p.w_hh, w.h_all, w.gates, w.dh, w.dgi, w.dgh_all, g.b_ih, g.b_hh, s));
+        int32_t* order = nullptr;
+        if (T <= 63) {               // tiles of equally long sessions: a tile stops at its own last step
+            INTEL_TRY(gru_order_by_len(B, T, lens, w.order, s));
+            order = w.order;
+        }
+        INTEL_TRY(gru_seq_bwd(B, T, h, lens, p.w_hh, w.h_all, w.gates, w.dh, w.dgi, w.dgh_all, g.b_ih, g.b_hh, s, order));
     } else {
         INTEL_TRY(fill_zero(w.dgh_all, (size_t)B * (T + 1) * 3 * h * 4, s));
         for (int64_t t = T - 1; t >= 0; --t) {
@@ -427,19 +440,28 @@ int intel_ensemble_fwd(const intel_dims_t* d, const intel_tensors_t* P, const in
 
     if (d->cross_attention) {
         const float scale = 1.0f / sqrtf((float)d->qsize);
+        // q_item | q_score | intent_embeddings(intent): one product over the predicted intents (read once instead of
+        // three times); the weights are stacked into Wcat unless the caller already keeps them back to back
+        const int dc = di + ds + dint;
+        const float* Wc = P->xq_item;
+        if (!(P->xq_score == P->xq_item + (int64_t)di * I && P->intent_w == P->xq_score + (int64_t)ds * I)) {
+            INTEL_TRY(copy_d2d(w.Wcat, P->xq_item, (size_t)di * I * 4, s));
+            INTEL_TRY(copy_d2d(w.Wcat + (int64_t)di * I, P->xq_score, (size_t)ds * I * 4, s));
+            INTEL_TRY(copy_d2d(w.Wcat + (int64_t)(di + ds) * I, P->intent_w, (size_t)dint * I * 4, s));
+            Wc = w.Wcat;
+        }
+        INTEL_TRY(linear(B, dc, I, intents, I, Wc, I, nullptr, w.qcat, dc, s));
         // item stream
-        INTEL_TRY(linear(B, di, I, intents, I, P->xq_item, I, nullptr, w.q_i, di, s));
-        INTEL_TRY(linear_dx(B, di, di, w.q_i, di, P->xk_item, di, w.qk_i, di, s));            // qk = W_k^T q
+        INTEL_TRY(linear_dx(B, di, di, w.q_i, dc, P->xk_item, di, w.qk_i, di, s));            // qk = W_k^T q
         INTEL_TRY(cross_pool_fwd(B, L, di, Xi, w.qk_i, bt->session_len, scale, w.p_i, w.xbar_i, s));
         INTEL_TRY(linear(B, di, di, w.xbar_i, di, P->xv_item, di, nullptr, w.all, D, s));
         // score stream
-        INTEL_TRY(linear(B, ds, I, intents, I, P->xq_score, I, nullptr, w.q_s, ds, s));
-        INTEL_TRY(linear_dx(B, ds, ds, w.q_s, ds, P->xk_score, ds, w.qk_s, ds, s));
+        INTEL_TRY(linear_dx(B, ds, ds, w.q_s, dc, P->xk_score, ds, w.qk_s, ds, s));
         INTEL_TRY(cross_pool_fwd(B, L, ds, Xs, w.qk_s, bt->session_len, scale, w.p_s, w.xbar_s, s));
         INTEL_TRY(linear(B, ds, ds, w.xbar_s, ds, P->xv_score, ds, nullptr, w.all + di, D, s));
         // user + intent parts of the head input
         INTEL_TRY(gather_rows(B, du, P->uid_emb, bt->u_id, w.all + off_u, D, 1, s, d->user_rows));
-        INTEL_TRY(linear(B, dint, I, intents, I, P->intent_w, I, P->intent_b, w.all + off_h, D, s, false, true));
+        INTEL_TRY(bias_relu_rows(B, dint, w.qcat + di + ds, dc, P->intent_b, w.all + off_h, D, s));
         // weights of the valid rows and of the pad rows (whose pooled inputs are zero)
         INTEL_TRY(linear(B, K, D, w.all, D, P->head_w, D, P->head_b, w.w_valid, K, s));
         INTEL_TRY(linear(B, K, du + dint, w.all + off_u, D, P->head_w + off_u, D, P->head_b, w.w_pad, K, s));
@@ -493,10 +515,9 @@ int intel_ensemble_bwd_phase(const intel_dims_t* d, const intel_tensors_t* P, co
         INTEL_TRY(linear_dw(B, K, du + dint, w.dwp, K, w.all + off_u, D, G->head_w + off_u, D, G->head_b, s));
         INTEL_TRY(linear_dx(B, K, D, w.dwv, K, P->head_w, D, w.dall, D, s));
         INTEL_TRY(linear_dx(B, K, du + dint, w.dwp, K, P->head_w + off_u, D, w.dall + off_u, D, s, 1));
-        // h_intent = relu(intent_embeddings(intent))
-        INTEL_TRY(relu_bwd(B, dint, w.dall + off_h, D, w.all + off_h, D, w.dall + off_h, D, s));
-        INTEL_TRY(linear_dw(B, dint, I, w.dall + off_h, D, intents, I, G->intent_w, I, G->intent_b, s));
-        INTEL_TRY(linear_dx(B, dint, I, w.dall + off_h, D, P->intent_w, I, d_intents_out, I, s, 0));
+        // h_intent = relu(intent_embeddings(intent)): its gradient is the third column block of dcat
+        const int dc = di + ds + dint;
+        INTEL_TRY(relu_bwd(B, dint, w.dall + off_h, D, w.all + off_h, D, w.dcat + di + ds, dc, s));
         // h_u = relu(uid_embeddings[u])
         INTEL_TRY(scatter_add_rows(B, du, w.dall + off_u, D, bt->u_id, G->uid_emb, P->uid_emb, s, d->user_rows));
         // the two pooled cross attentions
@@ -513,10 +534,23 @@ int intel_ensemble_bwd_phase(const intel_dims_t* d, const intel_tensors_t* P, co
             INTEL_TRY(linear_dw(B, dd, dd, w.dall + off, D, xbar, dd, gxv, dd, nullptr, s));
             INTEL_TRY(linear_dx(B, dd, dd, w.dall + off, D, xv, dd, w.dxbar, dd, s));
             INTEL_TRY(cross_pool_bwd(B, L, dd, X, qk, bt->session_len, scale, p, w.dxbar, dXst[st], w.dqk, s));
-            INTEL_TRY(linear_dw(B, dd, dd, q, dd, w.dqk, dd, gxk, dd, nullptr, s));            // dW_k[a,c] = sum q_a dqk_c
-            INTEL_TRY(linear(B, dd, dd, w.dqk, dd, xk, dd, nullptr, w.dq, dd, s));              // dq = W_k dqk
-            INTEL_TRY(linear_dw(B, dd, I, w.dq, dd, intents, I, gxq, I, nullptr, s));
-            INTEL_TRY(linear_dx(B, dd, I, w.dq, dd, xq, I, d_intents_out, I, s, 1));
+            INTEL_TRY(linear_dw(B, dd, dd, q, dc, w.dqk, dd, gxk, dd, nullptr, s));            // dW_k[a,c] = sum q_a dqk_c
+            INTEL_TRY(linear(B, dd, dd, w.dqk, dd, xk, dd, nullptr, w.dcat + off, dc, s));      // dq = W_k dqk -> its block of dcat
+            (void)xq; (void)gxq;
+        }
+        // the three products against the predicted intents as one: d_intents = dcat Wcat, dWcat += dcat^T intents
+        {
+            const float* Wc = P->xq_item;
+            if (!(P->xq_score == P->xq_item + (int64_t)di * I && P->intent_w == P->xq_score + (int64_t)ds * I)) Wc = w.Wcat;   // stacked by the forward call
+            INTEL_TRY(linear_dx(B, dc, I, w.dcat, dc, Wc, I, d_intents_out, I, s, 0));
+            if (G->xq_score == G->xq_item + (int64_t)di * I && G->intent_w == G->xq_score + (int64_t)ds * I) {
+                INTEL_TRY(linear_dw(B, dc, I, w.dcat, dc, intents, I, G->xq_item, I, nullptr, s));
+            } else {
+                INTEL_TRY(linear_dw(B, di, I, w.dcat, dc, intents, I, G->xq_item, I, nullptr, s));
+                INTEL_TRY(linear_dw(B, ds, I, w.dcat + di, dc, intents, I, G->xq_score, I, nullptr, s));
+                INTEL_TRY(linear_dw(B, dint, I, w.dcat + di + ds, dc, intents, I, G->intent_w, I, nullptr, s));
+            }
+            INTEL_TRY(colsum(B, dint, w.dcat + di + ds, dc, G->intent_b, s));
         }
         }
     } else {

@@ -382,6 +382,13 @@ int take_last_bwd(int64_t B, int64_t T, int d, const int64_t* lens, const float*
     return check_launch("take_last_bwd");
 }
 
+int copy_d2d(void* dst, const void* src, size_t bytes, cudaStream_t s) {
+    if (!bytes) return INTEL_OK;
+    cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, s);
+    if (e != cudaSuccess) { set_error("cudaMemcpyAsync: %s", cudaGetErrorString(e)); return INTEL_ERR_CUDA; }
+    return INTEL_OK;
+}
+
 int fill_zero(void* p, size_t bytes, cudaStream_t s) {
     if (!bytes) return INTEL_OK;
     cudaError_t e = cudaMemsetAsync(p, 0, bytes, s);

@@ -231,6 +231,24 @@ int relu_bwd(int64_t rows, int cols, const float* dy, int64_t lddy, const float*
     return check_launch("relu_bwd");
 }
 
+// y[r, c] = relu(x[r, c] + b[c]) on strided [rows, cols] views (the intent_embeddings column block of the merged
+// intent projection, IntEL.py:212)
+__global__ void __launch_bounds__(256) bias_relu_kernel(int64_t rows, int cols, const float* __restrict__ x, int64_t ldx,
+                                                        const float* __restrict__ b, float* __restrict__ y, int64_t ldy) {
+    const int64_t n = rows * cols;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = e / cols;
+        const int c = (int)(e % cols);
+        y[r * ldy + c] = fmaxf(x[r * ldx + c] + (b ? b[c] : 0.f), 0.f);
+    }
+}
+int bias_relu_rows(int64_t rows, int cols, const float* x, int64_t ldx, const float* b, float* y, int64_t ldy, cudaStream_t s) {
+    if (rows * cols <= 0) return INTEL_OK;
+    unsigned grid = stream_grid(ceil_div(rows * cols, 256), 8);
+    LAUNCH(bias_relu_kernel, dim3(grid), dim3(256), 0, s, rows, cols, x, ldx, b, y, ldy);
+    return check_launch("bias_relu");
+}
+
 // staged path of the stacks: y[r,c] = x[r,c] * dropout_scale(r,c) (+ add[r,c]); y may alias x
 __global__ void __launch_bounds__(256) dropout_kernel(int64_t rows, int width, const float* x, const float* __restrict__ add,
                                                       float* y, Dropout dr) {

@@ -250,6 +250,54 @@ int gru_seq_fwd(int64_t B, int64_t T, int h, const int64_t* lens, const float* g
     return check_launch("gru_seq_fwd", (double)B * T * (3 + 4 + 1) * GH * 4.0, 2.0 * B * T * 3 * GH * GH);
 }
 
+// Sessions in order of decreasing length (stable), the way pack_padded_sequence orders them (GeneralSeq.py:64-71): a tile
+// of consecutive sessions of that order then shares one loop bound, and tiles that end early make room for the next ones.
+// One block; a chunk of 1024 sessions per pass, rank inside a chunk from warp ballots, so the order is deterministic.
+__global__ void __launch_bounds__(1024) gru_order_kernel(int64_t B, int T, const int64_t* __restrict__ lens, int32_t* __restrict__ order) {
+    __shared__ int cnt[64], start[64], run[64], wcnt[32][64];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < 64) { cnt[tid] = 0; run[tid] = 0; }
+    if (tid == 0) order[B] = 0;              // tile counter of the backward recurrence, kept behind the B entries
+    __syncthreads();
+    auto key = [&](int64_t e) { const int64_t v = lens[e]; return (int)(v < 0 ? 0 : (v > T ? T : v)); };
+    for (int64_t e = tid; e < B; e += 1024) atomicAdd(&cnt[key(e)], 1);
+    __syncthreads();
+    if (tid == 0) {
+        int acc = 0;
+        for (int v = T; v >= 0; --v) { start[v] = acc; acc += cnt[v]; }
+    }
+    __syncthreads();
+    for (int64_t c0 = 0; c0 < B; c0 += 1024) {
+        const int64_t e = c0 + tid;
+        const int v = e < B ? key(e) : -1;
+        int rank = 0;
+        for (int u = 0; u <= T; ++u) {
+            const unsigned m = __ballot_sync(0xffffffffu, v == u);
+            if (lane == 0) wcnt[warp][u] = __popc(m);
+            if (v == u) rank = __popc(m & ((1u << lane) - 1u));
+        }
+        __syncthreads();
+        if (v >= 0) {
+            int pre = 0;
+            for (int w = 0; w < warp; ++w) pre += wcnt[w][v];
+            order[start[v] + run[v] + pre + rank] = (int32_t)e;
+        }
+        __syncthreads();
+        if (tid <= T) {
+            int tot = 0;
+            for (int w = 0; w < 32; ++w) tot += wcnt[w][tid];
+            run[tid] += tot;
+        }
+        __syncthreads();
+    }
+}
+int gru_order_by_len(int64_t B, int64_t T, const int64_t* lens, int32_t* order, cudaStream_t s) {
+    if (B <= 0) return INTEL_OK;
+    INTEL_REQUIRE(T >= 1 && T <= 63 && B < (1LL << 31), INTEL_ERR_UNSUPPORTED, "gru_order_by_len: T must be in [1, 63]");
+    LAUNCH(gru_order_kernel, dim3(1), dim3(1024), 0, s, B, (int)T, lens, order);
+    return check_launch("gru_order");
+}
+
 // Backward recurrence.  dh [B,128] holds d(loss)/d h_T on entry.  Writes dgi [B,T,384] and
 // dgh_all [B,T+1,384] (slot T untouched: the caller clears the buffer) for the weight-gradient GEMMs.
 __global__ void __launch_bounds__(256, 1) gru_seq_bwd_kernel(int64_t B, int64_t T, const int64_t* __restrict__ lens,
@@ -258,19 +306,62 @@ __global__ void __launch_bounds__(256, 1) gru_seq_bwd_kernel(int64_t B, int64_t 
                                                              const float* __restrict__ gates,
                                                              const float* __restrict__ dh_in, float* __restrict__ dgi,
                                                              float* __restrict__ dgh_all, float* __restrict__ db_ih,
-                                                             float* __restrict__ db_hh) {
+                                                             float* __restrict__ db_hh, const int32_t* __restrict__ order,
+                                                             int32_t* __restrict__ counter) {
     DYN_SMEM(float, sm);
+    __shared__ int s_tile;
     float* Ws = sm;                          // [384][GW]   W_hh[k = gate column][n = hidden]
     float* ds = Ws + 3 * GH * GW;            // [GB_SB][GD] dgh of the current step
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gq = lane >> 2, tq = lane & 3;
-    const int64_t b0 = (int64_t)blockIdx.x * GB_SB;
-    stage_whh(Ws, w_hh);
-    int64_t len_r[2];
+    stage_whh(Ws, w_hh);                     // once per CTA: the CTA is persistent and walks tiles of GB_SB sessions
+    float sum_i[2][3][2], sum_h[2][2];        // bias-gradient partial sums: [ct][gate][e] of dgi, [ct][e] of the n-gate of dgh
+#pragma unroll
+    for (int ct = 0; ct < 2; ++ct)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            sum_h[ct][e] = 0.f;
+#pragma unroll
+            for (int q = 0; q < 3; ++q) sum_i[ct][q][e] = 0.f;
+        }
+    const int64_t ntiles = (B + GB_SB - 1) / GB_SB;
+    for (int64_t it = 0;; ++it) {
+    // next tile: with the length-sorted order the tiles are handed out longest first from a device counter (the CTAs that
+    // drew short tiles come back for more), otherwise round robin
+    int64_t tile = (int64_t)blockIdx.x + it * gridDim.x;
+    if (counter) {
+        if (threadIdx.x == 0) s_tile = atomicAdd(counter, 1);
+        __syncthreads();
+        tile = s_tile;
+    }
+    if (tile >= ntiles) break;
+    const int64_t b0 = tile * GB_SB;
+    // the tile's sessions: consecutive entries of the length-sorted order (longest first), so the first one bounds the loop;
+    // session slots beyond B are marked with B (every access below is guarded by b < B)
+    auto sess = [&](int64_t i) -> int64_t { return i < B ? (order ? (int64_t)order[i] : i) : B; };
+    int64_t tmax = T;
+    if (order) {
+        const int64_t l0 = lens[sess(b0)];
+        tmax = l0 < 0 ? 0 : (l0 > T ? T : l0);
+    }
+    // gradient rows behind the tile's last live step are zero (the weight-gradient products read every row)
+    if (tmax < T) {
+        const int64_t per = (T - tmax) * (3 * GH / 4);
+        for (int64_t e = threadIdx.x; e < (int64_t)GB_SB * per; e += blockDim.x) {
+            const int64_t b = sess(b0 + e / per), r = e % per;
+            if (b < B) {
+                const int64_t t = tmax + r / (3 * GH / 4), c4 = (r % (3 * GH / 4)) * 4;
+                *reinterpret_cast<float4*>(dgi + (b * T + t) * 3 * GH + c4) = make_float4(0.f, 0.f, 0.f, 0.f);
+                *reinterpret_cast<float4*>(dgh_all + (b * (T + 1) + t) * 3 * GH + c4) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+    }
+    int64_t len_r[2], b_r[2];
     float dh[2][2][2];                       // [half][ct][e]: rows gq / gq+8, cols 16*warp + 8*ct + 2*tq + e
 #pragma unroll
     for (int hh = 0; hh < 2; ++hh) {
-        const int64_t b = b0 + hh * 8 + gq;
+        const int64_t b = sess(b0 + hh * 8 + gq);
+        b_r[hh] = b;
         len_r[hh] = (b < B) ? lens[b] : 0;
 #pragma unroll
         for (int ct = 0; ct < 2; ++ct) {
@@ -288,7 +379,7 @@ __global__ void __launch_bounds__(256, 1) gru_seq_bwd_kernel(int64_t B, int64_t 
     auto fetch = [&](int64_t t, float2 (&v)[2][2][5]) {
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
-            const int64_t b = b0 + hh * 8 + gq;
+            const int64_t b = b_r[hh];
             const bool live = (b < B) && (t >= 0) && (t < len_r[hh]);
 #pragma unroll
             for (int ct = 0; ct < 2; ++ct) {
@@ -304,22 +395,13 @@ __global__ void __launch_bounds__(256, 1) gru_seq_bwd_kernel(int64_t B, int64_t 
             }
         }
     };
-    fetch(T - 1, sv);
-    float sum_i[2][3][2], sum_h[2][2];        // bias-gradient partial sums: [ct][gate][e] of dgi, [ct][e] of the n-gate of dgh
-#pragma unroll
-    for (int ct = 0; ct < 2; ++ct)
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            sum_h[ct][e] = 0.f;
-#pragma unroll
-            for (int q = 0; q < 3; ++q) sum_i[ct][q][e] = 0.f;
-        }
-    for (int64_t t = T - 1; t >= 0; --t) {
+    fetch(tmax - 1, sv);
+    for (int64_t t = tmax - 1; t >= 0; --t) {
         // ---- gate derivatives for the elements this lane owns ----
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
             const int row = hh * 8 + gq;
-            const int64_t b = b0 + row;
+            const int64_t b = b_r[hh];
             const bool live = (b < B) && (t < len_r[hh]);
 #pragma unroll
             for (int ct = 0; ct < 2; ++ct) {
@@ -400,6 +482,7 @@ __global__ void __launch_bounds__(256, 1) gru_seq_bwd_kernel(int64_t B, int64_t 
             }
         __syncthreads();                    // the dgh tile is rewritten by the next step
     }
+    }   // tile loop
     // ---- bias gradients: db_ih = column sums of dgi, db_hh = column sums of dgh (r and z parts are shared) ----
     if (db_ih != nullptr || db_hh != nullptr) {
 #pragma unroll
@@ -423,13 +506,16 @@ __global__ void __launch_bounds__(256, 1) gru_seq_bwd_kernel(int64_t B, int64_t 
 }
 
 int gru_seq_bwd(int64_t B, int64_t T, int h, const int64_t* lens, const float* w_hh, const float* h_all,
-                const float* gates, const float* dh_in, float* dgi, float* dgh_all, float* db_ih, float* db_hh, cudaStream_t s) {
+                const float* gates, const float* dh_in, float* dgi, float* dgh_all, float* db_ih, float* db_hh, cudaStream_t s,
+                int32_t* order) {
     if (B <= 0 || T <= 0) return INTEL_OK;
     INTEL_REQUIRE(h == GH, INTEL_ERR_UNSUPPORTED, "fused GRU needs hidden size 128");
     const size_t smem = (size_t)(3 * GH * GW + GB_SB * GD) * 4;
     ensure_smem(gru_seq_bwd_kernel, smem);
-    LAUNCH(gru_seq_bwd_kernel, dim3((unsigned)ceil_div(B, GB_SB)), dim3(256), smem, s, B, T, lens, w_hh, h_all, gates,
-           dh_in, dgi, dgh_all, db_ih, db_hh);
+    // persistent: one CTA per SM (W_hh fills its shared memory), tiles drawn from the counter behind `order` (order[B])
+    const unsigned grid = stream_grid(ceil_div(B, GB_SB), 1);
+    LAUNCH(gru_seq_bwd_kernel, dim3(grid), dim3(256), smem, s, B, T, lens, w_hh, h_all, gates,
+           dh_in, dgi, dgh_all, db_ih, db_hh, (const int32_t*)order, order ? order + B : (int32_t*)nullptr);
     return check_launch("gru_seq_bwd", (double)B * T * (4 + 1 + 3 + 3) * GH * 4.0, 2.0 * B * T * 3 * GH * GH);
 }
 

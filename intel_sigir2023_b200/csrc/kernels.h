@@ -88,6 +88,7 @@ int take_last(int64_t B, int64_t T, int d, const int64_t* lens, const float* X, 
 int take_last_bwd(int64_t B, int64_t T, int d, const int64_t* lens, const float* d_out, int64_t ld, float* dX,
                   cudaStream_t s);
 int fill_zero(void* p, size_t bytes, cudaStream_t s);
+int copy_d2d(void* dst, const void* src, size_t bytes, cudaStream_t s);
 
 // ---- attn.cu ------------------------------------------------------------------------------------
 // LayerNorm over the last dim (eps 1e-5); stats[r] = {mean, rstd}
@@ -135,7 +136,11 @@ int gru_tc_fwd(int64_t B, int64_t T, const int64_t* lens, const float* gi, const
                float* gates, cudaStream_t s, bool save_gates = true);
 void gru_debug_use_tcgen05(int on);
 int gru_seq_bwd(int64_t B, int64_t T, int h, const int64_t* lens, const float* w_hh, const float* h_all,
-                const float* gates, const float* dh_in, float* dgi, float* dgh_all, float* db_ih, float* db_hh, cudaStream_t s);
+                const float* gates, const float* dh_in, float* dgi, float* dgh_all, float* db_ih, float* db_hh, cudaStream_t s,
+                int32_t* order = nullptr);
+// order [B + 1]: order[i] = session with the i-th longest history (stable; T <= 63), order[B] = 0 (the tile counter).  With it the backward recurrence walks tiles of
+// equally long sessions and stops each tile at its own last step (the reference packs the sequences: GeneralSeq.py:64-71).
+int gru_order_by_len(int64_t B, int64_t T, const int64_t* lens, int32_t* order, cudaStream_t s);
 
 // ---- trunk.cu: fused self-attention stack (d = 32, L <= 64): all layers of a session on chip -----
 struct StackParams { const float *wq, *wk, *wv, *w1, *b1, *w2, *b2, *lnw, *lnb; };
@@ -208,6 +213,8 @@ int bcast_rows_bwd(int64_t B, int64_t L, int d, const float* dout, int64_t ldo, 
 int relu_bwd(int64_t rows, int cols, const float* dy, int64_t lddy, const float* v, int64_t ldv, float* dx,
              int64_t lddx, cudaStream_t s);
 int add_inplace(int64_t n, float* y, const float* x, cudaStream_t s);
+// y = relu(x + b) on strided row views (b nullable)
+int bias_relu_rows(int64_t rows, int cols, const float* x, int64_t ldx, const float* b, float* y, int64_t ldy, cudaStream_t s);
 // y = x * dropout mask/(1-p) (+ add); used by the staged path of the stacks, forward and backward
 int dropout_apply(int64_t rows, int width, const float* x, const float* add, float* y, const Dropout& dr, cudaStream_t s);
 
