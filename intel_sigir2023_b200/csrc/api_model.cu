@@ -185,7 +185,7 @@ struct BertWs {
     float *QKV[INTEL_MAX_BERT_LAYERS], *Z1[INTEL_MAX_BERT_LAYERS], *st1[INTEL_MAX_BERT_LAYERS], *C[INTEL_MAX_BERT_LAYERS],
         *F[INTEL_MAX_BERT_LAYERS], *Z2[INTEL_MAX_BERT_LAYERS], *st2[INTEL_MAX_BERT_LAYERS];
 };
-struct GruWs { float *gi, *h_all, *gates, *gh, *dh, *dgi, *dgh_all; int32_t* order; };
+struct GruWs { float *gi, *h_all, *gates, *gh, *dh, *dgi, *dgh_all; int32_t *order, *rows_t, *rows_t1, *nlive; };
 struct EncWs {
     int64_t T; int d;
     float* seq;          // [B*T, d] token embeddings (BERT: positions added in place)
@@ -231,6 +231,9 @@ void enc_layout(const intel_dims_t* d, Arena& a, EncWs& e, int64_t T, int dd) {
         e.gru.dgi = a.take<float>(R * 3 * h);
         e.gru.dgh_all = a.take<float>(B * (T + 1) * 3 * h);
         e.gru.order = a.take<int32_t>(B + 1);
+        e.gru.rows_t = a.take<int32_t>(R);
+        e.gru.rows_t1 = a.take<int32_t>(R);
+        e.gru.nlive = a.take<int32_t>(4);
     }
 }
 
@@ -315,7 +318,12 @@ int gru_fwd(const intel_dims_t* d, const intel_encoder_t& p, EncWs& e, const int
     const int64_t B = d->B, T = e.T, R = B * T;
     const int dd = e.d, h = d->gru_hidden;
     GruWs& w = e.gru;
-    INTEL_TRY(linear(R, 3 * h, dd, e.seq, dd, p.w_ih, dd, p.b_ih, w.gi, 3 * h, s));
+    // the products over the [B, T] history rows walk the live rows only (about half of them are padding behind a session's
+    // length; the reference packs the sequences: GeneralSeq.py:64-71).  gi rows of padding slots stay unwritten: nobody reads them.
+    const bool packed = B * (T + 1) < (1LL << 31);
+    if (packed) INTEL_TRY(gru_live_rows(B, T, lens, w.rows_t, w.rows_t1, w.nlive, s));
+    INTEL_TRY(linear(R, 3 * h, dd, e.seq, dd, p.w_ih, dd, p.b_ih, w.gi, 3 * h, s, false, false, nullptr, 0,
+                     packed ? w.rows_t : nullptr, packed ? w.nlive : nullptr));
     if (h == 128) {
         // the fused kernels write h_all[:, 1..T] of every session themselves: only the initial state h_0 needs clearing
         // (2 MB instead of a 44 MB memset per encoder and step)
@@ -358,9 +366,14 @@ int gru_bwd(const intel_dims_t* d, const intel_encoder_t& p, intel_encoder_t& g,
             INTEL_TRY(linear_dx(B, 3 * h, h, w.dgh_all + t * 3 * h, (T + 1) * 3 * h, p.w_hh, h, w.dh, h, s, 1));
         }
     }
-    INTEL_TRY(linear_dw(B * (T + 1), 3 * h, h, w.dgh_all, 3 * h, w.h_all, h, g.w_hh, h, h == 128 ? nullptr : g.b_hh, s));
-    INTEL_TRY(linear_dw(R, 3 * h, dd, w.dgi, 3 * h, e.seq, dd, g.w_ih, dd, h == 128 ? nullptr : g.b_ih, s));
-    return linear_dx(R, 3 * h, dd, w.dgi, 3 * h, p.w_ih, dd, e.dseq, dd, s);
+    // gradient rows of padding slots are zero: the three products below contract / map the live rows only (the list was
+    // built by the forward call); d(seq) of the padding slots is cleared for the scatters that read every row
+    const bool packed = B * (T + 1) < (1LL << 31);
+    const int32_t *rt = packed ? w.rows_t : nullptr, *rt1 = packed ? w.rows_t1 : nullptr, *nl = packed ? w.nlive : nullptr;
+    INTEL_TRY(linear_dw(B * (T + 1), 3 * h, h, w.dgh_all, 3 * h, w.h_all, h, g.w_hh, h, h == 128 ? nullptr : g.b_hh, s, false, rt1, nl));
+    INTEL_TRY(linear_dw(R, 3 * h, dd, w.dgi, 3 * h, e.seq, dd, g.w_ih, dd, h == 128 ? nullptr : g.b_ih, s, false, rt, nl));
+    if (packed) INTEL_TRY(fill_zero(e.dseq, (size_t)R * dd * 4, s));
+    return linear_dx(R, 3 * h, dd, w.dgi, 3 * h, p.w_ih, dd, e.dseq, dd, s, 0, nullptr, 0, rt, nl);
 }
 
 }  // namespace

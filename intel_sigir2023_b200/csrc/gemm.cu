@@ -875,25 +875,28 @@ int gemm(const Gemm& g, cudaStream_t s) {
 
 int linear(int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* W, int64_t ldw,
            const float* bias, float* C, int64_t ldc, cudaStream_t s, bool relu_a, bool relu_out,
-           const float* add, int64_t ldadd) {
+           const float* add, int64_t ldadd, const int32_t* rows, const int32_t* nrows) {
     Gemm g;
     g.M = M; g.N = N; g.K = K; g.A = A; g.lda = lda; g.B = W; g.ldb = ldw; g.C = C; g.ldc = ldc;
-    g.bias = bias; g.relu_a = relu_a; g.relu_out = relu_out; g.add = add; g.ldadd = ldadd;
+    g.bias = bias; g.relu_a = relu_a; g.relu_out = relu_out; g.add = add; g.ldadd = ldadd; g.rows = rows; g.nrows = nrows;
     return gemm(g, s);
 }
 
 int linear_dx(int64_t M, int64_t N, int64_t K, const float* dY, int64_t lddy, const float* W, int64_t ldw,
-              float* dX, int64_t lddx, cudaStream_t s, int accumulate, const float* mask, int64_t ldmask) {
+              float* dX, int64_t lddx, cudaStream_t s, int accumulate, const float* mask, int64_t ldmask,
+              const int32_t* rows, const int32_t* nrows) {
     Gemm g;   // dX[M,K] = dY[M,N] * W[N,K]: inner dimension N, B operand stored [inner][out]
+    g.rows = rows; g.nrows = nrows;
     g.M = M; g.N = K; g.K = N; g.A = dY; g.lda = lddy; g.B = W; g.ldb = ldw; g.b_t = true;
     g.C = dX; g.ldc = lddx; g.accumulate = accumulate; g.mask = mask; g.ldmask = ldmask;
     return gemm(g, s);
 }
 
 int linear_dw(int64_t M, int64_t N, int64_t K, const float* dY, int64_t lddy, const float* X, int64_t ldx,
-              float* dW, int64_t lddw, float* db, cudaStream_t s, bool relu_x) {
+              float* dW, int64_t lddw, float* db, cudaStream_t s, bool relu_x, const int32_t* rows, const int32_t* nrows) {
     if (dW) {
         Gemm g;   // dW[N,K] += sum_m dY[m,n] X[m,k]: both operands stored [inner][out]
+        g.rows = rows; g.nrows = nrows;
         g.M = N; g.N = K; g.K = M; g.A = dY; g.lda = lddy; g.a_t = true; g.B = X; g.ldb = ldx; g.b_t = true;
         g.C = dW; g.ldc = lddw; g.accumulate = 2; g.splits = 0; g.relu_b = relu_x;
         INTEL_TRY(gemm(g, s));

@@ -34,6 +34,8 @@ struct RowsArgs {
     const float* bias;
     float* C; int64_t ldc;
     int nkc, nnc;                         // K chunks of RT_KC, N blocks of RT_NB (one of them is 1)
+    const int32_t* rows;                  // optional: the rows of A / C to process (Gemm::rows), *nrows of them
+    const int32_t* nrows;
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -97,7 +99,13 @@ __global__ void __launch_bounds__(RT_THREADS, 1) gemm_rows_tc_kernel(RowsArgs a)
     __syncthreads();
     tc05::fence_after();
     const uint32_t tm = *tmem_slot;
-    const int64_t tiles = (a.M + 127) / 128;
+    // with a row list the tile loop runs over the listed rows only (tile i = entries [128 i, 128 i + 128) of the list)
+    int64_t Mrows = a.M;
+    if (a.rows) {
+        const int64_t n = *a.nrows;
+        Mrows = n < 0 ? 0 : (n > a.M ? a.M : n);
+    }
+    const int64_t tiles = (Mrows + 127) / 128;
     uint64_t *a_full = bars, *a_empty = bars + 2, *d_full = bars + 4, *d_empty = bars + 6;
     const uint32_t cA = 0, cD = 256;                                 // A buffers: 2 x (64 hi | 64 lo); accumulators: 2 x 128
 
@@ -112,12 +120,14 @@ __global__ void __launch_bounds__(RT_THREADS, 1) gemm_rows_tc_kernel(RowsArgs a)
         auto load_chunk = [&](int64_t i, float4 (&x)[RT_KC / 4]) {
             const int64_t tile = blockIdx.x + (i / a.nkc) * gridDim.x;
             const int kc = (int)(i % a.nkc);
-            const int64_t row = tile * 128 + tid;
+            const int64_t idx = tile * 128 + tid;
+            const bool on = idx < Mrows;
+            const int64_t row = (on && a.rows) ? (int64_t)a.rows[idx] : idx;
             const float* src = a.A + row * a.lda;
 #pragma unroll
             for (int j = 0; j < RT_KC / 4; ++j) {
                 const int k = kc * RT_KC + 4 * j;
-                x[j] = (row < a.M && k < a.K) ? *reinterpret_cast<const float4*>(src + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+                x[j] = (on && k < a.K) ? *reinterpret_cast<const float4*>(src + k) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         };
         if (nch > 0) load_chunk(0, v);
@@ -212,6 +222,9 @@ __global__ void __launch_bounds__(RT_THREADS, 1) gemm_rows_tc_kernel(RowsArgs a)
         const int groups = a.nkc > 1 ? (a.nkc + RT_GK - 1) / RT_GK : 1;
         for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
             const int64_t m0 = tile * 128 + ew * 32;
+            // destination row of this lane's tile row (-1: none); the store loops fetch the row of tile row r from lane r
+            int64_t myrow = -1;
+            if (m0 + lane < Mrows) myrow = a.rows ? (int64_t)a.rows[m0 + lane] : m0 + lane;
             if (a.nkc > 1) {
                 // ---- partial blocks of one 128 x Np (<= 64) output block: summed in registers, stored once ----
                 float acc[64];
@@ -246,9 +259,9 @@ __global__ void __launch_bounds__(RT_THREADS, 1) gemm_rows_tc_kernel(RowsArgs a)
                     for (int i = 0; i < 8; ++i) {
                         const int r = 4 * i + (lane >> 3), ch = lane & 7;
                         const float4 v4 = *reinterpret_cast<const float4*>(st + r * 32 + ((ch + r) & 7) * 4);
-                        const int64_t row = m0 + r;
+                        const int64_t row = __shfl_sync(0xffffffffu, myrow, r);
                         const int col = g + 4 * ch;
-                        if (row < a.M && col < a.N) *reinterpret_cast<float4*>(a.C + row * a.ldc + col) = v4;
+                        if (row >= 0 && col < a.N) *reinterpret_cast<float4*>(a.C + row * a.ldc + col) = v4;
                     }
                     __syncwarp();
                 }
@@ -284,9 +297,9 @@ __global__ void __launch_bounds__(RT_THREADS, 1) gemm_rows_tc_kernel(RowsArgs a)
                     for (int i = 0; i < 8; ++i) {                     // 4 rows x 128 contiguous bytes per instruction
                         const int r = 4 * i + (lane >> 3), ch = lane & 7;
                         const float4 v = *reinterpret_cast<const float4*>(st + r * 32 + ((ch + r) & 7) * 4);
-                        const int64_t row = m0 + r;
+                        const int64_t row = __shfl_sync(0xffffffffu, myrow, r);
                         const int col = n0 + 4 * ch;
-                        if (row < a.M && col < a.N) *reinterpret_cast<float4*>(a.C + row * a.ldc + col) = v;
+                        if (row >= 0 && col < a.N) *reinterpret_cast<float4*>(a.C + row * a.ldc + col) = v;
                     }
                     __syncwarp();
                 }
@@ -318,6 +331,7 @@ bool gemm_rows_tc_try(const Gemm& g, cudaStream_t s, const char* what, int* stat
     RowsArgs a;
     a.M = g.M; a.N = (int)g.N; a.K = (int)g.K; a.A = g.A; a.lda = g.lda; a.W = g.B; a.ldw = g.ldb; a.w_t = g.b_t ? 1 : 0;
     a.bias = g.bias; a.C = g.C; a.ldc = g.ldc; a.nkc = nkc; a.nnc = nnc;
+    a.rows = (g.rows && g.nrows) ? g.rows : nullptr; a.nrows = g.nrows;
     ensure_smem(gemm_rows_tc_kernel, smem);
     const unsigned grid = stream_grid((g.M + 127) / 128, 1);
     LAUNCH(gemm_rows_tc_kernel, dim3(grid), dim3(RT_THREADS), smem, s, a);

@@ -29,6 +29,8 @@ struct WgradArgs {
     const float* X; int64_t ldx;
     float* dW; int64_t ldw;
     int64_t blocks_per_cta;                // 128-row blocks per CTA along the rows
+    const int32_t* rows;                   // optional: the rows to contract over (Gemm::rows), *nrows of them
+    const int32_t* nrows;
 };
 
 __device__ __forceinline__ void mbar_arrive_w(uint64_t* bar) {
@@ -62,10 +64,17 @@ __global__ void __launch_bounds__(WG_THREADS, 1) gemm_wgrad_tc_kernel(WgradArgs 
     tc05::fence_after();
     const uint32_t tm = tmem_slot;
     const int m0 = blockIdx.x * 128;
-    const int64_t blk0 = (int64_t)blockIdx.y * a.blocks_per_cta;
-    const int64_t total_blocks = (a.R + 127) / 128;
+    // with a row list the contraction runs over the listed rows only; the split over the grid follows their number
+    int64_t R = a.R, bpc = a.blocks_per_cta;
+    if (a.rows) {
+        const int64_t n = *a.nrows;
+        R = n < 0 ? 0 : (n > a.R ? a.R : n);
+        bpc = ((R + 127) / 128 + gridDim.y - 1) / gridDim.y;
+    }
+    const int64_t blk0 = (int64_t)blockIdx.y * bpc;
+    const int64_t total_blocks = (R + 127) / 128;
     int64_t nblk = total_blocks - blk0;
-    if (nblk > a.blocks_per_cta) nblk = a.blocks_per_cta;
+    if (nblk > bpc) nblk = bpc;
     if (nblk < 0) nblk = 0;
 
     if (warp < 8) {
@@ -112,12 +121,14 @@ __global__ void __launch_bounds__(WG_THREADS, 1) gemm_wgrad_tc_kernel(WgradArgs 
         const int64_t nst = nblk * WG_BLOCK_STAGES;
         float4 va[4], vb[4], na[4], nb[4];
         auto load_stage = [&](int64_t it, float4 (&xa)[4], float4 (&xb)[4]) {
-            const int64_t row = (blk0 * WG_BLOCK_STAGES + it) * WG_STAGE_ROWS + r;
+            const int64_t idx = (blk0 * WG_BLOCK_STAGES + it) * WG_STAGE_ROWS + r;
+            const bool on = idx < R;
+            const int64_t row = (on && a.rows) ? (int64_t)a.rows[idx] : idx;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                xa[i] = row < a.R ? *reinterpret_cast<const float4*>(a.dY + row * a.ldy + m0 + 32 * i + 4 * ch) : make_float4(0.f, 0.f, 0.f, 0.f);
+                xa[i] = on ? *reinterpret_cast<const float4*>(a.dY + row * a.ldy + m0 + 32 * i + 4 * ch) : make_float4(0.f, 0.f, 0.f, 0.f);
                 const int col = 32 * i + 4 * ch;
-                xb[i] = (i < nsub && row < a.R && col < a.N) ? *reinterpret_cast<const float4*>(a.X + row * a.ldx + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+                xb[i] = (i < nsub && on && col < a.N) ? *reinterpret_cast<const float4*>(a.X + row * a.ldx + col) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         };
         if (nst > 0) load_stage(0, va, vb);
@@ -202,6 +213,7 @@ bool gemm_wgrad_tc_try(const Gemm& g, cudaStream_t s, const char* what, int* sta
     if (nsub == 3) return false;                                          // N padded to 96: the fold assumes 32 / 64 / 128 columns
     WgradArgs a;
     a.R = g.K; a.M = (int)g.M; a.N = (int)g.N; a.dY = g.A; a.ldy = g.lda; a.X = g.B; a.ldx = g.ldb; a.dW = g.C; a.ldw = g.ldc;
+    a.rows = (g.rows && g.nrows) ? g.rows : nullptr; a.nrows = g.nrows;
     const int mslices = (int)(g.M / 128);
     const int64_t blocks = (g.K + 127) / 128;
     int64_t splits = kNumSMs / mslices;

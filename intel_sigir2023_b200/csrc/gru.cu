@@ -250,6 +250,61 @@ int gru_seq_fwd(int64_t B, int64_t T, int h, const int64_t* lens, const float* g
     return check_launch("gru_seq_fwd", (double)B * T * (3 + 4 + 1) * GH * 4.0, 2.0 * B * T * 3 * GH * GH);
 }
 
+// Row numbers of the live (session, step) pairs of a padded [B, T] history, in (b, t) order.  Block k owns sessions
+// [1024 k, 1024 k + 1024): it sums the lengths before them, scans its own and writes its rows; the last block writes the count.
+__global__ void __launch_bounds__(1024) gru_live_rows_kernel(int64_t B, int T, const int64_t* __restrict__ lens, int32_t* __restrict__ rows_t,
+                                                             int32_t* __restrict__ rows_t1, int32_t* __restrict__ count) {
+    __shared__ int warp_tot[32];
+    __shared__ int base_s;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    auto len_of = [&](int64_t e) { const int64_t v = lens[e]; return (int)(v < 0 ? 0 : (v > T ? T : v)); };
+    const int64_t first = (int64_t)blockIdx.x * 1024;
+    // lengths before this block
+    int part = 0;
+    for (int64_t e = tid; e < first; e += 1024) part += len_of(e);
+    part = warp_sum_i(part);
+    if (lane == 0) warp_tot[warp] = part;
+    __syncthreads();
+    if (tid == 0) {
+        int t = 0;
+        for (int w = 0; w < 32; ++w) t += warp_tot[w];
+        base_s = t;
+    }
+    __syncthreads();
+    const int base = base_s;
+    __syncthreads();
+    // exclusive scan of the block's own lengths
+    const int64_t b = first + tid;
+    const int n = b < B ? len_of(b) : 0;
+    int incl = n;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += o;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    int before = 0;
+    for (int w = 0; w < warp; ++w) before += warp_tot[w];
+    const int off = base + before + incl - n;
+    // a warp writes the rows of its 32 sessions one session at a time: lane t takes step t (contiguous stores)
+    for (int i = 0; i < 32; ++i) {
+        const int o = __shfl_sync(0xffffffffu, off, i), m = __shfl_sync(0xffffffffu, n, i);
+        const int64_t bb = first + warp * 32 + i;
+        for (int t = lane; t < m; t += 32) {
+            rows_t[o + t] = (int32_t)(bb * T + t);
+            rows_t1[o + t] = (int32_t)(bb * (T + 1) + t);
+        }
+    }
+    if (blockIdx.x == gridDim.x - 1 && tid == 1023) *count = off + n;
+}
+int gru_live_rows(int64_t B, int64_t T, const int64_t* lens, int32_t* rows_t, int32_t* rows_t1, int32_t* count, cudaStream_t s) {
+    if (B <= 0) return INTEL_OK;
+    INTEL_REQUIRE(B * (T + 1) < (1LL << 31), INTEL_ERR_UNSUPPORTED, "gru_live_rows: more than 2^31 history rows");
+    LAUNCH(gru_live_rows_kernel, dim3((unsigned)ceil_div(B, 1024)), dim3(1024), 0, s, B, (int)T, lens, rows_t, rows_t1, count);
+    return check_launch("gru_live_rows");
+}
+
 // Sessions in order of decreasing length (stable), the way pack_padded_sequence orders them (GeneralSeq.py:64-71): a tile
 // of consecutive sessions of that order then shares one loop bound, and tiles that end early make room for the next ones.
 // One block; a chunk of 1024 sessions per pass, rank inside a chunk from warp ballots, so the order is deterministic.

@@ -17,6 +17,12 @@ struct Gemm {
     bool relu_a = false, relu_b = false, relu_out = false;
     int accumulate = 0;   // 0: C = r   1: C += r   2: atomicAdd(C, r) (required when splits > 1)
     int splits = 1;       // split of the inner dimension (0 = pick automatically for accumulate == 2)
+    // optional list of the rows that matter (device int32 [*nrows], *nrows on the device too): the rows of A and C for a
+    // forward / input-gradient product, the contracted rows for a weight gradient.  Rows that are not listed are padding
+    // (history slots behind a session's length): the persistent tcgen05 kernels walk the list and never touch them, the
+    // generic kernels ignore the list and compute them as well - the listed rows come out the same either way.
+    const int32_t* rows = nullptr;
+    const int32_t* nrows = nullptr;
 };
 int gemm(const Gemm& g, cudaStream_t s);
 // gemm_rows_tc.cu: persistent tcgen05 kernel for tall products with a resident weight operand; false = shape not taken
@@ -28,14 +34,15 @@ void gemm_debug_use_wgrad_tc(int on);
 // C[M,N] = A[M,K] W[N,K]^T (+bias)
 int linear(int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* W, int64_t ldw,
            const float* bias, float* C, int64_t ldc, cudaStream_t s, bool relu_a = false, bool relu_out = false,
-           const float* add = nullptr, int64_t ldadd = 0);
+           const float* add = nullptr, int64_t ldadd = 0, const int32_t* rows = nullptr, const int32_t* nrows = nullptr);
 // dX[M,K] (=|+=) dY[M,N] W[N,K]  (optionally masked by relu input)
 int linear_dx(int64_t M, int64_t N, int64_t K, const float* dY, int64_t lddy, const float* W, int64_t ldw,
               float* dX, int64_t lddx, cudaStream_t s, int accumulate = 0, const float* mask = nullptr,
-              int64_t ldmask = 0);
+              int64_t ldmask = 0, const int32_t* rows = nullptr, const int32_t* nrows = nullptr);
 // dW[N,K] += dY[M,N]^T X[M,K];  db[N] += colsum(dY)   (db may be null)
 int linear_dw(int64_t M, int64_t N, int64_t K, const float* dY, int64_t lddy, const float* X, int64_t ldx,
-              float* dW, int64_t lddw, float* db, cudaStream_t s, bool relu_x = false);
+              float* dW, int64_t lddw, float* db, cudaStream_t s, bool relu_x = false, const int32_t* rows = nullptr,
+              const int32_t* nrows = nullptr);
 int colsum(int64_t M, int64_t N, const float* X, int64_t ld, float* out, cudaStream_t s);
 
 // ---- embed.cu ---------------------------------------------------------------------------------
@@ -141,6 +148,9 @@ int gru_seq_bwd(int64_t B, int64_t T, int h, const int64_t* lens, const float* w
 // order [B + 1]: order[i] = session with the i-th longest history (stable; T <= 63), order[B] = 0 (the tile counter).  With it the backward recurrence walks tiles of
 // equally long sessions and stops each tile at its own last step (the reference packs the sequences: GeneralSeq.py:64-71).
 int gru_order_by_len(int64_t B, int64_t T, const int64_t* lens, int32_t* order, cudaStream_t s);
+// the live (session, step) pairs of a padded [B, T] history as row numbers, in (b, t) order: rows_t[i] = b T + t into the
+// [B, T, .] tensors, rows_t1[i] = b (T + 1) + t into the [B, T + 1, .] ones; *count = sum of the (clamped) lengths
+int gru_live_rows(int64_t B, int64_t T, const int64_t* lens, int32_t* rows_t, int32_t* rows_t1, int32_t* count, cudaStream_t s);
 
 // ---- trunk.cu: fused self-attention stack (d = 32, L <= 64): all layers of a session on chip -----
 struct StackParams { const float *wq, *wk, *wv, *w1, *b1, *w2, *b2, *lnw, *lnb; };
