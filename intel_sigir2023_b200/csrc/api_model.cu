@@ -185,7 +185,7 @@ struct BertWs {
     float *QKV[INTEL_MAX_BERT_LAYERS], *Z1[INTEL_MAX_BERT_LAYERS], *st1[INTEL_MAX_BERT_LAYERS], *C[INTEL_MAX_BERT_LAYERS],
         *F[INTEL_MAX_BERT_LAYERS], *Z2[INTEL_MAX_BERT_LAYERS], *st2[INTEL_MAX_BERT_LAYERS];
 };
-struct GruWs { float *gi, *h_all, *gates, *gh, *dh, *dgi, *dgh_all; int32_t *order, *rows_t, *rows_t1, *nlive; };
+struct GruWs { float *gi, *h_all, *gates, *gh, *dh, *dgi, *dgh_all; int32_t *order, *rows_t, *rows_t1, *nlive; bool sorted; };   // sorted: set and read inside one call only
 struct EncWs {
     int64_t T; int d;
     float* seq;          // [B*T, d] token embeddings (BERT: positions added in place)
@@ -313,31 +313,66 @@ int bert_bwd(const intel_dims_t* d, const intel_encoder_t& p, intel_encoder_t& g
 }
 
 // ---- GRU4RecEncoder (GeneralSeq.py:58-78) ----------------------------------------------------------
-int gru_fwd(const intel_dims_t* d, const intel_encoder_t& p, EncWs& e, const int64_t* lens, float* out, int64_t ld_out,
-            cudaStream_t s) {
-    const int64_t B = d->B, T = e.T, R = B * T;
-    const int dd = e.d, h = d->gru_hidden;
-    GruWs& w = e.gru;
-    // the products over the [B, T] history rows walk the live rows only (about half of them are padding behind a session's
-    // length; the reference packs the sequences: GeneralSeq.py:64-71).  gi rows of padding slots stay unwritten: nobody reads them.
-    const bool packed = B * (T + 1) < (1LL << 31);
-    if (packed) INTEL_TRY(gru_live_rows(B, T, lens, w.rows_t, w.rows_t1, w.nlive, s));
-    INTEL_TRY(linear(R, 3 * h, dd, e.seq, dd, p.w_ih, dd, p.b_ih, w.gi, 3 * h, s, false, false, nullptr, 0,
-                     packed ? w.rows_t : nullptr, packed ? w.nlive : nullptr));
-    if (h == 128) {
-        // the fused kernels write h_all[:, 1..T] of every session themselves: only the initial state h_0 needs clearing
-        // (2 MB instead of a 44 MB memset per encoder and step)
-        cudaError_t ce = cudaMemset2DAsync(w.h_all, (size_t)(T + 1) * h * 4, 0, (size_t)h * 4, (size_t)B, s);
-        INTEL_REQUIRE(ce == cudaSuccess, INTEL_ERR_CUDA, "cudaMemset2DAsync: %s", cudaGetErrorString(ce));
-        INTEL_TRY(gru_seq_fwd(B, T, h, lens, w.gi, p.w_hh, p.b_hh, w.h_all, w.gates, s, d->inference == 0));
-    } else {
-        INTEL_TRY(fill_zero(w.h_all, (size_t)B * (T + 1) * h * 4, s));
-        for (int64_t t = 0; t < T; ++t) {
-            INTEL_TRY(linear(B, 3 * h, h, w.h_all + t * h, (T + 1) * h, p.w_hh, h, p.b_hh, w.gh, 3 * h, s));
-            INTEL_TRY(gru_step_fwd(B, T, h, (int)t, lens, w.gi, w.gh, w.h_all, w.gates, s));
+// Both GRU encoders of predict_intent (session history, item history) in three stages: input projections, recurrences,
+// output projections.  The recurrences of the two encoders share one launch (gru_tc.cu): each is a chain of T dependent steps
+// that leaves the tensor pipe idle most of the time, so they are overlapped instead of run back to back.
+int gru_fwd_pair(const intel_dims_t* d, const intel_encoder_t* const (&p)[2], EncWs* const (&e)[2], const int64_t* const (&lens)[2],
+                 float* const (&out)[2], int64_t ld_out, cudaStream_t s) {
+    const int64_t B = d->B;
+    const int h = d->gru_hidden;
+    bool fused = h == 128 && gru_tc_supported(h);
+    for (int i = 0; i < 2; ++i) {
+        const int64_t T = e[i]->T, R = B * T;
+        const int dd = e[i]->d;
+        GruWs& w = e[i]->gru;
+        // the products over the [B, T] history rows walk the live rows only (about half of them are padding behind a
+        // session's length; the reference packs the sequences: GeneralSeq.py:64-71).  gi rows of padding slots stay
+        // unwritten: nobody reads them.
+        const bool packed = B * (T + 1) < (1LL << 31);
+        if (packed) INTEL_TRY(gru_live_rows(B, T, lens[i], w.rows_t, w.rows_t1, w.nlive, s));
+        INTEL_TRY(linear(R, 3 * h, dd, e[i]->seq, dd, p[i]->w_ih, dd, p[i]->b_ih, w.gi, 3 * h, s, false, false, nullptr, 0,
+                         packed ? w.rows_t : nullptr, packed ? w.nlive : nullptr));
+        // sessions by decreasing length: tiles of equally long sessions stop at their own last step (forward and backward)
+        w.sorted = T <= 63;
+        if (w.sorted) INTEL_TRY(gru_order_by_len(B, T, lens[i], w.order, s));
+        fused = fused && w.sorted;
+        if (h == 128) {
+            // the fused kernels write h_all[:, 1..T] of every session themselves: only the initial state h_0 needs clearing
+            // (2 MB instead of a 44 MB memset per encoder and step)
+            cudaError_t ce = cudaMemset2DAsync(w.h_all, (size_t)(T + 1) * h * 4, 0, (size_t)h * 4, (size_t)B, s);
+            INTEL_REQUIRE(ce == cudaSuccess, INTEL_ERR_CUDA, "cudaMemset2DAsync: %s", cudaGetErrorString(ce));
+        } else {
+            INTEL_TRY(fill_zero(w.h_all, (size_t)B * (T + 1) * h * 4, s));
         }
     }
-    return linear(B, dd, h, w.h_all + T * h, (T + 1) * h, p.w_out, h, nullptr, out, ld_out, s);
+    if (fused) {
+        GruTcPair pr;
+        pr.n = 2;
+        for (int i = 0; i < 2; ++i) {
+            GruWs& w = e[i]->gru;
+            pr.e[i] = GruTcOne{B, e[i]->T, lens[i], w.gi, p[i]->w_hh, p[i]->b_hh, w.h_all, w.gates, w.order};
+        }
+        INTEL_TRY(gru_tc_fwd_pair(pr, s, d->inference == 0));
+    } else {
+        for (int i = 0; i < 2; ++i) {
+            const int64_t T = e[i]->T;
+            GruWs& w = e[i]->gru;
+            if (h == 128) {
+                INTEL_TRY(gru_seq_fwd(B, T, h, lens[i], w.gi, p[i]->w_hh, p[i]->b_hh, w.h_all, w.gates, s, d->inference == 0));
+            } else {
+                for (int64_t t = 0; t < T; ++t) {
+                    INTEL_TRY(linear(B, 3 * h, h, w.h_all + t * h, (T + 1) * h, p[i]->w_hh, h, p[i]->b_hh, w.gh, 3 * h, s));
+                    INTEL_TRY(gru_step_fwd(B, T, h, (int)t, lens[i], w.gi, w.gh, w.h_all, w.gates, s));
+                }
+            }
+        }
+    }
+    for (int i = 0; i < 2; ++i) {
+        const int64_t T = e[i]->T;
+        GruWs& w = e[i]->gru;
+        INTEL_TRY(linear(B, e[i]->d, h, w.h_all + T * h, (T + 1) * h, p[i]->w_out, h, nullptr, out[i], ld_out, s));
+    }
+    return INTEL_OK;
 }
 
 int gru_bwd(const intel_dims_t* d, const intel_encoder_t& p, intel_encoder_t& g, EncWs& e, const int64_t* lens,
@@ -355,7 +390,7 @@ int gru_bwd(const intel_dims_t* d, const intel_encoder_t& p, intel_encoder_t& g,
         // the fused kernel also sums the bias gradients (column sums of dgi / dgh) on its way
         int32_t* order = nullptr;
         if (T <= 63) {               // tiles of equally long sessions: a tile stops at its own last step
-            INTEL_TRY(gru_order_by_len(B, T, lens, w.order, s));
+            INTEL_TRY(fill_zero(w.order + B, sizeof(int32_t), s));     // the order is the forward call's; reset the tile counter
             order = w.order;
         }
         INTEL_TRY(gru_seq_bwd(B, T, h, lens, p.w_hh, w.h_all, w.gates, w.dh, w.dgi, w.dgh_all, g.b_ih, g.b_hh, s, order));
@@ -671,8 +706,11 @@ int intel_intent_fwd(const intel_dims_t* d, const intel_tensors_t* P, const inte
         INTEL_TRY(bert_fwd(d, P->enc, w.e1, bt->history_len, w.feat + off_v1, Dp, s));
         INTEL_TRY(bert_fwd(d, P->item_enc, w.e2, bt->history_item_len, w.feat + off_v2, Dp, s));
     } else {
-        INTEL_TRY(gru_fwd(d, P->enc, w.e1, bt->history_len, w.feat + off_v1, Dp, s));
-        INTEL_TRY(gru_fwd(d, P->item_enc, w.e2, bt->history_item_len, w.feat + off_v2, Dp, s));
+        const intel_encoder_t* const pe[2] = {&P->enc, &P->item_enc};
+        EncWs* const ee[2] = {&w.e1, &w.e2};
+        const int64_t* const ll[2] = {bt->history_len, bt->history_item_len};
+        float* const oo[2] = {w.feat + off_v1, w.feat + off_v2};
+        INTEL_TRY(gru_fwd_pair(d, pe, ee, ll, oo, Dp, s));
     }
     INTEL_TRY(gather_rows(B, dctx, P->ctx_emb, bt->context_mh, w.feat, Dp, 0, s, d->ctx_rows));
     INTEL_TRY(gather_rows(B, du, P->uid_emb, bt->u_id, w.feat + dctx, Dp, 0, s, d->user_rows));

@@ -63,13 +63,47 @@ __device__ __forceinline__ bool elect_lane() {
 }
 }  // namespace
 
-__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(128, 1)
-    gru_tc_fwd_kernel(int64_t B, int64_t T, const int64_t* __restrict__ lens, const float* __restrict__ gi, const float* __restrict__ w_hh,
-                      const float* __restrict__ b_hh, float* __restrict__ h_all, float* __restrict__ gates, int save_gates) {
+// Up to two encoders (the session-history and the item-history GRU of IntEL.predict_intent) share one launch: cluster q
+// serves encoder q % nenc, tile q / nenc.  With the length-sorted session order of each encoder (longest first) the hardware
+// hands out the clusters in blockIdx order = by decreasing length of both encoders interleaved, a cluster stops at the last
+// live step of its tile, and the SMs it frees take the next cluster: the two recurrences, each a chain of T dependent steps,
+// overlap instead of running back to back.
+struct GruTcEnc {
+    int64_t B, T;
+    const int64_t* lens;
+    const float *gi, *w_hh, *b_hh;
+    float *h_all, *gates;
+    const int32_t* order;        // nullable: sessions by decreasing length
+};
+struct GruTcArgs {
+    GruTcEnc e[2];
+    int nenc, save_gates;
+};
+
+__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(128, 1) gru_tc_fwd_kernel(GruTcArgs args) {
     extern __shared__ __align__(1024) uint8_t gsm[];
     const int t = threadIdx.x, warp = t >> 5;
     const uint32_t c = cluster_rank();                              // hidden-unit slice of this CTA
-    const int64_t b = (int64_t)(blockIdx.x >> 2) * 128 + t;          // this thread's session
+    const int cq = (int)(blockIdx.x >> 2);
+    const GruTcEnc& E = args.e[cq % args.nenc];
+    const int64_t tile = cq / args.nenc;
+    const int64_t B = E.B, T = E.T;
+    if (tile * 128 >= B) return;                                     // the whole cluster leaves (no barrier was touched)
+    const int64_t* __restrict__ lens = E.lens;
+    const float* __restrict__ gi = E.gi;
+    const float* __restrict__ w_hh = E.w_hh;
+    const float* __restrict__ b_hh = E.b_hh;
+    float* __restrict__ h_all = E.h_all;
+    float* __restrict__ gates = E.gates;
+    const int save_gates = args.save_gates;
+    const int64_t slot = tile * 128 + t;
+    const int64_t b = slot < B ? (E.order ? (int64_t)E.order[slot] : slot) : B;      // this thread's session (B: none)
+    // the tile's loop bound: the longest session comes first in the sorted order (same value in all four CTAs)
+    int64_t tmax = T;
+    if (E.order) {
+        const int64_t l0 = lens[E.order[tile * 128]];
+        tmax = l0 < 0 ? 0 : (l0 > T ? T : l0);
+    }
     uint64_t* bar = reinterpret_cast<uint64_t*>(gsm + GT_BAR);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gsm + GT_TMEM);
     float* bias = reinterpret_cast<float*>(gsm + GT_BIAS);           // [3][32] of the own units
@@ -117,7 +151,7 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(128, 1)
     cluster_arrive();                                                // every CTA of the cluster has zeroed its staging tile
     cluster_wait();
 
-    for (int64_t ts = 0; ts < T; ++ts) {
+    for (int64_t ts = 0; ts < tmax; ++ts) {
         const bool live = ts < len;
         const float* gin = gi + (b * T + ts) * 3 * GT_H + (int)c * GT_U;
         // ---- h_{t-1} of the row: staging tile -> hi / lo planes in tensor memory ----
@@ -212,6 +246,17 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(128, 1)
         }
         cluster_wait();
     }
+    // a tile that stopped early: the final state goes to slot T (the output projection reads it there), the slots between
+    // are cleared (only weight-gradient paths that ignore the live-row list read them, against zero gradient rows)
+    if (tmax < T && b < B) {
+        for (int64_t ts = tmax + 1; ts <= T; ++ts) {
+            float* ho = h_all + (b * (T + 1) + ts) * GT_H + (int)c * GT_U;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                *reinterpret_cast<float4*>(ho + 4 * j) = ts == T ? make_float4(hp[4 * j], hp[4 * j + 1], hp[4 * j + 2], hp[4 * j + 3])
+                                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
     tc05::fence_before();
     __syncthreads();
     if (t < 32) tc05::tmem_free(tm, 512);
@@ -224,11 +269,33 @@ void gru_debug_use_tcgen05(int on) { g_use_gru_tc = on ? 1 : 0; }
 bool gru_tc_supported(int h) { return g_use_gru_tc && h == GT_H; }
 
 int gru_tc_fwd(int64_t B, int64_t T, const int64_t* lens, const float* gi, const float* w_hh, const float* b_hh, float* h_all,
-               float* gates, cudaStream_t s, bool save_gates) {
-    const unsigned grid = (unsigned)(4 * ceil_div(B, 128));
+               float* gates, cudaStream_t s, bool save_gates, const int32_t* order) {
+    GruTcPair p;
+    p.n = 1;
+    p.e[0] = GruTcOne{B, T, lens, gi, w_hh, b_hh, h_all, gates, order};
+    return gru_tc_fwd_pair(p, s, save_gates);
+}
+
+int gru_tc_fwd_pair(const GruTcPair& p, cudaStream_t s, bool save_gates) {
+    GruTcArgs a;
+    memset(&a, 0, sizeof(a));
+    a.nenc = p.n;
+    a.save_gates = save_gates ? 1 : 0;
+    int64_t tiles = 0;
+    double bytes = 0.0, flops = 0.0;
+    for (int i = 0; i < p.n; ++i) {
+        const GruTcOne& o = p.e[i];
+        a.e[i] = GruTcEnc{o.B, o.T, o.lens, o.gi, o.w_hh, o.b_hh, o.h_all, o.gates, o.order};
+        const int64_t ti = ceil_div(o.B, 128);
+        tiles = ti > tiles ? ti : tiles;
+        bytes += (double)o.B * o.T * (3 + (save_gates ? 4 : 0) + 1) * GT_H * 4.0;
+        flops += 2.0 * o.B * o.T * 3 * GT_H * GT_H;
+    }
+    if (tiles <= 0) return INTEL_OK;
+    const unsigned grid = (unsigned)(4 * tiles * p.n);
     ensure_smem(gru_tc_fwd_kernel, (size_t)GT_BYTES);
-    LAUNCH(gru_tc_fwd_kernel, dim3(grid), dim3(128), (size_t)GT_BYTES, s, B, T, lens, gi, w_hh, b_hh, h_all, gates, save_gates ? 1 : 0);
-    return check_launch("gru_seq_fwd", (double)B * T * (3 + (save_gates ? 4 : 0) + 1) * GT_H * 4.0, 2.0 * B * T * 3 * GT_H * GT_H);
+    LAUNCH(gru_tc_fwd_kernel, dim3(grid), dim3(128), (size_t)GT_BYTES, s, a);
+    return check_launch("gru_seq_fwd", bytes, flops);
 }
 
 }  // namespace intel
@@ -236,8 +303,10 @@ int gru_tc_fwd(int64_t B, int64_t T, const int64_t* lens, const float* gi, const
 namespace intel {
 void gru_debug_use_tcgen05(int) {}
 bool gru_tc_supported(int) { return false; }
-int gru_tc_fwd(int64_t, int64_t, const int64_t*, const float*, const float*, const float*, float*, float*, cudaStream_t, bool) {
+int gru_tc_fwd(int64_t, int64_t, const int64_t*, const float*, const float*, const float*, float*, float*, cudaStream_t, bool,
+               const int32_t*) {
     return INTEL_ERR_UNSUPPORTED;
 }
+int gru_tc_fwd_pair(const GruTcPair&, cudaStream_t, bool) { return INTEL_ERR_UNSUPPORTED; }
 }  // namespace intel
 #endif

@@ -140,7 +140,17 @@ int gru_seq_fwd(int64_t B, int64_t T, int h, const int64_t* lens, const float* g
 // tcgen05 forward recurrence (gru_tc.cu): clusters of four CTAs, W_hh slices resident as UMMA B operands; same outputs
 bool gru_tc_supported(int h);
 int gru_tc_fwd(int64_t B, int64_t T, const int64_t* lens, const float* gi, const float* w_hh, const float* b_hh, float* h_all,
-               float* gates, cudaStream_t s, bool save_gates = true);
+               float* gates, cudaStream_t s, bool save_gates = true, const int32_t* order = nullptr);
+// one launch for the recurrences of up to two encoders; order (nullable): sessions by decreasing length (gru_order_by_len)
+struct GruTcOne {
+    int64_t B, T;
+    const int64_t* lens;
+    const float *gi, *w_hh, *b_hh;
+    float *h_all, *gates;
+    const int32_t* order;
+};
+struct GruTcPair { GruTcOne e[2]; int n; };
+int gru_tc_fwd_pair(const GruTcPair& p, cudaStream_t s, bool save_gates);
 void gru_debug_use_tcgen05(int on);
 int gru_seq_bwd(int64_t B, int64_t T, int h, const int64_t* lens, const float* w_hh, const float* h_all,
                 const float* gates, const float* dh_in, float* dgi, float* dgh_all, float* db_ih, float* db_hh, cudaStream_t s,
