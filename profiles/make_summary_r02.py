@@ -33,9 +33,11 @@ f = lambda rr, k: (rr.get(k, '') or '-').split()[0]
 rows, traffic, seen = [], {}, set()
 name_map = {'trunk_bwd_kernel': 'trunk_bwd', 'trunk_tc_fwd_kernel': 'trunk_fwd', 'gru_tc_fwd_kernel': 'gru_seq_fwd',
             'gru_seq_bwd_kernel': 'gru_seq_bwd', 'dense_rows_fwd_kernel': 'dense_rows_fwd', 'ndcg_kernel': 'ndcg',
-            'batch_build_kernel': 'batch_build', 'scatter_add_kernel': 'scatter_add', 'reduce_partials_kernel': 'ndcg_reduce'}
-for src, note in (('r02_ncu_trunk_tc_fwd_train.jsonl', 'train step (activations saved)'), ('r02_ncu_gru_tc_fwd_train.jsonl', 'train step (gates saved)'),
-                  ('r02_ncu_full.jsonl', 'second train step, then the eval step (inference mode: nothing saved)')):
+            'batch_build_kernel': 'batch_build', 'scatter_add_kernel': 'scatter_add', 'reduce_partials_kernel': 'ndcg_reduce',
+            'loss_pl_kernel': 'loss_pl', 'intent_loss_kernel': 'intent_loss', 'gemm_wgrad_tc_kernel': 'gemm_wgrad',
+            'gemm_rows_tc_kernel': 'gemm_rows', 'cross_pool_bwd_kernel': 'cross_pool_bwd', 'gemm_umma_kernel': 'gemm_umma'}
+for src, note in (('r02_ncu_train.jsonl', 'train step (activations saved)'),
+                  ('r02_ncu_eval.jsonl', 'eval step (inference mode: nothing saved) + one device-built batch')):
     if not os.path.exists(P(src)):
         continue
     for line in open(P(src)):
@@ -82,6 +84,7 @@ for c, base in (('c2', 'r02_bench_c2.json'), ('c4', 'r02_bench_c4.json')):
         continue
     b1 = last_json(base)
     for n, fn in ((1, base), (2, 'r02_bench_%s_2gpu.json' % c if c != 'c2' else 'r02_bench_2gpu.json'),
+                  (4, 'r02_bench_%s_4gpu.json' % c if c != 'c2' else 'r02_bench_4gpu.json'),
                   (8, 'r02_bench_%s_8gpu.json' % c if c != 'c2' else 'r02_bench_8gpu.json')):
         if os.path.exists(P(fn)):
             x = last_json(fn)
@@ -124,7 +127,11 @@ ndcg kernel: {json.dumps(ev.get('ndcg_kernel', {}))[:400]}
 
 r02_traffic.json holds the per-launch DRAM bytes of these captures; `bench.py` copies the entry of the dominant kernel into
 `roofline.traffic`.  r02_sass_summary.txt: per-kernel counts of UTCHMMA / LDTM / STTM / UTCBAR / HMMA in libintel_b200.so.
-r02_probe.log: the tcgen05 forms checked bit-exact on the hardware before the kernels were written (tests/hw/umma_probe.cu).
+r02_probe.log: the tcgen05 forms checked bit-exact on the hardware before the kernels were written (tests/hw/umma_probe.cu; 13 and
+14 are layouts the hardware rejects, kept as negative results; 15-17: the tensor cores ignore the low 13 operand bits).
+r02_trunk_bwd_lines.txt / r02_gru_tc_fwd_lines.txt / r02_gemm_umma_lines.txt: instructions and stall samples per source
+statement (profiles/tools/sass_lines.py).  r02_shapes.log: CUDA-event time of every kernel / GEMM shape of one train step.
+r02_bench_8gpu_overlap.json / r02_bench_8gpu_no_overlap.json: the gradient exchange hidden behind the backward pass, A/B.
 """
 open(P('r02_summary.md'), 'w').write(md)
 print(md[:3000])
