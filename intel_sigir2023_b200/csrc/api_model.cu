@@ -510,10 +510,14 @@ int intel_ensemble_fwd(const intel_dims_t* d, const intel_tensors_t* P, const in
         // user + intent parts of the head input
         INTEL_TRY(gather_rows(B, du, P->uid_emb, bt->u_id, w.all + off_u, D, 1, s, d->user_rows));
         INTEL_TRY(bias_relu_rows(B, dint, w.qcat + di + ds, dc, P->intent_b, w.all + off_h, D, s));
-        // weights of the valid rows and of the pad rows (whose pooled inputs are zero)
-        INTEL_TRY(linear(B, K, D, w.all, D, P->head_w, D, P->head_b, w.w_valid, K, s));
-        INTEL_TRY(linear(B, K, du + dint, w.all + off_u, D, P->head_w + off_u, D, P->head_b, w.w_pad, K, s));
-        INTEL_TRY(head_fuse_fwd(B, L, K, w.w_valid, w.w_pad, bt->scores, bt->session_len, weights_out, ens_out, s));
+        // weights of the valid rows and of the pad rows (whose pooled inputs are zero), then the fusion
+        if (head_full_ok(K, D)) {
+            INTEL_TRY(head_full_fwd(B, L, K, D, off_u, w.all, P->head_w, P->head_b, bt->scores, bt->session_len, weights_out, ens_out, s));
+        } else {
+            INTEL_TRY(linear(B, K, D, w.all, D, P->head_w, D, P->head_b, w.w_valid, K, s));
+            INTEL_TRY(linear(B, K, du + dint, w.all + off_u, D, P->head_w + off_u, D, P->head_b, w.w_pad, K, s));
+            INTEL_TRY(head_fuse_fwd(B, L, K, w.w_valid, w.w_pad, bt->scores, bt->session_len, weights_out, ens_out, s));
+        }
     } else {
         const int q = d->qsize;
         INTEL_TRY(linear(B, q, I, intents, I, P->gate_item_w0, I, P->gate_item_b0, w.t_i, q, s, false, true));
@@ -558,11 +562,16 @@ int intel_ensemble_bwd_phase(const intel_dims_t* d, const intel_tensors_t* P, co
     if (d->cross_attention) {
         const float scale = 1.0f / sqrtf((float)d->qsize);
         if (do_head) {
-        INTEL_TRY(head_fuse_bwd(B, L, K, d_weights, d_ens, bt->scores, bt->session_len, w.dwv, w.dwp, s));
-        INTEL_TRY(linear_dw(B, K, D, w.dwv, K, w.all, D, G->head_w, D, G->head_b, s));
-        INTEL_TRY(linear_dw(B, K, du + dint, w.dwp, K, w.all + off_u, D, G->head_w + off_u, D, G->head_b, s));
-        INTEL_TRY(linear_dx(B, K, D, w.dwv, K, P->head_w, D, w.dall, D, s));
-        INTEL_TRY(linear_dx(B, K, du + dint, w.dwp, K, P->head_w + off_u, D, w.dall + off_u, D, s, 1));
+        if (head_full_ok(K, D)) {
+            INTEL_TRY(head_full_bwd(B, L, K, D, off_u, w.all, P->head_w, d_weights, d_ens, bt->scores, bt->session_len, w.dall,
+                                    G->head_w, G->head_b, s));
+        } else {
+            INTEL_TRY(head_fuse_bwd(B, L, K, d_weights, d_ens, bt->scores, bt->session_len, w.dwv, w.dwp, s));
+            INTEL_TRY(linear_dw(B, K, D, w.dwv, K, w.all, D, G->head_w, D, G->head_b, s));
+            INTEL_TRY(linear_dw(B, K, du + dint, w.dwp, K, w.all + off_u, D, G->head_w + off_u, D, G->head_b, s));
+            INTEL_TRY(linear_dx(B, K, D, w.dwv, K, P->head_w, D, w.dall, D, s));
+            INTEL_TRY(linear_dx(B, K, du + dint, w.dwp, K, P->head_w + off_u, D, w.dall + off_u, D, s, 1));
+        }
         // h_intent = relu(intent_embeddings(intent)): its gradient is the third column block of dcat
         const int dc = di + ds + dint;
         INTEL_TRY(relu_bwd(B, dint, w.dall + off_h, D, w.all + off_h, D, w.dcat + di + ds, dc, s));

@@ -97,6 +97,163 @@ int head_fuse_bwd(int64_t B, int64_t L, int K, const float* d_weights, const flo
     return check_launch("head_fuse_bwd", (double)B * L * (8.0 * K + 4.0 * K + 4.0), 2.0 * B * L * K);
 }
 
+// ---- weight head + fusion in one pass (IntEL.py:212-215): the head is nn.Linear(D, K) with K = model_num (2..4), far too
+// small for a GEMM launch of its own (six launches of 13..27 us each in round 2).  One warp per session: lanes own the head
+// inputs d = lane + 32 j, the K dot products of the valid rows (all D inputs) and of the pad rows (inputs >= off_u only: the
+// pooled cross-attention blocks are zero there) are warp sums; the backward kernel forms d(all) on the same lanes and keeps
+// the head's weight / bias gradient in registers across the sessions of a CTA (one flush per CTA).
+
+template <int KK, int DV>
+__global__ void __launch_bounds__(256) head_full_fwd_kernel(int64_t B, int64_t L, int D, int off_u, const float* __restrict__ all,
+                                                            const float* __restrict__ Wh, const float* __restrict__ bh,
+                                                            const double* __restrict__ scores, const int64_t* __restrict__ lens,
+                                                            float* __restrict__ weights, float* __restrict__ ens) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    float w[KK][DV];
+#pragma unroll
+    for (int k = 0; k < KK; ++k)
+#pragma unroll
+        for (int j = 0; j < DV; ++j) { const int d = lane + 32 * j; w[k][j] = d < D ? Wh[k * D + d] : 0.f; }
+    for (int64_t b = warp; b < B; b += nwarps) {
+        const int64_t n = lens[b];
+        float x[DV];
+#pragma unroll
+        for (int j = 0; j < DV; ++j) { const int d = lane + 32 * j; x[j] = d < D ? all[b * D + d] : 0.f; }
+        float wv[KK], wp[KK];
+#pragma unroll
+        for (int k = 0; k < KK; ++k) {
+            float av = 0.f, ap = 0.f;
+#pragma unroll
+            for (int j = 0; j < DV; ++j) {
+                const float t = x[j] * w[k][j];
+                av += t;
+                if (lane + 32 * j >= off_u) ap += t;
+            }
+            wv[k] = warp_sum(av) + bh[k];
+            wp[k] = warp_sum(ap) + bh[k];
+        }
+        for (int64_t l = lane; l < L; l += 32) {
+            const bool valid = l < n;
+            const double* xs = scores + (b * L + l) * KK;
+            float* wo = weights + (b * L + l) * KK;
+            float acc = 0.f;
+#pragma unroll
+            for (int k = 0; k < KK; ++k) {
+                const float wk = valid ? wv[k] : wp[k];
+                wo[k] = wk;
+                acc = fmaf(wk, (float)xs[k], acc);
+            }
+            ens[b * L + l] = acc;
+        }
+    }
+}
+
+template <int KK, int DV>
+__global__ void __launch_bounds__(256) head_full_bwd_kernel(int64_t B, int64_t L, int D, int off_u, const float* __restrict__ all,
+                                                            const float* __restrict__ Wh, const float* __restrict__ d_weights,
+                                                            const float* __restrict__ d_ens, const double* __restrict__ scores,
+                                                            const int64_t* __restrict__ lens, float* __restrict__ dall,
+                                                            float* __restrict__ gWh, float* __restrict__ gbh) {
+    __shared__ float red[8][KK * DV * 32 + KK];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    float w[KK][DV], gw[KK][DV], gb[KK];
+#pragma unroll
+    for (int k = 0; k < KK; ++k) {
+        gb[k] = 0.f;
+#pragma unroll
+        for (int j = 0; j < DV; ++j) { const int d = lane + 32 * j; w[k][j] = d < D ? Wh[k * D + d] : 0.f; gw[k][j] = 0.f; }
+    }
+    for (int64_t b = warp; b < B; b += nwarps) {
+        const int64_t n = lens[b];
+        float av[KK], ap[KK];
+#pragma unroll
+        for (int k = 0; k < KK; ++k) { av[k] = 0.f; ap[k] = 0.f; }
+        for (int64_t l = lane; l < L; l += 32) {
+            const bool valid = l < n;
+            const float ge = d_ens ? d_ens[b * L + l] : 0.f;
+#pragma unroll
+            for (int k = 0; k < KK; ++k) {
+                float g = ge * (float)scores[(b * L + l) * KK + k];
+                if (d_weights) g += d_weights[(b * L + l) * KK + k];
+                if (valid) av[k] += g; else ap[k] += g;
+            }
+        }
+        float x[DV], dx[DV];
+#pragma unroll
+        for (int j = 0; j < DV; ++j) { const int d = lane + 32 * j; x[j] = d < D ? all[b * D + d] : 0.f; dx[j] = 0.f; }
+#pragma unroll
+        for (int k = 0; k < KK; ++k) {
+            const float sv = warp_sum(av[k]), sp = warp_sum(ap[k]);     // d(w_valid[b,k]), d(w_pad[b,k])
+            gb[k] += sv + sp;
+#pragma unroll
+            for (int j = 0; j < DV; ++j) {
+                const float g = (lane + 32 * j >= off_u) ? sv + sp : sv;   // pad rows see the inputs >= off_u only
+                dx[j] = fmaf(g, w[k][j], dx[j]);
+                gw[k][j] = fmaf(g, x[j], gw[k][j]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < DV; ++j) { const int d = lane + 32 * j; if (d < D) dall[b * D + d] = dx[j]; }
+    }
+    // the CTA's share of the head gradients: warps -> shared memory -> one atomic per entry
+#pragma unroll
+    for (int k = 0; k < KK; ++k) {
+#pragma unroll
+        for (int j = 0; j < DV; ++j) red[wib][(k * DV + j) * 32 + lane] = gw[k][j];
+        if (lane == 0) red[wib][KK * DV * 32 + k] = gb[k];            // every lane holds the same warp sums
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < KK * DV * 32 + KK; e += blockDim.x) {
+        float t = 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) t += red[q][e];
+        if (e < KK * DV * 32) {
+            const int k = e / (DV * 32), j = (e / 32) % DV, d = (e & 31) + 32 * j;
+            if (d < D) atomicAdd(gWh + k * D + d, t);
+        } else {
+            atomicAdd(gbh + (e - KK * DV * 32), t);
+        }
+    }
+}
+
+#define HEAD_DISPATCH(CALL)                                         \
+    do {                                                            \
+        const int dv = (D + 31) / 32;                               \
+        if (K == 2 && dv <= 4) { CALL(2, 4); }                      \
+        else if (K == 2 && dv <= 8) { CALL(2, 8); }                 \
+        else if (K == 3 && dv <= 4) { CALL(3, 4); }                 \
+        else if (K == 3 && dv <= 8) { CALL(3, 8); }                 \
+        else if (K == 4 && dv <= 4) { CALL(4, 4); }                 \
+        else if (K == 4 && dv <= 8) { CALL(4, 8); }                 \
+        else return INTEL_ERR_UNSUPPORTED;                          \
+    } while (0)
+
+bool head_full_ok(int K, int D) { return (K >= 2 && K <= 4) && D >= 1 && D <= 256; }
+
+int head_full_fwd(int64_t B, int64_t L, int K, int D, int off_u, const float* all, const float* Wh, const float* bh,
+                  const double* scores, const int64_t* lens, float* weights, float* ens, cudaStream_t s) {
+    if (B <= 0) return INTEL_OK;
+    unsigned grid = stream_grid(ceil_div(B, 8), 4);
+#define HEAD_FWD(KK, DV) LAUNCH((head_full_fwd_kernel<KK, DV>), dim3(grid), dim3(256), 0, s, B, L, D, off_u, all, Wh, bh, scores, lens, weights, ens)
+    HEAD_DISPATCH(HEAD_FWD);
+#undef HEAD_FWD
+    return check_launch("head_fuse_fwd", (double)B * (L * (8.0 * K + 4.0 * K + 4.0) + 4.0 * D), 2.0 * B * (L * K + 2.0 * D * K));
+}
+
+int head_full_bwd(int64_t B, int64_t L, int K, int D, int off_u, const float* all, const float* Wh, const float* d_weights,
+                  const float* d_ens, const double* scores, const int64_t* lens, float* dall, float* gWh, float* gbh, cudaStream_t s) {
+    if (B <= 0) return INTEL_OK;
+    unsigned grid = stream_grid(ceil_div(B, 8), 2);
+#define HEAD_BWD(KK, DV) LAUNCH((head_full_bwd_kernel<KK, DV>), dim3(grid), dim3(256), 0, s, B, L, D, off_u, all, Wh, d_weights, d_ens, scores, lens, dall, gWh, gbh)
+    HEAD_DISPATCH(HEAD_BWD);
+#undef HEAD_BWD
+    return check_launch("head_fuse_bwd", (double)B * (L * (8.0 * K + 4.0 * K + 4.0) + 8.0 * D), 2.0 * B * (L * K + 4.0 * D * K));
+}
+
 // ---- per-item fusion: ens[r] = sum_k weights[r,k] * float(scores[r,k]) (fixed-weight baselines and
 //      the cross_attention=0 branch) ----
 __global__ void __launch_bounds__(256) item_fuse_fwd_kernel(int64_t R, int K, const float* __restrict__ weights,

@@ -217,6 +217,13 @@ int head_fuse_fwd(int64_t B, int64_t L, int K, const float* w_valid, const float
 // dw_valid[b,k] = sum_{l<n} g, dw_pad[b,k] = sum_{l>=n} g with g = d_weights[b,l,k] + d_ens[b,l] x[b,l,k]
 int head_fuse_bwd(int64_t B, int64_t L, int K, const float* d_weights, const float* d_ens, const double* scores,
                   const int64_t* lens, float* dw_valid, float* dw_pad, cudaStream_t s);
+// the head's nn.Linear(D, K) folded into the two kernels above (K = 2..4, D <= 256): all [B, D] = head input of the valid rows,
+// pad rows see the inputs >= off_u only; the backward call writes d(all) [B, D] and accumulates the head's weight / bias gradient
+bool head_full_ok(int K, int D);
+int head_full_fwd(int64_t B, int64_t L, int K, int D, int off_u, const float* all, const float* Wh, const float* bh,
+                  const double* scores, const int64_t* lens, float* weights, float* ens, cudaStream_t s);
+int head_full_bwd(int64_t B, int64_t L, int K, int D, int off_u, const float* all, const float* Wh, const float* d_weights,
+                  const float* d_ens, const double* scores, const int64_t* lens, float* dall, float* gWh, float* gbh, cudaStream_t s);
 // per-item variant (cross_attention = 0): ens[b,l] = sum_k weights[b,l,k] x ; g[b,l,k] as above
 int item_fuse_fwd(int64_t R, int K, const float* weights, const double* scores, float* ens, cudaStream_t s);
 int item_fuse_bwd(int64_t R, int K, const float* d_weights, const float* d_ens, const double* scores, float* g,
