@@ -499,14 +499,22 @@ int intel_ensemble_fwd(const intel_dims_t* d, const intel_tensors_t* P, const in
             Wc = w.Wcat;
         }
         INTEL_TRY(linear(B, dc, I, intents, I, Wc, I, nullptr, w.qcat, dc, s));
-        // item stream
-        INTEL_TRY(linear_dx(B, di, di, w.q_i, dc, P->xk_item, di, w.qk_i, di, s));            // qk = W_k^T q
-        INTEL_TRY(cross_pool_fwd(B, L, di, Xi, w.qk_i, bt->session_len, scale, w.p_i, w.xbar_i, s));
-        INTEL_TRY(linear(B, di, di, w.xbar_i, di, P->xv_item, di, nullptr, w.all, D, s));
-        // score stream
-        INTEL_TRY(linear_dx(B, ds, ds, w.q_s, dc, P->xk_score, ds, w.qk_s, ds, s));
-        INTEL_TRY(cross_pool_fwd(B, L, ds, Xs, w.qk_s, bt->session_len, scale, w.p_s, w.xbar_s, s));
-        INTEL_TRY(linear(B, ds, ds, w.xbar_s, ds, P->xv_score, ds, nullptr, w.all + di, D, s));
+        // item stream, score stream: qk = W_k^T q, the pooling, the value projection into the head input
+        if (cross_full_ok(di, L)) {
+            INTEL_TRY(cross_full_fwd(B, L, Xi, w.q_i, dc, P->xk_item, P->xv_item, bt->session_len, scale, w.p_i, w.qk_i, w.xbar_i, w.all, D, s));
+        } else {
+            INTEL_TRY(linear_dx(B, di, di, w.q_i, dc, P->xk_item, di, w.qk_i, di, s));            // qk = W_k^T q
+            INTEL_TRY(cross_pool_fwd(B, L, di, Xi, w.qk_i, bt->session_len, scale, w.p_i, w.xbar_i, s));
+            INTEL_TRY(linear(B, di, di, w.xbar_i, di, P->xv_item, di, nullptr, w.all, D, s));
+        }
+        if (cross_full_ok(ds, L)) {
+            INTEL_TRY(cross_full_fwd(B, L, Xs, w.q_s, dc, P->xk_score, P->xv_score, bt->session_len, scale, w.p_s, w.qk_s, w.xbar_s,
+                                     w.all + di, D, s));
+        } else {
+            INTEL_TRY(linear_dx(B, ds, ds, w.q_s, dc, P->xk_score, ds, w.qk_s, ds, s));
+            INTEL_TRY(cross_pool_fwd(B, L, ds, Xs, w.qk_s, bt->session_len, scale, w.p_s, w.xbar_s, s));
+            INTEL_TRY(linear(B, ds, ds, w.xbar_s, ds, P->xv_score, ds, nullptr, w.all + di, D, s));
+        }
         // user + intent parts of the head input
         INTEL_TRY(gather_rows(B, du, P->uid_emb, bt->u_id, w.all + off_u, D, 1, s, d->user_rows));
         INTEL_TRY(bias_relu_rows(B, dint, w.qcat + di + ds, dc, P->intent_b, w.all + off_h, D, s));
@@ -588,11 +596,16 @@ int intel_ensemble_bwd_phase(const intel_dims_t* d, const intel_tensors_t* P, co
                         *xv = st == 0 ? P->xv_item : P->xv_score;
             float *gxq = st == 0 ? G->xq_item : G->xq_score, *gxk = st == 0 ? G->xk_item : G->xk_score,
                   *gxv = st == 0 ? G->xv_item : G->xv_score;
-            INTEL_TRY(linear_dw(B, dd, dd, w.dall + off, D, xbar, dd, gxv, dd, nullptr, s));
-            INTEL_TRY(linear_dx(B, dd, dd, w.dall + off, D, xv, dd, w.dxbar, dd, s));
-            INTEL_TRY(cross_pool_bwd(B, L, dd, X, qk, bt->session_len, scale, p, w.dxbar, dXst[st], w.dqk, s));
-            INTEL_TRY(linear_dw(B, dd, dd, q, dc, w.dqk, dd, gxk, dd, nullptr, s));            // dW_k[a,c] = sum q_a dqk_c
-            INTEL_TRY(linear(B, dd, dd, w.dqk, dd, xk, dd, nullptr, w.dcat + off, dc, s));      // dq = W_k dqk -> its block of dcat
+            if (cross_full_ok(dd, L)) {
+                INTEL_TRY(cross_full_bwd(B, L, X, q, dc, qk, xk, xv, bt->session_len, scale, p, xbar, w.dall + off, D, dXst[st],
+                                         w.dcat + off, dc, gxk, gxv, s));
+            } else {
+                INTEL_TRY(linear_dw(B, dd, dd, w.dall + off, D, xbar, dd, gxv, dd, nullptr, s));
+                INTEL_TRY(linear_dx(B, dd, dd, w.dall + off, D, xv, dd, w.dxbar, dd, s));
+                INTEL_TRY(cross_pool_bwd(B, L, dd, X, qk, bt->session_len, scale, p, w.dxbar, dXst[st], w.dqk, s));
+                INTEL_TRY(linear_dw(B, dd, dd, q, dc, w.dqk, dd, gxk, dd, nullptr, s));            // dW_k[a,c] = sum q_a dqk_c
+                INTEL_TRY(linear(B, dd, dd, w.dqk, dd, xk, dd, nullptr, w.dcat + off, dc, s));      // dq = W_k dqk -> its block of dcat
+            }
             (void)xq; (void)gxq;
         }
         // the three products against the predicted intents as one: d_intents = dcat Wcat, dWcat += dcat^T intents

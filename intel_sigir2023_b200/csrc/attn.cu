@@ -310,6 +310,216 @@ int cross_pool_bwd(int64_t B, int64_t L, int d, const float* X, const float* qk,
 }
 
 // ------------------------------------------------------------------------------------------------
+// The pooled cross attention of a width-32 stream with its three 32 x 32 projections folded in (CrossAtt / MultiQueryAtt,
+// attention.py:54-63, 149-161): qk = W_k^T q before the pooling, out = W_v xbar after it; the backward kernel returns
+// d(q) and keeps d(W_k), d(W_v) in registers across the sessions of a warp (lane c owns column c of both).  In round 2 these
+// were twelve [4096 x 32 x 32] GEMM launches per step around the two pooling kernels.  One warp per session, persistent CTAs;
+// the 32-vector-by-matrix products broadcast the vector with shuffles, the matrices sit in shared memory ([32][33]).
+static const int XF_WARPS = 4;
+
+__global__ void __launch_bounds__(XF_WARPS * 32) cross_full_fwd_kernel(int64_t B, int64_t L, const float* __restrict__ X,
+                                                                       const float* __restrict__ q, int64_t ldq,
+                                                                       const float* __restrict__ Wk, const float* __restrict__ Wv,
+                                                                       const int64_t* __restrict__ lens, float scale,
+                                                                       float* __restrict__ p, float* __restrict__ qk_out,
+                                                                       float* __restrict__ xbar_out, float* __restrict__ out, int64_t ldo) {
+    DYN_SMEM(float, sm);
+    constexpr int d = 32;
+    float* Wk_s = sm;                        // [a][c] stride 33
+    float* Wv_s = Wk_s + 32 * 33;            // [e][c]
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    float* vec = Wv_s + 32 * 33 + w * 32;    // the warp's qk
+    float* pb = Wv_s + 32 * 33 + XF_WARPS * 32 + w * L;
+    for (int e = threadIdx.x; e < 32 * 32; e += blockDim.x) {
+        Wk_s[(e >> 5) * 33 + (e & 31)] = Wk[e];
+        Wv_s[(e >> 5) * 33 + (e & 31)] = Wv[e];
+    }
+    __syncthreads();
+    const int64_t nwarps = (int64_t)gridDim.x * XF_WARPS;
+    for (int64_t b = (int64_t)blockIdx.x * XF_WARPS + w; b < B; b += nwarps) {
+        int64_t n = lens[b];
+        if (n > L) n = L;
+        const float* x = X + b * L * d;
+        // qk[c] = sum_a q[a] W_k[a][c]
+        const float qa = q[b * ldq + lane];
+        float qkc = 0.f;
+#pragma unroll
+        for (int a = 0; a < 32; ++a) qkc = fmaf(__shfl_sync(0xffffffffu, qa, a), Wk_s[a * 33 + lane], qkc);
+        qk_out[b * d + lane] = qkc;
+        vec[lane] = qkc;
+        __syncwarp();
+        float mx = -INFINITY;
+        {
+            const int sub = lane & 7, rr = lane >> 3;           // 8 lanes per row, 4 rows per pass
+            const float4 qv = *reinterpret_cast<const float4*>(vec + 4 * sub);
+            for (int64_t j0 = 0; j0 < L; j0 += 4) {
+                const int64_t j = j0 + rr;
+                float a = 0.f;
+                if (j < L) {
+                    const float4 xv = *reinterpret_cast<const float4*>(x + j * d + 4 * sub);
+                    a = fmaf(xv.x, qv.x, fmaf(xv.y, qv.y, fmaf(xv.z, qv.z, xv.w * qv.w)));
+                }
+                a += __shfl_xor_sync(0xffffffffu, a, 4);
+                a += __shfl_xor_sync(0xffffffffu, a, 2);
+                a += __shfl_xor_sync(0xffffffffu, a, 1);
+                a *= scale;
+                if (j < L) {
+                    if (sub == 0) pb[j] = a;
+                    if (j < n) mx = fmaxf(mx, a);
+                }
+            }
+            __syncwarp();
+        }
+        mx = warp_max(mx);                   // shift by the largest VALID logit (see cross_pool_fwd_kernel)
+        float sum = 0.f;
+        for (int64_t j = lane; j < L; j += 32) {
+            const float e = (j < n) ? expf(pb[j] - mx) : 0.f;
+            pb[j] = e;
+            sum += e;
+        }
+        sum = warp_sum(sum);
+        const float inv = (sum > 0.f) ? 1.0f / sum : 0.f;
+        for (int64_t j = lane; j < L; j += 32) { pb[j] *= inv; p[b * L + j] = pb[j]; }
+        __syncwarp();
+        float xb = 0.f;
+        for (int64_t j = 0; j < n; ++j) xb = fmaf(pb[j], x[j * d + lane], xb);
+        xbar_out[b * d + lane] = xb;
+        // out[e] = sum_c W_v[e][c] xbar[c]
+        float oe = 0.f;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) oe = fmaf(__shfl_sync(0xffffffffu, xb, c), Wv_s[lane * 33 + c], oe);
+        out[b * ldo + lane] = oe;
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(XF_WARPS * 32) cross_full_bwd_kernel(int64_t B, int64_t L, const float* __restrict__ X,
+                                                                       const float* __restrict__ q, int64_t ldq,
+                                                                       const float* __restrict__ qk, const float* __restrict__ Wk,
+                                                                       const float* __restrict__ Wv, const int64_t* __restrict__ lens,
+                                                                       float scale, const float* __restrict__ p,
+                                                                       const float* __restrict__ xbar, const float* __restrict__ dout,
+                                                                       int64_t ldd, float* __restrict__ dX, float* __restrict__ dq_out,
+                                                                       int64_t lddq, float* __restrict__ gWk, float* __restrict__ gWv) {
+    DYN_SMEM(float, sm);
+    constexpr int d = 32;
+    float* Wk_s = sm;
+    float* Wv_s = Wk_s + 32 * 33;
+    float* gk_s = Wv_s + 32 * 33;            // the CTA's gradient sums [a][c], [e][c]
+    float* gv_s = gk_s + 32 * 33;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    float* vec = gv_s + 32 * 33 + w * 32;    // the warp's d(xbar)
+    float* ab = gv_s + 32 * 33 + XF_WARPS * 32 + w * L;
+    for (int e = threadIdx.x; e < 32 * 32; e += blockDim.x) {
+        Wk_s[(e >> 5) * 33 + (e & 31)] = Wk[e];
+        Wv_s[(e >> 5) * 33 + (e & 31)] = Wv[e];
+        gk_s[(e >> 5) * 33 + (e & 31)] = 0.f;
+        gv_s[(e >> 5) * 33 + (e & 31)] = 0.f;
+    }
+    __syncthreads();
+    float gk[32], gv[32];                    // lane c: d W_k[a][c], d W_v[e][c]
+#pragma unroll
+    for (int i = 0; i < 32; ++i) { gk[i] = 0.f; gv[i] = 0.f; }
+    const int64_t nwarps = (int64_t)gridDim.x * XF_WARPS;
+    for (int64_t b = (int64_t)blockIdx.x * XF_WARPS + w; b < B; b += nwarps) {
+        int64_t n = lens[b];
+        if (n > L) n = L;
+        const float* x = X + b * L * d;
+        const float ge = dout[b * ldd + lane];
+        const float xbc = xbar[b * d + lane];
+        // d(xbar)[c] = sum_e dout[e] W_v[e][c];  d W_v[e][c] += dout[e] xbar[c]
+        float dxb = 0.f;
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+            const float g = __shfl_sync(0xffffffffu, ge, e);
+            dxb = fmaf(g, Wv_s[e * 33 + lane], dxb);
+            gv[e] = fmaf(g, xbc, gv[e]);
+        }
+        vec[lane] = dxb;
+        __syncwarp();
+        float delta = 0.f;
+        {
+            const int sub = lane & 7, rr = lane >> 3;
+            const float4 g4 = *reinterpret_cast<const float4*>(vec + 4 * sub);
+            for (int64_t j0 = 0; j0 < n; j0 += 4) {
+                const int64_t j = j0 + rr;
+                float a = 0.f;
+                if (j < n) {
+                    const float4 xv = *reinterpret_cast<const float4*>(x + j * d + 4 * sub);
+                    a = fmaf(xv.x, g4.x, fmaf(xv.y, g4.y, fmaf(xv.z, g4.z, xv.w * g4.w)));
+                }
+                a += __shfl_xor_sync(0xffffffffu, a, 4);
+                a += __shfl_xor_sync(0xffffffffu, a, 2);
+                a += __shfl_xor_sync(0xffffffffu, a, 1);
+                if (j < n && sub == 0) {
+                    ab[j] = a;                            // dp_j
+                    delta = fmaf(p[b * L + j], a, delta);
+                }
+            }
+            __syncwarp();
+        }
+        delta = warp_sum(delta);
+        for (int64_t j = lane; j < n; j += 32) ab[j] = p[b * L + j] * (ab[j] - delta) * scale;   // datt_j * scale
+        __syncwarp();
+        const float qc = qk[b * d + lane];
+        float dqk = 0.f;
+        for (int64_t j = 0; j < L; ++j) {
+            float v = 0.f;
+            if (j < n) {
+                v = fmaf(p[b * L + j], dxb, ab[j] * qc);
+                dqk = fmaf(ab[j], x[j * d + lane], dqk);
+            }
+            dX[(b * L + j) * d + lane] = v;
+        }
+        // d W_k[a][c] += q[a] dqk[c];  d(q)[a] = sum_c W_k[a][c] dqk[c]
+        const float qa = q[b * ldq + lane];
+        float dqa = 0.f;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            gk[i] = fmaf(__shfl_sync(0xffffffffu, qa, i), dqk, gk[i]);
+            dqa = fmaf(__shfl_sync(0xffffffffu, dqk, i), Wk_s[lane * 33 + i], dqa);
+        }
+        dq_out[b * lddq + lane] = dqa;
+        __syncwarp();
+    }
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        atomicAdd(&gk_s[i * 33 + lane], gk[i]);
+        atomicAdd(&gv_s[i * 33 + lane], gv[i]);
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < 32 * 32; e += blockDim.x) {
+        atomicAdd(gWk + e, gk_s[(e >> 5) * 33 + (e & 31)]);
+        atomicAdd(gWv + e, gv_s[(e >> 5) * 33 + (e & 31)]);
+    }
+}
+
+bool cross_full_ok(int d, int64_t L) { return d == 32 && L >= 1 && L <= 2048; }
+
+int cross_full_fwd(int64_t B, int64_t L, const float* X, const float* q, int64_t ldq, const float* Wk, const float* Wv,
+                   const int64_t* lens, float scale, float* p, float* qk_out, float* xbar_out, float* out, int64_t ldo, cudaStream_t s) {
+    if (B <= 0) return INTEL_OK;
+    const size_t smem = (size_t)(2 * 32 * 33 + XF_WARPS * 32 + XF_WARPS * L) * 4;
+    ensure_smem(cross_full_fwd_kernel, smem);
+    const unsigned grid = stream_grid(ceil_div(B, XF_WARPS), 8);
+    LAUNCH(cross_full_fwd_kernel, dim3(grid), dim3(XF_WARPS * 32), smem, s, B, L, X, q, ldq, Wk, Wv, lens, scale, p, qk_out, xbar_out,
+           out, ldo);
+    return check_launch("cross_pool_fwd", 4.0 * B * L * (32 + 1), 4.0 * B * L * 32);
+}
+
+int cross_full_bwd(int64_t B, int64_t L, const float* X, const float* q, int64_t ldq, const float* qk, const float* Wk, const float* Wv,
+                   const int64_t* lens, float scale, const float* p, const float* xbar, const float* dout, int64_t ldd, float* dX,
+                   float* dq_out, int64_t lddq, float* gWk, float* gWv, cudaStream_t s) {
+    if (B <= 0) return INTEL_OK;
+    const size_t smem = (size_t)(4 * 32 * 33 + XF_WARPS * 32 + XF_WARPS * L) * 4;
+    ensure_smem(cross_full_bwd_kernel, smem);
+    const unsigned grid = stream_grid(ceil_div(B, XF_WARPS), 2);      // few CTAs: each ends with 2 x 1024 global atomics
+    LAUNCH(cross_full_bwd_kernel, dim3(grid), dim3(XF_WARPS * 32), smem, s, B, L, X, q, ldq, qk, Wk, Wv, lens, scale, p, xbar, dout, ldd,
+           dX, dq_out, lddq, gWk, gWv);
+    return check_launch("cross_pool_bwd", 4.0 * B * L * (2 * 32 + 1), 8.0 * B * L * 32);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Row softmax (pred_layer(...).softmax, IntEL.py:153) and its backward; one warp per row.
 // ldz: row stride of Z (the logits workspace pads its rows to a multiple of four floats so that the GEMM that writes it and
 // the two that read its gradient move 16-byte vectors although N = intent_num is odd); P is dense [R, N].

@@ -111,6 +111,14 @@ int mha_bwd(int64_t B, int64_t T, int d, int heads, const float* QKV, const int6
             float* dQKV, cudaStream_t s);
 // Pooled cross attention (attention.py:54-63 collapsed): att_j = scale * X[b,j].qk[b],
 // shift by the max over all L slots, softmax over j < n_b, xbar = sum_j p_j X[b,j].
+// width-32 streams: the pooling with q -> qk = W_k^T q in front and xbar -> W_v xbar behind it in one kernel; the backward
+// kernel returns d(q) and accumulates d(W_k), d(W_v)
+bool cross_full_ok(int d, int64_t L);
+int cross_full_fwd(int64_t B, int64_t L, const float* X, const float* q, int64_t ldq, const float* Wk, const float* Wv,
+                   const int64_t* lens, float scale, float* p, float* qk_out, float* xbar_out, float* out, int64_t ldo, cudaStream_t s);
+int cross_full_bwd(int64_t B, int64_t L, const float* X, const float* q, int64_t ldq, const float* qk, const float* Wk, const float* Wv,
+                   const int64_t* lens, float scale, const float* p, const float* xbar, const float* dout, int64_t ldd, float* dX,
+                   float* dq_out, int64_t lddq, float* gWk, float* gWv, cudaStream_t s);
 int cross_pool_fwd(int64_t B, int64_t L, int d, const float* X, const float* qk, const int64_t* lens,
                    float scale, float* p, float* xbar, cudaStream_t s);
 // dX[b,j] (=) p_j dxbar + scale datt_j qk ; dqk[b] = scale sum_j datt_j X[b,j]
