@@ -321,6 +321,21 @@ int gru_fwd_pair(const intel_dims_t* d, const intel_encoder_t* const (&p)[2], En
     const int64_t B = d->B;
     const int h = d->gru_hidden;
     bool fused = h == 128 && gru_tc_supported(h);
+    {   // live rows and length order of both encoders: one launch
+        int64_t Bs[2], Ts[2];
+        const int64_t* ls[2];
+        int32_t *rt[2], *rt1[2], *cn[2], *od[2];
+        for (int i = 0; i < 2; ++i) {
+            GruWs& w = e[i]->gru;
+            Bs[i] = B; Ts[i] = e[i]->T; ls[i] = lens[i];
+            const bool packed = B * (Ts[i] + 1) < (1LL << 31);
+            rt[i] = packed ? w.rows_t : nullptr; rt1[i] = packed ? w.rows_t1 : nullptr; cn[i] = packed ? w.nlive : nullptr;
+            w.sorted = Ts[i] <= 63;
+            od[i] = w.sorted ? w.order : nullptr;
+            fused = fused && w.sorted;
+        }
+        INTEL_TRY(gru_prep(2, Bs, Ts, ls, rt, rt1, cn, od, s));
+    }
     for (int i = 0; i < 2; ++i) {
         const int64_t T = e[i]->T, R = B * T;
         const int dd = e[i]->d;
@@ -329,13 +344,8 @@ int gru_fwd_pair(const intel_dims_t* d, const intel_encoder_t* const (&p)[2], En
         // session's length; the reference packs the sequences: GeneralSeq.py:64-71).  gi rows of padding slots stay
         // unwritten: nobody reads them.
         const bool packed = B * (T + 1) < (1LL << 31);
-        if (packed) INTEL_TRY(gru_live_rows(B, T, lens[i], w.rows_t, w.rows_t1, w.nlive, s));
         INTEL_TRY(linear(R, 3 * h, dd, e[i]->seq, dd, p[i]->w_ih, dd, p[i]->b_ih, w.gi, 3 * h, s, false, false, nullptr, 0,
                          packed ? w.rows_t : nullptr, packed ? w.nlive : nullptr));
-        // sessions by decreasing length: tiles of equally long sessions stop at their own last step (forward and backward)
-        w.sorted = T <= 63;
-        if (w.sorted) INTEL_TRY(gru_order_by_len(B, T, lens[i], w.order, s));
-        fused = fused && w.sorted;
         if (h == 128) {
             // the fused kernels write h_all[:, 1..T] of every session themselves: only the initial state h_0 needs clearing
             // (2 MB instead of a 44 MB memset per encoder and step)

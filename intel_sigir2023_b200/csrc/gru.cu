@@ -252,13 +252,13 @@ int gru_seq_fwd(int64_t B, int64_t T, int h, const int64_t* lens, const float* g
 
 // Row numbers of the live (session, step) pairs of a padded [B, T] history, in (b, t) order.  Block k owns sessions
 // [1024 k, 1024 k + 1024): it sums the lengths before them, scans its own and writes its rows; the last block writes the count.
-__global__ void __launch_bounds__(1024) gru_live_rows_kernel(int64_t B, int T, const int64_t* __restrict__ lens, int32_t* __restrict__ rows_t,
-                                                             int32_t* __restrict__ rows_t1, int32_t* __restrict__ count) {
+__device__ void gru_live_rows_body(int blk, int nblk, int64_t B, int T, const int64_t* __restrict__ lens, int32_t* __restrict__ rows_t,
+                                   int32_t* __restrict__ rows_t1, int32_t* __restrict__ count) {
     __shared__ int warp_tot[32];
     __shared__ int base_s;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     auto len_of = [&](int64_t e) { const int64_t v = lens[e]; return (int)(v < 0 ? 0 : (v > T ? T : v)); };
-    const int64_t first = (int64_t)blockIdx.x * 1024;
+    const int64_t first = (int64_t)blk * 1024;
     // lengths before this block
     int part = 0;
     for (int64_t e = tid; e < first; e += 1024) part += len_of(e);
@@ -296,26 +296,26 @@ __global__ void __launch_bounds__(1024) gru_live_rows_kernel(int64_t B, int T, c
             rows_t1[o + t] = (int32_t)(bb * (T + 1) + t);
         }
     }
-    if (blockIdx.x == gridDim.x - 1 && tid == 1023) *count = off + n;
+    if (blk == nblk - 1 && tid == 1023) *count = off + n;
 }
-int gru_live_rows(int64_t B, int64_t T, const int64_t* lens, int32_t* rows_t, int32_t* rows_t1, int32_t* count, cudaStream_t s) {
-    if (B <= 0) return INTEL_OK;
-    INTEL_REQUIRE(B * (T + 1) < (1LL << 31), INTEL_ERR_UNSUPPORTED, "gru_live_rows: more than 2^31 history rows");
-    LAUNCH(gru_live_rows_kernel, dim3((unsigned)ceil_div(B, 1024)), dim3(1024), 0, s, B, (int)T, lens, rows_t, rows_t1, count);
-    return check_launch("gru_live_rows");
-}
-
 // Sessions in order of decreasing length (stable), the way pack_padded_sequence orders them (GeneralSeq.py:64-71): a tile
 // of consecutive sessions of that order then shares one loop bound, and tiles that end early make room for the next ones.
 // One block; a chunk of 1024 sessions per pass, rank inside a chunk from warp ballots, so the order is deterministic.
-__global__ void __launch_bounds__(1024) gru_order_kernel(int64_t B, int T, const int64_t* __restrict__ lens, int32_t* __restrict__ order) {
+__device__ void gru_order_body(int64_t B, int T, const int64_t* __restrict__ lens, int32_t* __restrict__ order) {
     __shared__ int cnt[64], start[64], run[64], wcnt[32][64];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid < 64) { cnt[tid] = 0; run[tid] = 0; }
     if (tid == 0) order[B] = 0;              // tile counter of the backward recurrence, kept behind the B entries
     __syncthreads();
     auto key = [&](int64_t e) { const int64_t v = lens[e]; return (int)(v < 0 ? 0 : (v > T ? T : v)); };
-    for (int64_t e = tid; e < B; e += 1024) atomicAdd(&cnt[key(e)], 1);
+    for (int64_t c0 = 0; c0 < B; c0 += 1024) {           // histogram: one shared-memory atomic per warp and length
+        const int64_t e = c0 + tid;
+        const int v = e < B ? key(e) : -1;
+        for (int u = 0; u <= T; ++u) {
+            const unsigned m = __ballot_sync(0xffffffffu, v == u);
+            if (lane == 0 && m) atomicAdd(&cnt[u], __popc(m));
+        }
+    }
     __syncthreads();
     if (tid == 0) {
         int acc = 0;
@@ -346,11 +346,47 @@ __global__ void __launch_bounds__(1024) gru_order_kernel(int64_t B, int T, const
         __syncthreads();
     }
 }
+// One launch prepares both encoders: blocks [0, nb) of row y list the live rows of encoder y, block nb sorts its sessions.
+struct GruPrepArgs {
+    struct One { int64_t B; int T; const int64_t* lens; int32_t *rows_t, *rows_t1, *count, *order; } e[2];
+    int n;
+};
+__global__ void __launch_bounds__(1024) gru_prep_kernel(GruPrepArgs a) {
+    const GruPrepArgs::One& E = a.e[blockIdx.y];
+    const int nb = (int)((E.B + 1023) / 1024);
+    if ((int)blockIdx.x < nb) {
+        if (E.rows_t) gru_live_rows_body((int)blockIdx.x, nb, E.B, E.T, E.lens, E.rows_t, E.rows_t1, E.count);
+    } else if ((int)blockIdx.x == nb) {
+        if (E.order) gru_order_body(E.B, E.T, E.lens, E.order);
+    }
+}
+int gru_prep(int n, const int64_t* B, const int64_t* T, const int64_t* const* lens, int32_t* const* rows_t, int32_t* const* rows_t1,
+             int32_t* const* count, int32_t* const* order, cudaStream_t s) {
+    GruPrepArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n = n;
+    int64_t nb = 0;
+    for (int i = 0; i < n; ++i) {
+        INTEL_REQUIRE(B[i] * (T[i] + 1) < (1LL << 31) || !rows_t[i], INTEL_ERR_UNSUPPORTED, "gru_prep: more than 2^31 history rows");
+        INTEL_REQUIRE(!order[i] || (T[i] >= 1 && T[i] <= 63), INTEL_ERR_UNSUPPORTED, "gru_prep: sorting needs T in [1, 63]");
+        a.e[i].B = B[i]; a.e[i].T = (int)T[i]; a.e[i].lens = lens[i];
+        a.e[i].rows_t = rows_t[i]; a.e[i].rows_t1 = rows_t1[i]; a.e[i].count = count[i]; a.e[i].order = order[i];
+        const int64_t x = ceil_div(B[i], 1024);
+        nb = x > nb ? x : nb;
+    }
+    if (n <= 0 || nb <= 0) return INTEL_OK;
+    LAUNCH(gru_prep_kernel, dim3((unsigned)(nb + 1), (unsigned)n), dim3(1024), 0, s, a);
+    return check_launch("gru_prep");
+}
+int gru_live_rows(int64_t B, int64_t T, const int64_t* lens, int32_t* rows_t, int32_t* rows_t1, int32_t* count, cudaStream_t s) {
+    if (B <= 0) return INTEL_OK;
+    int32_t* none = nullptr;
+    return gru_prep(1, &B, &T, &lens, &rows_t, &rows_t1, &count, &none, s);
+}
 int gru_order_by_len(int64_t B, int64_t T, const int64_t* lens, int32_t* order, cudaStream_t s) {
     if (B <= 0) return INTEL_OK;
-    INTEL_REQUIRE(T >= 1 && T <= 63 && B < (1LL << 31), INTEL_ERR_UNSUPPORTED, "gru_order_by_len: T must be in [1, 63]");
-    LAUNCH(gru_order_kernel, dim3(1), dim3(1024), 0, s, B, (int)T, lens, order);
-    return check_launch("gru_order");
+    int32_t* none = nullptr;
+    return gru_prep(1, &B, &T, &lens, &none, &none, &none, &order, s);
 }
 
 // Backward recurrence.  dh [B,128] holds d(loss)/d h_T on entry.  Writes dgi [B,T,384] and

@@ -169,6 +169,9 @@ int gru_order_by_len(int64_t B, int64_t T, const int64_t* lens, int32_t* order, 
 // the live (session, step) pairs of a padded [B, T] history as row numbers, in (b, t) order: rows_t[i] = b T + t into the
 // [B, T, .] tensors, rows_t1[i] = b (T + 1) + t into the [B, T + 1, .] ones; *count = sum of the (clamped) lengths
 int gru_live_rows(int64_t B, int64_t T, const int64_t* lens, int32_t* rows_t, int32_t* rows_t1, int32_t* count, cudaStream_t s);
+// both of the above for up to two encoders in one launch (null pointers skip a part)
+int gru_prep(int n, const int64_t* B, const int64_t* T, const int64_t* const* lens, int32_t* const* rows_t, int32_t* const* rows_t1,
+             int32_t* const* count, int32_t* const* order, cudaStream_t s);
 
 // ---- trunk.cu: fused self-attention stack (d = 32, L <= 64): all layers of a session on chip -----
 struct StackParams { const float *wq, *wk, *wv, *w1, *b1, *w2, *b2, *lnw, *lnb; };
