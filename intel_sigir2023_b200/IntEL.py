@@ -166,22 +166,23 @@ class _IntelFn(torch.autograd.Function):
 
         # order of the pass: head + cross attentions (the gradient w.r.t. the predicted intents is final) ->
         # intent predictor -> item stack + embedding rows -> [every gradient but the score stream's is final] -> score stack
+        single = getattr(model, "_single_call_backward", False)       # test hook: intel_ensemble_bwd in one call
         if have_ens:
             d_int_ens = torch.empty_like(intents)
             dw = d_weights.contiguous() if d_weights is not None else None
             de = d_ens.contiguous() if d_ens is not None else None
-            ens_bwd(_lib.ENS_BWD_HEAD)
+            ens_bwd(_lib.ENS_BWD_HEAD | _lib.ENS_BWD_ITEM | _lib.ENS_BWD_SCORE if single else _lib.ENS_BWD_HEAD)
         first = d_intents.contiguous() if d_intents is not None else d_int_ens
         extra = d_int_ens if d_intents is not None else None
         if first is not None:
             _lib.check(lib.intel_intent_bwd(dims, P, bt, _lib.ptr(intents), _lib.ptr(first), _lib.ptr(extra), G,
                                             _lib.ptr(ctx.ws_int), ctx.ws_int.numel(), stream))
-        if have_ens:
+        if have_ens and not single:
             ens_bwd(_lib.ENS_BWD_ITEM)
         early = getattr(model, "_early_reduce", None)
-        if early is not None:
+        if early is not None and not single:
             early(flat, late)            # asynchronous: runs beside the score stack below
-        if have_ens:
+        if have_ens and not single:
             ens_bwd(_lib.ENS_BWD_SCORE)
         _give_ws(model, ctx.ws_int)
         _give_ws(model, ctx.ws_ens)

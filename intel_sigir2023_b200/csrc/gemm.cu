@@ -786,7 +786,9 @@ int gemm(const Gemm& g, cudaStream_t s) {
         d.splits = splits;
         d.kchunk = ceil_div(ceil_div(g.K, splits), umma::UBK) * umma::UBK;
         // short inner dimension: the epilogue dominates; a 2-deep raw ring keeps two CTAs per SM
-        const int nraw = d.kchunk <= 128 ? 2 : 4;
+        // (up to 256 inner columns the forward layout keeps the 2-deep ring as well - 121 registers, two CTAs per SM: 54 -> 39 us
+        // for the pred_layer product; the transposing variants need 154+ registers, one CTA per SM either way)
+        const int nraw = (d.kchunk <= 128 || (d.kchunk <= 256 && !g.a_t && !g.b_t)) ? 2 : 4;
         size_t smem = (size_t)umma::USTAGES * 2 * (umma::plane_bytes(umma::UM) + umma::plane_bytes(bn)) +
                       (size_t)nraw * (umma::raw_bytes(umma::UM) + umma::raw_bytes(bn));
         const size_t tile_bytes = (size_t)umma::UM * (bn + 4) * 4;      // epilogue staging tile reuses the operand stages
@@ -797,7 +799,8 @@ int gemm(const Gemm& g, cudaStream_t s) {
         const bool multi = d.kchunk > (int64_t)umma::UCH * umma::UBK;
 #define INTEL_UMMA_N(ATR, BTR, NACC)                                                                                  \
     do {                                                                                                              \
-        if (multi) { auto k = umma::gemm_umma_kernel<ATR, BTR, NACC, true, 4>; ensure_smem(k, smem); LAUNCH(k, grid, dim3(umma::UTHREADS), smem, s, d, bn, vec_c4); }   \
+        if (multi && nraw == 2) { auto k = umma::gemm_umma_kernel<ATR, BTR, NACC, true, 2>; ensure_smem(k, smem); LAUNCH(k, grid, dim3(umma::UTHREADS), smem, s, d, bn, vec_c4); }   \
+        else if (multi) { auto k = umma::gemm_umma_kernel<ATR, BTR, NACC, true, 4>; ensure_smem(k, smem); LAUNCH(k, grid, dim3(umma::UTHREADS), smem, s, d, bn, vec_c4); }   \
         else { auto k = umma::gemm_umma_kernel<ATR, BTR, NACC, false, 2>; ensure_smem(k, smem); LAUNCH(k, grid, dim3(umma::UTHREADS), smem, s, d, bn, vec_c4); }       \
     } while (0)
 #define INTEL_UMMA(ATR, BTR)                                                                                          \

@@ -753,3 +753,33 @@ def check_lambdarank_model(device, name):
     gmax = max(float(np.abs(z["grad." + n]).max()) for n, _ in model.named_parameters())
     for n, p in model.named_parameters():
         assert_grad_close(p.grad.cpu().numpy(), z["grad." + n], gmax, n)
+
+
+def check_phased_backward(device, name="script_pl_gru"):
+    """IntEL's backward pass runs intel_ensemble_bwd_phase (HEAD -> intent predictor -> ITEM -> SCORE, the order a data-parallel
+    caller overlaps its gradient exchange with); the one-call intel_ensemble_bwd must give the same gradients, and the flat
+    gradient buffer must end with the score stream's parameters."""
+    from intel_sigir2023_b200 import losses
+    cfg, batch, state, _ = load_model_case(name, device)
+    grads = []
+    for single in (False, True):
+        model = make_model(cfg, state, device).train()
+        model._single_call_backward = single
+        crit = losses.IntListloss(loss_args())
+        out = model(batch)
+        crit(out, batch)[0].backward()
+        grads.append({n: p.grad.detach().cpu().numpy().copy() for n, p in model.named_parameters()})
+        if not single:
+            late, flat = model._flat_late, model._flat_grad
+            assert 0 < late < flat.numel()
+            base = flat.data_ptr()
+            for n, p in model.named_parameters():
+                off = (p.grad.data_ptr() - base) // 4
+                assert (off >= late) == (n in model._late_grad_names), n
+            pk = [dict(model.named_parameters())[n].grad for n in model._packed_grad_names]
+            for a, b in zip(pk, pk[1:]):        # the three intent-projection gradients sit back to back
+                assert b.data_ptr() == a.data_ptr() + 4 * a.numel()
+    gmax = max(float(np.abs(g).max()) for g in grads[1].values())
+    for n, g in grads[1].items():
+        err = float(np.abs(grads[0][n] - g).max())
+        assert err <= 1e-6 * float(np.abs(g).max()) + 1e-7 * gmax, (n, err)

@@ -85,3 +85,27 @@ def test_two_rank_grads_match_single_process(case, overlap):
         assert err <= 1e-4 * float(g.abs().max()) + 2e-6 * gmax, (k, err)
     for k, v in res1.items():
         assert (np.isnan(v) and np.isnan(res2[k])) or abs(v - res2[k]) < 1e-9, (k, v, res2[k])
+
+
+def test_overlap_refuses_gradient_accumulation():
+    """The early all-reduce works on the flat gradient buffer of the backward pass: if the .grad tensors do not alias it
+    (gradients accumulated into existing .grad), allreduce() must say so instead of exchanging the wrong memory."""
+    from intel_sigir2023_b200 import dp
+
+    class Work:
+        waited = False
+        def wait(self):
+            Work.waited = True
+
+    lin = torch.nn.Linear(3, 2)
+    lin._early_reduce = None
+    red = dp.GradReducer.__new__(dp.GradReducer)
+    red.model, red.params, red.world, red.small_numel = lin, list(lin.parameters()), 2, 1 << 16
+    red.avg_op, red.post_scale, red.overlap = None, 1.0, True
+    flat = torch.zeros(16)
+    for p in lin.parameters():
+        p.grad = torch.zeros_like(p)                    # own storage: not views of `flat`
+    red._pending = (Work(), flat, 8)
+    with pytest.raises(RuntimeError, match="do not alias"):
+        red.allreduce()
+    assert Work.waited and red._pending is None

@@ -130,3 +130,7 @@ def test_fused_stack_shapes():
 
 def test_dropout():
     P.check_dropout("cpu")
+
+
+def test_phased_backward_equals_single_call():
+    P.check_phased_backward("cpu")

@@ -57,6 +57,12 @@ def test_loss_edge_cases():
     P.check_loss_edge_cases(DEV)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["script_pl_gru", "default_bert"])
+def test_phased_backward_equals_single_call(name):
+    P.check_phased_backward(DEV, name)
+
+
 def test_list_loss_bucket_and_pair_forms():
     P.check_list_loss_forms(DEV)
 
