@@ -441,6 +441,12 @@ int intel_debug_use_rows_gemm(int on) {
     return INTEL_OK;
 }
 
+int intel_debug_gru_prep(int64_t B, int64_t T, const int64_t* lens, int32_t* order, int32_t* rows_t, int32_t* rows_t1,
+                         int32_t* count, intel_stream_t stream) {
+    INTEL_REQUIRE(lens && order && rows_t && rows_t1 && count, INTEL_ERR_ARG, "gru_prep: null argument");
+    return gru_prep(1, &B, &T, &lens, &rows_t, &rows_t1, &count, &order, S(stream));
+}
+
 int intel_debug_use_tcgen05_gru(int on) {
     gru_debug_use_tcgen05(on);
     return INTEL_OK;

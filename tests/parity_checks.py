@@ -783,3 +783,33 @@ def check_phased_backward(device, name="script_pl_gru"):
     for n, g in grads[1].items():
         err = float(np.abs(grads[0][n] - g).max())
         assert err <= 1e-6 * float(np.abs(g).max()) + 1e-7 * gmax, (n, err)
+
+
+def check_gru_prep(device):
+    """The index kernels of the packed GRU path against numpy: stable order by decreasing (clamped) length, the list of live
+    (session, step) rows in (b, t) order, their count.  Index work: bit exact.  Sizes cross the 1024-session chunk of the kernels."""
+    from intel_sigir2023_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(3)
+    for B, T in ((1, 1), (37, 5), (1024, 20), (1025, 20), (4096, 20), (3000, 63)):
+        lens_np = rng.integers(0, T + 3, size=B).astype(np.int64)          # 0 and > T occur: both are clamped
+        lens_np[rng.integers(0, B)] = T
+        lens = torch.from_numpy(lens_np).to(device)
+        order = torch.full((B + 1,), -7, dtype=torch.int32, device=device)
+        rows_t = torch.full((B * T,), -1, dtype=torch.int32, device=device)
+        rows_t1 = torch.full((B * T,), -1, dtype=torch.int32, device=device)
+        count = torch.zeros(1, dtype=torch.int32, device=device)
+        _lib.check(lib.intel_debug_gru_prep(B, T, _lib.ptr(lens), _lib.ptr(order), _lib.ptr(rows_t), _lib.ptr(rows_t1), _lib.ptr(count),
+                                            _lib.stream_ptr(torch.device(device))))
+        cl = np.clip(lens_np, 0, T)
+        ref_order = np.argsort(-cl, kind="stable").astype(np.int32)
+        got = order.cpu().numpy()
+        assert np.array_equal(got[:B], ref_order), (B, T)
+        assert got[B] == 0
+        n = int(cl.sum())
+        assert int(count.cpu()[0]) == n
+        b = np.repeat(np.arange(B), cl)
+        t = np.concatenate([np.arange(k) for k in cl]) if n else np.zeros(0, dtype=np.int64)
+        assert np.array_equal(rows_t.cpu().numpy()[:n], (b * T + t).astype(np.int32))
+        assert np.array_equal(rows_t1.cpu().numpy()[:n], (b * (T + 1) + t).astype(np.int32))
+        assert (rows_t.cpu().numpy()[n:] == -1).all()

@@ -88,7 +88,10 @@ def test_one_epoch_of_basrunner_fit_and_final_evaluation(tmp_path):
         # whose top-k changes at a near tie (296 dev sessions, per-behaviour metrics average over fewer)
         tol = 1e-6 if k.startswith("NDCG@") else 1.5 / 40
         assert abs(m[k] - m_ref[k]) <= tol, (k, m[k], m_ref[k])
-    # three Adam steps later the weights still agree
+    # three Adam steps later the weights still agree.  Adam divides by sqrt(v): an entry whose gradient is rounding noise
+    # (|g| ~ 1e-7 of the tensor's largest) still moves by ~lr per step, in a direction the last bits decide, so the bound is
+    # not the 1e-5 of the gradients but a fraction of the 3 lr = 6e-3 an entry can travel: the largest difference observed on
+    # the B200 over a dozen runs is 2.0e-4 of the tensor's largest weight (the order of the fp32 atomics varies from run to run)
     sd = b2.model.state_dict()
     for k, v in ref.model.state_dict().items():
-        assert rel_err(sd[k].cpu().numpy(), v.numpy()) < 2e-4, k
+        assert rel_err(sd[k].cpu().numpy(), v.numpy()) < 5e-4, k

@@ -134,3 +134,7 @@ def test_dropout():
 
 def test_phased_backward_equals_single_call():
     P.check_phased_backward("cpu")
+
+
+def test_gru_prep_index_kernels():
+    P.check_gru_prep("cpu")

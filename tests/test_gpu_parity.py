@@ -57,6 +57,10 @@ def test_loss_edge_cases():
     P.check_loss_edge_cases(DEV)
 
 
+def test_gru_prep_index_kernels():
+    P.check_gru_prep(DEV)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ["script_pl_gru", "default_bert"])
 def test_phased_backward_equals_single_call(name):
