@@ -782,7 +782,8 @@ def check_phased_backward(device, name="script_pl_gru"):
     gmax = max(float(np.abs(g).max()) for g in grads[1].values())
     for n, g in grads[1].items():
         err = float(np.abs(grads[0][n] - g).max())
-        assert err <= 1e-6 * float(np.abs(g).max()) + 1e-7 * gmax, (n, err)
+        # same kernels, same inputs: the only difference is the order of the fp32 atomic adds into the shared tables
+        assert err <= 3e-6 * float(np.abs(g).max()) + 3e-7 * gmax, (n, err)
 
 
 def check_gru_prep(device):
