@@ -333,6 +333,8 @@ int intel_debug_use_tcgen05_gru(int on);
 /* test hook: 0 keeps the tall resident-weight products and the tall weight gradients on the generic tcgen05 GEMM instead of the
  * persistent kernels (gemm_rows_tc.cu, gemm_wgrad_tc.cu). Default 1. */
 int intel_debug_use_rows_gemm(int on);
+/* test hook: 0 keeps the BERT4Rec encoder forward on the staged path instead of the fused kernel (bert_fused.cu). Default 1. */
+int intel_debug_use_fused_bert(int on);
 /* test hook: the index kernels behind the packed GRU path (pack_padded_sequence of GeneralSeq.py:64-71), for one encoder.
  * lens: device int64 [B]; T <= 63.  order: device int32 [B + 1], sessions by decreasing (clamped) length, stable, order[B] = 0;
  * rows_t / rows_t1: device int32 [B * T], the live (session, step) pairs in (b, t) order as row numbers b T + t / b (T + 1) + t;

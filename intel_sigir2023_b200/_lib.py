@@ -113,6 +113,7 @@ def _declare(lib: C.CDLL) -> None:
         "intel_debug_use_tcgen05_gru": (i32, [i32]),
         "intel_debug_use_rows_gemm": (i32, [i32]),
         "intel_debug_gru_prep": (i32, [i64, i64, _p, _p, _p, _p, _p, _p]),
+        "intel_debug_use_fused_bert": (i32, [i32]),
         "intel_host_pack_rows": (i64, [i64, i64, _p, i32, _p, _p, _p, i32, i64, _p]),
         "intel_awelv_fwd": (i32, [i64, i64, i32, i32, _p, _p, _p, _p, _p, _p, _p, _p]),
         "intel_awelv_bwd": (i32, [i64, i64, i32, i32, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
@@ -139,7 +140,7 @@ EXPORTED = ["intel_ensemble_bwd_phase", "intel_reserve_sms", "intel_last_error",
             "intel_mha_bwd", "intel_debug_use_fused_stack", "intel_debug_stack_sessions_per_cta", "intel_debug_use_tcgen05_gemm", "intel_host_pack_rows", "intel_adam_step", "intel_awelv_fwd", "intel_awelv_bwd",
             "intel_lambdarank_lambdas", "intel_pool_head_fwd", "intel_pool_head_bwd",
             "intel_linear_fwd_ex", "intel_linear_dx_ex", "intel_linear_dw_ex", "intel_softmax_rows_fwd", "intel_softmax_rows_bwd",
-            "intel_batch_validate", "intel_debug_use_tcgen05_stack", "intel_batch_build", "intel_debug_use_tcgen05_gru", "intel_debug_use_rows_gemm", "intel_debug_gru_prep"]
+            "intel_batch_validate", "intel_debug_use_tcgen05_stack", "intel_batch_build", "intel_debug_use_tcgen05_gru", "intel_debug_use_rows_gemm", "intel_debug_gru_prep", "intel_debug_use_fused_bert"]
 
 
 def load(path: Optional[str] = None) -> C.CDLL:

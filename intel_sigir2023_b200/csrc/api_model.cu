@@ -261,6 +261,11 @@ int bert_fwd(const intel_dims_t* d, const intel_encoder_t& p, EncWs& e, const in
     const int64_t B = d->B, T = e.T, R = B * T;
     const int dd = e.d;
     INTEL_REQUIRE(T <= d->history_max + 1, INTEL_ERR_ARG, "history length %lld exceeds history_max+1", (long long)T);
+    if (bert_fused_ok(T, dd, d->bert_heads, d->bert_layers)) {       // the whole encoder in one kernel (bert_fused.cu)
+        BertWs& w = e.bert;
+        return bert_fused_fwd(B, T, d->bert_heads, d->bert_layers, lens, p, e.seq, w.X, w.QKV, w.Z1, w.st1, w.C, w.F, w.Z2, w.st2,
+                              d->inference == 0, out, ld_out, s);
+    }
     INTEL_TRY(add_positions(B, T, dd, lens, p.pos, e.seq, s));
     for (int l = 0; l < d->bert_layers; ++l) {
         const intel_bert_layer_t& q = p.layer[l];
@@ -445,6 +450,11 @@ int intel_debug_gru_prep(int64_t B, int64_t T, const int64_t* lens, int32_t* ord
                          int32_t* count, intel_stream_t stream) {
     INTEL_REQUIRE(lens && order && rows_t && rows_t1 && count, INTEL_ERR_ARG, "gru_prep: null argument");
     return gru_prep(1, &B, &T, &lens, &rows_t, &rows_t1, &count, &order, S(stream));
+}
+
+int intel_debug_use_fused_bert(int on) {
+    bert_debug_use_fused(on);
+    return INTEL_OK;
 }
 
 int intel_debug_use_tcgen05_gru(int on) {

@@ -2,6 +2,7 @@
 // Everything is asynchronous on `s`; int return = INTEL_* status.
 #pragma once
 #include "common.cuh"
+#include "intel_b200.h"   // parameter structs of the C ABI (intel_encoder_t) used by the fused encoder
 
 namespace intel {
 
@@ -128,6 +129,15 @@ int cross_pool_bwd(int64_t B, int64_t L, int d, const float* X, const float* qk,
 int softmax_rows(int64_t R, int64_t N, const float* Z, float* P, cudaStream_t s, int64_t ldz = 0);   // ldz: row stride of Z (0 = N)
 int softmax_rows_bwd(int64_t R, int64_t N, const float* P, const float* dP, const float* dP2, float* dZ,
                      cudaStream_t s, int64_t ldz = 0);   // incoming gradient dP + dP2 (dP2 nullable)
+
+// ---- bert_fused.cu: BERT4RecEncoder forward in one kernel (d = 32, T <= 24, 1 or 2 heads) -------------------------------
+bool bert_fused_ok(int64_t T, int d, int heads, int layers);
+void bert_debug_use_fused(int on);
+// seq [B,T,32]: token embeddings in; with save it receives X[0] (positions added) and the per-layer activations of bert_bwd
+// are written (QKV [B*T,96], Z1, C, F, Z2, X[l+1] [B*T,32], st1 / st2 [B*T,2]); out[b, :] = state at len - 1
+int bert_fused_fwd(int64_t B, int64_t T, int heads, int layers, const int64_t* lens, const intel_encoder_t& p, float* seq,
+                   float* const* X, float* const* QKV, float* const* Z1, float* const* st1, float* const* C, float* const* F,
+                   float* const* Z2, float* const* st2, bool save, float* out, int64_t ld_out, cudaStream_t s);
 
 // ---- gru.cu -------------------------------------------------------------------------------------
 // One masked GRU step for all sessions (gate order r,z,n; torch.nn.GRU equations).

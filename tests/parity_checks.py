@@ -814,3 +814,32 @@ def check_gru_prep(device):
         assert np.array_equal(rows_t.cpu().numpy()[:n], (b * T + t).astype(np.int32))
         assert np.array_equal(rows_t1.cpu().numpy()[:n], (b * (T + 1) + t).astype(np.int32))
         assert (rows_t.cpu().numpy()[n:] == -1).all()
+
+
+def check_bert_fused_vs_staged(device, names=("default_bert", "wide_intent_bert_full")):
+    """The one-kernel BERT4Rec encoder forward (bert_fused.cu) against the staged path (~25 launches per encoder): same
+    outputs, and - through the activations it leaves for the staged backward pass - the same gradients."""
+    from intel_sigir2023_b200 import _lib, losses
+    lib = _lib.load()
+    for name in names:
+        cfg, batch, state, _ = load_model_case(name, device)
+        res = []
+        for on in (1, 0):
+            _lib.check(lib.intel_debug_use_fused_bert(on))
+            try:
+                model = make_model(cfg, state, device).train()
+                out = model(batch)
+                losses.IntListloss(loss_args())(out, batch)[0].backward()
+                res.append(({k: v.detach().cpu().numpy() for k, v in out.items()},
+                            {n: p.grad.detach().cpu().numpy().copy() for n, p in model.named_parameters()}))
+                model.eval()
+                with torch.no_grad():
+                    res[-1][0]["intents_eval"] = model(batch)["intents"].cpu().numpy()
+            finally:
+                _lib.check(lib.intel_debug_use_fused_bert(1))
+        (oa, ga), (ob, gb) = res
+        for k in ob:
+            assert rel_err(oa[k], ob[k]) < 3e-6, (name, k, rel_err(oa[k], ob[k]))
+        gmax = max(float(np.abs(g).max()) for g in gb.values())
+        for n, g in gb.items():
+            assert_grad_close(ga[n], g, gmax, f"{name}:{n}")

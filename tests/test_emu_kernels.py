@@ -138,3 +138,7 @@ def test_phased_backward_equals_single_call():
 
 def test_gru_prep_index_kernels():
     P.check_gru_prep("cpu")
+
+
+def test_bert_fused_vs_staged():
+    P.check_bert_fused_vs_staged("cpu", names=("default_bert",))

@@ -61,6 +61,10 @@ def test_gru_prep_index_kernels():
     P.check_gru_prep(DEV)
 
 
+def test_bert_fused_vs_staged():
+    P.check_bert_fused_vs_staged(DEV)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ["script_pl_gru", "default_bert"])
 def test_phased_backward_equals_single_call(name):
