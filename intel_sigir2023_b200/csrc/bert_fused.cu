@@ -24,7 +24,7 @@ constexpr int BF_WARP = 3 * BF_CM + BF_TP * BF_WS + 2 * BF_TP * BF_TP;   // x | 
 
 struct BertFusedArgs {
     int64_t B;
-    int T, layers, heads, save;
+    int T, layers, heads, save, vecw;            // vecw: every weight matrix is 16-byte aligned
     const int64_t* lens;
     const float* pos;
     float* seq;                                  // [B, T, 32]: token embeddings in, X[0] (positions added) out when save
@@ -89,15 +89,27 @@ __global__ void __launch_bounds__(BF_WARPS * 32) bert_fused_fwd_kernel(BertFused
     float* ks = qs + BF_CM;
     float* vs = ks + BF_CM;                                            // token-major [24][33]
     float* ps = vs + BF_TP * BF_WS;                                    // [head][key][24 queries]
-    for (int l = 0; l < a.layers; ++l) {
-        const intel_bert_layer_t& q = a.L[l];
-        const float* mats[5] = {q.qw, q.kw, q.vw, q.l1w, q.l2w};
-        const float* vecs[9] = {q.qb, q.kb, q.vb, q.ln1w, q.ln1b, q.l1b, q.l2b, q.ln2w, q.ln2b};
-        float* base = Wsm + l * BF_LAYER;
-        for (int m = 0; m < 5; ++m)
-            for (int e = threadIdx.x; e < BF_D * BF_D; e += blockDim.x) base[m * BF_D * BF_WS + (e >> 5) * BF_WS + (e & 31)] = mats[m][e];
-        for (int m = 0; m < 9; ++m)
-            for (int e = threadIdx.x; e < BF_D; e += blockDim.x) base[5 * BF_D * BF_WS + m * BF_D + e] = vecs[m][e];
+    // weights -> shared memory: one flat loop over (layer, matrix, 16-byte chunk) so that every thread has several
+    // independent global loads in flight (ten short loops in sequence cost 15 % of the kernel: one latency each)
+    {
+        const int chunks = a.layers * 5 * (BF_D * BF_D / 4);
+#pragma unroll 4
+        for (int e = threadIdx.x; e < chunks; e += blockDim.x) {
+            const int l = e / (5 * 256), m = (e / 256) % 5, c = e % 256;       // chunk c = row c / 8, columns 4 (c % 8) ..
+            const intel_bert_layer_t& q = a.L[l];
+            const float* src = m == 0 ? q.qw : (m == 1 ? q.kw : (m == 2 ? q.vw : (m == 3 ? q.l1w : q.l2w)));
+            const float4 v = a.vecw ? *reinterpret_cast<const float4*>(src + 4 * c)
+                                    : make_float4(src[4 * c], src[4 * c + 1], src[4 * c + 2], src[4 * c + 3]);
+            float* dst = Wsm + l * BF_LAYER + m * BF_D * BF_WS + (c >> 3) * BF_WS + 4 * (c & 7);
+            dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+        }
+        for (int e = threadIdx.x; e < a.layers * 9 * BF_D; e += blockDim.x) {
+            const int l = e / (9 * BF_D), m = (e / BF_D) % 9, c = e % BF_D;
+            const intel_bert_layer_t& q = a.L[l];
+            const float* src = m == 0 ? q.qb : (m == 1 ? q.kb : (m == 2 ? q.vb : (m == 3 ? q.ln1w : (m == 4 ? q.ln1b : (m == 5 ? q.l1b :
+                               (m == 6 ? q.l2b : (m == 7 ? q.ln2w : q.ln2b)))))));
+            Wsm[l * BF_LAYER + 5 * BF_D * BF_WS + m * BF_D + c] = src[c];
+        }
     }
     __syncthreads();
     const float scale = 1.0f / sqrtf((float)dk);
@@ -227,8 +239,12 @@ int bert_fused_fwd(int64_t B, int64_t T, int heads, int layers, const int64_t* l
     memset(&a, 0, sizeof(a));
     a.B = B; a.T = (int)T; a.layers = layers; a.heads = heads; a.save = save ? 1 : 0;
     a.lens = lens; a.pos = p.pos; a.seq = seq; a.out = out; a.ld_out = ld_out;
+    a.vecw = 1;
     for (int l = 0; l < layers; ++l) {
         a.L[l] = p.layer[l];
+        const float* ws[5] = {p.layer[l].qw, p.layer[l].kw, p.layer[l].vw, p.layer[l].l1w, p.layer[l].l2w};
+        for (int m = 0; m < 5; ++m)
+            if ((uintptr_t)ws[m] % 16) a.vecw = 0;
         a.QKV[l] = QKV[l]; a.Z1[l] = Z1[l]; a.st1[l] = st1[l]; a.C[l] = C[l]; a.F[l] = F[l]; a.Z2[l] = Z2[l]; a.st2[l] = st2[l];
         a.X[l + 1] = X[l + 1];
     }
