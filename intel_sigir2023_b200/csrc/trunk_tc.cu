@@ -433,7 +433,8 @@ __global__ void __launch_bounds__(256, 1) trunk_tc_fwd_kernel(TrunkArgs a, int C
 // per CTA; thread t owns rows t and 128 + t.  Per layer: q|k|v of both tiles first (K rows and V^T columns of all keys go
 // to shared memory, the Q rows to an fp32 stash), then per tile and head S = Q_h K_h^T over all keys (N = padded key
 // count, no lane mask), softmax in 32-column passes over tensor memory, O_h = P V_h, and the FFN + LayerNorm of the tile.
-// Tensor memory: A planes 64 | O 32 | S / P hi KP | P lo KP  (KP <= 208 -> 512 columns).
+// Tensor memory: A planes 64 | O 32 | S / P hi KP | P lo KP  (KP <= 208 -> 512 columns).  A second warpgroup shares the tile's
+// tensor-memory lanes and takes every other 32-column chunk of the two softmax passes.
 namespace {
 constexpr int TL_K_LBO = 4096;                                  // K planes [k-chunk][256 rows][4]
 constexpr int TL_K_HI = 0, TL_K_LO = 32768, TL_VT_HI = 65536, TL_VT_LO = 65536 + 28672, TL_Q = 65536 + 2 * 28672;
@@ -441,11 +442,14 @@ constexpr int TL_BYTES = TL_Q + 256 * 128;                       // + Q stash [2
 }  // namespace
 
 template <int HEADS>
-__global__ void __launch_bounds__(128, 1) trunk_tc_long_fwd_kernel(TrunkArgs a, int KP) {
+__global__ void __launch_bounds__(256, 1) trunk_tc_long_fwd_kernel(TrunkArgs a, int KP) {
     constexpr int DK = TD / HEADS;
     extern __shared__ __align__(1024) uint8_t tc_smem[];
     uint8_t* sm = tc_smem;
-    const int t = threadIdx.x, warp = t >> 5;
+    // two warpgroups on the one tile: warpgroup 0 owns the rows (thread t = row t: operands, FFN, LayerNorm, stores);
+    // warpgroup 1 shares its tensor-memory lanes (warps w and w + 4 see the same 32 lanes) and takes every other 32-column
+    // chunk of the softmax passes, which are three quarters of the thread work at 200 keys
+    const int tid = threadIdx.x, g = tid >> 7, t = tid & 127, warp = t >> 5;
     uint64_t* bar = reinterpret_cast<uint64_t*>(sm + TC_BAR);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + TC_TMEM);
     const float* vec = reinterpret_cast<const float*>(sm + TC_VEC);
@@ -454,15 +458,15 @@ __global__ void __launch_bounds__(128, 1) trunk_tc_long_fwd_kernel(TrunkArgs a, 
     stage_weight(sm + TC_WQKV_HI, sm + TC_WQKV_LO, a.wv, 96, 64);
     stage_weight(sm + TC_W1_HI, sm + TC_W1_LO, a.w1, 32, 0);
     stage_weight(sm + TC_W2_HI, sm + TC_W2_LO, a.w2, 32, 0);
-    if (t < TD) {
+    if (tid < TD) {
         float* v = reinterpret_cast<float*>(sm + TC_VEC);
-        v[t] = a.b1[t]; v[TD + t] = a.b2[t]; v[2 * TD + t] = a.lnw[t]; v[3 * TD + t] = a.lnb[t];
+        v[tid] = a.b1[tid]; v[TD + tid] = a.b2[tid]; v[2 * TD + tid] = a.lnw[tid]; v[3 * TD + tid] = a.lnb[tid];
     }
-    if (t == 0) {
+    if (tid == 0) {
         tc05::mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (t < 32) tc05::tmem_alloc(tmem_slot, 512);
+    if (tid < 32) tc05::tmem_alloc(tmem_slot, 512);
     tc05::fence_smem_to_mma();
     tc05::fence_before();
     __syncthreads();
@@ -482,6 +486,8 @@ __global__ void __launch_bounds__(128, 1) trunk_tc_long_fwd_kernel(TrunkArgs a, 
     const int L = a.L, pv_steps = (L + 7) >> 3;
     const float sl2 = 1.4426950408889634f / sqrtf((float)DK);
     float* qs = reinterpret_cast<float*>(wg + TL_Q);
+    float* pstat = reinterpret_cast<float*>(wg + TL_BYTES);          // [2 warpgroups][128 rows]: partial row max / row sum
+    const bool rows = g == 0;                                        // this thread owns a tile row
 
 #define TL_PUBLISH()               \
     do {                           \
@@ -504,7 +510,7 @@ __global__ void __launch_bounds__(128, 1) trunk_tc_long_fwd_kernel(TrunkArgs a, 
 #pragma unroll
         for (int tt = 0; tt < 2; ++tt) {
             const int r = tt * 128 + t;
-            live[tt] = r < L;
+            live[tt] = rows && r < L;
             grow[tt] = b * L + r;
             load_row(x[tt], a.X[0] + grow[tt] * TD, live[tt]);
         }
@@ -513,14 +519,14 @@ __global__ void __launch_bounds__(128, 1) trunk_tc_long_fwd_kernel(TrunkArgs a, 
 #pragma unroll
             for (int tt = 0; tt < 2; ++tt) {
                 const int r = tt * 128 + t;
-                {
+                if (rows) {
                     uint32_t h[32], lo[32];
                     split32(x[tt], h, lo);
                     tc05::st32(tl + cA, h);
                     tc05::st32(tl + cA + 32, lo);
                 }
                 TL_PUBLISH();
-                if (warp == 0) {
+                if (warp == 0 && rows) {
                     tc05::fence_after();
                     if (elect_one()) {
 #pragma unroll
@@ -533,6 +539,7 @@ __global__ void __launch_bounds__(128, 1) trunk_tc_long_fwd_kernel(TrunkArgs a, 
                 }
                 if (l > 0 && a.save) store_row(a.X[l] + grow[tt] * TD, x[tt], live[tt]);
                 TL_WAIT();
+                if (!rows) continue;                                  // the rest of this step is row-owner work without barriers
                 uint32_t uq[32], uk[32], uv[32], h[32], lo[32];
                 tc05::ld32(tl + cS, uq);
                 tc05::ld32(tl + cS + 32, uk);
@@ -572,12 +579,12 @@ __global__ void __launch_bounds__(128, 1) trunk_tc_long_fwd_kernel(TrunkArgs a, 
 #pragma unroll 1
             for (int tt = 0; tt < 2; ++tt) {
                 const int r = tt * 128 + t;
-                const bool lv = r < L;
+                const bool lv = rows && r < L;
                 const int64_t gr = b * L + r;
                 float inv[HEADS];
 #pragma unroll
                 for (int hd = 0; hd < HEADS; ++hd) {
-                    {
+                    if (rows && hd == 0) {
                         uint32_t h[32], lo[32];
 #pragma unroll
                         for (int c = 0; c < 8; ++c) {
@@ -587,13 +594,11 @@ __global__ void __launch_bounds__(128, 1) trunk_tc_long_fwd_kernel(TrunkArgs a, 
                             split_tf32(__uint_as_float(q4.z), h[4 * c + 2], lo[4 * c + 2]);
                             split_tf32(__uint_as_float(q4.w), h[4 * c + 3], lo[4 * c + 3]);
                         }
-                        if (hd == 0) {
-                            tc05::st32(tl + cA, h);
-                            tc05::st32(tl + cA + 32, lo);
-                        }
+                        tc05::st32(tl + cA, h);
+                        tc05::st32(tl + cA + 32, lo);
                     }
                     TL_PUBLISH();
-                    if (warp == 0) {
+                    if (warp == 0 && rows) {
                         tc05::fence_after();
                         if (elect_one()) {
 #pragma unroll
@@ -607,8 +612,9 @@ __global__ void __launch_bounds__(128, 1) trunk_tc_long_fwd_kernel(TrunkArgs a, 
                         __syncwarp();
                     }
                     TL_WAIT();
+                    // softmax numerators: warpgroup g takes the 32-column chunks c with (c / 32) % 2 == g
                     float mx = -INFINITY, sum = 0.f;
-                    for (int c = 0; c < KP; c += 32) {
+                    for (int c = 32 * g; c < KP; c += 64) {
                         if (c + 32 <= KP) {
                             uint32_t u[32];
                             tc05::ld32(tl + cS + c, u);
@@ -623,8 +629,12 @@ __global__ void __launch_bounds__(128, 1) trunk_tc_long_fwd_kernel(TrunkArgs a, 
                             for (int j = 0; j < 16; ++j) mx = fmaxf(mx, (c + j < L) ? __uint_as_float(u[j]) : -INFINITY);
                         }
                     }
+                    pstat[g * 128 + t] = mx;
+                    __syncthreads();
+                    mx = fmaxf(pstat[t], pstat[128 + t]);
+                    __syncthreads();                                  // the slots are reused for the sums below
                     const float sh = -mx * sl2;
-                    for (int c = 0; c < KP; c += 32) {
+                    for (int c = 32 * g; c < KP; c += 64) {
                         if (c + 32 <= KP) {
                             uint32_t u[32], h[32], lo[32];
                             tc05::ld32(tl + cS + c, u);
@@ -651,9 +661,10 @@ __global__ void __launch_bounds__(128, 1) trunk_tc_long_fwd_kernel(TrunkArgs a, 
                             tc05::st16(tl + cPlo + c, lo);
                         }
                     }
-                    inv[hd] = 1.0f / sum;
+                    pstat[g * 128 + t] = sum;
                     TL_PUBLISH();
-                    if (warp == 0) {
+                    inv[hd] = 1.0f / (pstat[t] + pstat[128 + t]);
+                    if (warp == 0 && rows) {
                         tc05::fence_after();
                         if (elect_one()) {
 #pragma unroll 2
@@ -667,20 +678,23 @@ __global__ void __launch_bounds__(128, 1) trunk_tc_long_fwd_kernel(TrunkArgs a, 
                         __syncwarp();
                     }
                     TL_WAIT();
+                    __syncthreads();                                  // every thread has read the sums: the next head may overwrite them
                 }
                 // FFN
                 {
-                    uint32_t u[32], h[32], lo[32];
                     float att[32];
-                    tc05::ld32(tl + cO, u);
-                    tc05::wait_ld();
+                    if (rows) {
+                        uint32_t u[32], h[32], lo[32];
+                        tc05::ld32(tl + cO, u);
+                        tc05::wait_ld();
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) att[j] = __uint_as_float(u[j]) * inv[j / DK];
-                    split32(att, h, lo);
-                    tc05::st32(tl + cA, h);
-                    tc05::st32(tl + cA + 32, lo);
+                        for (int j = 0; j < 32; ++j) att[j] = __uint_as_float(u[j]) * inv[j / DK];
+                        split32(att, h, lo);
+                        tc05::st32(tl + cA, h);
+                        tc05::st32(tl + cA + 32, lo);
+                    }
                     TL_PUBLISH();
-                    if (warp == 0) {
+                    if (warp == 0 && rows) {
                         tc05::fence_after();
                         if (elect_one()) {
 #pragma unroll
@@ -691,23 +705,25 @@ __global__ void __launch_bounds__(128, 1) trunk_tc_long_fwd_kernel(TrunkArgs a, 
                         }
                         __syncwarp();
                     }
-                    if (a.save) store_row(a.A[l] + gr * TD, att, lv);
+                    if (rows && a.save) store_row(a.A[l] + gr * TD, att, lv);
                 }
                 TL_WAIT();
                 {
-                    uint32_t u[32], h[32], lo[32];
                     float uu[32];
-                    tc05::ld32(tl + cS, u);
-                    tc05::wait_ld();
+                    if (rows) {
+                        uint32_t u[32], h[32], lo[32];
+                        tc05::ld32(tl + cS, u);
+                        tc05::wait_ld();
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        uu[j] = __uint_as_float(u[j]) + vec[j];
-                        split_tf32(fmaxf(uu[j], 0.f), h[j], lo[j]);
+                        for (int j = 0; j < 32; ++j) {
+                            uu[j] = __uint_as_float(u[j]) + vec[j];
+                            split_tf32(fmaxf(uu[j], 0.f), h[j], lo[j]);
+                        }
+                        tc05::st32(tl + cA, h);
+                        tc05::st32(tl + cA + 32, lo);
                     }
-                    tc05::st32(tl + cA, h);
-                    tc05::st32(tl + cA + 32, lo);
                     TL_PUBLISH();
-                    if (warp == 0) {
+                    if (warp == 0 && rows) {
                         tc05::fence_after();
                         if (elect_one()) {
 #pragma unroll
@@ -718,10 +734,10 @@ __global__ void __launch_bounds__(128, 1) trunk_tc_long_fwd_kernel(TrunkArgs a, 
                         }
                         __syncwarp();
                     }
-                    if (a.save) store_row(a.U[l] + gr * TD, uu, lv);
+                    if (rows && a.save) store_row(a.U[l] + gr * TD, uu, lv);
                 }
                 TL_WAIT();
-                {
+                if (rows) {
                     uint32_t u[32];
                     float z[32];
                     tc05::ld32(tl + cS + 32, u);
@@ -765,7 +781,7 @@ __global__ void __launch_bounds__(128, 1) trunk_tc_long_fwd_kernel(TrunkArgs a, 
 #undef TL_WAIT
     tc05::fence_before();
     __syncthreads();
-    if (t < 32) tc05::tmem_free(*tmem_slot, 512);
+    if (tid < 32) tc05::tmem_free(*tmem_slot, 512);
 }
 
 static int g_use_tc = 1;
@@ -785,16 +801,16 @@ static void trunk_tc_launch(const TrunkArgs& a, int WGS, unsigned grid, size_t s
 int trunk_tc_fwd(const TrunkArgs& a, cudaStream_t s) {
     if (a.L > 128) {                                               // two row tiles per session
         const int KP = (a.L + 15) / 16 * 16;
-        const size_t smem = (size_t)TC_WG + TL_BYTES;
+        const size_t smem = (size_t)TC_WG + TL_BYTES + 2 * 128 * 4;      // + the partial row statistics of the two warpgroups
         const unsigned grid = stream_grid(a.B, 1);
         if (a.heads == 1) {
             auto k = trunk_tc_long_fwd_kernel<1>;
             ensure_smem(k, smem);
-            LAUNCH(k, dim3(grid), dim3(128), smem, s, a, KP);
+            LAUNCH(k, dim3(grid), dim3(256), smem, s, a, KP);
         } else {
             auto k = trunk_tc_long_fwd_kernel<2>;
             ensure_smem(k, smem);
-            LAUNCH(k, dim3(grid), dim3(128), smem, s, a, KP);
+            LAUNCH(k, dim3(grid), dim3(256), smem, s, a, KP);
         }
         const double tok = (double)a.B * a.L;
         return check_launch("trunk_fwd", tok * (4.0 * TD + (a.save ? 4.0 * (3 * TD + 4 * TD + 2) * a.layers : 4.0 * TD)),
