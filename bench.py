@@ -408,6 +408,9 @@ def run_b200(a):
         except Exception:
             pass
     roofline = roofline_of(prof, prof_steps, traffic)
+    # the eval step runs the same kernels in inference mode (nothing saved): their captures are filed under "<kernel>@eval"
+    eval_traffic = dict(traffic)
+    eval_traffic.update({k[:-5]: v for k, v in traffic.items() if k.endswith("@eval")})
 
     # ---- eval rate of the train configs (BASELINE metric: "train fwd+bwd and eval"), with the roofline of its own kernels ----
     eval_rate = roofline_eval = None
@@ -419,9 +422,9 @@ def run_b200(a):
         eval_rate = world * B / (ms_eval * 1e-3)
         eprof = profile(eval_step, prof_steps)
         roofline_eval = {"step": "forward (no_grad) + intel_ndcg_topk", "ms_per_step": ms_eval,
-                         "dominant": {k: v for k, v in roofline_of(eprof, prof_steps, traffic).items() if k != "per_kernel"}}
+                         "dominant": {k: v for k, v in roofline_of(eprof, prof_steps, eval_traffic).items() if k != "per_kernel"}}
         if "ndcg" in eprof:
-            roofline_eval["ndcg_kernel"] = {k: v for k, v in roofline_of(eprof, prof_steps, traffic, pick="ndcg").items() if k != "per_kernel"}
+            roofline_eval["ndcg_kernel"] = {k: v for k, v in roofline_of(eprof, prof_steps, eval_traffic, pick="ndcg").items() if k != "per_kernel"}
         model.train()
 
     # ---- end to end: host indices -> H2D -> device batch builder -> step -> result D2H, every step ----

@@ -59,6 +59,8 @@ for src, note in (('r02_ncu_train.jsonl', 'train step (activations saved)'),
             float(f(rr, 'smsp__issue_active.avg.pct_of_peak_sustained_active')), tens, dr, dw,
             ", ".join("%s %.0f" % (a, b) for a, b in list(rr['stalls_pct'].items())[:4])))
         for kk, vv in name_map.items():
+            if src == 'r02_ncu_eval.jsonl':
+                vv = vv + '@eval'               # the same kernel in inference mode (bench.py: roofline_eval)
             if kk in rr['kernel'] and vv not in traffic:
                 traffic[vv] = {"dram_bytes_per_launch": int((dr + dw) * 1e6), "kernel": rr['kernel'],
                                "time_us_under_ncu": float(f(rr, 'gpu__time_duration.sum')),
