@@ -93,6 +93,7 @@ for c, base in (('c2', 'r02_bench_c2.json'), ('c4', 'r02_bench_c4.json')):
             scale.append("| %d | %s | %.0f | %.3f | %.3f | %.0f | %.3f |" % (n, c, x['value'], x['ms_per_step'], x['value'] / (n * b1['value']),
                          x['e2e']['value'], x['e2e']['value'] / (n * b1['e2e']['value'])))
 ev = d.get('roofline_eval', {})
+c4f = last_json('r02_bench_c4_fused_bert.json')
 md = f"""# Round 2 - B200, BASELINE.json configs c2..c5 (bench.py --config), IntEL-PL flags for c2 / c3
 
 `bench.py` c2 (r02_bench_c2.json): value = {d['value']:.0f} sessions/s ({d['ms_per_step']:.3f} ms/step of 4096 sessions, inputs resident in HBM,
@@ -103,6 +104,10 @@ clocks {d['clocks']}; {d['gpu_launches'] / d['steps']:.0f} kernel launches per s
 
 ## every BASELINE config, 1 GPU
 {chr(10).join(cfg_rows)}
+
+(the c4 line and the c4 multi-GPU lines below were taken before the fused BERT4Rec encoder and the second warpgroup of the
+200-slot stack kernel: with them the single-GPU c4 line is {c4f['value']:.0f} sessions/s, {c4f['ms_per_step']:.3f} ms per step -
+r02_bench_c4_fused_bert.json, r02_ncu_bert_fused.jsonl; the c2 / c3 / c5 paths do not run those kernels)
 
 ## weak scaling (one rank per GPU, NCCL gradient all-reduce for the train step; none for eval)
 {chr(10).join(scale)}
