@@ -382,6 +382,13 @@ int gru_fwd_pair(const intel_dims_t* d, const intel_encoder_t* const (&p)[2], En
             }
         }
     }
+    if (gru_outproj_pair_ok(h, e[0]->d, e[1]->d)) {          // both output projections in one launch
+        const int n[2] = {e[0]->d, e[1]->d};
+        const float* W[2] = {p[0]->w_out, p[1]->w_out};
+        const float* hl[2] = {e[0]->gru.h_all + e[0]->T * h, e[1]->gru.h_all + e[1]->T * h};
+        const int64_t ldh[2] = {(e[0]->T + 1) * h, (e[1]->T + 1) * h}, ldo[2] = {ld_out, ld_out};
+        return gru_outproj_pair_fwd(B, n, W, hl, ldh, out, ldo, s);
+    }
     for (int i = 0; i < 2; ++i) {
         const int64_t T = e[i]->T;
         GruWs& w = e[i]->gru;
@@ -390,13 +397,14 @@ int gru_fwd_pair(const intel_dims_t* d, const intel_encoder_t* const (&p)[2], En
     return INTEL_OK;
 }
 
+// have_dh: d(last state) was already formed (for both encoders at once, gru_outproj_pair_dx)
 int gru_bwd(const intel_dims_t* d, const intel_encoder_t& p, intel_encoder_t& g, EncWs& e, const int64_t* lens,
-            const float* dout, int64_t ld, cudaStream_t s) {
+            const float* dout, int64_t ld, cudaStream_t s, bool have_dh = false) {
     const int64_t B = d->B, T = e.T, R = B * T;
     const int dd = e.d, h = d->gru_hidden;
     GruWs& w = e.gru;
     INTEL_TRY(linear_dw(B, dd, h, dout, ld, w.h_all + T * h, (T + 1) * h, g.w_out, h, nullptr, s));
-    INTEL_TRY(linear_dx(B, dd, h, dout, ld, p.w_out, h, w.dh, h, s));
+    if (!have_dh) INTEL_TRY(linear_dx(B, dd, h, dout, ld, p.w_out, h, w.dh, h, s));
     if (h == 128) {
         // the fused kernel writes dgh_all[:, 0..T-1] of every session (zeros behind a session's end): only slot T, which
         // pairs with the final state in the weight-gradient product below, needs clearing (6 MB instead of 132 MB)
@@ -790,8 +798,18 @@ int intel_intent_bwd(const intel_dims_t* d, const intel_tensors_t* P, const inte
         INTEL_TRY(bert_bwd(d, P->enc, G->enc, w.e1, bt->history_len, w.dfeat + off_v1, Dp, w.t1, w.t2, w.dqkv, s));
         INTEL_TRY(bert_bwd(d, P->item_enc, G->item_enc, w.e2, bt->history_item_len, w.dfeat + off_v2, Dp, w.t1, w.t2, w.dqkv, s));
     } else {
-        INTEL_TRY(gru_bwd(d, P->enc, G->enc, w.e1, bt->history_len, w.dfeat + off_v1, Dp, s));
-        INTEL_TRY(gru_bwd(d, P->item_enc, G->item_enc, w.e2, bt->history_item_len, w.dfeat + off_v2, Dp, s));
+        bool have_dh = false;
+        if (gru_outproj_pair_ok(d->gru_hidden, w.e1.d, w.e2.d)) {      // d(last state) of both encoders in one launch
+            const int n[2] = {w.e1.d, w.e2.d};
+            const float* W[2] = {P->enc.w_out, P->item_enc.w_out};
+            const float* dv[2] = {w.dfeat + off_v1, w.dfeat + off_v2};
+            float* dh[2] = {w.e1.gru.dh, w.e2.gru.dh};
+            const int64_t ldd[2] = {Dp, Dp}, ldh[2] = {d->gru_hidden, d->gru_hidden};
+            INTEL_TRY(gru_outproj_pair_dx(B, n, W, dv, ldd, dh, ldh, s));
+            have_dh = true;
+        }
+        INTEL_TRY(gru_bwd(d, P->enc, G->enc, w.e1, bt->history_len, w.dfeat + off_v1, Dp, s, have_dh));
+        INTEL_TRY(gru_bwd(d, P->item_enc, G->item_enc, w.e2, bt->history_item_len, w.dfeat + off_v2, Dp, s, have_dh));
     }
     INTEL_TRY(fill_zero(w.dWt, (size_t)I * dint * 4, s));
     INTEL_TRY(scatter_add_rows(B * d->H1, dctx, w.e1.dseq, d1, bt->his_context, G->ctx_emb, nullptr, s, d->ctx_rows));

@@ -250,6 +250,128 @@ int gru_seq_fwd(int64_t B, int64_t T, int h, const int64_t* lens, const float* g
     return check_launch("gru_seq_fwd", (double)B * T * (3 + 4 + 1) * GH * 4.0, 2.0 * B * T * 3 * GH * GH);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Output projections of the two GRU encoders (GeneralSeq.py:76-77: out = Linear(128 -> d, no bias) of the last state) and
+// their input gradients, both encoders in one launch: a [4096 x 48..64 x 128] product is far too small for a GEMM launch of
+// its own (four launches of 22 us each in round 2).  One warp per session; W [n][128] sits in shared memory with row stride 129.
+namespace {
+constexpr int OP_H = 128, OP_WS = OP_H + 1, OP_WARPS = 8, OP_NMAX = 64;
+struct OutProjArgs {
+    int64_t B;
+    int n[2];
+    const float* W[2];
+    const float* x[2]; int64_t ldx[2];      // forward: the last states; backward: d(out) rows
+    float* y[2]; int64_t ldy[2];            // forward: out rows; backward: d(last state) [B, 128]
+};
+}  // namespace
+
+__global__ void __launch_bounds__(OP_WARPS * 32) gru_outproj_fwd_kernel(OutProjArgs a) {
+    DYN_SMEM(float, sm);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    float* Ws[2] = {sm, sm + OP_NMAX * OP_WS};
+    float* xb = sm + 2 * OP_NMAX * OP_WS + w * OP_H;
+    // weights -> shared memory with independent 16-byte loads (nn.Linear weights are 16-byte aligned allocations)
+    for (int i = 0; i < 2; ++i) {
+#pragma unroll 8
+        for (int e = threadIdx.x; e < a.n[i] * (OP_H / 4); e += blockDim.x) {
+            const float4 v = *reinterpret_cast<const float4*>(a.W[i] + 4 * e);
+            float* dst = Ws[i] + (e >> 5) * OP_WS + 4 * (e & 31);
+            dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+        }
+    }
+    __syncthreads();
+    const int64_t nwarps = (int64_t)gridDim.x * OP_WARPS;
+    for (int64_t b = (int64_t)blockIdx.x * OP_WARPS + w; b < a.B; b += nwarps) {
+        for (int i = 0; i < 2; ++i) {
+            const float4 v = *reinterpret_cast<const float4*>(a.x[i] + b * a.ldx[i] + 4 * lane);
+            __syncwarp();
+            *reinterpret_cast<float4*>(xb + 4 * lane) = v;
+            __syncwarp();
+            const int j0 = lane, j1 = lane + 32;
+            const bool on0 = j0 < a.n[i], on1 = j1 < a.n[i];
+            const float* w0 = Ws[i] + (on0 ? j0 : 0) * OP_WS;
+            const float* w1 = Ws[i] + (on1 ? j1 : 0) * OP_WS;
+            float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll 8
+            for (int u = 0; u < OP_H; u += 4) {
+                const float4 h4 = *reinterpret_cast<const float4*>(xb + u);
+                acc0 = fmaf(h4.x, w0[u], fmaf(h4.y, w0[u + 1], fmaf(h4.z, w0[u + 2], fmaf(h4.w, w0[u + 3], acc0))));
+                acc1 = fmaf(h4.x, w1[u], fmaf(h4.y, w1[u + 1], fmaf(h4.z, w1[u + 2], fmaf(h4.w, w1[u + 3], acc1))));
+            }
+            if (on0) a.y[i][b * a.ldy[i] + j0] = acc0;
+            if (on1) a.y[i][b * a.ldy[i] + j1] = acc1;
+        }
+    }
+}
+
+// d(last state)[b, u] = sum_j d(out)[b, j] W[j][u]
+__global__ void __launch_bounds__(OP_WARPS * 32) gru_outproj_dx_kernel(OutProjArgs a) {
+    DYN_SMEM(float, sm);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    float* Ws[2] = {sm, sm + OP_NMAX * OP_WS};
+    float* gb = sm + 2 * OP_NMAX * OP_WS + w * OP_NMAX;
+    // weights -> shared memory with independent 16-byte loads (nn.Linear weights are 16-byte aligned allocations)
+    for (int i = 0; i < 2; ++i) {
+#pragma unroll 8
+        for (int e = threadIdx.x; e < a.n[i] * (OP_H / 4); e += blockDim.x) {
+            const float4 v = *reinterpret_cast<const float4*>(a.W[i] + 4 * e);
+            float* dst = Ws[i] + (e >> 5) * OP_WS + 4 * (e & 31);
+            dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+        }
+    }
+    __syncthreads();
+    const int64_t nwarps = (int64_t)gridDim.x * OP_WARPS;
+    for (int64_t b = (int64_t)blockIdx.x * OP_WARPS + w; b < a.B; b += nwarps) {
+        for (int i = 0; i < 2; ++i) {
+            __syncwarp();
+            gb[lane] = lane < a.n[i] ? a.x[i][b * a.ldx[i] + lane] : 0.f;
+            gb[lane + 32] = lane + 32 < a.n[i] ? a.x[i][b * a.ldx[i] + lane + 32] : 0.f;
+            __syncwarp();
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int j = 0; j < a.n[i]; ++j) {
+                const float g = gb[j];
+                const float* wr = Ws[i] + j * OP_WS + lane;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) acc[q] = fmaf(g, wr[32 * q], acc[q]);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) a.y[i][b * a.ldy[i] + lane + 32 * q] = acc[q];
+        }
+    }
+}
+
+bool gru_outproj_pair_ok(int h, int n0, int n1) { return h == OP_H && n0 >= 1 && n0 <= OP_NMAX && n1 >= 1 && n1 <= OP_NMAX; }
+
+static int gru_outproj_launch(bool dx, int64_t B, const int* n, const float* const* W, const float* const* x, const int64_t* ldx,
+                              float* const* y, const int64_t* ldy, cudaStream_t s) {
+    if (B <= 0) return INTEL_OK;
+    OutProjArgs a;
+    a.B = B;
+    for (int i = 0; i < 2; ++i) {
+        a.n[i] = n[i]; a.W[i] = W[i]; a.x[i] = x[i]; a.ldx[i] = ldx[i]; a.y[i] = y[i]; a.ldy[i] = ldy[i];
+        INTEL_REQUIRE(dx || (ldx[i] % 4 == 0 && (uintptr_t)x[i] % 16 == 0), INTEL_ERR_ARG, "gru_outproj: state rows must be 16-byte aligned");
+        INTEL_REQUIRE((uintptr_t)W[i] % 16 == 0, INTEL_ERR_ARG, "gru_outproj: weights must be 16-byte aligned");
+    }
+    const size_t smem = (size_t)(2 * OP_NMAX * OP_WS + OP_WARPS * OP_H) * 4;
+    const unsigned grid = stream_grid(ceil_div(B, OP_WARPS), 2);
+    if (dx) {
+        ensure_smem(gru_outproj_dx_kernel, smem);
+        LAUNCH(gru_outproj_dx_kernel, dim3(grid), dim3(OP_WARPS * 32), smem, s, a);
+    } else {
+        ensure_smem(gru_outproj_fwd_kernel, smem);
+        LAUNCH(gru_outproj_fwd_kernel, dim3(grid), dim3(OP_WARPS * 32), smem, s, a);
+    }
+    return check_launch(dx ? "gru_outproj_dx" : "gru_outproj_fwd", (double)B * 4.0 * (2 * OP_H + n[0] + n[1]), 2.0 * B * OP_H * (n[0] + n[1]));
+}
+int gru_outproj_pair_fwd(int64_t B, const int* n, const float* const* W, const float* const* h_last, const int64_t* ldh,
+                         float* const* out, const int64_t* ldo, cudaStream_t s) {
+    return gru_outproj_launch(false, B, n, W, h_last, ldh, out, ldo, s);
+}
+int gru_outproj_pair_dx(int64_t B, const int* n, const float* const* W, const float* const* dout, const int64_t* ldd,
+                        float* const* dh, const int64_t* ldh, cudaStream_t s) {
+    return gru_outproj_launch(true, B, n, W, dout, ldd, dh, ldh, s);
+}
+
 // Row numbers of the live (session, step) pairs of a padded [B, T] history, in (b, t) order.  Block k owns sessions
 // [1024 k, 1024 k + 1024): it sums the lengths before them, scans its own and writes its rows; the last block writes the count.
 __device__ void gru_live_rows_body(int blk, int nblk, int64_t B, int T, const int64_t* __restrict__ lens, int32_t* __restrict__ rows_t,

@@ -179,6 +179,12 @@ int gru_order_by_len(int64_t B, int64_t T, const int64_t* lens, int32_t* order, 
 // the live (session, step) pairs of a padded [B, T] history as row numbers, in (b, t) order: rows_t[i] = b T + t into the
 // [B, T, .] tensors, rows_t1[i] = b (T + 1) + t into the [B, T + 1, .] ones; *count = sum of the (clamped) lengths
 int gru_live_rows(int64_t B, int64_t T, const int64_t* lens, int32_t* rows_t, int32_t* rows_t1, int32_t* count, cudaStream_t s);
+// output projections (Linear(128 -> d <= 64), no bias) of both encoders in one launch, and their input gradients
+bool gru_outproj_pair_ok(int h, int n0, int n1);
+int gru_outproj_pair_fwd(int64_t B, const int* n, const float* const* W, const float* const* h_last, const int64_t* ldh,
+                         float* const* out, const int64_t* ldo, cudaStream_t s);
+int gru_outproj_pair_dx(int64_t B, const int* n, const float* const* W, const float* const* dout, const int64_t* ldd,
+                        float* const* dh, const int64_t* ldh, cudaStream_t s);
 // both of the above for up to two encoders in one launch (null pointers skip a part)
 int gru_prep(int n, const int64_t* B, const int64_t* T, const int64_t* const* lens, int32_t* const* rows_t, int32_t* const* rows_t1,
              int32_t* const* count, int32_t* const* order, cudaStream_t s);
