@@ -10,6 +10,7 @@ namespace {
 
 const int NZ_CAP = 16;   // compacted non-zeros kept per dense history row
 inline int64_t pad4(int64_t n) { return (n + 3) & ~(int64_t)3; }
+inline bool al16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
 inline cudaStream_t S(intel_stream_t s) { return (cudaStream_t)s; }
 
@@ -534,14 +535,14 @@ int intel_ensemble_fwd(const intel_dims_t* d, const intel_tensors_t* P, const in
         }
         INTEL_TRY(linear(B, dc, I, intents, I, Wc, I, nullptr, w.qcat, dc, s));
         // item stream, score stream: qk = W_k^T q, the pooling, the value projection into the head input
-        if (cross_full_ok(di, L)) {
+        if (cross_full_ok(di, L) && al16(P->xk_item) && al16(P->xv_item)) {
             INTEL_TRY(cross_full_fwd(B, L, Xi, w.q_i, dc, P->xk_item, P->xv_item, bt->session_len, scale, w.p_i, w.qk_i, w.xbar_i, w.all, D, s));
         } else {
             INTEL_TRY(linear_dx(B, di, di, w.q_i, dc, P->xk_item, di, w.qk_i, di, s));            // qk = W_k^T q
             INTEL_TRY(cross_pool_fwd(B, L, di, Xi, w.qk_i, bt->session_len, scale, w.p_i, w.xbar_i, s));
             INTEL_TRY(linear(B, di, di, w.xbar_i, di, P->xv_item, di, nullptr, w.all, D, s));
         }
-        if (cross_full_ok(ds, L)) {
+        if (cross_full_ok(ds, L) && al16(P->xk_score) && al16(P->xv_score)) {
             INTEL_TRY(cross_full_fwd(B, L, Xs, w.q_s, dc, P->xk_score, P->xv_score, bt->session_len, scale, w.p_s, w.qk_s, w.xbar_s,
                                      w.all + di, D, s));
         } else {
@@ -630,7 +631,7 @@ int intel_ensemble_bwd_phase(const intel_dims_t* d, const intel_tensors_t* P, co
                         *xv = st == 0 ? P->xv_item : P->xv_score;
             float *gxq = st == 0 ? G->xq_item : G->xq_score, *gxk = st == 0 ? G->xk_item : G->xk_score,
                   *gxv = st == 0 ? G->xv_item : G->xv_score;
-            if (cross_full_ok(dd, L)) {
+            if (cross_full_ok(dd, L) && al16(xk) && al16(xv)) {
                 INTEL_TRY(cross_full_bwd(B, L, X, q, dc, qk, xk, xv, bt->session_len, scale, p, xbar, w.dall + off, D, dXst[st],
                                          w.dcat + off, dc, gxk, gxv, s));
             } else {

@@ -330,9 +330,13 @@ __global__ void __launch_bounds__(XF_WARPS * 32) cross_full_fwd_kernel(int64_t B
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     float* vec = Wv_s + 32 * 33 + w * 32;    // the warp's qk
     float* pb = Wv_s + 32 * 33 + XF_WARPS * 32 + w * L;
-    for (int e = threadIdx.x; e < 32 * 32; e += blockDim.x) {
-        Wk_s[(e >> 5) * 33 + (e & 31)] = Wk[e];
-        Wv_s[(e >> 5) * 33 + (e & 31)] = Wv[e];
+#pragma unroll
+    for (int e = threadIdx.x; e < 32 * 32 / 4; e += XF_WARPS * 32) {      // 16-byte loads, all in flight at once
+        const float4 k4 = *reinterpret_cast<const float4*>(Wk + 4 * e), v4 = *reinterpret_cast<const float4*>(Wv + 4 * e);
+        float* dk = Wk_s + (e >> 3) * 33 + 4 * (e & 7);
+        float* dv = Wv_s + (e >> 3) * 33 + 4 * (e & 7);
+        dk[0] = k4.x; dk[1] = k4.y; dk[2] = k4.z; dk[3] = k4.w;
+        dv[0] = v4.x; dv[1] = v4.y; dv[2] = v4.z; dv[3] = v4.w;
     }
     __syncthreads();
     const int64_t nwarps = (int64_t)gridDim.x * XF_WARPS;
@@ -410,11 +414,14 @@ __global__ void __launch_bounds__(XF_WARPS * 32) cross_full_bwd_kernel(int64_t B
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     float* vec = gv_s + 32 * 33 + w * 32;    // the warp's d(xbar)
     float* ab = gv_s + 32 * 33 + XF_WARPS * 32 + w * L;
-    for (int e = threadIdx.x; e < 32 * 32; e += blockDim.x) {
-        Wk_s[(e >> 5) * 33 + (e & 31)] = Wk[e];
-        Wv_s[(e >> 5) * 33 + (e & 31)] = Wv[e];
-        gk_s[(e >> 5) * 33 + (e & 31)] = 0.f;
-        gv_s[(e >> 5) * 33 + (e & 31)] = 0.f;
+#pragma unroll
+    for (int e = threadIdx.x; e < 32 * 32 / 4; e += XF_WARPS * 32) {
+        const float4 k4 = *reinterpret_cast<const float4*>(Wk + 4 * e), v4 = *reinterpret_cast<const float4*>(Wv + 4 * e);
+        const int o = (e >> 3) * 33 + 4 * (e & 7);
+        Wk_s[o] = k4.x; Wk_s[o + 1] = k4.y; Wk_s[o + 2] = k4.z; Wk_s[o + 3] = k4.w;
+        Wv_s[o] = v4.x; Wv_s[o + 1] = v4.y; Wv_s[o + 2] = v4.z; Wv_s[o + 3] = v4.w;
+        gk_s[o] = 0.f; gk_s[o + 1] = 0.f; gk_s[o + 2] = 0.f; gk_s[o + 3] = 0.f;
+        gv_s[o] = 0.f; gv_s[o + 1] = 0.f; gv_s[o + 2] = 0.f; gv_s[o + 3] = 0.f;
     }
     __syncthreads();
     float gk[32], gv[32];                    // lane c: d W_k[a][c], d W_v[e][c]
@@ -494,7 +501,7 @@ __global__ void __launch_bounds__(XF_WARPS * 32) cross_full_bwd_kernel(int64_t B
     }
 }
 
-bool cross_full_ok(int d, int64_t L) { return d == 32 && L >= 1 && L <= 2048; }
+bool cross_full_ok(int d, int64_t L) { return d == 32 && L >= 1 && L <= 2048; }      // (the caller also checks the 16-byte alignment of W_k / W_v)
 
 int cross_full_fwd(int64_t B, int64_t L, const float* X, const float* q, int64_t ldq, const float* Wk, const float* Wv,
                    const int64_t* lens, float scale, float* p, float* qk_out, float* xbar_out, float* out, int64_t ldo, cudaStream_t s) {
