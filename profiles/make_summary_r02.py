@@ -84,6 +84,11 @@ scale = ["| GPUs | config | sessions/s | ms/step | per-GPU efficiency | e2e sess
 for c, base in (('c2', 'r02_bench_c2.json'), ('c4', 'r02_bench_c4.json')):
     if not os.path.exists(P(base)):
         continue
+    # the multi-GPU lines are compared with the single-GPU line measured in the same session (later kernel work moved the
+    # single-GPU line on; the base of the scaling table stays the one the multi-GPU runs were taken with)
+    sb = base.replace('.json', '_scaling_base.json')
+    if os.path.exists(P(sb)):
+        base = sb
     b1 = last_json(base)
     for n, fn in ((1, base), (2, 'r02_bench_%s_2gpu.json' % c if c != 'c2' else 'r02_bench_2gpu.json'),
                   (4, 'r02_bench_%s_4gpu.json' % c if c != 'c2' else 'r02_bench_4gpu.json'),
@@ -109,7 +114,7 @@ clocks {d['clocks']}; {d['gpu_launches'] / d['steps']:.0f} kernel launches per s
 200-slot stack kernel: with them the single-GPU c4 line is {c4f['value']:.0f} sessions/s, {c4f['ms_per_step']:.3f} ms per step -
 r02_bench_c4_fused_bert.json, r02_ncu_bert_fused.jsonl; the c2 / c3 / c5 paths do not run those kernels)
 
-## weak scaling (one rank per GPU, NCCL gradient all-reduce for the train step; none for eval)
+## weak scaling (one rank per GPU, NCCL gradient all-reduce for the train step; none for eval; all lines of one config from one session: *_scaling_base.json is the single-GPU line of that session)
 {chr(10).join(scale)}
 
 ## ncu launch list of one train step
