@@ -843,3 +843,12 @@ def check_bert_fused_vs_staged(device, names=("default_bert", "wide_intent_bert_
         gmax = max(float(np.abs(g).max()) for g in gb.values())
         for n, g in gb.items():
             assert_grad_close(ga[n], g, gmax, f"{name}:{n}")
+
+
+def check_bert_fused_token_tiles(device, B=10):
+    """The fused BERT4Rec encoder is instantiated per token tile (history slots rounded up to 12 / 16 / 20 / 24): each one
+    against the CPU oracle (forward, loss and - through the activations it leaves for the staged backward - gradients);
+    one and two encoder heads."""
+    for hm, heads, bh in ((7, 1, 2), (13, 2, 1), (19, 2, 2), (23, 1, 2)):
+        check_against_oracle(device, seed=hm, B=B, L=9, min_len=2, encoder="BERT4Rec", num_heads=heads, bert_heads=bh,
+                             corpus_kw=dict(history_max=hm))

@@ -142,3 +142,7 @@ def test_gru_prep_index_kernels():
 
 def test_bert_fused_vs_staged():
     P.check_bert_fused_vs_staged("cpu", names=("default_bert",))
+
+
+def test_bert_fused_token_tiles():
+    P.check_bert_fused_token_tiles("cpu", B=6)

@@ -65,6 +65,10 @@ def test_bert_fused_vs_staged():
     P.check_bert_fused_vs_staged(DEV)
 
 
+def test_bert_fused_token_tiles():
+    P.check_bert_fused_token_tiles(DEV, B=37)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ["script_pl_gru", "default_bert"])
 def test_phased_backward_equals_single_call(name):
