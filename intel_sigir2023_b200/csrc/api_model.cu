@@ -816,21 +816,19 @@ int intel_intent_bwd(const intel_dims_t* d, const intel_tensors_t* P, const inte
     INTEL_TRY(scatter_add_rows(B * d->H1, dctx, w.e1.dseq, d1, bt->his_context, G->ctx_emb, nullptr, s, d->ctx_rows));
     if (bt->his_intents_idx) {
         INTEL_TRY(dense_rows_linear_bwd(B * d->H1, I, dint, nullptr, w.e1.dseq + dctx, d1, bt->his_intents_idx,
-                                        bt->his_intents_val, nullptr, bt->nz1, w.dWt, s));
+                                        bt->his_intents_val, nullptr, bt->nz1, w.dWt, s, G->intent_b));
     } else {
         INTEL_TRY(dense_rows_linear_bwd(B * d->H1, I, dint, bt->his_intents, w.e1.dseq + dctx, d1, w.e1.nz_idx, w.e1.nz_val,
-                                        w.e1.nz_cnt, NZ_CAP, w.dWt, s));
+                                        w.e1.nz_cnt, NZ_CAP, w.dWt, s, G->intent_b));      // + the bias gradient (column sums)
     }
-    INTEL_TRY(colsum(B * d->H1, dint, w.e1.dseq + dctx, d1, G->intent_b, s));
     INTEL_TRY(scatter_add_rows(B * d->H2, diid, w.e2.dseq, d2, bt->his_item_id, G->iid_emb, nullptr, s, d->item_rows));
     if (bt->his_item_int_idx) {
         INTEL_TRY(dense_rows_linear_bwd(B * d->H2, I, dint, nullptr, w.e2.dseq + diid, d2, bt->his_item_int_idx,
-                                        bt->his_item_int_val, nullptr, bt->nz2, w.dWt, s));
+                                        bt->his_item_int_val, nullptr, bt->nz2, w.dWt, s, G->intent_b));
     } else {
         INTEL_TRY(dense_rows_linear_bwd(B * d->H2, I, dint, bt->his_item_int, w.e2.dseq + diid, d2, w.e2.nz_idx, w.e2.nz_val,
-                                        w.e2.nz_cnt, NZ_CAP, w.dWt, s));
+                                        w.e2.nz_cnt, NZ_CAP, w.dWt, s, G->intent_b));
     }
-    INTEL_TRY(colsum(B * d->H2, dint, w.e2.dseq + diid, d2, G->intent_b, s));
     return transpose(I, dint, w.dWt, G->intent_w, 1, s);
 }
 

@@ -215,13 +215,16 @@ __global__ void __launch_bounds__(256) dense_rows_bwd_kernel(int64_t R, int64_t 
                                                              const float* __restrict__ dY, int64_t lddy,
                                                              const int32_t* __restrict__ nz_idx,
                                                              const float* __restrict__ nz_val,
-                                                             const int32_t* __restrict__ nz_cnt, int cap, float* dWt) {
+                                                             const int32_t* __restrict__ nz_cnt, int cap, float* dWt, float* db) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    float b0 = 0.f, b1 = 0.f;                  // column sums of dY over this warp's rows = its share of the bias gradient
     for (int64_t r = warp; r < R; r += nwarps) {
         const float g0 = (lane < d) ? dY[r * lddy + lane] : 0.f;
         const float g1 = (lane + 32 < d) ? dY[r * lddy + lane + 32] : 0.f;
+        b0 += g0;
+        b1 += g1;
         const int cnt = nz_cnt ? nz_cnt[r] : (X ? cap + 1 : cap);     // X == null: caller-provided compact rows
         if (cnt <= cap) {
             for (int e = 0; e < cnt; ++e) {
@@ -248,15 +251,28 @@ __global__ void __launch_bounds__(256) dense_rows_bwd_kernel(int64_t R, int64_t 
             }
         }
     }
+    if (db) {                                  // CTA-level sum first: one atomic per column and CTA
+        __shared__ float red[8][64];
+        const int wib = threadIdx.x >> 5;
+        red[wib][lane] = b0;
+        red[wib][lane + 32] = b1;
+        __syncthreads();
+        if (threadIdx.x < 64 && (int)threadIdx.x < d) {
+            float t = 0.f;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) t += red[q][threadIdx.x];
+            if (t != 0.f) atomicAdd(db + threadIdx.x, t);
+        }
+    }
 }
 
 int dense_rows_linear_bwd(int64_t R, int64_t I, int d, const double* X, const float* dY, int64_t lddy,
                           const int32_t* nz_idx, const float* nz_val, const int32_t* nz_cnt, int cap, float* dWt,
-                          cudaStream_t s) {
+                          cudaStream_t s, float* db) {
     if (R <= 0) return INTEL_OK;
     INTEL_REQUIRE(d <= 64, INTEL_ERR_UNSUPPORTED, "intent_emb_size %d > 64 not supported", d);
     unsigned grid = stream_grid(ceil_div(R, 8), 8);
-    LAUNCH(dense_rows_bwd_kernel, dim3(grid), dim3(256), 0, s, R, I, d, X, dY, lddy, nz_idx, nz_val, nz_cnt, cap, dWt);
+    LAUNCH(dense_rows_bwd_kernel, dim3(grid), dim3(256), 0, s, R, I, d, X, dY, lddy, nz_idx, nz_val, nz_cnt, cap, dWt, db);
     return check_launch("dense_rows_bwd", (double)R * (4.0 * d + 4.0), 0.0);
 }
 

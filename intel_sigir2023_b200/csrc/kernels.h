@@ -75,7 +75,7 @@ int dense_rows_linear_fwd(int64_t R, int64_t I, int d, const double* X, const fl
 // dWt[i, :] += float(X[r,i]) * dY[r, :]
 int dense_rows_linear_bwd(int64_t R, int64_t I, int d, const double* X, const float* dY, int64_t lddy,
                           const int32_t* nz_idx, const float* nz_val, const int32_t* nz_cnt, int cap,
-                          float* dWt, cudaStream_t s);
+                          float* dWt, cudaStream_t s, float* db = nullptr);   // db (nullable): += column sums of dY (the bias gradient)
 // compact rows: Y[r,:] = sum_e val[r,e] * Wt[idx[r,e],:] + bias.  Its backward is dense_rows_linear_bwd with
 // X = null, nz_idx/nz_val = the caller's arrays, nz_cnt = null, cap = nz.
 int sparse_rows_linear_fwd(int64_t R, int nz, int d, const int32_t* idx, const float* val, const float* Wt,
