@@ -701,7 +701,8 @@ int intel_ensemble_bwd_phase(const intel_dims_t* d, const intel_tensors_t* P, co
                                  d->dropout_seed, 1, s);
         trunk_reserve_apply(false);
         INTEL_TRY(st);
-        INTEL_TRY(linear_dw(R, ds, K, w.dXs, ds, w.xs, K, G->score_w, K, G->score_b, s));
+        if (score_embed_bwd_ok(K, ds)) INTEL_TRY(score_embed_bwd(R, K, ds, w.dXs, ds, w.xs, G->score_w, G->score_b, s));
+        else INTEL_TRY(linear_dw(R, ds, K, w.dXs, ds, w.xs, K, G->score_w, K, G->score_b, s));
     }
     return INTEL_OK;
 }

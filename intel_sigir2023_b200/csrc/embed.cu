@@ -320,13 +320,128 @@ __global__ void __launch_bounds__(256) score_embed_kernel(int64_t R, int K, int 
     }
 }
 
+// Same, four output channels per thread: the thread's channel group is fixed (the grid stride is a multiple of d/4), so
+// its 4 x K weights and biases stay in registers and every row costs K loads and one 16-byte store.
+constexpr int SE_K = 8;
+__global__ void __launch_bounds__(256) score_embed_v4_kernel(int64_t R, int K, int d, const double* __restrict__ scores,
+                                                             const float* __restrict__ W, const float* __restrict__ b,
+                                                             float* __restrict__ Y, float* __restrict__ xs) {
+    const int gpr = d >> 2;                                    // channel groups per row
+    const int cg = (int)(threadIdx.x % gpr);
+    float wr[4][SE_K], br[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        br[j] = b[cg * 4 + j];
+#pragma unroll
+        for (int k = 0; k < SE_K; ++k) wr[j][k] = (k < K) ? W[(cg * 4 + j) * K + k] : 0.f;
+    }
+    const int64_t rpb = blockDim.x / gpr;                      // rows one CTA covers per sweep
+    const int64_t r0 = (int64_t)blockIdx.x * rpb + threadIdx.x / gpr;
+    for (int64_t r = r0; r < R; r += (int64_t)gridDim.x * rpb) {
+        float x[SE_K];
+#pragma unroll
+        for (int k = 0; k < SE_K; ++k) x[k] = (k < K) ? (float)scores[r * K + k] : 0.f;
+        float4 y;
+        float* yy = &y.x;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float acc = br[j];
+#pragma unroll
+            for (int k = 0; k < SE_K; ++k)
+                if (k < K) acc = fmaf(wr[j][k], x[k], acc);
+            yy[j] = acc;
+        }
+        *reinterpret_cast<float4*>(Y + r * d + cg * 4) = y;
+        if (xs) {
+#pragma unroll
+            for (int k = 0; k < SE_K; ++k)
+                if (k < K && (k >> 2) == cg) xs[r * K + k] = x[k];
+        }
+    }
+}
+
 int score_embed_fwd(int64_t R, int K, int d, const double* scores, const float* W, const float* b, float* Y, float* xs,
                     cudaStream_t s) {
     if (R <= 0) return INTEL_OK;
     INTEL_REQUIRE(!xs || K <= d, INTEL_ERR_UNSUPPORTED, "score_embed: model_num %d > s_emb_size %d", K, d);
-    unsigned grid = stream_grid(ceil_div(R * d, 256), 8);
-    LAUNCH(score_embed_kernel, dim3(grid), dim3(256), 0, s, R, K, d, scores, W, b, Y, xs);
+    if (K <= SE_K && d % 4 == 0 && 256 % (d / 4) == 0 && (reinterpret_cast<uintptr_t>(Y) & 15) == 0) {
+        unsigned grid = stream_grid(ceil_div(R * (d / 4), 256 * 4), 8);
+        LAUNCH(score_embed_v4_kernel, dim3(grid), dim3(256), 0, s, R, K, d, scores, W, b, Y, xs);
+    } else {
+        unsigned grid = stream_grid(ceil_div(R * d, 256), 8);
+        LAUNCH(score_embed_kernel, dim3(grid), dim3(256), 0, s, R, K, d, scores, W, b, Y, xs);
+    }
     return check_launch("score_embed", (double)R * (8.0 * K + 4.0 * d + 4.0 * K), 2.0 * R * K * d);
+}
+
+// Backward of score_embeddings: gW[c,k] += sum_r dY[r,c] xs[r,k],  gb[c] += sum_r dY[r,c].  One pass over dY (the
+// product has only K <= 8 columns, so a warp keeps its share of gW in registers: lane = output channel), summed per CTA
+// in shared memory, one global atomic per entry and CTA (the 9 x d addresses sit in a handful of L2 lines, so the number
+// of CTAs, not the bytes, sets the cost of that tail).
+constexpr int SEB_K = 8;
+constexpr int SEB_THREADS = 768;               // one CTA per SM: the atomics at the end are per CTA, so few large CTAs
+__global__ void __launch_bounds__(SEB_THREADS, 1) score_embed_bwd_kernel(int64_t R, int K, int d, const float* __restrict__ dY,
+                                                                          int64_t lddy, const float* __restrict__ xs,
+                                                                          float* gW, float* gb) {
+    __shared__ float red[SEB_K + 1][64];
+    for (int e = threadIdx.x; e < (SEB_K + 1) * 64; e += blockDim.x) (&red[0][0])[e] = 0.f;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    float a0[SEB_K + 1], a1[SEB_K + 1];        // [k] = weight gradient column k, [SEB_K] = bias gradient
+#pragma unroll
+    for (int k = 0; k <= SEB_K; ++k) a0[k] = a1[k] = 0.f;
+    const bool c0 = lane < d, c1 = lane + 32 < d;
+    constexpr int U = 8;                       // rows in flight per warp (the loop is otherwise one 128-byte load deep)
+    for (int64_t rb = warp * U; rb < R; rb += nwarps * U) {
+        float g0[U], g1[U], xv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t r = rb + u;
+            const bool live = r < R;
+            g0[u] = (live && c0) ? dY[r * lddy + lane] : 0.f;
+            g1[u] = (live && c1) ? dY[r * lddy + lane + 32] : 0.f;
+            xv[u] = (live && lane < K) ? xs[r * K + lane] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+#pragma unroll
+            for (int k = 0; k < SEB_K; ++k) {
+                const float x = __shfl_sync(0xffffffffu, xv[u], k);
+                a0[k] = fmaf(g0[u], x, a0[k]);
+                a1[k] = fmaf(g1[u], x, a1[k]);
+            }
+            a0[SEB_K] += g0[u];
+            a1[SEB_K] += g1[u];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k <= SEB_K; ++k) {
+        if (k < SEB_K && k >= K) continue;
+        if (c0) atomicAdd(&red[k][lane], a0[k]);
+        if (c1) atomicAdd(&red[k][lane + 32], a1[k]);
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < (SEB_K + 1) * 64; e += blockDim.x) {
+        const int k = e >> 6, c = e & 63;
+        if (c >= d || (k < SEB_K && k >= K)) continue;
+        const float t = red[k][c];
+        if (t == 0.f) continue;
+        if (k < SEB_K) atomicAdd(gW + (int64_t)c * K + k, t);
+        else if (gb) atomicAdd(gb + c, t);
+    }
+}
+
+bool score_embed_bwd_ok(int K, int d) { return K <= SEB_K && d <= 64; }
+
+int score_embed_bwd(int64_t R, int K, int d, const float* dY, int64_t lddy, const float* xs, float* gW, float* gb,
+                    cudaStream_t s) {
+    if (R <= 0) return INTEL_OK;
+    INTEL_REQUIRE(score_embed_bwd_ok(K, d), INTEL_ERR_UNSUPPORTED, "score_embed_bwd: model_num %d / s_emb_size %d", K, d);
+    unsigned grid = stream_grid(ceil_div(R, (SEB_THREADS / 32) * 8), 1);
+    LAUNCH(score_embed_bwd_kernel, dim3(grid), dim3(SEB_THREADS), 0, s, R, K, d, dY, lddy, xs, gW, gb);
+    return check_launch("score_embed_bwd", (double)R * (4.0 * d + 4.0 * K), 2.0 * R * K * d);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -85,6 +85,10 @@ int transpose(int64_t rows, int64_t cols, const float* in, float* out, int accum
 // scores f64 [R,K] -> Y[R, d] = W[d,K] x + b  (score_embeddings) and the f32 copy xs[R,K]
 int score_embed_fwd(int64_t R, int K, int d, const double* scores, const float* W, const float* b, float* Y,
                     float* xs, cudaStream_t s);
+// backward of score_embeddings in one pass over dY: gW[d,K] += dY^T xs, gb[d] += column sums  (K <= 8, d <= 64)
+bool score_embed_bwd_ok(int K, int d);
+int score_embed_bwd(int64_t R, int K, int d, const float* dY, int64_t lddy, const float* xs, float* gW, float* gb,
+                    cudaStream_t s);
 // seq[b, t, :] += pos[(t < len[b]) ? t : 0, :]   (BERT4RecEncoder positions)
 int add_positions(int64_t B, int64_t T, int d, const int64_t* lens, const float* pos, float* seq, cudaStream_t s);
 // d_pos[(t < len[b]) ? t : 0, :] += d_seq[b, t, :]
