@@ -146,6 +146,9 @@ __device__ __noinline__ void pl_pairs_session(const LossArgs& a, int64_t b, int 
 
 static const int PL_LEVELS = 3;         // rank levels that can sit below a positive: 0, 1, 2
 
+// KM = compile-time bound on model_num: the bucket sums are KM-wide register arrays (K <= 4 covers the reference's datasets
+// at a third of the registers of the general instance, i.e. twice the sessions in flight per SM)
+template <int KM>
 __global__ void __launch_bounds__(LOSS_WARPS * 32) loss_pl_kernel(LossArgs a) {
     DYN_SMEM(float, sm);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -180,12 +183,12 @@ __global__ void __launch_bounds__(LOSS_WARPS * 32) loss_pl_kernel(LossArgs a) {
     float m = -INFINITY;
     for (int64_t j = lane; j < n; j += 32) m = fmaxf(m, s[j]);
     m = warp_max(m);
-    float A[PL_LEVELS], C[PL_LEVELS][LOSS_MAX_K];
+    float A[PL_LEVELS], C[PL_LEVELS][KM];
 #pragma unroll
     for (int q = 0; q < PL_LEVELS; ++q) {
         A[q] = 0.f;
 #pragma unroll
-        for (int k = 0; k < LOSS_MAX_K; ++k) C[q][k] = 0.f;
+        for (int k = 0; k < KM; ++k) C[q][k] = 0.f;
     }
     for (int64_t j = lane; j < n; j += 32) {
         const int rj = r[j];
@@ -195,7 +198,7 @@ __global__ void __launch_bounds__(LOSS_WARPS * 32) loss_pl_kernel(LossArgs a) {
         for (int q = 0; q < PL_LEVELS; ++q) A[q] += (rj == q) ? e : 0.f;
         if (div) {
 #pragma unroll
-            for (int k = 0; k < LOSS_MAX_K; ++k) {
+            for (int k = 0; k < KM; ++k) {
                 if (k < K) {
                     const float eu = e * ((float)xb[j * K + k] - s[j]);
 #pragma unroll
@@ -209,7 +212,7 @@ __global__ void __launch_bounds__(LOSS_WARPS * 32) loss_pl_kernel(LossArgs a) {
         A[q] = warp_sum(A[q]);
         if (div) {
 #pragma unroll
-            for (int k = 0; k < LOSS_MAX_K; ++k)
+            for (int k = 0; k < KM; ++k)
                 if (k < K) C[q][k] = warp_sum(C[q][k]);
         }
     }
@@ -218,15 +221,15 @@ __global__ void __launch_bounds__(LOSS_WARPS * 32) loss_pl_kernel(LossArgs a) {
     for (int q = 1; q < PL_LEVELS; ++q) {
         A[q] += A[q - 1];
 #pragma unroll
-        for (int k = 0; k < LOSS_MAX_K; ++k) C[q][k] += C[q - 1][k];
+        for (int k = 0; k < KM; ++k) C[q][k] += C[q - 1][k];
     }
     // ---- pass B: the positives (lanes over items), bucket sums of their gradient coefficients by rank ----
-    float Ga[PL_LEVELS], Gb[PL_LEVELS][LOSS_MAX_K];      // level q: positives of rank q + 1
+    float Ga[PL_LEVELS], Gb[PL_LEVELS][KM];      // level q: positives of rank q + 1
 #pragma unroll
     for (int q = 0; q < PL_LEVELS; ++q) {
         Ga[q] = 0.f;
 #pragma unroll
-        for (int k = 0; k < LOSS_MAX_K; ++k) Gb[q][k] = 0.f;
+        for (int k = 0; k < KM; ++k) Gb[q][k] = 0.f;
     }
     double loss_acc = 0.0;
     for (int64_t i = lane; i < L; i += 32) {
@@ -247,9 +250,9 @@ __global__ void __launch_bounds__(LOSS_WARPS * 32) loss_pl_kernel(LossArgs a) {
         float alpha_i = cl * inv1;
         if (div) {
             float G = 0.f, H = 0.f, t1 = 0.f;
-            float F[LOSS_MAX_K], wi[LOSS_MAX_K], ui[LOSS_MAX_K];
+            float F[KM], wi[KM], ui[KM];
 #pragma unroll
-            for (int k = 0; k < LOSS_MAX_K; ++k) {
+            for (int k = 0; k < KM; ++k) {
                 F[k] = 0.f; wi[k] = 0.f; ui[k] = 0.f;
                 if (k < K) {
                     float Clo = 0.f;
@@ -266,7 +269,7 @@ __global__ void __launch_bounds__(LOSS_WARPS * 32) loss_pl_kernel(LossArgs a) {
             dsi += cd * (H * inv2 + G * E * inv3);
             alpha_i -= cd * G * inv3;
 #pragma unroll
-            for (int k = 0; k < LOSS_MAX_K; ++k) {
+            for (int k = 0; k < KM; ++k) {
                 if (k < K) {
                     const float q_ik = cd * inv2 * wi[k] * F[k];
                     t1 = fmaf(q_ik, ui[k] + 1.f, t1);
@@ -288,7 +291,7 @@ __global__ void __launch_bounds__(LOSS_WARPS * 32) loss_pl_kernel(LossArgs a) {
         Ga[q] = warp_sum(Ga[q]);
         if (div) {
 #pragma unroll
-            for (int k = 0; k < LOSS_MAX_K; ++k)
+            for (int k = 0; k < KM; ++k)
                 if (k < K) Gb[q][k] = warp_sum(Gb[q][k]);
         }
     }
@@ -297,7 +300,7 @@ __global__ void __launch_bounds__(LOSS_WARPS * 32) loss_pl_kernel(LossArgs a) {
     for (int q = PL_LEVELS - 2; q >= 0; --q) {
         Ga[q] += Ga[q + 1];
 #pragma unroll
-        for (int k = 0; k < LOSS_MAX_K; ++k) Gb[q][k] += Gb[q + 1][k];
+        for (int k = 0; k < KM; ++k) Gb[q][k] += Gb[q + 1][k];
     }
     __syncwarp();
     // ---- pass C: what every valid item receives from the positives ranked above it ----
@@ -311,7 +314,7 @@ __global__ void __launch_bounds__(LOSS_WARPS * 32) loss_pl_kernel(LossArgs a) {
             float acc = ga;
             if (div) {
 #pragma unroll
-                for (int k = 0; k < LOSS_MAX_K; ++k) {
+                for (int k = 0; k < KM; ++k) {
                     if (k < K) {
                         float gb = 0.f;
 #pragma unroll
@@ -464,8 +467,13 @@ static int launch_loss(int which, LossArgs a, cudaStream_t s) {
     INTEL_REQUIRE(smem <= 200 * 1024, INTEL_ERR_UNSUPPORTED, "loss: list length %lld too long", (long long)a.L);
     dim3 grid((unsigned)ceil_div(a.B, LOSS_WARPS)), block(LOSS_WARPS * 32);
     if (which == 0) {
-        ensure_smem(loss_pl_kernel, smem);
-        LAUNCH(loss_pl_kernel, grid, block, smem, s, a);
+        if (a.K <= 4) {
+            ensure_smem(loss_pl_kernel<4>, smem);
+            LAUNCH(loss_pl_kernel<4>, grid, block, smem, s, a);
+        } else {
+            ensure_smem(loss_pl_kernel<LOSS_MAX_K>, smem);
+            LAUNCH(loss_pl_kernel<LOSS_MAX_K>, grid, block, smem, s, a);
+        }
     } else if (which == 1) {
         ensure_smem(loss_bpr_kernel, smem);
         LAUNCH(loss_bpr_kernel, grid, block, smem, s, a);
@@ -486,6 +494,7 @@ __device__ __forceinline__ int float_order_key(float f) {
 
 __global__ void __launch_bounds__(256) intent_min_kernel(int64_t n, const float* __restrict__ p, int* key_out) {
     int best = 0x7fffffff;
+#pragma unroll 8
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
         const int k = float_order_key(p[e]);
         best = k < best ? k : best;
@@ -515,23 +524,38 @@ __global__ void __launch_bounds__(256) intent_loss_kernel(int64_t B, int64_t I, 
         }
         double ce = 0.0, kl = 0.0;
         float gdot = 0.f;
-        for (int64_t c = lane; c < I; c += 32) {
-            const float q = soften ? (p[c] + 1e-6f) / S : p[c];
-            const double tc = t[c];
-            const float lq = logf(q);
-            float g = 0.f;
-            if (tc > 0.0) {
-                ce -= tc * (double)lq;
-                const float t32 = (float)tc;
-                kl += (double)(t32 * logf(t32) - t32 * lq);
-                g = -((1.f - kw) * (float)tc + kw * T2 * t32) / q;
-            } else if (tc == 0.0) {
-                ce -= (double)logf(1.f - q);
-                g = (1.f - kw) / (1.f - q);
+        // four elements per lane in flight (the loop is otherwise one 4 + 8 byte load deep and latency bound); each lane
+        // still accumulates its elements in ascending order
+        for (int64_t c0 = lane; c0 < I; c0 += 128) {
+            float pv[4];
+            double tv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int64_t c = c0 + 32 * u;
+                pv[u] = c < I ? p[c] : 1.f;
+                tv[u] = c < I ? t[c] : -1.0;
             }
-            g *= invB;
-            gdot = fmaf(g, q, gdot);
-            d_pred[b * I + c] = g;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int64_t c = c0 + 32 * u;
+                if (c >= I) break;
+                const float q = soften ? (pv[u] + 1e-6f) / S : pv[u];
+                const double tc = tv[u];
+                const float lq = logf(q);
+                float g = 0.f;
+                if (tc > 0.0) {
+                    ce -= tc * (double)lq;
+                    const float t32 = (float)tc;
+                    kl += (double)(t32 * logf(t32) - t32 * lq);
+                    g = -((1.f - kw) * (float)tc + kw * T2 * t32) / q;
+                } else if (tc == 0.0) {
+                    ce -= (double)logf(1.f - q);
+                    g = (1.f - kw) / (1.f - q);
+                }
+                g *= invB;
+                gdot = fmaf(g, q, gdot);
+                d_pred[b * I + c] = g;
+            }
         }
         ce = warp_sum_d(ce);
         kl = warp_sum_d(kl) * (double)T2;

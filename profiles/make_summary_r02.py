@@ -110,9 +110,10 @@ clocks {d['clocks']}; {d['gpu_launches'] / d['steps']:.0f} kernel launches per s
 ## every BASELINE config, 1 GPU
 {chr(10).join(cfg_rows)}
 
-(the c4 line and the c4 multi-GPU lines below were taken before the fused BERT4Rec encoder and the second warpgroup of the
-200-slot stack kernel: with them the single-GPU c4 line is {c4f['value']:.0f} sessions/s, {c4f['ms_per_step']:.3f} ms per step -
-r02_bench_c4_fused_bert.json, r02_ncu_bert_fused.jsonl; the c2 / c3 / c5 paths do not run those kernels)
+(all four lines above are from the final kernels of the round.  The multi-GPU lines below are older: the c2 ones were taken
+at a 4.30 ms step, the c4 ones before the fused BERT4Rec encoder and the second warpgroup of the 200-slot stack kernel, which
+took the single-GPU c4 line from 1.27 M to {c4f['value']:.0f} sessions/s that day - r02_bench_c4_fused_bert.json,
+r02_ncu_bert_fused.jsonl; efficiencies are computed against the single-GPU line of the same session)
 
 ## weak scaling (one rank per GPU, NCCL gradient all-reduce for the train step; none for eval; all lines of one config from one session: *_scaling_base.json is the single-GPU line of that session)
 {chr(10).join(scale)}
