@@ -337,25 +337,37 @@ __global__ void __launch_bounds__(256) score_embed_v4_kernel(int64_t R, int K, i
     }
     const int64_t rpb = blockDim.x / gpr;                      // rows one CTA covers per sweep
     const int64_t r0 = (int64_t)blockIdx.x * rpb + threadIdx.x / gpr;
-    for (int64_t r = r0; r < R; r += (int64_t)gridDim.x * rpb) {
-        float x[SE_K];
+    const int64_t stride = (int64_t)gridDim.x * rpb;
+    constexpr int UR = 1;                                      // rows in flight per thread (2 measured slower on the B200: 101
+                                                               // registers, 29 us against 23 us per launch)
+    for (int64_t rb = r0; rb < R; rb += UR * stride) {
+        float x[UR][SE_K];
 #pragma unroll
-        for (int k = 0; k < SE_K; ++k) x[k] = (k < K) ? (float)scores[r * K + k] : 0.f;
-        float4 y;
-        float* yy = &y.x;
+        for (int u = 0; u < UR; ++u) {
+            const int64_t r = rb + u * stride;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            float acc = br[j];
-#pragma unroll
-            for (int k = 0; k < SE_K; ++k)
-                if (k < K) acc = fmaf(wr[j][k], x[k], acc);
-            yy[j] = acc;
+            for (int k = 0; k < SE_K; ++k) x[u][k] = (k < K && r < R) ? (float)scores[r * K + k] : 0.f;
         }
-        *reinterpret_cast<float4*>(Y + r * d + cg * 4) = y;
-        if (xs) {
 #pragma unroll
-            for (int k = 0; k < SE_K; ++k)
-                if (k < K && (k >> 2) == cg) xs[r * K + k] = x[k];
+        for (int u = 0; u < UR; ++u) {
+            const int64_t r = rb + u * stride;
+            if (r >= R) break;
+            float4 y;
+            float* yy = &y.x;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float acc = br[j];
+#pragma unroll
+                for (int k = 0; k < SE_K; ++k)
+                    if (k < K) acc = fmaf(wr[j][k], x[u][k], acc);
+                yy[j] = acc;
+            }
+            *reinterpret_cast<float4*>(Y + r * d + cg * 4) = y;
+            if (xs) {
+#pragma unroll
+                for (int k = 0; k < SE_K; ++k)
+                    if (k < K && (k >> 2) == cg) xs[r * K + k] = x[u][k];
+            }
         }
     }
 }
@@ -380,6 +392,7 @@ int score_embed_fwd(int64_t R, int K, int d, const double* scores, const float* 
 // of CTAs, not the bytes, sets the cost of that tail).
 constexpr int SEB_K = 8;
 constexpr int SEB_THREADS = 768;               // one CTA per SM: the atomics at the end are per CTA, so few large CTAs
+template <bool WIDE>                           // WIDE: d > 32, a second channel per lane
 __global__ void __launch_bounds__(SEB_THREADS, 1) score_embed_bwd_kernel(int64_t R, int K, int d, const float* __restrict__ dY,
                                                                           int64_t lddy, const float* __restrict__ xs,
                                                                           float* gW, float* gb) {
@@ -392,7 +405,7 @@ __global__ void __launch_bounds__(SEB_THREADS, 1) score_embed_bwd_kernel(int64_t
     float a0[SEB_K + 1], a1[SEB_K + 1];        // [k] = weight gradient column k, [SEB_K] = bias gradient
 #pragma unroll
     for (int k = 0; k <= SEB_K; ++k) a0[k] = a1[k] = 0.f;
-    const bool c0 = lane < d, c1 = lane + 32 < d;
+    const bool c0 = lane < d, c1 = WIDE && lane + 32 < d;
     constexpr int U = 8;                       // rows in flight per warp (the loop is otherwise one 128-byte load deep)
     for (int64_t rb = warp * U; rb < R; rb += nwarps * U) {
         float g0[U], g1[U], xv[U];
@@ -401,7 +414,7 @@ __global__ void __launch_bounds__(SEB_THREADS, 1) score_embed_bwd_kernel(int64_t
             const int64_t r = rb + u;
             const bool live = r < R;
             g0[u] = (live && c0) ? dY[r * lddy + lane] : 0.f;
-            g1[u] = (live && c1) ? dY[r * lddy + lane + 32] : 0.f;
+            g1[u] = (WIDE && live && c1) ? dY[r * lddy + lane + 32] : 0.f;
             xv[u] = (live && lane < K) ? xs[r * K + lane] : 0.f;
         }
 #pragma unroll
@@ -410,10 +423,10 @@ __global__ void __launch_bounds__(SEB_THREADS, 1) score_embed_bwd_kernel(int64_t
             for (int k = 0; k < SEB_K; ++k) {
                 const float x = __shfl_sync(0xffffffffu, xv[u], k);
                 a0[k] = fmaf(g0[u], x, a0[k]);
-                a1[k] = fmaf(g1[u], x, a1[k]);
+                if (WIDE) a1[k] = fmaf(g1[u], x, a1[k]);
             }
             a0[SEB_K] += g0[u];
-            a1[SEB_K] += g1[u];
+            if (WIDE) a1[SEB_K] += g1[u];
         }
     }
 #pragma unroll
@@ -440,7 +453,11 @@ int score_embed_bwd(int64_t R, int K, int d, const float* dY, int64_t lddy, cons
     if (R <= 0) return INTEL_OK;
     INTEL_REQUIRE(score_embed_bwd_ok(K, d), INTEL_ERR_UNSUPPORTED, "score_embed_bwd: model_num %d / s_emb_size %d", K, d);
     unsigned grid = stream_grid(ceil_div(R, (SEB_THREADS / 32) * 8), 1);
-    LAUNCH(score_embed_bwd_kernel, dim3(grid), dim3(SEB_THREADS), 0, s, R, K, d, dY, lddy, xs, gW, gb);
+    if (d > 32) {
+        LAUNCH(score_embed_bwd_kernel<true>, dim3(grid), dim3(SEB_THREADS), 0, s, R, K, d, dY, lddy, xs, gW, gb);
+    } else {
+        LAUNCH(score_embed_bwd_kernel<false>, dim3(grid), dim3(SEB_THREADS), 0, s, R, K, d, dY, lddy, xs, gW, gb);
+    }
     return check_launch("score_embed_bwd", (double)R * (4.0 * d + 4.0 * K), 2.0 * R * K * d);
 }
 

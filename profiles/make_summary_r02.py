@@ -37,7 +37,8 @@ name_map = {'trunk_bwd_kernel': 'trunk_bwd', 'trunk_tc_fwd_kernel': 'trunk_fwd',
             'loss_pl_kernel': 'loss_pl', 'intent_loss_kernel': 'intent_loss', 'gemm_wgrad_tc_kernel': 'gemm_wgrad',
             'gemm_rows_tc_kernel': 'gemm_rows', 'cross_pool_bwd_kernel': 'cross_pool_bwd', 'gemm_umma_kernel': 'gemm_umma'}
 for src, note in (('r02_ncu_train.jsonl', 'train step (activations saved)'),
-                  ('r02_ncu_eval.jsonl', 'eval step (inference mode: nothing saved) + one device-built batch')):
+                  ('r02_ncu_eval.jsonl', 'eval step (inference mode: nothing saved) + one device-built batch'),
+                  ('r02_ncu_late.jsonl', 'train step, late (the small kernels rewritten after the main capture; these rows replace the older ones above)')):
     if not os.path.exists(P(src)):
         continue
     for line in open(P(src)):
@@ -47,7 +48,11 @@ for src, note in (('r02_ncu_train.jsonl', 'train step (activations saved)'),
         if key in seen:
             continue
         seen.add(key)
-        dr, dw = float(f(rr, 'dram__bytes_read.sum')), float(f(rr, 'dram__bytes_write.sum'))
+        def mb(key):                            # ncu prints "12.3 Mbyte" / "721.4 Kbyte" / "1.2 Gbyte" / "512 byte"
+            t = (rr.get(key, '') or '0 byte').split()
+            unit = (t[1] if len(t) > 1 else 'byte').lower()
+            return float(t[0]) * {'byte': 1e-6, 'kbyte': 1e-3, 'mbyte': 1.0, 'gbyte': 1e3}.get(unit, 1.0)
+        dr, dw = mb('dram__bytes_read.sum'), mb('dram__bytes_write.sum')
         tens = rr.get('sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active',
                       f(rr, 'sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active'))
         try:
