@@ -84,6 +84,23 @@ def test_against_oracle_multi_tile():
                            corpus_kw=dict(history_max=4, intent_num=24))
 
 
+def test_against_oracle_six_basic_models():
+    """model_num = 6: the general instances of the list-loss kernel (bucket sums bounded at 16 models) and of the score
+    embedding kernels, and the staged weight head (the folded one covers K = 2..4)"""
+    P.check_against_oracle("cpu", seed=4, B=11, L=10, encoder="GRU4Rec", num_heads=2, num_layers=1,
+                           corpus_kw=dict(model_num=6, history_max=4, intent_num=24))
+
+
+def test_against_oracle_wide_score_embedding():
+    """s_emb_size = 48: the two-channels-per-lane instance of the score embedding backward and the scalar forward"""
+    P.check_against_oracle("cpu", seed=6, B=7, L=8, encoder="GRU4Rec", num_heads=2, num_layers=1, s_emb_size=48,
+                           corpus_kw=dict(model_num=5, history_max=4, intent_num=24))
+
+
+def test_list_loss_forms_seven_models():
+    P.check_list_loss_forms("cpu", B=13, L=19, K=7, seed=9)
+
+
 @pytest.mark.parametrize("intent_num", [12, 2048])
 def test_config3_shapes_against_the_oracle(intent_num):
     P.check_config3_shapes("cpu", intent_num)
